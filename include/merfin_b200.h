@@ -1,0 +1,233 @@
+/*
+ * merfin_b200.h -- C ABI of the B200-native per-base k-mer multiplicity path.
+ *
+ * This is the drop-in boundary for merfin's -hist / -dump / -completeness inner
+ * loops and the -polish/-filter path scoring.  Plain C: opaque handles, plain
+ * pointers and sizes.  No C++ or torch types cross it.  Every entry point
+ * returns MFN_OK (0) or a negative mfn_status; nothing here calls exit().
+ *
+ * One mfn_ctx drives ONE CUDA device (one process per GPU).  Multi-GPU runs
+ * shard the tiles of a sequence set across ranks (shard, nshards arguments),
+ * each rank accumulates into an mfn_accum whose device buffer is a flat
+ * uint64 array that the caller sum-all-reduces (NCCL) before mfn_accum_fetch.
+ *
+ * There is NO CPU fallback: without a CUDA device mfn_ctx_create fails with
+ * MFN_ERR_NO_DEVICE and every other call needs a ctx.
+ *
+ * Citations (file:line) are relative to the reference tree
+ * (arangrhie/merfin @ 04c4332e); each entry point names the reference
+ * interface it replaces.
+ */
+#ifndef MERFIN_B200_H
+#define MERFIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MFN_OK                 =  0,
+  MFN_ERR_NO_DEVICE      = -1,   /* no usable CUDA device (there is no CPU path)        */
+  MFN_ERR_CUDA           = -2,   /* a CUDA call failed; see mfn_last_error()            */
+  MFN_ERR_IO             = -3,   /* file missing / unreadable                           */
+  MFN_ERR_FORMAT         = -4,   /* not a meryl database / corrupt block                */
+  MFN_ERR_UNSUPPORTED    = -5,   /* k > 32, multiset database, ...                      */
+  MFN_ERR_INVALID        = -6,   /* bad argument                                        */
+  MFN_ERR_CAPACITY       = -7,   /* caller buffer or internal side table too small      */
+  MFN_ERR_K_MISMATCH     = -8,   /* tables built for different k (kmers-reader.C:171)   */
+  MFN_ERR_NOMEM          = -9
+} mfn_status;
+
+typedef struct mfn_ctx   mfn_ctx;     /* one device, its streams and staging buffers      */
+typedef struct mfn_table mfn_table;   /* one k-mer -> value table resident in HBM         */
+typedef struct mfn_seq   mfn_seq;     /* a set of sequences, 2-bit packed, resident       */
+typedef struct mfn_accum mfn_accum;   /* joint (v_read, v_asm) histogram + record counters */
+
+const char *mfn_strerror(int status);
+const char *mfn_last_error(void);          /* thread-local detail of the last failure */
+const char *mfn_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+
+int  mfn_ctx_create(mfn_ctx **ctx, int device);
+void mfn_ctx_destroy(mfn_ctx *ctx);
+int  mfn_ctx_device(const mfn_ctx *ctx);
+/* Run all subsequent work of this ctx on an existing CUDA stream (cudaStream_t
+ * passed as void*; NULL = the ctx's own stream).  Lets a host framework that
+ * owns the device (e.g. torch) order our kernels with its collectives. */
+int  mfn_ctx_set_stream(mfn_ctx *ctx, void *cuda_stream);
+int  mfn_ctx_sync(mfn_ctx *ctx);
+/* Pinned host memory for callers that want full-rate H2D/D2H of their buffers. */
+int  mfn_host_alloc(void **p, size_t bytes);
+void mfn_host_free(void *p);
+
+/* ---- tables: replaces merylExactLookup::load / ::value -------------------
+ * kmers-lookup.H:118-137, kmers-exact.C:34-73 (filter, offset), 648-671.      */
+
+/* Load an on-disk meryl database (formats v01-v03; kmers-reader.C:127-206,
+ * kmers-files.C:24-128).  minV/maxV follow merfin's -min/-max: 0 -> 1,
+ * UINT32_MAX -> largest value in the DB; entries outside are dropped and the
+ * stored value is v-(minV-1), which is what value() returns (Q1). */
+int  mfn_table_load(mfn_ctx *ctx, const char *meryl_dir, uint32_t minV, uint32_t maxV,
+                    mfn_table **out);
+/* Build from host arrays of (k-mer, value); k-mers use meryl's 2-bit code
+ * A=0 C=1 T=2 G=3, first base in the high bits (kmers-tiny.H:69-83). */
+int  mfn_table_from_kmers(mfn_ctx *ctx, uint32_t k, const uint64_t *kmers, const uint32_t *values,
+                          uint64_t n, uint32_t minV, uint32_t maxV, mfn_table **out);
+/* Count the canonical k-mers of a resident sequence set straight into a table:
+ * replaces the system("meryl count ...") merfin runs when -seqmers is absent
+ * (merfin-globals.C:168-189). */
+int  mfn_table_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, mfn_table **out);
+/* Synthetic read database for benchmarks: for every distinct canonical k-mer of
+ * seq with assembly count a (taken from asm_), value = Poisson(cov_per_copy * a)
+ * drawn from a hash of the k-mer (zeros are dropped -> "missing"), plus n_error
+ * pseudo-random error k-mers with value 1..2.  Deterministic in seed. */
+int  mfn_table_synth_reads(mfn_ctx *ctx, const mfn_seq *seq, const mfn_table *asm_,
+                           double cov_per_copy, uint64_t n_error, uint64_t seed, mfn_table **out);
+
+typedef struct {
+  uint32_t k;
+  uint32_t canonical;        /* 1: every stored k-mer <= its reverse complement   */
+  uint32_t slot_bits;        /* 32 or 64                                          */
+  uint32_t tag_bits, value_bits;
+  uint32_t min_value, max_value, value_offset;
+  uint64_t n_kmers;          /* entries stored                                    */
+  uint64_t n_level1, n_level2, n_stash, n_bigvalue;
+  uint64_t buckets_level1, buckets_level2;
+  uint64_t device_bytes;
+} mfn_table_info_t;
+
+int  mfn_table_info(const mfn_table *t, mfn_table_info_t *info);
+void mfn_table_free(mfn_table *t);
+/* Batch merylExactLookup::value(kmer) (kmers-lookup.H:334-380): out[i] = stored
+ * value of kmers[i] exactly as given (no canonicalisation), 0 if absent. */
+int  mfn_table_lookup(mfn_ctx *ctx, const mfn_table *t, const uint64_t *kmers, uint64_t n,
+                      uint32_t *out);
+/* Export every stored (k-mer, stored value), ascending k-mer order. */
+int  mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmers, uint32_t *values,
+                      uint64_t cap, uint64_t *n);
+
+/* ---- meryl database writer (generator side; kmers-writer.C:117-288) ------ */
+/* Writes a v03 database the reference's merylFileReader loads.  k-mers must be
+ * distinct; they are sorted here. */
+int  mfn_meryl_write(const char *meryl_dir, uint32_t k, const uint64_t *kmers,
+                     const uint32_t *values, uint64_t n);
+
+/* ---- sequences: replaces dnaSeq + kmerIterator::nextBase ------------------
+ * kmers-iterator.H:93-160.  bases = concatenated ASCII records, record i is
+ * bases[seq_off[i] .. seq_off[i+1]).  Any byte outside ACGTacgt breaks windows;
+ * windows never span records. */
+int  mfn_seq_create(mfn_ctx *ctx, const char *bases, const uint64_t *seq_off, uint32_t nseq,
+                    mfn_seq **out);
+int  mfn_seq_info(const mfn_seq *s, uint64_t *total_bases, uint32_t *nseq, uint64_t *device_bytes);
+void mfn_seq_free(mfn_seq *s);
+
+/* ---- K* model pieces the device needs ------------------------------------
+ * merfin-globals.C:66-98: readK==0 <=> v_read==0, or v_read within the -prob
+ * table and its readK column is 0.  Only that predicate is evaluated on the
+ * device (for per-record kmissing); all floating point stays on the host. */
+typedef struct {
+  double          peak;
+  uint32_t        nprob;
+  const uint32_t *probK;
+  const double   *probP;
+} mfn_kmodel;
+
+/* ---- accumulators --------------------------------------------------------- */
+
+typedef struct { uint64_t kasm, kmissing; } mfn_seq_counts;
+typedef struct { uint32_t v_read, v_asm; uint64_t count; } mfn_pair_count;
+
+int  mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out);
+int  mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a);
+void mfn_accum_free(mfn_accum *a);
+/* Flat device buffer (uint64 words) holding the dense joint histogram and the
+ * per-record counters: sum-all-reduce it across ranks, then fetch on any rank. */
+int  mfn_accum_device_buffer(const mfn_accum *a, void **dptr, uint64_t *nwords);
+/* Number of (v_read, v_asm) pairs that fell outside the dense tier on THIS rank
+ * (they live in a rank-local side table; gather with mfn_accum_fetch per rank). */
+int  mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int include_sparse,
+                     mfn_seq_counts *per_seq /*[nseq] or NULL*/,
+                     mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+
+/* ---- the hot path ---------------------------------------------------------- */
+
+/* -hist inner loop (merfin-histogram.C:54-91 + merfin-globals.C:101-110) over the
+ * tiles of 'seq' owned by (shard, nshards), resident inputs, asynchronous on the
+ * ctx stream.  Adds into 'acc'. */
+int  mfn_hist_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+                       const mfn_seq *seq, const mfn_kmodel *km /*NULL: v_read==0 only*/,
+                       uint32_t shard, uint32_t nshards, mfn_accum *acc);
+
+/* The same over HOST buffers for one shard: uploads (pinned memory gives full PCIe rate) and
+ * packs only the bases behind the shard's tiles, overlapping H2D with the scan.  Adds into acc;
+ * the caller all-reduces and fetches. */
+int  mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+                   const char *bases, const uint64_t *seq_off, uint32_t nseq, const mfn_kmodel *km,
+                   uint32_t shard, uint32_t nshards, mfn_accum *acc);
+
+/* Whole -hist call with HOST buffers: H2D + pack + probe + fetch.  Replaces
+ * loadSequence/processHistogram/outputHistogram (merfin.C:30-53,
+ * merfin-histogram.C:35-136) for one batch of records. */
+int  mfn_hist(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+              const char *bases, const uint64_t *seq_off, uint32_t nseq, const mfn_kmodel *km,
+              mfn_seq_counts *per_seq /*[nseq]*/,
+              mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+
+/* -dump inner loop (merfin-dump.C:44-67): per window start position of every
+ * record (index = seq_off[i] + p), the integer pair and validity.  Positions
+ * with no window (last k-1 of a record) get valid=0. */
+int  mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+                       const mfn_seq *seq, uint32_t *d_v_read, uint32_t *d_v_asm, uint8_t *d_valid);
+int  mfn_dump(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+              const char *bases, const uint64_t *seq_off, uint32_t nseq,
+              uint32_t *v_read /*[total bases]*/, uint32_t *v_asm, uint8_t *valid);
+
+/* Variant path scoring (varMer.C:66-90 probes): same as mfn_dump over a batch of
+ * short path strings. */
+int  mfn_score_paths(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
+                     const char *paths, const uint64_t *path_off, uint64_t npaths,
+                     uint32_t *v_read, uint32_t *v_asm, uint8_t *valid);
+
+/* -completeness (merfin-completeness.C:48-144): every k-mer of the read DB as
+ * stored (one strand, raw values, no -min/-max, Q4) joined with the raw
+ * assembly DB value; result = joint histogram of (raw v_read, raw v_asm). */
+int  mfn_completeness(mfn_ctx *ctx, const char *reads_dir, const char *asm_dir,
+                      mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+
+/* ---- host replay of the K* arithmetic (bit-exact doubles) ------------------ */
+
+typedef struct {
+  uint64_t  kasm, kmissing;
+  double    koverCpy;
+  double    qv_missing, qv_star;      /* histoQV, merfin-histogram.C:22-31 */
+  uint32_t  n_undr, n_over;           /* bins filled below                 */
+} mfn_hist_summary;
+
+/* From the joint histogram: undr/over K* bins (merfin-histogram.C:71-90).
+ * undr/over are caller arrays of cap entries; returns MFN_ERR_CAPACITY with
+ * n_undr/n_over set to what is needed. */
+int  mfn_hist_report(const mfn_pair_count *pairs, uint64_t npairs, const mfn_kmodel *km,
+                     uint32_t k, uint64_t *undr, uint64_t *over, uint32_t cap,
+                     mfn_hist_summary *summary);
+/* Text of the -hist output file (merfin-histogram.C:151-163) into buf. */
+int  mfn_hist_format(const uint64_t *undr, uint32_t n_undr, const uint64_t *over, uint32_t n_over,
+                     char *buf, uint64_t buflen, uint64_t *needed);
+void mfn_getK(const mfn_kmodel *km, uint32_t v_read, uint32_t v_asm,
+              double *readK, double *asmK, double *prob);          /* merfin-globals.C:66-98   */
+double mfn_getKmetric(double readK, double asmK);                  /* merfin-globals.H:248-261 */
+/* -completeness sums from the joint histogram of raw values. */
+int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const mfn_kmodel *km,
+                             double *total, double *undr);
+
+/* ---- timing hooks for benchmarks -------------------------------------------- */
+/* Number of kernels this library launched on the ctx since creation. */
+uint64_t mfn_ctx_launch_count(const mfn_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERFIN_B200_H */

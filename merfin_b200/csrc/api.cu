@@ -1,0 +1,253 @@
+// C ABI glue: context, errors, the host-buffer entry points and -completeness.
+#include "table.cuh"
+#include "table_host.h"
+
+#include <algorithm>
+#include <map>
+
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void mfn_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *mfn_last_error(void) { return g_err; }
+extern "C" const char *mfn_version(void) { return "merfin_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *mfn_strerror(int s) {
+  switch (s) {
+    case MFN_OK: return "ok";
+    case MFN_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU path)";
+    case MFN_ERR_CUDA: return "CUDA error";
+    case MFN_ERR_IO: return "I/O error";
+    case MFN_ERR_FORMAT: return "not a meryl database / corrupt data";
+    case MFN_ERR_UNSUPPORTED: return "unsupported input";
+    case MFN_ERR_INVALID: return "invalid argument";
+    case MFN_ERR_CAPACITY: return "buffer or table capacity exceeded";
+    case MFN_ERR_K_MISMATCH: return "mer size mismatch";
+    case MFN_ERR_NOMEM: return "out of memory";
+  }
+  return "unknown error";
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int mfn_ctx_create(mfn_ctx **out, int device) {
+  if (!out) return MFN_ERR_INVALID;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    mfn_set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return MFN_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { mfn_set_error("device %d out of range (0..%d)", device, n - 1); return MFN_ERR_INVALID; }
+  MFN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MFN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { mfn_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MFN_ERR_NO_DEVICE; }
+  mfn_ctx *c = new mfn_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  MFN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  MFN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) MFN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  c->stream = c->own_stream;
+  *out = c;
+  return MFN_OK;
+}
+
+extern "C" void mfn_ctx_destroy(mfn_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  mfn_seq_free(c->scratch_seq);
+  mfn_accum_free(c->scratch_acc);
+  for (int i = 0; i < 2; i++) cudaFree(c->d_ascii[i]);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->own_stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" int mfn_ctx_device(const mfn_ctx *c) { return c ? c->device : -1; }
+
+extern "C" int mfn_ctx_set_stream(mfn_ctx *c, void *stream) {
+  if (!c) return MFN_ERR_INVALID;
+  c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+  return MFN_OK;
+}
+
+extern "C" int mfn_ctx_sync(mfn_ctx *c) {
+  if (!c) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaStreamSynchronize(c->stream));
+  return MFN_OK;
+}
+
+extern "C" uint64_t mfn_ctx_launch_count(const mfn_ctx *c) { return c ? c->launches.load() : 0; }
+
+extern "C" int mfn_host_alloc(void **p, size_t bytes) {
+  if (!p) return MFN_ERR_INVALID;
+  cudaError_t e = cudaMallocHost(p, bytes ? bytes : 1);
+  if (e != cudaSuccess) { mfn_set_error("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); return MFN_ERR_NOMEM; }
+  return MFN_OK;
+}
+
+extern "C" void mfn_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------
+
+// Scratch sequence set kept in the ctx between host-buffer calls: a caller that streams batches
+// of the same shape (the benchmark, a pipeline over chromosomes) does not pay cudaMalloc per call.
+static int scratch_seq(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out) {
+  mfn_seq *s = ctx->scratch_seq;
+  bool reuse = s && s->nseq == nseq;
+  for (uint32_t i = 0; reuse && i <= nseq; i++) reuse = s->rec_start[i] == (seq_off[i] - seq_off[0]) + i;
+  if (reuse) {
+    uint64_t gpad = (s->ntiles + 1) * MFN_TILE + 256;
+    MFN_CUDA(cudaMemsetAsync(s->d_seq2, 0, (gpad / 32 + 8) * 8, ctx->stream));
+    MFN_CUDA(cudaMemsetAsync(s->d_ok, 0, (gpad / 64 + 8) * 8, ctx->stream));
+  } else {
+    mfn_seq_free(s);
+    ctx->scratch_seq = nullptr;
+    MFN_TRY(mfn_seq_alloc(ctx, seq_off, nseq, &s));
+    ctx->scratch_seq = s;
+  }
+  *out = s;
+  return MFN_OK;
+}
+
+// H2D + pack + scan of one shard, pipelined: the shard's tile range is cut into pieces; while
+// the scan kernel of piece i runs, the copy stream is already uploading piece i+1.
+extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *bases,
+                             const uint64_t *seq_off, uint32_t nseq, const mfn_kmodel *km,
+                             uint32_t shard, uint32_t nshards, mfn_accum *acc) {
+  if (!ctx || !reads || !asm_ || !seq_off || !acc || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  if (nseq == 0) return MFN_OK;
+  mfn_seq *seq = nullptr;
+  MFN_TRY(scratch_seq(ctx, seq_off, nseq, &seq));
+  const uint64_t tb = seq->ntiles * shard / nshards, te = seq->ntiles * (shard + 1) / nshards;
+  const uint64_t pieces = std::max<uint64_t>(1, std::min<uint64_t>(16, (te - tb) / 8192));
+  for (uint64_t p = 0; p < pieces; p++) {
+    uint64_t a = tb + (te - tb) * p / pieces, b = tb + (te - tb) * (p + 1) / pieces;
+    MFN_TRY(mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128));
+    MFN_TRY(mfn_hist_tiles(ctx, reads, asm_, seq, km, a, b, acc));
+  }
+  return MFN_OK;
+}
+
+extern "C" int mfn_hist(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *bases,
+                        const uint64_t *seq_off, uint32_t nseq, const mfn_kmodel *km, mfn_seq_counts *per_seq,
+                        mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!ctx || !reads || !asm_ || !seq_off || !npairs) return MFN_ERR_INVALID;
+  mfn_accum *acc = ctx->scratch_acc;
+  if (acc && acc->nseq < nseq) { mfn_accum_free(acc); acc = ctx->scratch_acc = nullptr; }
+  if (!acc) { MFN_TRY(mfn_accum_create(ctx, nseq, &acc)); ctx->scratch_acc = acc; }
+  else MFN_TRY(mfn_accum_reset(ctx, acc));
+  MFN_TRY(mfn_hist_host(ctx, reads, asm_, bases, seq_off, nseq, km, 0, 1, acc));
+  uint32_t keep = acc->nseq;
+  acc->nseq = nseq;                      // fetch exactly the caller's records
+  int st = mfn_accum_fetch(ctx, acc, 1, 1, per_seq, pairs, cap, npairs);
+  acc->nseq = keep;
+  return st;
+}
+
+static int dump_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *bases,
+                     const uint64_t *off, uint64_t nrec, uint32_t *v_read, uint32_t *v_asm, uint8_t *valid) {
+  if (!ctx || !reads || !asm_ || !off) return MFN_ERR_INVALID;
+  if (nrec > 0xfffffff0ull) return MFN_ERR_INVALID;
+  if (nrec == 0 || off[nrec] == off[0]) return MFN_OK;
+  mfn_seq *seq = nullptr;
+  MFN_TRY(mfn_seq_create(ctx, bases, off, (uint32_t)nrec, &seq));
+  uint64_t n = seq->total_bases;
+  uint32_t *dr = nullptr, *da = nullptr; uint8_t *dv = nullptr;
+  int st = MFN_OK;
+  if (cudaMalloc(&dr, n * 4) != cudaSuccess || cudaMalloc(&da, n * 4) != cudaSuccess || cudaMalloc(&dv, n) != cudaSuccess) {
+    mfn_set_error("cudaMalloc(dump output, %llu positions)", (unsigned long long)n);
+    st = MFN_ERR_NOMEM;
+  }
+  if (st == MFN_OK) st = mfn_dump_resident(ctx, reads, asm_, seq, dr, da, dv);
+  if (st == MFN_OK) {
+    cudaMemcpyAsync(v_read, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(v_asm, da, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(valid, dv, n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { mfn_set_error("dump: %s", cudaGetErrorString(e)); st = MFN_ERR_CUDA; }
+  }
+  cudaFree(dr); cudaFree(da); cudaFree(dv);
+  mfn_seq_free(seq);
+  return st;
+}
+
+extern "C" int mfn_dump(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *bases,
+                        const uint64_t *seq_off, uint32_t nseq, uint32_t *v_read, uint32_t *v_asm, uint8_t *valid) {
+  return dump_host(ctx, reads, asm_, bases, seq_off, nseq, v_read, v_asm, valid);
+}
+
+extern "C" int mfn_score_paths(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *paths,
+                               const uint64_t *path_off, uint64_t npaths, uint32_t *v_read, uint32_t *v_asm,
+                               uint8_t *valid) {
+  return dump_host(ctx, reads, asm_, paths, path_off, npaths, v_read, v_asm, valid);
+}
+
+// ---------------------------------------------------------------------------
+// -completeness: stream the read DB, probe the (raw) assembly table
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_join(DevTable A, const unsigned long long *kmers, const uint32_t *values,
+                                              uint64_t n, unsigned long long *acc, PairTable sparse) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t vr = values[i];
+    uint32_t va = mfn_value(A, kmers[i]);
+    if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
+    else {
+      // same side table as the scan kernel
+      unsigned long long key = ((unsigned long long)vr << 32) | va;
+      if (key == MFN_EMPTY64) { atomicAdd(&acc[3], 1ull); continue; }
+      uint32_t j = mfn_oa_hash(key) & sparse.mask;
+      bool done = false;
+      for (uint32_t t = 0; t <= sparse.mask && !done; t++) {
+        unsigned long long cur = sparse.keys[j];
+        if (cur == MFN_EMPTY64) {
+          cur = atomicCAS(&sparse.keys[j], MFN_EMPTY64, key);
+          if (cur == MFN_EMPTY64) { cur = key; atomicAdd(&acc[1], 1ull); }
+        }
+        if (cur == key) { atomicAdd(&sparse.counts[j], 1ull); done = true; }
+        j = (j + 1) & sparse.mask;
+      }
+      if (!done) atomicAdd(&acc[2], 1ull);
+    }
+  }
+}
+
+extern "C" int mfn_completeness(mfn_ctx *ctx, const char *reads_dir, const char *asm_dir,
+                                mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!ctx || !reads_dir || !asm_dir || !npairs) return MFN_ERR_INVALID;
+  mfn_table *A = nullptr;
+  MFN_TRY(mfn_table_load(ctx, asm_dir, 0, 0xffffffffu, &A));      // raw values: offset 0
+  MerylIndex idx;
+  int st = meryl_open(reads_dir, idx);
+  if (st == MFN_OK && idx.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", idx.k, A->dev.k); st = MFN_ERR_K_MISMATCH; }
+  mfn_accum *acc = nullptr;
+  if (st == MFN_OK) st = mfn_accum_create(ctx, 0, &acc);
+  if (st == MFN_OK)
+    st = meryl_stream_to_device(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
+      int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
+      k_join<<<grid, 256, 0, ctx->stream>>>(A->dev, dk, dv, n, acc->d_buf, acc->sparse);
+      ctx->launches++;
+      return cudaGetLastError() == cudaSuccess ? MFN_OK : MFN_ERR_CUDA;
+    });
+  if (st == MFN_OK) st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs, cap, npairs);
+  mfn_accum_free(acc);
+  mfn_table_free(A);
+  return st;
+}

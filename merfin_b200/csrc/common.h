@@ -1,0 +1,142 @@
+// Internal declarations shared by the host and device parts of libmerfin_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/merfin_b200.h"
+
+void mfn_set_error(const char *fmt, ...);
+
+#define MFN_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      mfn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+      return MFN_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define MFN_TRY(call)                 \
+  do {                                \
+    int s_ = (call);                  \
+    if (s_ != MFN_OK) return s_;      \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// Device-side table description (passed to kernels by value).
+//
+// Layout in HBM (DESIGN.md "Table layout"): two levels of 32-byte buckets, one
+// bucket = one DRAM sector.  A k-mer c is mapped by a bijective mix of its 2k
+// bits to h; bucket = h / D, tag = h % D, so (bucket, tag) identifies c exactly
+// and only tag + value are stored: slot = tag << vbits | value, value != 0,
+// slot == 0 means empty.  A bucket whose slots are all occupied may have spilled
+// entries to the next level; level 3 is a small open-addressing side table with
+// full keys.  Values >= vmax saturate in the slot and keep their excess in a
+// second side table.
+// ---------------------------------------------------------------------------
+
+struct OaTable {          // open addressing, 64-bit keys, EMPTY = ~0
+  unsigned long long *keys;
+  uint32_t           *vals;
+  uint32_t            mask;      // capacity - 1
+  uint32_t           *special;   // value for key == ~0 (only reachable when k == 32)
+};
+
+struct TableLevel {
+  void    *slots;         // buckets * 32 bytes
+  uint64_t buckets;
+  uint64_t D;             // divisor: bucket = h / D
+  uint64_t magic;         // floor(2^64 / D) for the division
+  uint64_t seed;
+};
+
+struct TableStats {       // updated by the build kernels
+  unsigned long long n_l1, n_l2, n_stash, n_big, n_dup, n_noncanon, errors;
+};
+
+struct DevTable {
+  TableLevel lv[2];
+  OaTable    stash, big;
+  uint64_t   kmask;       // low 2k bits
+  uint32_t   k;
+  uint32_t   w64;         // slots are 64-bit (4 per bucket) instead of 32-bit (8 per bucket)
+  uint32_t   vbits;       // value field width
+  uint32_t   vmax;        // saturated value (== value field mask, capped to 32 bits)
+  uint32_t   probe_both;  // table is not canonical: look up f and r (Q2), else min(f, r)
+  TableStats *stats;
+};
+
+struct mfn_ctx {
+  int          device = 0;
+  cudaStream_t stream = nullptr;       // stream in use
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int          sm_count = 0;
+  std::atomic<uint64_t> launches{0};
+  // staging for host-buffer calls
+  char  *d_ascii[2] = {nullptr, nullptr};
+  size_t ascii_cap = 0;
+  void  *h_pinned = nullptr;
+  size_t pinned_cap = 0;
+  struct mfn_seq   *scratch_seq = nullptr;
+  struct mfn_accum *scratch_acc = nullptr;
+};
+
+struct mfn_table {
+  mfn_ctx   *ctx = nullptr;
+  DevTable   dev{};
+  TableStats host_stats{};
+  uint32_t   min_value = 0, max_value = 0, value_offset = 0;
+  uint32_t   tag_bits = 0;
+  uint64_t   device_bytes = 0;
+  uint64_t   n_kmers = 0;
+  std::vector<void *> allocs;
+};
+
+struct mfn_seq {
+  mfn_ctx  *ctx = nullptr;
+  uint32_t  nseq = 0;
+  uint64_t  total_bases = 0;      // caller's concatenated length
+  uint64_t  G = 0;                // global coordinates incl. one separator per record
+  uint64_t  ntiles = 0;
+  unsigned long long *d_seq2 = nullptr;   // 2 bits per base, base g at bits 2*(g%32) of word g/32
+  unsigned long long *d_ok = nullptr;     // 1 bit per base: set iff the byte is one of ACGTacgt
+  unsigned long long *d_rec_start = nullptr;   // [nseq+1] global coordinate of each record start
+  std::vector<uint64_t> rec_start;             // host copy
+  uint64_t  device_bytes = 0;
+};
+
+// Dense tier of the joint histogram: v_read < MFN_DENSE_R and v_asm < MFN_DENSE_A.
+#define MFN_DENSE_R 4096u
+#define MFN_DENSE_A 64u
+#define MFN_ACC_HEADER 8u           // words: [0] valid windows, [1] sparse pairs inserted, [2] errors
+#define MFN_SPARSE_CAP (1u << 22)
+
+struct PairTable {                  // (v_read << 32 | v_asm) -> count, EMPTY = ~0
+  unsigned long long *keys;
+  unsigned long long *counts;
+  uint32_t            mask;
+};
+
+struct mfn_accum {
+  mfn_ctx  *ctx = nullptr;
+  uint32_t  nseq = 0;
+  uint64_t  nwords = 0;             // header + dense + 2*nseq
+  unsigned long long *d_buf = nullptr;
+  PairTable sparse{};
+};
+
+// tile geometry of the scan kernels
+#define MFN_TILE 2048               // window start positions per tile (multiple of 64)
+
+static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

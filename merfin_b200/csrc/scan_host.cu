@@ -1,0 +1,178 @@
+// Host side of the scan kernels: launches, accumulators, fetch.
+#include "scan_kernel.cuh"
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+
+static int check_tables(const mfn_table *R, const mfn_table *A) {
+  if (!R || !A) return MFN_ERR_INVALID;
+  if (R->dev.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", R->dev.k, A->dev.k); return MFN_ERR_K_MISMATCH; }
+  return MFN_OK;
+}
+
+// tile range [begin, end) of shard s out of n
+static void shard_tiles(uint64_t ntiles, uint32_t s, uint32_t n, uint64_t &b, uint64_t &e) {
+  b = ntiles * s / n;
+  e = ntiles * (s + 1) / n;
+}
+
+struct ScanScratch { unsigned long long *counter = nullptr; unsigned long long *zmap = nullptr; };
+
+static int launch_scan(mfn_ctx *ctx, ScanParams &P, bool dump) {
+  if (P.tile_begin >= P.tile_end) return MFN_OK;
+  unsigned long long *counter;
+  MFN_CUDA(cudaMallocAsync(&counter, 8, ctx->stream));
+  MFN_CUDA(cudaMemsetAsync(counter, 0, 8, ctx->stream));
+  P.tile_counter = counter;
+  int grid = dump ? mfn_scan_grid_dump(ctx) : mfn_scan_grid_hist(ctx);
+  grid = (int)std::min<uint64_t>((uint64_t)grid, P.tile_end - P.tile_begin);
+  if (dump) mfn_scan_launch_dump(P, grid, ctx->stream);
+  else      mfn_scan_launch_hist(P, grid, ctx->stream);
+  ctx->launches++;
+  MFN_CUDA(cudaGetLastError());
+  MFN_CUDA(cudaFreeAsync(counter, ctx->stream));
+  return MFN_OK;
+}
+
+// bitmap of read multiplicities whose readK is 0 under the -prob table (merfin-globals.C:93-97)
+static int build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen) {
+  *d_zmap = nullptr; *zlen = 0;
+  if (!km || km->nprob == 0) return MFN_OK;
+  uint32_t n = km->nprob + 1;                    // values 0 .. nprob
+  std::vector<unsigned long long> bits((n + 63) / 64, 0);
+  bits[0] |= 1;                                  // v == 0
+  for (uint32_t v = 1; v <= km->nprob; v++)
+    if (km->probK[v - 1] == 0) bits[v >> 6] |= 1ull << (v & 63);
+  MFN_CUDA(cudaMallocAsync(d_zmap, bits.size() * 8, ctx->stream));
+  MFN_CUDA(cudaMemcpyAsync(*d_zmap, bits.data(), bits.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));  // 'bits' is a local
+  *zlen = n;
+  return MFN_OK;
+}
+
+int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                   const mfn_kmodel *km, uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc) {
+  if (!ctx || !seq || !acc) return MFN_ERR_INVALID;
+  MFN_TRY(check_tables(reads, asm_));
+  if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  ScanParams P{};
+  P.R = reads->dev; P.A = asm_->dev;
+  P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
+  P.tile_begin = tile_begin; P.tile_end = std::min(tile_end, seq->ntiles);
+  P.acc = acc->d_buf; P.sparse = acc->sparse;
+  unsigned long long *zmap = nullptr;
+  MFN_TRY(build_zmap(ctx, km, &zmap, &P.zlen));
+  P.zmap = zmap;
+  int st = launch_scan(ctx, P, false);
+  if (zmap) cudaFreeAsync(zmap, ctx->stream);
+  return st;
+}
+
+extern "C" int mfn_hist_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                                 const mfn_kmodel *km, uint32_t shard, uint32_t nshards, mfn_accum *acc) {
+  if (!seq || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  uint64_t tb, te;
+  shard_tiles(seq->ntiles, shard, nshards, tb, te);
+  return mfn_hist_tiles(ctx, reads, asm_, seq, km, tb, te, acc);
+}
+
+extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                                 uint32_t *d_v_read, uint32_t *d_v_asm, uint8_t *d_valid) {
+  if (!ctx || !seq || !d_v_read || !d_v_asm || !d_valid) return MFN_ERR_INVALID;
+  MFN_TRY(check_tables(reads, asm_));
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  MFN_CUDA(cudaMemsetAsync(d_v_read, 0, seq->total_bases * 4, ctx->stream));
+  MFN_CUDA(cudaMemsetAsync(d_v_asm, 0, seq->total_bases * 4, ctx->stream));
+  MFN_CUDA(cudaMemsetAsync(d_valid, 0, seq->total_bases, ctx->stream));
+  ScanParams P{};
+  P.R = reads->dev; P.A = asm_->dev;
+  P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
+  P.tile_begin = 0; P.tile_end = seq->ntiles;
+  P.out_vr = d_v_read; P.out_va = d_v_asm; P.out_valid = d_valid;
+  return launch_scan(ctx, P, true);
+}
+
+// ---------------------------------------------------------------------------
+// accumulators
+// ---------------------------------------------------------------------------
+extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
+  if (!ctx || !out) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  mfn_accum *a = new mfn_accum();
+  a->ctx = ctx; a->nseq = nseq;
+  a->nwords = MFN_ACC_HEADER + (uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2ull * nseq;
+  a->sparse.mask = MFN_SPARSE_CAP - 1;
+  cudaError_t e = cudaMalloc(&a->d_buf, a->nwords * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8);
+  if (e != cudaSuccess) { mfn_set_error("cudaMalloc(accumulator): %s", cudaGetErrorString(e)); mfn_accum_free(a); return MFN_ERR_NOMEM; }
+  int st = mfn_accum_reset(ctx, a);
+  if (st != MFN_OK) { mfn_accum_free(a); return st; }
+  *out = a;
+  return MFN_OK;
+}
+
+extern "C" int mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a) {
+  if (!ctx || !a) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaMemsetAsync(a->d_buf, 0, a->nwords * 8, ctx->stream));
+  MFN_CUDA(cudaMemsetAsync(a->sparse.keys, 0xff, (size_t)MFN_SPARSE_CAP * 8, ctx->stream));
+  MFN_CUDA(cudaMemsetAsync(a->sparse.counts, 0, (size_t)MFN_SPARSE_CAP * 8, ctx->stream));
+  return MFN_OK;
+}
+
+extern "C" void mfn_accum_free(mfn_accum *a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  cudaFree(a->d_buf); cudaFree(a->sparse.keys); cudaFree(a->sparse.counts);
+  delete a;
+}
+
+extern "C" int mfn_accum_device_buffer(const mfn_accum *a, void **dptr, uint64_t *nwords) {
+  if (!a) return MFN_ERR_INVALID;
+  if (dptr) *dptr = a->d_buf;
+  if (nwords) *nwords = a->nwords;
+  return MFN_OK;
+}
+
+extern "C" int mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int include_sparse,
+                               mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!ctx || !a || !npairs) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  std::vector<unsigned long long> h(a->nwords);
+  MFN_CUDA(cudaMemcpyAsync(h.data(), a->d_buf, a->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", h[2]); return MFN_ERR_CAPACITY; }
+  uint64_t n = 0;
+  bool full = false;
+  auto push = [&](uint32_t vr, uint32_t va, uint64_t c) {
+    if (pairs && n < cap) { pairs[n].v_read = vr; pairs[n].v_asm = va; pairs[n].count = c; } else full = true;
+    n++;
+  };
+  if (include_dense) {
+    const unsigned long long *d = h.data() + MFN_ACC_HEADER;
+    for (uint32_t va = 0; va < MFN_DENSE_A; va++)
+      for (uint32_t vr = 0; vr < MFN_DENSE_R; vr++)
+        if (d[(uint64_t)va * MFN_DENSE_R + vr]) push(vr, va, d[(uint64_t)va * MFN_DENSE_R + vr]);
+    if (per_seq)
+      for (uint32_t i = 0; i < a->nseq; i++) {
+        per_seq[i].kasm = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i];
+        per_seq[i].kmissing = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i + 1];
+      }
+    if (h[3]) push(0xffffffffu, 0xffffffffu, h[3]);
+  }
+  if (include_sparse && h[1]) {
+    // rank-local: read the inserted-pair count from the device table itself, not the (possibly reduced) header
+    std::vector<unsigned long long> keys(MFN_SPARSE_CAP), counts(MFN_SPARSE_CAP);
+    MFN_CUDA(cudaMemcpyAsync(keys.data(), a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MFN_CUDA(cudaMemcpyAsync(counts.data(), a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<unsigned long long, unsigned long long>> v;
+    for (uint32_t i = 0; i < MFN_SPARSE_CAP; i++) if (keys[i] != MFN_EMPTY64) v.emplace_back(keys[i], counts[i]);
+    std::sort(v.begin(), v.end());
+    for (auto &kv : v) push((uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second);
+  }
+  *npairs = n;
+  return (pairs && full) ? MFN_ERR_CAPACITY : MFN_OK;
+}

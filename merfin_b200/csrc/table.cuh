@@ -1,0 +1,131 @@
+// Device-side table primitives: bijective k-mer mix, bucket probe, find-or-insert.
+// See common.h for the layout.  Everything here is integer arithmetic.
+#pragma once
+
+#include "common.h"
+
+#define MFN_EMPTY64 0xffffffffffffffffull
+
+// --- bijection on [0, 2^2k): xor-seed, xorshift and odd multiplies are all invertible -----
+__host__ __device__ __forceinline__ uint64_t mfn_mix(uint64_t c, uint64_t seed, uint64_t kmask, uint32_t k) {
+  uint64_t x = (c ^ seed) & kmask;
+  x ^= x >> k;
+  x = (x * 0xff51afd7ed558ccdull) & kmask;
+  x ^= x >> k;
+  x = (x * 0xc4ceb9fe1a85ec53ull) & kmask;
+  x ^= x >> k;
+  return x;
+}
+
+// h -> (bucket, tag) with bucket = h / D, tag = h % D.  magic = floor(2^64 / D) (or ~0 for D == 1).
+__device__ __forceinline__ void mfn_split(uint64_t h, uint64_t D, uint64_t magic, uint64_t &bucket, uint64_t &tag) {
+  uint64_t q = __umul64hi(h, magic);
+  uint64_t r = h - q * D;
+  if (r >= D) { q++; r -= D; }
+  bucket = q; tag = r;
+}
+
+__host__ __device__ __forceinline__ uint64_t mfn_revcomp(uint64_t f, uint32_t k) {
+  // complement every base (A=00 <-> T=10, C=01 <-> G=11), reverse the 2-bit groups, realign
+  uint64_t x = f ^ 0xaaaaaaaaaaaaaaaaull;
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+  x = ((x >> 8) & 0x00ff00ff00ff00ffull) | ((x & 0x00ff00ff00ff00ffull) << 8);
+  x = ((x >> 16) & 0x0000ffff0000ffffull) | ((x & 0x0000ffff0000ffffull) << 16);
+  x = (x >> 32) | (x << 32);
+  return x >> (64 - 2 * k);
+}
+
+// 32-byte bucket load: one LDG.256, read-only path, no L1 allocation (no reuse).
+struct Bucket { uint32_t w[8]; };
+
+__device__ __forceinline__ void mfn_load_bucket(const void *slots, uint64_t bucket, Bucket &b) {
+  const char *p = (const char *)slots + bucket * 32;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]),
+                 "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+               : "l"(p));
+}
+
+// Search a loaded bucket.  Returns the stored value (0 = not here); full = all slots occupied.
+__device__ __forceinline__ uint32_t mfn_match32(const Bucket &b, uint64_t tag, uint32_t vbits, uint32_t vmax, bool &full) {
+  uint32_t want = (uint32_t)tag << vbits;
+  uint32_t val = 0;
+  bool f = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t d = b.w[i] ^ want;            // equal tag and non-zero value  <=>  1 <= d <= vmax
+    if (d - 1u < vmax) val = d;
+    f = f && (b.w[i] != 0);
+  }
+  full = f;
+  return val;
+}
+
+__device__ __forceinline__ uint32_t mfn_match64(const Bucket &b, uint64_t tag, uint32_t vbits, uint32_t vmax, bool &full) {
+  uint64_t want = tag << vbits;
+  uint32_t val = 0;
+  bool f = true;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint64_t s = ((uint64_t)b.w[2 * i + 1] << 32) | b.w[2 * i];
+    uint64_t d = s ^ want;
+    if (d - 1ull < (uint64_t)vmax) val = (uint32_t)d;
+    f = f && (s != 0);
+  }
+  full = f;
+  return val;
+}
+
+__device__ __forceinline__ uint32_t mfn_oa_hash(uint64_t key) {
+  key ^= key >> 33; key *= 0xff51afd7ed558ccdull; key ^= key >> 29;
+  return (uint32_t)key;
+}
+
+__device__ __forceinline__ uint32_t mfn_oa_get(const OaTable &t, uint64_t key) {
+  if (key == MFN_EMPTY64) return *t.special;
+  uint32_t i = mfn_oa_hash(key) & t.mask;
+  while (true) {
+    uint64_t cur = t.keys[i];
+    if (cur == key) return t.vals[i];
+    if (cur == MFN_EMPTY64) return 0;
+    i = (i + 1) & t.mask;
+  }
+}
+
+// Levels 2 and 3 and the saturated-value excess: rare, kept out of line.
+static __device__ __noinline__ uint32_t mfn_probe_slow(const DevTable &t, uint64_t c, uint32_t val, bool full) {
+  if (val == 0 && full) {
+    uint64_t bucket, tag;
+    mfn_split(mfn_mix(c, t.lv[1].seed, t.kmask, t.k), t.lv[1].D, t.lv[1].magic, bucket, tag);
+    Bucket b;
+    mfn_load_bucket(t.lv[1].slots, bucket, b);
+    bool full2;
+    val = t.w64 ? mfn_match64(b, tag, t.vbits, t.vmax, full2) : mfn_match32(b, tag, t.vbits, t.vmax, full2);
+    if (val == 0 && full2) return mfn_oa_get(t.stash, c);     // stash keeps full values
+  }
+  if (val == t.vmax) val += mfn_oa_get(t.big, c);
+  return val;
+}
+
+// Address of the level-1 bucket of k-mer c and its tag.
+__device__ __forceinline__ void mfn_locate(const DevTable &t, uint64_t c, uint64_t &bucket, uint64_t &tag) {
+  mfn_split(mfn_mix(c, t.lv[0].seed, t.kmask, t.k), t.lv[0].D, t.lv[0].magic, bucket, tag);
+}
+
+// Finish a probe whose level-1 bucket is already in registers.
+__device__ __forceinline__ uint32_t mfn_resolve(const DevTable &t, uint64_t c, const Bucket &b, uint64_t tag) {
+  bool full;
+  uint32_t val = t.w64 ? mfn_match64(b, tag, t.vbits, t.vmax, full) : mfn_match32(b, tag, t.vbits, t.vmax, full);
+  if ((val == 0 && full) || val == t.vmax) val = mfn_probe_slow(t, c, val, full);
+  return val;
+}
+
+// Complete lookup of one k-mer exactly as given: merylExactLookup::value() (kmers-lookup.H:334-380).
+__device__ __forceinline__ uint32_t mfn_value(const DevTable &t, uint64_t c) {
+  uint64_t bucket, tag;
+  mfn_locate(t, c, bucket, tag);
+  Bucket b;
+  mfn_load_bucket(t.lv[0].slots, bucket, b);
+  return mfn_resolve(t, c, b, tag);
+}

@@ -1,0 +1,38 @@
+// Host-side entry points shared between translation units of libmerfin_b200.
+#pragma once
+
+#include "common.h"
+
+#include <functional>
+
+int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out);
+int mfn_table_insert_device(mfn_table *t, const unsigned long long *d_kmers, const uint32_t *d_values,
+                            uint64_t n, uint32_t minV, uint32_t maxV, uint32_t voff, bool add);
+int mfn_table_finalize(mfn_table *t, bool counted);
+
+// ---- meryl on-disk database (host) ------------------------------------------
+struct MerylIndex {
+  uint32_t version = 0, prefixSize = 0, suffixSize = 0, numFilesBits = 0, numBlocksBits = 0, flags = 0;
+  uint32_t k = 0;
+  uint64_t numUnique = 0, numDistinct = 0, numTotal = 0;
+  std::vector<uint64_t> histValue, histCount;     // ascending by value (v03)
+  std::string dir;
+};
+
+int meryl_open(const char *dir, MerylIndex &idx);
+std::string meryl_file_name(const MerylIndex &idx, uint32_t file, bool index);
+// Decode data file 'file' block by block; sink(kmers, values, n) is called once per block.
+// k-mers are 64-bit (k <= 32).
+int meryl_decode_file(const MerylIndex &idx, uint32_t file,
+                      const std::function<void(const uint64_t *, const uint32_t *, uint64_t)> &sink);
+// Stream a whole database to the device in chunks; fn(d_kmers, d_values, n) is called per chunk
+// on ctx->stream with device arrays that stay valid until the next call.
+int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
+                           const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn);
+
+// ---- sequences ------------------------------------------------------------------
+int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out);
+int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end);
+// -hist scan of tiles [tile_begin, tile_end) of a resident sequence set
+int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                   const mfn_kmodel *km, uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc);

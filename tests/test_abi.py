@@ -1,0 +1,120 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol the
+header declares, fails loudly without a GPU, and the meryl writer is readable by the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from merfin_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "merfin_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mfn_[a-z_0-9A-Z]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/merfin_b200.h but not exported"
+    # the ctypes stub covers the same set
+    assert sorted(L.SIGNATURES) == names
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = L.load()
+    h = C.c_void_p()
+    st = lib.mfn_ctx_create(C.byref(h), 0)
+    assert st == L.MFN_ERR_NO_DEVICE
+    assert b"CUDA" in lib.mfn_last_error() or b"device" in lib.mfn_last_error()
+    with pytest.raises(L.MfnError):
+        L.check(st)
+
+
+def test_product_does_not_reference_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "merfin_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dp, fn), errors="replace").read()
+                assert "mfn_oracle" not in text and "oracle_lib" not in text and "oracle/" not in text, os.path.join(dp, fn)
+    out = subprocess.run(["ldd", L.SO_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_host_replay_matches_oracle_kmodel():
+    lib = L.load()
+    K = np.array([0, 0, 1, 1, 1, 2], dtype=np.uint32)
+    P = np.array([0.9, 0.8, 0.7, 0.75, 0.9, 0.5])
+    km = L.KModel(7.5, len(K), K.ctypes.data_as(C.POINTER(C.c_uint32)), P.ctypes.data_as(C.POINTER(C.c_double)))
+    okm = O.KModel(7.5, K, P)
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    for vr in list(range(0, 64)) + [100, 1000, 4095, 65536, 2 ** 31, 2 ** 32 - 1]:
+        for va in (0, 1, 2, 3, 7, 1000):
+            lib.mfn_getK(C.byref(km), vr, va, C.byref(a), C.byref(b), C.byref(c))
+            assert (a.value, b.value, c.value) == okm.getK(vr, va)
+            assert lib.mfn_getKmetric(a.value, b.value) == O.L.o_getKmetric(a.value, b.value) or \
+                (np.isnan(lib.mfn_getKmetric(a.value, b.value)) and np.isnan(O.L.o_getKmetric(a.value, b.value)))
+
+
+def test_host_hist_report_matches_oracle():
+    """mfn_hist_report / mfn_hist_format replay of the K* bins == the oracle's per-window accumulation."""
+    from merfin_b200 import api
+    rng = np.random.default_rng(5)
+    vr = rng.integers(0, 90, size=4000).astype(np.uint32)
+    va = rng.integers(0, 6, size=4000).astype(np.uint32)
+    vr[:50] = 0
+    K = np.array([0, 1, 1], dtype=np.uint32); P = np.array([0.5, 0.25, 0.75])
+    for probK, probP in (((), ()), (K, P)):
+        okm = O.KModel(9.0, probK, probP)
+        h = O.Hist()
+        for a, b in zip(vr, va):
+            h.add_pair(okm, a, b)
+        keys, counts = np.unique(np.stack([va, vr], 1), axis=0, return_counts=True)
+        pairs = np.zeros(len(keys), dtype=api.PAIR_DTYPE)
+        pairs["v_asm"], pairs["v_read"], pairs["count"] = keys[:, 0], keys[:, 1], counts
+        res = api.HistResult(["x"], np.zeros(1, dtype=api.COUNTS_DTYPE), pairs, 21, api.KModel(9.0, probK, probP))
+        assert res.file_text() == h.report()
+        s, _, _ = res.report()
+        assert (s.kasm, s.kmissing) == (h.kasm, h.kmissing)
+        assert abs(s.koverCpy - h.koverCpy) < 1e-9
+        assert res.summary_text() == h.summary(21)
+
+
+def test_meryl_writer_roundtrip(tmp_path):
+    """mfn_meryl_write output is decoded identically by the oracle reader (and, where the
+    reference build exists, by the reference's own `meryl print`)."""
+    from merfin_b200 import api
+    rng = np.random.default_rng(3)
+    for k, n in ((21, 5000), (6, 300), (31, 2000), (16, 70000)):
+        kmers = np.unique(rng.integers(0, 1 << min(62, 2 * k), size=n, dtype=np.uint64))
+        values = rng.integers(1, 300, size=len(kmers)).astype(np.uint32)
+        values[:3] = [1, 70000, 4000000000]
+        d = str(tmp_path / f"w{k}.meryl")
+        api.meryl_write(d, k, kmers, values)
+        db = O.DB(d)
+        assert db.k == k and db.n == len(kmers)
+        assert (db.lo == kmers).all() and (db.hi == 0).all() and (db.val == values).all()
+        vals, cnts = np.unique(values, return_counts=True)
+        assert (db.histValue == vals).all() and (db.histCount == cnts).all()
+        meryl = os.path.join(ROOT, "oracle", "_ref", "meryl")
+        if os.path.exists(meryl):
+            p = subprocess.run([meryl, "threads=1", "print", d], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            lines = [l.split("\t") for l in p.stdout.splitlines()]
+            assert len(lines) == len(kmers)
+            assert [O.kmer_from_string(a) for a, _ in lines] == [int(x) for x in kmers]
+            assert [int(b) for _, b in lines] == [int(x) for x in values]

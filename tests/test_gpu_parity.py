@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle and the committed
+reference outputs.  Integer results must be bit-exact; text files byte-identical; QV within 1e-6."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+SETS = [("g1_k21", 21, 8.0), ("g2_k6", 6, 3.0), ("g3_k31", 31, 6.0)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from merfin_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _golden(golden_dir, name):
+    d = os.path.join(golden_dir, name)
+    return d, O.read_fasta(os.path.join(d, "asm.fa"))
+
+
+def _all_window_kmers(recs, k):
+    fs, rs = [], []
+    for _, b in recs:
+        f, fh, r, rh, ok = O.windows(b, k)
+        fs.append(f[ok == 1]); rs.append(r[ok == 1])
+    return np.concatenate(fs), np.concatenate(rs)
+
+
+# ---------------------------------------------------------------------------------- tables
+@pytest.mark.parametrize("name,k,peak", SETS)
+def test_table_load_and_value(ctx, golden_dir, name, k, peak):
+    """mfn_table_load + mfn_table_lookup == merylExactLookup::load + value()."""
+    from merfin_b200 import api
+    d, recs = _golden(golden_dir, name)
+    for sub in ("reads.meryl", "asm.meryl"):
+        db = O.DB(os.path.join(d, sub))
+        for mn, mx in ((0, 0xFFFFFFFF), (2, 0xFFFFFFFF), (3, 9), (50, 40)):
+            t = api.MerylExactLookup.load(ctx, os.path.join(d, sub), mn, mx)
+            ref = O.Lookup(db, mn, mx)
+            assert t.nKmers() == ref.n
+            f, r = _all_window_kmers(recs, k)
+            rng = np.random.default_rng(1)
+            rnd = rng.integers(0, 1 << (2 * k), size=5000, dtype=np.uint64)
+            q = np.concatenate([db.lo, f, r, rnd, np.array([0, (1 << (2 * k)) - 1], dtype=np.uint64)])
+            assert (t.values(q) == ref.values(q)).all()
+            info = t.info
+            assert info.k == k and info.canonical == 1
+            assert info.n_level1 + info.n_level2 + info.n_stash == info.n_kmers
+            km, vv = t.export()
+            keep = (db.val >= max(mn, 1)) & (db.val <= (mx if mx != 0xFFFFFFFF else db.val.max()))
+            assert (km == db.lo[keep]).all() and (vv == db.val[keep] - (max(mn, 1) - 1)).all()
+            t.close()
+
+
+def test_table_levels_stash_and_big_values(ctx, monkeypatch):
+    """Overloaded buckets spill to level 2 and the side table; huge values keep their excess exactly."""
+    from merfin_b200 import api
+    monkeypatch.setenv("MFN_TABLE_LOAD", "1.9")
+    rng = np.random.default_rng(7)
+    for k in (15, 21, 32):
+        n = 300000
+        kmers = np.unique(rng.integers(0, (1 << (2 * k)) - 1, size=n, dtype=np.uint64, endpoint=True))
+        values = rng.integers(1, 50, size=len(kmers)).astype(np.uint32)
+        values[::97] = rng.integers(1 << 20, 0xFFFFFFFF, size=len(values[::97]), dtype=np.uint64).astype(np.uint32)
+        values[5] = 0xFFFFFFFF
+        t = api.MerylExactLookup.from_kmers(ctx, k, kmers, values)
+        info = t.info
+        assert info.n_kmers == len(kmers)
+        assert info.n_level2 > 0 and info.n_bigvalue > 0
+        assert (t.values(kmers) == values).all()
+        absent = np.setdiff1d(rng.integers(0, (1 << (2 * k)) - 1, size=20000, dtype=np.uint64, endpoint=True), kmers)
+        assert (t.values(absent) == 0).all()
+        km, vv = t.export()
+        assert (km == kmers).all() and (vv == values).all()
+        t.close()
+
+
+def test_count_sequence_equals_meryl_count(ctx, golden_dir):
+    """mfn_table_count_seq builds what `meryl count` of the assembly builds (asm.meryl)."""
+    from merfin_b200 import api
+    for name, k, _ in SETS:
+        d, recs = _golden(golden_dir, name)
+        db = O.DB(os.path.join(d, "asm.meryl"))
+        seq = api.SeqSet(ctx, recs)
+        t = api.MerylExactLookup.count_sequence(ctx, k, seq)
+        km, vv = t.export()
+        assert (km == db.lo).all() and (vv == db.val).all()
+        t.close(); seq.close()
+
+
+# ---------------------------------------------------------------------------------- -hist
+def _hist_check(ctx, d, recs, k, peak, mn, mx, prob, tag):
+    from merfin_b200 import api
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"), mn, mx)
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    km = api.KModel.load_Kmetric(peak, prob)
+    res = api.hist(ctx, R, A, recs, km)
+    assert res.file_text() == open(os.path.join(d, f"{tag}.hist"), "rb").read()
+    assert res.summary_text() == open(os.path.join(d, f"{tag}.hist.summary")).read()
+    per = os.path.join(d, f"{tag}.hist.perseq")
+    if os.path.exists(per):
+        assert res.per_seq_text() == open(per).read()
+    # full-precision QV against the oracle's position-order accumulation (reference prints %.2f only)
+    oR, oA = O.Lookup(O.DB(os.path.join(d, "reads.meryl")), mn, mx), O.Lookup(O.DB(os.path.join(d, "asm.meryl")))
+    okm = O.KModel(peak, km.K, km.P)
+    h = O.Hist()
+    for _, b in recs:
+        h.add_record(oR, oA, okm, b)
+    s, _, _ = res.report()
+    assert (s.kasm, s.kmissing) == (h.kasm, h.kmissing)
+    assert abs(s.qv_star - O.histoQV(h.kmissing + h.koverCpy, h.kasm, k)) < 1e-6
+    assert abs(s.qv_missing - O.histoQV(h.kmissing, h.kasm, k)) < 1e-6
+    R.close(); A.close()
+
+
+@pytest.mark.parametrize("name,k,peak", SETS)
+def test_hist_matches_reference_files(ctx, golden_dir, name, k, peak):
+    d, recs = _golden(golden_dir, name)
+    _hist_check(ctx, d, recs, k, peak, 0, 0xFFFFFFFF, None, "ref")
+
+
+def test_hist_min_max_and_prob(ctx, golden_dir):
+    d, recs = _golden(golden_dir, "g1_k21")
+    _hist_check(ctx, d, recs, 21, 1.0, 3, 0xFFFFFFFF, None, "ref.min3")
+    _hist_check(ctx, d, recs, 21, 8.0, 2, 12, None, "ref.min2max12")
+    _hist_check(ctx, d, recs, 21, 8.0, 0, 0xFFFFFFFF, os.path.join(d, "prob.csv"), "ref.prob")
+
+
+# ---------------------------------------------------------------------------------- -dump
+@pytest.mark.parametrize("name,k,peak", SETS)
+def test_dump_matches_reference_files(ctx, golden_dir, name, k, peak):
+    from merfin_b200 import api
+    d, recs = _golden(golden_dir, name)
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    idents, off, vr, va, ok = api.dump(ctx, R, A, recs)
+    text, per = api.dump_text(idents, off, vr, va, ok, api.KModel(peak), k)
+    assert text == gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
+    assert per == open(os.path.join(d, "ref.dump.perseq")).read()
+    if name == "g1_k21":
+        km = api.KModel.load_Kmetric(peak, os.path.join(d, "prob.csv"))
+        text, _ = api.dump_text(idents, off, vr, va, ok, km, k)
+        assert text == gzip.open(os.path.join(d, "ref.prob.dump.gz"), "rb").read()
+    # integer pairs against the oracle, position by position
+    oR, oA = O.Lookup(O.DB(os.path.join(d, "reads.meryl"))), O.Lookup(O.DB(os.path.join(d, "asm.meryl")))
+    for i, (_, b) in enumerate(recs):
+        evr, eva, eok = O.pairs(oR, oA, b)
+        a = int(off[i]); n = len(eok)
+        assert (ok[a:a + n] == eok).all() and (vr[a:a + n] == evr).all() and (va[a:a + n] == eva).all()
+        assert (ok[a + n:int(off[i + 1])] == 0).all()
+    R.close(); A.close()
+
+
+# ---------------------------------------------------------------------------------- -completeness
+@pytest.mark.parametrize("name,k,peak", SETS)
+def test_completeness_matches_reference(ctx, golden_dir, name, k, peak):
+    from merfin_b200 import api
+    d, _ = _golden(golden_dir, name)
+    t, u, pairs = api.completeness(ctx, os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), api.KModel(peak))
+    assert open(os.path.join(d, "ref.completeness")).read().endswith(api.completeness_text(t, u))
+    assert int(pairs["count"].sum()) == O.DB(os.path.join(d, "reads.meryl")).n
+    if name == "g1_k21":
+        km = api.KModel.load_Kmetric(peak, os.path.join(d, "prob.csv"))
+        t, u, _ = api.completeness(ctx, os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), km)
+        assert open(os.path.join(d, "ref.prob.completeness")).read().endswith(api.completeness_text(t, u))
+
+
+# ---------------------------------------------------------------------------------- path scoring
+def test_score_paths_matches_oracle(ctx, golden_dir):
+    from merfin_b200 import api
+    d, recs = _golden(golden_dir, "g1_k21")
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    oR, oA = O.Lookup(O.DB(os.path.join(d, "reads.meryl"))), O.Lookup(O.DB(os.path.join(d, "asm.meryl")))
+    rng = np.random.default_rng(9)
+    b = recs[0][1]
+    paths = []
+    for i in range(400):
+        p = int(rng.integers(0, len(b) - 80))
+        s = bytearray(b[p:p + int(rng.integers(1, 80))])
+        if len(s) > 30 and i % 3 == 0:
+            s[int(rng.integers(0, len(s)))] = ord("ACGTN"[int(rng.integers(0, 5))])
+        paths.append(bytes(s))
+    paths += [b"", b"A", b"N" * 30, b"acgt" * 10]
+    off, vr, va, ok = api.score_paths(ctx, R, A, paths)
+    for i, s in enumerate(paths):
+        evr, eva, eok = O.pairs(oR, oA, s)
+        a = int(off[i]); n = len(eok)
+        assert (ok[a:a + n] == eok).all() and (vr[a:a + n] == evr).all() and (va[a:a + n] == eva).all()
+    R.close(); A.close()
+
+
+# ---------------------------------------------------------------------------------- bigger / edge cases
+def _synthetic_case(k, total, seed, noncanonical=False):
+    from merfin_b200 import synth
+    recs = synth.make_assembly(total, 5, seed, dup_len=2000)
+    recs = [(n, b.tobytes()) for n, b in recs]
+    recs.insert(2, ("empty", b""))
+    recs.insert(3, ("short", b"ACGTACGTAC"[:k - 1]))
+    recs.append(("allN", b"N" * 100))
+    f, r = _all_window_kmers(recs, k)
+    canon = np.minimum(f, r)
+    rng = np.random.default_rng(seed)
+    # asm table = true counts; read table = noisy multiples with dropouts and a few huge values
+    ak, ac = np.unique(canon, return_counts=True)
+    keep = rng.random(len(ak)) > 0.02
+    rk = ak[keep]
+    rv = (ac[keep] * rng.poisson(12, size=keep.sum())).astype(np.uint32) + 1
+    rv[::1000] = 5000 + rng.integers(0, 100000, size=len(rv[::1000])).astype(np.uint32)
+    extra = np.setdiff1d(rng.integers(0, 1 << (2 * k), size=len(ak) // 2, dtype=np.uint64), ak)
+    rk = np.concatenate([rk, extra]); rv = np.concatenate([rv, np.ones(len(extra), dtype=np.uint32)])
+    if noncanonical:        # store the strand the assembly shows, split counts between strands
+        fk, fc = np.unique(f, return_counts=True)
+        return recs, (fk, fc.astype(np.uint32)), (rk, rv)
+    return recs, (ak, ac.astype(np.uint32)), (rk, rv)
+
+
+class _ArrLookup:
+    """Oracle-side lookup over explicit arrays (same value semantics as o_lookup)."""
+    def __init__(self, k, kmers, vals):
+        o = np.argsort(kmers); self.k = k; self.km = kmers[o]; self.v = vals[o]
+
+    def values(self, q):
+        i = np.searchsorted(self.km, q)
+        i[i >= len(self.km)] = 0
+        hit = self.km[i] == q
+        return np.where(hit, self.v[i], 0).astype(np.uint32)
+
+
+def _expected_pairs(recs, k, Rl, Al):
+    exp = {}
+    per = []
+    for _, b in recs:
+        f, _, r, _, ok = O.windows(b, k)
+        f, r = f[ok == 1], r[ok == 1]
+        vr = Rl.values(f) + Rl.values(r); va = Al.values(f) + Al.values(r)
+        per.append((len(f), int((vr == 0).sum())))
+        keys, cnt = np.unique(np.stack([vr, va], 1), axis=0, return_counts=True)
+        for (a, b2), c in zip(keys, cnt):
+            exp[(int(a), int(b2))] = exp.get((int(a), int(b2)), 0) + int(c)
+    return exp, per
+
+
+@pytest.mark.parametrize("k,noncanon", [(21, False), (16, False), (32, False), (21, True)])
+def test_hist_joint_histogram_2mbp(ctx, k, noncanon):
+    """Joint (v_read, v_asm) histogram and per-record counters on a 2 Mbp set with empty/short/all-N
+    records, dense-tier overflow pairs, palindromes (even k) and a non-canonical assembly DB."""
+    from merfin_b200 import api
+    recs, (ak, ac), (rk, rv) = _synthetic_case(k, 2_000_000, 100 + k, noncanon)
+    R = api.MerylExactLookup.from_kmers(ctx, k, rk, rv)
+    A = api.MerylExactLookup.from_kmers(ctx, k, ak, ac)
+    assert A.info.canonical == (0 if noncanon else 1)
+    exp, per = _expected_pairs(recs, k, _ArrLookup(k, rk, rv), _ArrLookup(k, ak, ac))
+    res = api.hist(ctx, R, A, recs, api.KModel(12.0))
+    got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in res.pairs}
+    assert got == exp
+    assert [(int(c["kasm"]), int(c["kmissing"])) for c in res.per_seq] == per
+    assert any(key[0] >= 4096 for key in got)          # the sparse side table was exercised
+
+    # resident + sharded: shards add up to the same accumulator
+    seq = api.SeqSet(ctx, recs)
+    acc = api.Accum(ctx, seq.nseq)
+    for s in range(3):
+        api.hist_resident(ctx, R, A, seq, None, acc, s, 3)
+    per2, pairs2 = acc.fetch()
+    got2 = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in pairs2}
+    assert got2 == exp
+    assert [(int(c["kasm"]), int(c["kmissing"])) for c in per2] == per
+    R.close(); A.close(); seq.close(); acc.close()
+
+
+def test_k_mismatch_is_an_error(ctx, golden_dir):
+    from merfin_b200 import api
+    from merfin_b200.lib import MfnError, MFN_ERR_K_MISMATCH
+    R = api.MerylExactLookup.load(ctx, os.path.join(golden_dir, "g1_k21", "reads.meryl"))
+    A = api.MerylExactLookup.load(ctx, os.path.join(golden_dir, "g3_k31", "asm.meryl"))
+    with pytest.raises(MfnError) as e:
+        api.hist(ctx, R, A, [b"ACGT" * 20], api.KModel(5.0))
+    assert e.value.status == MFN_ERR_K_MISMATCH
+    with pytest.raises(MfnError):
+        api.MerylExactLookup.load(ctx, "/nonexistent/db.meryl")
+    R.close(); A.close()
