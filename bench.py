@@ -271,7 +271,9 @@ def main():
     asm_np = asm_host.numpy()
 
     ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: our kernels, torch's events and NCCL are all ordered on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     lib = api.L.load()
     config = {"workload": f"{total / 1e9:.2f} Gbp synthetic diploid assembly (24 records, 0.1% SNVs, 1% N) + "

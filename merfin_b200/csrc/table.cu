@@ -252,6 +252,13 @@ __global__ void __launch_bounds__(256) k_synth_from_asm(DevTable reads, DevTable
 }
 
 template <bool W64>
+__global__ void __launch_bounds__(256) k_copy_table(DevTable dst, DevTable src) {
+  InsertCounts cnt = {0, 0, 0, 0, 0};
+  mfn_foreach_entry(src, [&](uint64_t c, uint32_t v) { mfn_insert<W64, false>(dst, c, v, cnt); });
+  mfn_flush_counts(dst, cnt);
+}
+
+template <bool W64>
 __global__ void __launch_bounds__(256) k_synth_errors(DevTable reads, uint64_t n_error, uint64_t seed) {
   InsertCounts cnt = {0, 0, 0, 0, 0};
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_error; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -522,6 +529,23 @@ extern "C" int mfn_table_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq,
   ctx->launches++;
   int st = (cudaGetLastError() == cudaSuccess) ? mfn_table_finalize(t, true) : MFN_ERR_CUDA;
   if (st != MFN_OK) { mfn_table_free(t); return st; }
+  // The table was sized for one k-mer per base.  When far fewer are distinct (diploid or
+  // repetitive assemblies), re-insert into a right-sized table: less HBM, fewer TLB misses.
+  if (t->n_kmers * 10 < seq->total_bases * 8 && seq->total_bases > (1u << 20)) {
+    mfn_table *c = nullptr;
+    st = mfn_table_alloc(ctx, k, t->n_kmers, &c);
+    if (st == MFN_OK) {
+      c->min_value = 1; c->max_value = 0xffffffffu; c->value_offset = 0;
+      if (c->dev.w64) k_copy_table<true><<<grid, 256, 0, ctx->stream>>>(c->dev, t->dev);
+      else            k_copy_table<false><<<grid, 256, 0, ctx->stream>>>(c->dev, t->dev);
+      ctx->launches++;
+      st = (cudaGetLastError() == cudaSuccess) ? mfn_table_finalize(c, false) : MFN_ERR_CUDA;
+    }
+    if (st == MFN_OK && c->n_kmers != t->n_kmers) { mfn_set_error("table compaction lost entries"); st = MFN_ERR_CUDA; }
+    if (st != MFN_OK) { mfn_table_free(c); mfn_table_free(t); return st; }
+    mfn_table_free(t);
+    t = c;
+  }
   *out = t;
   return MFN_OK;
 }

@@ -74,7 +74,9 @@ def test_table_levels_stash_and_big_values(ctx, monkeypatch):
         t = api.MerylExactLookup.from_kmers(ctx, k, kmers, values)
         info = t.info
         assert info.n_kmers == len(kmers)
-        assert info.n_level2 > 0 and info.n_bigvalue > 0
+        assert info.n_level2 > 0
+        if k != 21:      # k=21 at this size gets 64-bit slots with full 32-bit values: nothing saturates
+            assert info.n_bigvalue > 0 and info.value_bits < 20
         assert (t.values(kmers) == values).all()
         absent = np.setdiff1d(rng.integers(0, (1 << (2 * k)) - 1, size=20000, dtype=np.uint64, endpoint=True), kmers)
         assert (t.values(absent) == 0).all()
