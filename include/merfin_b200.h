@@ -110,6 +110,27 @@ int  mfn_table_lookup(mfn_ctx *ctx, const mfn_table *t, const uint64_t *kmers, u
 int  mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmers, uint32_t *values,
                       uint64_t cap, uint64_t *n);
 
+/* ---- fused (read, assembly) table ------------------------------------------------------
+ * merfin always looks a k-mer up in BOTH databases (merfin-globals.C:107-108).  Fusing the
+ * two tables into one whose 128-byte lines hold tag + read value + assembly value makes that
+ * ONE memory access per window.  The fused table is attached to `reads`; every scan entry
+ * point that is handed (reads, asm_) uses it automatically.  Needs canonical databases. */
+int  mfn_tables_fuse(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_);
+int  mfn_tables_unfuse(mfn_table *reads);
+
+typedef struct {
+  uint32_t fused;            /* 0: no fused table attached                          */
+  uint32_t slot_bits, tag_bits, read_bits, asm_bits;
+  uint64_t n_kmers;          /* size of the union                                   */
+  uint64_t n_home, n_spill, n_stash, n_bigvalue;
+  uint64_t lines, device_bytes;
+} mfn_joint_info_t;
+
+int  mfn_joint_info(const mfn_table *reads, mfn_joint_info_t *info);
+/* (value_read(kmer), value_asm(kmer)) for k-mers exactly as given, through the fused table. */
+int  mfn_joint_lookup(mfn_ctx *ctx, const mfn_table *reads, const uint64_t *kmers, uint64_t n,
+                      uint32_t *v_read, uint32_t *v_asm);
+
 /* ---- meryl database writer (generator side; kmers-writer.C:117-288) ------ */
 /* Writes a v03 database the reference's merylFileReader loads.  k-mers must be
  * distinct; they are sorted here. */

@@ -129,6 +129,26 @@ class MerylExactLookup:
     def value(self, kmer: int) -> int:
         return int(self.values([kmer])[0])
 
+    def fuse(self, asm: "MerylExactLookup"):
+        """Attach the fused (self, asm) table: scans over this pair then cost one probe per window."""
+        L.check(self._lib.mfn_tables_fuse(self.ctx.h, self.h, asm.h))
+
+    def unfuse(self):
+        L.check(self._lib.mfn_tables_unfuse(self.h))
+
+    @property
+    def joint_info(self) -> L.JointInfo:
+        i = L.JointInfo()
+        L.check(self._lib.mfn_joint_info(self.h, C.byref(i)))
+        return i
+
+    def joint_values(self, kmers):
+        km = np.ascontiguousarray(kmers, dtype=np.uint64)
+        vr = np.zeros(len(km), dtype=np.uint32)
+        va = np.zeros(len(km), dtype=np.uint32)
+        L.check(self._lib.mfn_joint_lookup(self.ctx.h, self.h, _ptr(km), len(km), _ptr(vr), _ptr(va)))
+        return vr, va
+
     def export(self):
         n = self.nKmers()
         km = np.zeros(max(n, 1), dtype=np.uint64)

@@ -92,8 +92,11 @@ struct mfn_ctx {
   struct mfn_accum *scratch_acc = nullptr;
 };
 
+struct mfn_joint;
+
 struct mfn_table {
   mfn_ctx   *ctx = nullptr;
+  mfn_joint *joint = nullptr;     // fused (this, assembly) table built by mfn_tables_fuse
   DevTable   dev{};
   TableStats host_stats{};
   uint32_t   min_value = 0, max_value = 0, value_offset = 0;

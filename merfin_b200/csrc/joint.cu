@@ -1,0 +1,251 @@
+// Building the joint (read, assembly) table from two per-database tables (see joint.cuh).
+#include "joint.cuh"
+#include "table_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <type_traits>
+
+struct JointCounts { uint32_t home, spill, stash, big; };
+
+__device__ __forceinline__ void oa2_add(const OaTable2 &t, uint64_t key, int which, uint32_t v, JointStats *st) {
+  if (key == MFN_EMPTY64) { atomicAdd(&t.special[which], v); return; }
+  uint32_t i = mfn_oa_hash(key) & t.mask;
+  for (uint32_t n = 0; n <= t.mask; n++) {
+    unsigned long long cur = t.keys[i];
+    if (cur == MFN_EMPTY64) {
+      cur = atomicCAS(&t.keys[i], MFN_EMPTY64, (unsigned long long)key);
+      if (cur == MFN_EMPTY64) cur = key;
+    }
+    if (cur == key) { atomicAdd(which ? &t.v1[i] : &t.v0[i], v); return; }
+    i = (i + 1) & t.mask;
+  }
+  atomicAdd(&st->errors, 1ull);
+}
+
+// Set field 'which' (0 = read value, 1 = assembly value) of k-mer c to v, creating the slot if needed.
+template <bool W64>
+__device__ __forceinline__ void joint_insert(const JointDev &J, uint64_t c, int which, uint32_t v, JointCounts &cnt) {
+  typedef typename std::conditional<W64, unsigned long long, unsigned int>::type slot_t;
+  constexpr int S = W64 ? 4 : 8;
+  const uint32_t vb = J.rbits + J.abits;
+  const uint32_t fmax = which ? J.amax : J.rmax;
+  const uint32_t sat = v < fmax ? v : fmax;
+  const slot_t field = which ? (slot_t)sat : ((slot_t)sat << J.abits);
+  uint64_t line, tag;
+  joint_locate(J, c, line, tag);
+  const slot_t want = (slot_t)tag << vb;
+  const uint32_t home = (uint32_t)tag & 3u;
+#pragma unroll 1
+  for (uint32_t j = 0; j < 4; j++) {
+    slot_t *slots = (slot_t *)((char *)J.lines + line * 128 + ((home + j) & 3u) * 32);
+#pragma unroll 1
+    for (int i = 0; i < S; i++) {
+      slot_t cur = *(volatile slot_t *)(slots + i);
+      if (cur == 0) {
+        slot_t old = atomicCAS(slots + i, (slot_t)0, (slot_t)(want | field));
+        if (old == 0) {
+          if (j == 0) cnt.home++; else cnt.spill++;
+          if (v > fmax) { oa2_add(J.big, c, which, v - fmax, J.stats); cnt.big++; }
+          return;
+        }
+        cur = old;
+      }
+      if ((cur >> vb) == (slot_t)tag) {            // the k-mer has a slot already: fill in our field
+        atomicOr(slots + i, field);
+        if (v > fmax) { oa2_add(J.big, c, which, v - fmax, J.stats); cnt.big++; }
+        return;
+      }
+    }
+  }
+  uint32_t a, b;
+  if (!oa2_get(J.stash, c, a, b)) cnt.stash++;
+  oa2_add(J.stash, c, which, v, J.stats);
+}
+
+template <bool W64>
+__global__ void __launch_bounds__(256) k_joint_fill(JointDev J, DevTable T, int which) {
+  JointCounts cnt = {0, 0, 0, 0};
+  mfn_foreach_entry(T, [&](uint64_t c, uint32_t v) { joint_insert<W64>(J, c, which, v, cnt); });
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt.home += __shfl_down_sync(0xffffffffu, cnt.home, o);
+    cnt.spill += __shfl_down_sync(0xffffffffu, cnt.spill, o);
+    cnt.stash += __shfl_down_sync(0xffffffffu, cnt.stash, o);
+    cnt.big += __shfl_down_sync(0xffffffffu, cnt.big, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt.home) atomicAdd(&J.stats->n_home, (unsigned long long)cnt.home);
+    if (cnt.spill) atomicAdd(&J.stats->n_spill, (unsigned long long)cnt.spill);
+    if (cnt.stash) atomicAdd(&J.stats->n_stash, (unsigned long long)cnt.stash);
+    if (cnt.big) atomicAdd(&J.stats->n_big, (unsigned long long)cnt.big);
+  }
+}
+
+// k-mers of A that R does not hold (sizes the union)
+__global__ void __launch_bounds__(256) k_count_absent(DevTable A, DevTable R, unsigned long long *count) {
+  unsigned long long n = 0;
+  mfn_foreach_entry(A, [&](uint64_t c, uint32_t) { if (mfn_value(R, c) == 0) n++; });
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
+}
+
+__global__ void __launch_bounds__(256) k_joint_lookup(JointDev J, const unsigned long long *kmers, uint64_t n,
+                                                      uint32_t *vr, uint32_t *va) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t a = 0, b = 0;
+    if (!(kmers[i] & ~J.kmask)) joint_value(J, kmers[i], a, b);
+    vr[i] = a; va[i] = b;
+  }
+}
+
+static uint32_t bits_of(uint64_t x) { uint32_t n = 0; while (x) { n++; x >>= 1; } return n; }
+static uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+void mfn_joint_free(mfn_joint *j) {
+  if (!j) return;
+  for (void *p : j->allocs) cudaFree(p);
+  delete j;
+}
+
+int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_joint **out) {
+  if (R->dev.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", R->dev.k, A->dev.k); return MFN_ERR_K_MISMATCH; }
+  if (R->dev.probe_both || A->dev.probe_both) { mfn_set_error("joint table needs canonical databases"); return MFN_ERR_UNSUPPORTED; }
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  const uint32_t k = R->dev.k;
+  const int grid = ctx->sm_count * 8;
+
+  unsigned long long *d_n, absent = 0;
+  MFN_CUDA(cudaMalloc(&d_n, 8));
+  MFN_CUDA(cudaMemsetAsync(d_n, 0, 8, ctx->stream));
+  k_count_absent<<<grid, 256, 0, ctx->stream>>>(A->dev, R->dev, d_n);
+  ctx->launches++;
+  MFN_CUDA(cudaMemcpyAsync(&absent, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_n);
+  const uint64_t n = std::max<uint64_t>(R->n_kmers + absent, 1024);
+
+  mfn_joint *j = new mfn_joint();
+  j->reads = R; j->asm_ = A; j->n_kmers = R->n_kmers + absent;
+  JointDev &J = j->dev;
+  J.k = k; J.kmask = R->dev.kmask; J.seed = R->dev.lv[0].seed;
+  const char *env = getenv("MFN_JOINT_LOAD");
+  double load = env ? atof(env) : 0.70;
+  if (!(load > 0.05 && load < 0.99)) load = 0.70;
+  for (int w64 = 0; w64 < 2; w64++) {
+    const int slots = w64 ? 16 : 32;
+    J.nlines = std::max<uint64_t>(16, (uint64_t)std::ceil(n / (slots * load)));
+    unsigned __int128 space = (unsigned __int128)1 << (2 * k);
+    unsigned __int128 D = (space + J.nlines - 1) / J.nlines;
+    if (D >> 64) D = ((unsigned __int128)1 << 64) - 1;
+    J.D = std::max<uint64_t>(1, (uint64_t)D);
+    J.magic = (J.D == 1) ? ~0ull : (uint64_t)((((unsigned __int128)1) << 64) / J.D);
+    const uint32_t T = std::max(1u, bits_of(J.D - 1));
+    J.w64 = w64;
+    if (!w64) {
+      if (T > 16) continue;                       // need >= 10 read-value bits next to 6 assembly bits
+      J.abits = 6; J.rbits = std::min(20u, 32u - T - 6u);
+    } else {
+      const uint32_t avail = 64 - std::min(T, 58u);
+      J.abits = std::min(20u, avail / 3);
+      J.rbits = std::min(32u, avail - J.abits);
+    }
+    j->tag_bits = T;
+    break;
+  }
+  J.rmax = J.rbits >= 32 ? 0xffffffffu : ((1u << J.rbits) - 1u);
+  J.amax = (1u << J.abits) - 1u;
+
+  auto dalloc = [&](void **p, size_t bytes, int fill) -> int {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { mfn_set_error("cudaMalloc(joint table, %zu bytes): %s", bytes, cudaGetErrorString(e)); return MFN_ERR_NOMEM; }
+    j->allocs.push_back(*p);
+    j->device_bytes += bytes;
+    MFN_CUDA(cudaMemsetAsync(*p, fill, bytes, ctx->stream));
+    return MFN_OK;
+  };
+  int st = dalloc(&J.lines, J.nlines * 128, 0);
+  OaTable2 *oas[2] = {&J.stash, &J.big};
+  uint64_t caps[2] = {next_pow2(std::max<uint64_t>(1 << 12, n / 128)), next_pow2(std::max<uint64_t>(1 << 12, n / 128))};
+  for (int i = 0; i < 2 && st == MFN_OK; i++) {
+    oas[i]->mask = (uint32_t)(caps[i] - 1);
+    st = dalloc((void **)&oas[i]->keys, caps[i] * 8, 0xff);
+    if (st == MFN_OK) st = dalloc((void **)&oas[i]->v0, caps[i] * 4, 0);
+    if (st == MFN_OK) st = dalloc((void **)&oas[i]->v1, caps[i] * 4, 0);
+    if (st == MFN_OK) st = dalloc((void **)&oas[i]->special, 8, 0);
+  }
+  if (st == MFN_OK) st = dalloc((void **)&J.stats, sizeof(JointStats), 0);
+  if (st == MFN_OK) {
+    if (J.w64) {
+      k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
+      k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
+    } else {
+      k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
+      k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
+    }
+    ctx->launches += 2;
+    if (cudaMemcpyAsync(&j->stats, J.stats, sizeof(JointStats), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      mfn_set_error("joint table build: %s", cudaGetErrorString(cudaGetLastError()));
+      st = MFN_ERR_CUDA;
+    } else if (j->stats.errors) {
+      mfn_set_error("joint table side tables overflowed (%llu)", j->stats.errors);
+      st = MFN_ERR_CAPACITY;
+    } else if (j->stats.n_home + j->stats.n_spill + j->stats.n_stash != j->n_kmers) {
+      mfn_set_error("joint table holds %llu k-mers, expected %llu", j->stats.n_home + j->stats.n_spill + j->stats.n_stash,
+                    (unsigned long long)j->n_kmers);
+      st = MFN_ERR_CUDA;
+    }
+  }
+  if (st != MFN_OK) { mfn_joint_free(j); return st; }
+  *out = j;
+  return MFN_OK;
+}
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" int mfn_tables_fuse(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_) {
+  if (!ctx || !reads || !asm_) return MFN_ERR_INVALID;
+  if (reads->joint && reads->joint->asm_ == asm_) return MFN_OK;
+  mfn_joint_free(reads->joint);
+  reads->joint = nullptr;
+  return mfn_joint_build(ctx, reads, asm_, &reads->joint);
+}
+
+extern "C" int mfn_tables_unfuse(mfn_table *reads) {
+  if (!reads) return MFN_ERR_INVALID;
+  mfn_joint_free(reads->joint);
+  reads->joint = nullptr;
+  return MFN_OK;
+}
+
+extern "C" int mfn_joint_info(const mfn_table *reads, mfn_joint_info_t *info) {
+  if (!reads || !info) return MFN_ERR_INVALID;
+  memset(info, 0, sizeof *info);
+  const mfn_joint *j = reads->joint;
+  if (!j) return MFN_OK;
+  info->fused = 1;
+  info->slot_bits = j->dev.w64 ? 64 : 32;
+  info->tag_bits = j->tag_bits; info->read_bits = j->dev.rbits; info->asm_bits = j->dev.abits;
+  info->n_kmers = j->n_kmers; info->n_home = j->stats.n_home; info->n_spill = j->stats.n_spill;
+  info->n_stash = j->stats.n_stash; info->n_bigvalue = j->stats.n_big;
+  info->lines = j->dev.nlines; info->device_bytes = j->device_bytes;
+  return MFN_OK;
+}
+
+extern "C" int mfn_joint_lookup(mfn_ctx *ctx, const mfn_table *reads, const uint64_t *kmers, uint64_t n,
+                                uint32_t *v_read, uint32_t *v_asm) {
+  if (!ctx || !reads || !reads->joint || (n && (!kmers || !v_read || !v_asm))) return MFN_ERR_INVALID;
+  if (n == 0) return MFN_OK;
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long *dk; uint32_t *dr, *da;
+  MFN_CUDA(cudaMalloc(&dk, n * 8)); MFN_CUDA(cudaMalloc(&dr, n * 4)); MFN_CUDA(cudaMalloc(&da, n * 4));
+  cudaMemcpyAsync(dk, kmers, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
+  k_joint_lookup<<<grid, 256, 0, ctx->stream>>>(reads->joint->dev, dk, n, dr, da);
+  ctx->launches++;
+  cudaMemcpyAsync(v_read, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaMemcpyAsync(v_asm, da, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dk); cudaFree(dr); cudaFree(da);
+  if (e != cudaSuccess) { mfn_set_error("joint lookup: %s", cudaGetErrorString(e)); return MFN_ERR_CUDA; }
+  return MFN_OK;
+}

@@ -19,16 +19,46 @@ static void shard_tiles(uint64_t ntiles, uint32_t s, uint32_t n, uint64_t &b, ui
 
 struct ScanScratch { unsigned long long *counter = nullptr; unsigned long long *zmap = nullptr; };
 
-static int launch_scan(mfn_ctx *ctx, ScanParams &P, bool dump) {
+int mfn_scan_grid_0(mfn_ctx *); int mfn_scan_grid_1(mfn_ctx *); int mfn_scan_grid_2(mfn_ctx *); int mfn_scan_grid_3(mfn_ctx *);
+void mfn_scan_launch_0(const ScanParams &, int, cudaStream_t); void mfn_scan_launch_1(const ScanParams &, int, cudaStream_t);
+void mfn_scan_launch_2(const ScanParams &, int, cudaStream_t); void mfn_scan_launch_3(const ScanParams &, int, cudaStream_t);
+
+int mfn_scan_grid(mfn_ctx *ctx, int mode) {
+  switch (mode) {
+    case 0: return mfn_scan_grid_0(ctx);
+    case 1: return mfn_scan_grid_1(ctx);
+    case 2: return mfn_scan_grid_2(ctx);
+    default: return mfn_scan_grid_3(ctx);
+  }
+}
+
+void mfn_scan_launch(const ScanParams &P, int mode, int grid, cudaStream_t stream) {
+  switch (mode) {
+    case 0: mfn_scan_launch_0(P, grid, stream); break;
+    case 1: mfn_scan_launch_1(P, grid, stream); break;
+    case 2: mfn_scan_launch_2(P, grid, stream); break;
+    default: mfn_scan_launch_3(P, grid, stream); break;
+  }
+}
+
+// The fused table is used whenever it has been built for exactly this pair of databases.
+static bool use_joint(const mfn_table *R, const mfn_table *A, ScanParams &P) {
+  const char *env = getenv("MFN_NO_JOINT");
+  if (env && atoi(env)) return false;
+  if (!R->joint || R->joint->asm_ != A) return false;
+  P.J = R->joint->dev;
+  return true;
+}
+
+static int launch_scan(mfn_ctx *ctx, ScanParams &P, bool dump, bool joint) {
   if (P.tile_begin >= P.tile_end) return MFN_OK;
   unsigned long long *counter;
   MFN_CUDA(cudaMallocAsync(&counter, 8, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(counter, 0, 8, ctx->stream));
   P.tile_counter = counter;
-  int grid = dump ? mfn_scan_grid_dump(ctx) : mfn_scan_grid_hist(ctx);
-  grid = (int)std::min<uint64_t>((uint64_t)grid, P.tile_end - P.tile_begin);
-  if (dump) mfn_scan_launch_dump(P, grid, ctx->stream);
-  else      mfn_scan_launch_hist(P, grid, ctx->stream);
+  const int mode = (dump ? SCAN_DUMP : 0) | (joint ? SCAN_JOINT : 0);
+  int grid = (int)std::min<uint64_t>((uint64_t)mfn_scan_grid(ctx, mode), P.tile_end - P.tile_begin);
+  mfn_scan_launch(P, mode, grid, ctx->stream);
   ctx->launches++;
   MFN_CUDA(cudaGetLastError());
   MFN_CUDA(cudaFreeAsync(counter, ctx->stream));
@@ -65,7 +95,7 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   unsigned long long *zmap = nullptr;
   MFN_TRY(build_zmap(ctx, km, &zmap, &P.zlen));
   P.zmap = zmap;
-  int st = launch_scan(ctx, P, false);
+  int st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));
   if (zmap) cudaFreeAsync(zmap, ctx->stream);
   return st;
 }
@@ -91,7 +121,7 @@ extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
   P.tile_begin = 0; P.tile_end = seq->ntiles;
   P.out_vr = d_v_read; P.out_va = d_v_asm; P.out_valid = d_valid;
-  return launch_scan(ctx, P, true);
+  return launch_scan(ctx, P, true, use_joint(reads, asm_, P));
 }
 
 // ---------------------------------------------------------------------------

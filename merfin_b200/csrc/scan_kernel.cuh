@@ -1,17 +1,21 @@
 // The hot path: scan every window of a packed sequence set, canonicalise the k-mer, probe the
-// read and assembly tables, and either accumulate the joint (v_read, v_asm) histogram (-hist,
-// merfin-histogram.C:54-91) or write the pair per position (-dump / path scoring,
+// read and assembly multiplicities, and either accumulate the joint (v_read, v_asm) histogram
+// (-hist, merfin-histogram.C:54-91) or write the pair per position (-dump / path scoring,
 // merfin-dump.C:44-67, varMer.C:66-90).  All integer work; the K* doubles are replayed on the host.
 //
 // Persistent CTAs pull 2048-window tiles from a global counter.  The tile's 2-bit words and
 // validity bits (528 + 272 bytes incl. a 64-base halo) are staged in shared memory by two
 // 1-D TMA bulk copies (cp.async.bulk + mbarrier), double-buffered against the probes of the
 // previous tile.  A thread owns 8 consecutive windows: it slices them out of a 128-bit
-// register window with shifts (no serial rolling dependency between threads), issues the
-// 32-byte bucket loads of 4 windows x 2 tables back to back (8 sectors in flight per thread),
-// then resolves them.
+// register window with shifts (no serial rolling dependency between threads), issues all its
+// bucket loads back to back (8 independent 32-byte sectors in flight per thread), then
+// resolves them.
+//
+// MODE bit 0: DUMP (write pairs per position) instead of histogram.
+// MODE bit 1: JOINT: one probe of the fused (read, assembly) table per window (joint.cuh)
+//             instead of one probe per database.
 #pragma once
-#include "table.cuh"
+#include "joint.cuh"
 #include "table_host.h"
 
 #include <algorithm>
@@ -22,12 +26,15 @@
 #define OK_WORDS (MFN_TILE / 64 + 2)       // 34 words = 272 B
 #define SH_R 512u                          // shared-memory tier of the joint histogram
 #define SH_A 8u
+#define SCAN_DUMP 1
+#define SCAN_JOINT 2
 
 static_assert(SCAN_THREADS * WPT == MFN_TILE, "tile geometry");
 static_assert((SEQ_WORDS * 8) % 16 == 0 && (OK_WORDS * 8) % 16 == 0, "TMA sizes are multiples of 16 B");
 
 struct ScanParams {
   DevTable R, A;
+  JointDev J;
   const unsigned long long *seq2, *ok, *rec_start;
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
@@ -63,24 +70,27 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 
 // ---- rare pairs outside the dense tier -----------------------------------------------------
-static __device__ __noinline__ void sparse_add(const PairTable &t, unsigned long long *acc, uint32_t vr, uint32_t va) {
+static __device__ __noinline__ void sparse_add(const PairTable &t, unsigned long long *acc, uint32_t vr, uint32_t va,
+                                               unsigned long long n) {
   unsigned long long key = ((unsigned long long)vr << 32) | va;
-  if (key == MFN_EMPTY64) { atomicAdd(&acc[3], 1ull); return; }
+  if (key == MFN_EMPTY64) { atomicAdd(&acc[3], n); return; }
   uint32_t i = mfn_oa_hash(key) & t.mask;
-  for (uint32_t n = 0; n <= t.mask; n++) {
+  for (uint32_t p = 0; p <= t.mask; p++) {
     unsigned long long cur = t.keys[i];
     if (cur == MFN_EMPTY64) {
       cur = atomicCAS(&t.keys[i], MFN_EMPTY64, key);
       if (cur == MFN_EMPTY64) { cur = key; atomicAdd(&acc[1], 1ull); }
     }
-    if (cur == key) { atomicAdd(&t.counts[i], 1ull); return; }
+    if (cur == key) { atomicAdd(&t.counts[i], n); return; }
     i = (i + 1) & t.mask;
   }
-  atomicAdd(&acc[2], 1ull);                  // table full: reported as MFN_ERR_CAPACITY
+  atomicAdd(&acc[2], n);                     // table full: reported as MFN_ERR_CAPACITY
 }
 
-template <bool DUMP>
+template <int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const __grid_constant__ ScanParams P) {
+  constexpr bool DUMP = (MODE & SCAN_DUMP) != 0;
+  constexpr bool JOINT = (MODE & SCAN_JOINT) != 0;
   __shared__ __align__(16) unsigned long long s_seq[2][SEQ_WORDS];
   __shared__ __align__(16) unsigned long long s_ok[2][OK_WORDS];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -160,67 +170,101 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const __grid_constant__ S
     uint32_t rec = r0;
     uint64_t next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull;
 
+    // forward / reverse-complement k-mer of window uu (kmers-tiny.H:82-83)
+    auto kmers_of = [&](int uu, uint64_t &f, uint64_t &r) {
+      uint64_t x = uu ? ((lo >> (2 * uu)) | (hi << (64 - 2 * uu))) : lo;
+      x &= kmask;                                          // base g in the low bits
+      r = x ^ cmask;
+      f = mfn_revcomp(r, k);
+    };
+    // what happens to the integer pair of window uu
+    auto emit = [&](int uu, bool valid, uint32_t vr, uint32_t va) {
+      const uint64_t g = g0 + uu;
+      while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
+      if (DUMP) {
+        // positions are reported in the caller's coordinates: one separator per earlier record
+        if (rec < P.nseq && g + 1 < next_start) {
+          const uint64_t s = g - rec;
+          P.out_vr[s] = vr; P.out_va[s] = va; P.out_valid[s] = valid ? 1 : 0;
+        }
+      } else if (valid) {
+        bool miss = (vr == 0);
+        if (vr != 0 && vr < P.zlen) miss = (__ldg(&P.zmap[vr >> 6]) >> (vr & 63)) & 1;
+        if (rec == r0) { n_ok0++; n_miss0 += miss; }
+        else {
+          atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec], 1ull);
+          if (miss) atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec + 1], 1ull);
+        }
+        my_valid++;
+        if (vr < SH_R && va < SH_A) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+        else if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
+        else sparse_add(P.sparse, P.acc, vr, va, 1ull);
+      }
+    };
+
+    if (JOINT) {
+      // one line of the fused table per window: 8 home sectors in flight per thread
+      uint64_t ck[WPT], ln[WPT], tg[WPT];
+      bool val[WPT], pal[WPT];
+      Bucket b[WPT];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      uint64_t fk[4], rk[4];
-      bool val[4];
-      Bucket br[4], ba[4];
-      uint64_t tr[4], ta[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int uu = half * 4 + u;
-        uint64_t x = uu ? ((lo >> (2 * uu)) | (hi << (64 - 2 * uu))) : lo;
-        x &= kmask;                                        // base g in the low bits
-        const uint64_t r = x ^ cmask;                      // reverse complement (kmers-tiny.H:83)
-        const uint64_t f = mfn_revcomp(r, k);              // forward k-mer    (kmers-tiny.H:82)
-        fk[u] = f; rk[u] = r;
-        val[u] = ((okb >> uu) & kbits) == kbits;
+      for (int u = 0; u < WPT; u++) {
+        uint64_t f, r;
+        kmers_of(u, f, r);
+        val[u] = ((okb >> u) & kbits) == kbits;
+        pal[u] = (f == r);
+        ck[u] = f < r ? f : r;
         if (val[u]) {
-          const uint64_t c = f < r ? f : r;
-          uint64_t bkt;
-          mfn_locate(P.R, P.R.probe_both ? f : c, bkt, tr[u]);
-          mfn_load_bucket(P.R.lv[0].slots, bkt, br[u]);
-          mfn_locate(P.A, P.A.probe_both ? f : c, bkt, ta[u]);
-          mfn_load_bucket(P.A.lv[0].slots, bkt, ba[u]);
+          joint_locate(P.J, ck[u], ln[u], tg[u]);
+          joint_load_sector(P.J, ln[u], (uint32_t)tg[u] & 3u, b[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int uu = half * 4 + u;
-        const uint64_t g = g0 + uu;
+      for (int u = 0; u < WPT; u++) {
         uint32_t vr = 0, va = 0;
         if (val[u]) {
-          const uint64_t f = fk[u], r = rk[u], c = f < r ? f : r;
-          vr = mfn_resolve(P.R, P.R.probe_both ? f : c, br[u], tr[u]);
-          va = mfn_resolve(P.A, P.A.probe_both ? f : c, ba[u], ta[u]);
-          // value(f) + value(r), uint32 adds (merfin-globals.C:107-108, Q2): a canonical table
-          // holds at most one of the two unless f == r, which then counts twice
-          if (P.R.probe_both) vr += mfn_value(P.R, r); else if (f == r) vr += vr;
-          if (P.A.probe_both) va += mfn_value(P.A, r); else if (f == r) va += va;
+          joint_resolve(P.J, ck[u], ln[u], tg[u], b[u], vr, va);
+          if (pal[u]) { vr += vr; va += va; }              // value(f) + value(r) with f == r (Q2)
         }
-        while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
-        if (DUMP) {
-          // positions are reported in the caller's coordinates: one separator per earlier record
-          if (rec < P.nseq && g + 1 < next_start) {
-            const uint64_t s = g - rec;
-            P.out_vr[s] = vr; P.out_va[s] = va; P.out_valid[s] = val[u] ? 1 : 0;
+        emit(u, val[u], vr, va);
+      }
+    } else {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint64_t fk[4], rk[4];
+        bool val[4];
+        Bucket br[4], ba[4];
+        uint64_t tr[4], ta[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int uu = half * 4 + u;
+          kmers_of(uu, fk[u], rk[u]);
+          val[u] = ((okb >> uu) & kbits) == kbits;
+          if (val[u]) {
+            const uint64_t c = fk[u] < rk[u] ? fk[u] : rk[u];
+            uint64_t bkt;
+            mfn_locate(P.R, P.R.probe_both ? fk[u] : c, bkt, tr[u]);
+            mfn_load_bucket(P.R.lv[0].slots, bkt, br[u]);
+            mfn_locate(P.A, P.A.probe_both ? fk[u] : c, bkt, ta[u]);
+            mfn_load_bucket(P.A.lv[0].slots, bkt, ba[u]);
           }
-        } else if (val[u]) {
-          bool miss = (vr == 0);
-          if (vr != 0 && vr < P.zlen) miss = (__ldg(&P.zmap[vr >> 6]) >> (vr & 63)) & 1;
-          if (rec == r0) { n_ok0++; n_miss0 += miss; }
-          else {
-            atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec], 1ull);
-            if (miss) atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec + 1], 1ull);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          uint32_t vr = 0, va = 0;
+          if (val[u]) {
+            const uint64_t f = fk[u], r = rk[u], c = f < r ? f : r;
+            vr = mfn_resolve(P.R, P.R.probe_both ? f : c, br[u], tr[u]);
+            va = mfn_resolve(P.A, P.A.probe_both ? f : c, ba[u], ta[u]);
+            // value(f) + value(r), uint32 adds (merfin-globals.C:107-108, Q2): a canonical table
+            // holds at most one of the two unless f == r, which then counts twice
+            if (P.R.probe_both) vr += mfn_value(P.R, r); else if (f == r) vr += vr;
+            if (P.A.probe_both) va += mfn_value(P.A, r); else if (f == r) va += va;
           }
-          my_valid++;
-          if (vr < SH_R && va < SH_A) atomicAdd(&s_hist[va * SH_R + vr], 1u);
-          else if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
-          else sparse_add(P.sparse, P.acc, vr, va);
+          emit(half * 4 + u, val[u], vr, va);
         }
       }
     }
-
   }
 
   flush_rec();
@@ -235,10 +279,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const __grid_constant__ S
   }
 }
 
+// One translation unit per instantiation (scan_mode*.cu): ptxas 12.9 crashes when several of
+// these entries share a module.
+int mfn_scan_grid(mfn_ctx *ctx, int mode);
+void mfn_scan_launch(const ScanParams &P, int mode, int grid, cudaStream_t stream);
 
-// One translation unit per instantiation (scan_hist.cu, scan_dump.cu): ptxas 12.9 crashes when
-// both entries share a module.
-int mfn_scan_grid_hist(mfn_ctx *ctx);
-int mfn_scan_grid_dump(mfn_ctx *ctx);
-void mfn_scan_launch_hist(const ScanParams &P, int grid, cudaStream_t stream);
-void mfn_scan_launch_dump(const ScanParams &P, int grid, cudaStream_t stream);
+#define MFN_SCAN_INSTANCE(MODE)                                                                     \
+  int mfn_scan_grid_##MODE(mfn_ctx *ctx) {                                                          \
+    int per_sm = 0;                                                                                 \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<MODE>, SCAN_THREADS, 0);          \
+    if (per_sm < 1) per_sm = 1;                                                                     \
+    const char *env = getenv("MFN_SCAN_CTAS_PER_SM");                                               \
+    if (env && atoi(env) > 0) per_sm = std::min(per_sm, atoi(env));                                 \
+    return ctx->sm_count * per_sm;                                                                  \
+  }                                                                                                 \
+  void mfn_scan_launch_##MODE(const ScanParams &P, int grid, cudaStream_t stream) {                 \
+    k_scan<MODE><<<grid, SCAN_THREADS, 0, stream>>>(P);                                             \
+  }

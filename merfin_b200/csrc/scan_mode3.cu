@@ -1,0 +1,4 @@
+// k_scan<3> instantiation (see scan_kernel.cuh: bit 0 = dump, bit 1 = joint table).
+#include "scan_kernel.cuh"
+
+MFN_SCAN_INSTANCE(3)

@@ -129,3 +129,49 @@ __device__ __forceinline__ uint32_t mfn_value(const DevTable &t, uint64_t c) {
   mfn_load_bucket(t.lv[0].slots, bucket, b);
   return mfn_resolve(t, c, b, tag);
 }
+
+// ---------------------------------------------------------------------------
+// inverse of mfn_mix (for export / iteration over stored entries)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mfn_unmix(uint64_t h, uint64_t seed, uint64_t kmask, uint32_t k) {
+  // xorshift by half the width is an involution; the multipliers are undone by their inverses mod 2^64
+  uint64_t x = h;
+  x ^= x >> k;
+  x = (x * 0x9cb4b2f8129337dbull) & kmask;     // inverse of 0xc4ceb9fe1a85ec53
+  x ^= x >> k;
+  x = (x * 0x4f74430c22a54005ull) & kmask;     // inverse of 0xff51afd7ed558ccd
+  x ^= x >> k;
+  return (x ^ seed) & kmask;
+}
+
+static_assert(0xff51afd7ed558ccdull * 0x4f74430c22a54005ull == 1ull, "mix multiplier 1 inverse");
+static_assert(0xc4ceb9fe1a85ec53ull * 0x9cb4b2f8129337dbull == 1ull, "mix multiplier 2 inverse");
+
+
+// Walk every stored entry: level slots (k-mer rebuilt from bucket and tag), then the stash.
+template <class F>
+__device__ __forceinline__ void mfn_foreach_entry(const DevTable &t, F f) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const int S = t.w64 ? 4 : 8;
+  for (int lvl = 0; lvl < 2; lvl++) {
+    const uint64_t nslots = t.lv[lvl].buckets * S;
+    for (uint64_t s = tid; s < nslots; s += stride) {
+      uint64_t slot = t.w64 ? ((const unsigned long long *)t.lv[lvl].slots)[s]
+                            : (uint64_t)((const unsigned int *)t.lv[lvl].slots)[s];
+      if (slot == 0) continue;
+      uint64_t tag = slot >> t.vbits;
+      uint32_t val = (uint32_t)(slot & t.vmax);
+      uint64_t h = (s / S) * t.lv[lvl].D + tag;
+      uint64_t c = mfn_unmix(h, t.lv[lvl].seed, t.kmask, t.k);
+      if (val == t.vmax) val += mfn_oa_get(t.big, c);
+      f(c, val);
+    }
+  }
+  for (uint64_t s = tid; s <= t.stash.mask; s += stride) {
+    uint64_t key = t.stash.keys[s];
+    if (key != MFN_EMPTY64) f(key, t.stash.vals[s]);
+  }
+  if (tid == 0 && *t.stash.special) f(MFN_EMPTY64, *t.stash.special);
+}
+

@@ -36,3 +36,16 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
 // -hist scan of tiles [tile_begin, tile_end) of a resident sequence set
 int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
                    const mfn_kmodel *km, uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc);
+
+// ---- fused (read, assembly) table ----------------------------------------------------------
+#include "joint.cuh"
+struct mfn_joint {
+  JointDev dev{};
+  JointStats stats{};
+  const mfn_table *reads = nullptr, *asm_ = nullptr;
+  uint64_t n_kmers = 0, device_bytes = 0;
+  uint32_t tag_bits = 0;
+  std::vector<void *> allocs;
+};
+int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_joint **out);
+void mfn_joint_free(mfn_joint *j);

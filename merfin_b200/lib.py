@@ -40,6 +40,14 @@ class TableInfo(C.Structure):
                 ("device_bytes", C.c_uint64)]
 
 
+class JointInfo(C.Structure):
+    _fields_ = [("fused", C.c_uint32), ("slot_bits", C.c_uint32), ("tag_bits", C.c_uint32),
+                ("read_bits", C.c_uint32), ("asm_bits", C.c_uint32),
+                ("n_kmers", C.c_uint64), ("n_home", C.c_uint64), ("n_spill", C.c_uint64),
+                ("n_stash", C.c_uint64), ("n_bigvalue", C.c_uint64),
+                ("lines", C.c_uint64), ("device_bytes", C.c_uint64)]
+
+
 class KModel(C.Structure):
     _fields_ = [("peak", C.c_double), ("nprob", C.c_uint32),
                 ("probK", C.POINTER(C.c_uint32)), ("probP", C.POINTER(C.c_double))]
@@ -82,6 +90,10 @@ SIGNATURES = {
     "mfn_table_free": (None, [_P]),
     "mfn_table_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "mfn_table_export": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_tables_fuse": (C.c_int, [_P, _P, _P]),
+    "mfn_tables_unfuse": (C.c_int, [_P]),
+    "mfn_joint_info": (C.c_int, [_P, C.POINTER(JointInfo)]),
+    "mfn_joint_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "mfn_meryl_write": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, C.c_uint64]),
     "mfn_seq_create": (C.c_int, [_P, _P, _P, C.c_uint32, _PP]),
     "mfn_seq_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),

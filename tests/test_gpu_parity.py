@@ -104,7 +104,11 @@ def _hist_check(ctx, d, recs, k, peak, mn, mx, prob, tag):
     R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"), mn, mx)
     A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
     km = api.KModel.load_Kmetric(peak, prob)
+    res0 = api.hist(ctx, R, A, recs, km)           # one probe per database
+    R.fuse(A)                                      # one probe of the fused table per window
+    assert R.joint_info.fused == 1
     res = api.hist(ctx, R, A, recs, km)
+    assert (res0.pairs == res.pairs).all() and (res0.per_seq == res.per_seq).all()
     assert res.file_text() == open(os.path.join(d, f"{tag}.hist"), "rb").read()
     assert res.summary_text() == open(os.path.join(d, f"{tag}.hist.summary")).read()
     per = os.path.join(d, f"{tag}.hist.perseq")
@@ -143,7 +147,10 @@ def test_dump_matches_reference_files(ctx, golden_dir, name, k, peak):
     d, recs = _golden(golden_dir, name)
     R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
     A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    idents, off, vr0, va0, ok0 = api.dump(ctx, R, A, recs)
+    R.fuse(A)
     idents, off, vr, va, ok = api.dump(ctx, R, A, recs)
+    assert (vr0 == vr).all() and (va0 == va).all() and (ok0 == ok).all()
     text, per = api.dump_text(idents, off, vr, va, ok, api.KModel(peak), k)
     assert text == gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
     assert per == open(os.path.join(d, "ref.dump.perseq")).read()
@@ -264,6 +271,16 @@ def test_hist_joint_histogram_2mbp(ctx, k, noncanon):
     res = api.hist(ctx, R, A, recs, api.KModel(12.0))
     got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in res.pairs}
     assert got == exp
+    if not noncanon:
+        R.fuse(A)
+        ji = R.joint_info
+        assert ji.fused and ji.n_home + ji.n_spill + ji.n_stash == ji.n_kmers == len(np.union1d(rk, ak))
+        q = np.concatenate([rk[::7], ak[::5], np.array([0, 1, (1 << (2 * k)) - 1], dtype=np.uint64)])
+        jr, ja = R.joint_values(q)
+        assert (jr == R.values(q)).all() and (ja == A.values(q)).all()
+        res = api.hist(ctx, R, A, recs, api.KModel(12.0))
+        got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in res.pairs}
+        assert got == exp
     assert [(int(c["kasm"]), int(c["kmissing"])) for c in res.per_seq] == per
     assert any(key[0] >= 4096 for key in got)          # the sparse side table was exercised
 
@@ -277,6 +294,32 @@ def test_hist_joint_histogram_2mbp(ctx, k, noncanon):
     assert got2 == exp
     assert [(int(c["kasm"]), int(c["kmissing"])) for c in per2] == per
     R.close(); A.close(); seq.close(); acc.close()
+
+
+def test_joint_table_spill_and_saturation(ctx, monkeypatch):
+    """Fused table under pressure: lines overflow into the side table, both value fields saturate."""
+    from merfin_b200 import api
+    monkeypatch.setenv("MFN_JOINT_LOAD", "0.97")
+    rng = np.random.default_rng(17)
+    for k in (21, 31):
+        n = 400000
+        keys = np.unique(rng.integers(0, (1 << (2 * k)) - 1, size=n, dtype=np.uint64, endpoint=True))
+        rk = keys[rng.random(len(keys)) < 0.8]
+        ak = keys[rng.random(len(keys)) < 0.6]
+        rv = rng.integers(1, 40, size=len(rk)).astype(np.uint32)
+        av = rng.integers(1, 4, size=len(ak)).astype(np.uint32)
+        rv[::50] = rng.integers(1 << 21, 0xFFFFFFFF, size=len(rv[::50]), dtype=np.uint64).astype(np.uint32)
+        av[::60] = rng.integers(70, 1 << 30, size=len(av[::60]), dtype=np.uint64).astype(np.uint32)
+        R = api.MerylExactLookup.from_kmers(ctx, k, rk, rv)
+        A = api.MerylExactLookup.from_kmers(ctx, k, ak, av)
+        R.fuse(A)
+        ji = R.joint_info
+        assert ji.n_kmers == len(np.union1d(rk, ak))
+        assert ji.n_spill > 0 and ji.n_stash > 0 and ji.n_bigvalue > 0
+        q = np.concatenate([keys, rng.integers(0, (1 << (2 * k)) - 1, size=50000, dtype=np.uint64, endpoint=True)])
+        jr, ja = R.joint_values(q)
+        assert (jr == R.values(q)).all() and (ja == A.values(q)).all()
+        R.close(); A.close()
 
 
 def test_k_mismatch_is_an_error(ctx, golden_dir):
