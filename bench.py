@@ -306,9 +306,16 @@ def main():
     seq = _Seq()
     A = api.MerylExactLookup.count_sequence(ctx, K, seq)
     R = api.MerylExactLookup.synth_reads(ctx, A, COV_PER_COPY, int(total * 0.67), 7)
+    if not os.environ.get("MFN_NO_JOINT"):
+        R.fuse(A)                                # one 128-byte line per window instead of two
     ctx.sync()
     setup_s = time.time() - t0
     ai, ri = A.info, R.info
+    ji = R.joint_info
+    if ji.fused:
+        config["joint_table"] = {"kmers": int(ji.n_kmers), "GB": round(ji.device_bytes / 1e9, 2),
+                                 "slot_bits": int(ji.slot_bits), "spill_frac": round(ji.n_spill / max(1, ji.n_kmers), 4),
+                                 "stash": int(ji.n_stash), "bigvalue": int(ji.n_bigvalue)}
     config["tables"] = {"asm_kmers": int(ai.n_kmers), "read_kmers": int(ri.n_kmers),
                         "asm_GB": round(ai.device_bytes / 1e9, 2), "read_GB": round(ri.device_bytes / 1e9, 2),
                         "read_level2_frac": round(ri.n_level2 / max(1, ri.n_kmers), 4),
@@ -423,7 +430,7 @@ def main():
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                             "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                            "kernel": "k_scan<false>", "kernel_ms": k_ms, "bases_per_launch": bases_rank,
+                            "kernel": "k_scan<2> (joint table)" if ji.fused else "k_scan<0> (two tables)", "kernel_ms": k_ms, "bases_per_launch": bases_rank,
                             "algorithmic_bytes_per_base": BYTES_PER_BASE},
                "clocks": clocks,
                "result": {"kasm": int(summary.kasm), "kmissing": int(summary.kmissing),

@@ -89,6 +89,13 @@ __global__ void __launch_bounds__(256) k_count_absent(DevTable A, DevTable R, un
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
 }
 
+__global__ void __launch_bounds__(256) k_count_above(DevTable T, uint32_t fmax, unsigned long long *count) {
+  unsigned long long n = 0;
+  mfn_foreach_entry(T, [&](uint64_t, uint32_t v) { if (v > fmax) n++; });
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
+}
+
 __global__ void __launch_bounds__(256) k_joint_lookup(JointDev J, const unsigned long long *kmers, uint64_t n,
                                                       uint32_t *vr, uint32_t *va) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -142,8 +149,8 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
     const uint32_t T = std::max(1u, bits_of(J.D - 1));
     J.w64 = w64;
     if (!w64) {
-      if (T > 16) continue;                       // need >= 10 read-value bits next to 6 assembly bits
-      J.abits = 6; J.rbits = std::min(20u, 32u - T - 6u);
+      if (T > 20) continue;                       // 32-bit slots need room for both value fields
+      J.abits = T > 16 ? 5 : 6; J.rbits = std::min(20u, 32u - T - J.abits);
     } else {
       const uint32_t avail = 64 - std::min(T, 58u);
       J.abits = std::min(20u, avail / 3);
@@ -165,7 +172,24 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
   };
   int st = dalloc(&J.lines, J.nlines * 128, 0);
   OaTable2 *oas[2] = {&J.stash, &J.big};
-  uint64_t caps[2] = {next_pow2(std::max<uint64_t>(1 << 12, n / 128)), next_pow2(std::max<uint64_t>(1 << 12, n / 128))};
+  // side-table capacity from the expected overflow of Poisson(slots * load) keys sharing a line
+  double lambda = (J.w64 ? 16 : 32) * load, pr = std::exp(-lambda), over = 0.0;
+  for (int x = 1; x < 400; x++) { pr *= lambda / x; if (x > (J.w64 ? 16 : 32)) over += (x - (J.w64 ? 16 : 32)) * pr; }
+  const uint64_t spill = (uint64_t)(4.0 * over / lambda * n) + 8192;
+  // saturated values: counted, so the excess table is sized exactly
+  unsigned long long nbig = 0;
+  {
+    unsigned long long *d_b;
+    MFN_CUDA(cudaMalloc(&d_b, 8));
+    MFN_CUDA(cudaMemsetAsync(d_b, 0, 8, ctx->stream));
+    k_count_above<<<grid, 256, 0, ctx->stream>>>(R->dev, J.rmax, d_b);
+    k_count_above<<<grid, 256, 0, ctx->stream>>>(A->dev, J.amax, d_b);
+    ctx->launches += 2;
+    MFN_CUDA(cudaMemcpyAsync(&nbig, d_b, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_b);
+  }
+  uint64_t caps[2] = {next_pow2(2 * spill), next_pow2(2 * nbig + 4096)};
   for (int i = 0; i < 2 && st == MFN_OK; i++) {
     oas[i]->mask = (uint32_t)(caps[i] - 1);
     st = dalloc((void **)&oas[i]->keys, caps[i] * 8, 0xff);

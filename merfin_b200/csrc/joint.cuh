@@ -76,12 +76,14 @@ __device__ __forceinline__ bool joint_match(const JointDev &J, const Bucket &b, 
 __device__ __forceinline__ bool oa2_get(const OaTable2 &t, uint64_t key, uint32_t &a, uint32_t &b) {
   if (key == MFN_EMPTY64) { a = t.special[0]; b = t.special[1]; return (a | b) != 0; }
   uint32_t i = mfn_oa_hash(key) & t.mask;
-  while (true) {
+  for (uint32_t n = 0; n <= t.mask; n++) {          // bounded even if the table is full
     uint64_t cur = t.keys[i];
     if (cur == key) { a = t.v0[i]; b = t.v1[i]; return true; }
-    if (cur == MFN_EMPTY64) { a = 0; b = 0; return false; }
+    if (cur == MFN_EMPTY64) break;
     i = (i + 1) & t.mask;
   }
+  a = 0; b = 0;
+  return false;
 }
 
 // Everything past the home sector: spill sectors, side table, saturated values.
@@ -119,6 +121,17 @@ __device__ __forceinline__ void joint_resolve(const JointDev &J, uint64_t c, uin
   vr = (uint32_t)(pay >> J.abits) & J.rmax;
   if ((!hit && full) || (hit && (vr == J.rmax || va == J.amax))) joint_slow(J, c, line, tag, hit, full, pay, vr, va);
   else if (!hit) { vr = 0; va = 0; }
+}
+
+// Complete lookup from scratch (used for the few lookups the home sector alone cannot answer).
+static __device__ __noinline__ void joint_full(const JointDev &J, uint64_t c, uint64_t line, uint64_t tag,
+                                               uint32_t &vr, uint32_t &va) {
+  Bucket b;
+  joint_load_sector(J, line, (uint32_t)tag & 3u, b);
+  uint64_t pay = 0;
+  bool full;
+  bool hit = joint_match(J, b, tag, pay, full);
+  joint_slow(J, c, line, tag, hit, full, pay, vr, va);
 }
 
 __device__ __forceinline__ void joint_value(const JointDev &J, uint64_t c, uint32_t &vr, uint32_t &va) {

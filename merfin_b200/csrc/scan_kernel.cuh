@@ -88,7 +88,7 @@ static __device__ __noinline__ void sparse_add(const PairTable &t, unsigned long
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(SCAN_THREADS, (MODE & SCAN_JOINT) ? 2 : 1) k_scan(const __grid_constant__ ScanParams P) {
   constexpr bool DUMP = (MODE & SCAN_DUMP) != 0;
   constexpr bool JOINT = (MODE & SCAN_JOINT) != 0;
   __shared__ __align__(16) unsigned long long s_seq[2][SEQ_WORDS];
@@ -203,30 +203,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const __grid_constant__ S
     };
 
     if (JOINT) {
-      // one line of the fused table per window: 8 home sectors in flight per thread
-      uint64_t ck[WPT], ln[WPT], tg[WPT];
-      bool val[WPT], pal[WPT];
-      Bucket b[WPT];
+      // one line of the fused table per window; 4 home sectors in flight per thread per batch.
+      // Lookups that need more than the home sector (spilled entry, side table, saturated
+      // value: a few %) are finished in a second, lane-parallel loop so that one lane's slow
+      // path does not serialise the whole warp once per window.
 #pragma unroll
-      for (int u = 0; u < WPT; u++) {
-        uint64_t f, r;
-        kmers_of(u, f, r);
-        val[u] = ((okb >> u) & kbits) == kbits;
-        pal[u] = (f == r);
-        ck[u] = f < r ? f : r;
-        if (val[u]) {
-          joint_locate(P.J, ck[u], ln[u], tg[u]);
-          joint_load_sector(P.J, ln[u], (uint32_t)tg[u] & 3u, b[u]);
-        }
-      }
+      for (int half = 0; half < 2; half++) {
+        uint64_t ck[4], ln[4], tg[4];
+        uint32_t vr[4], va[4];
+        bool val[4], pal[4];
+        Bucket b[4];
 #pragma unroll
-      for (int u = 0; u < WPT; u++) {
-        uint32_t vr = 0, va = 0;
-        if (val[u]) {
-          joint_resolve(P.J, ck[u], ln[u], tg[u], b[u], vr, va);
-          if (pal[u]) { vr += vr; va += va; }              // value(f) + value(r) with f == r (Q2)
+        for (int u = 0; u < 4; u++) {
+          const int uu = half * 4 + u;
+          uint64_t f, r;
+          kmers_of(uu, f, r);
+          val[u] = ((okb >> uu) & kbits) == kbits;
+          pal[u] = (f == r);
+          ck[u] = f < r ? f : r;
+          if (val[u]) {
+            joint_locate(P.J, ck[u], ln[u], tg[u]);
+            joint_load_sector(P.J, ln[u], (uint32_t)tg[u] & 3u, b[u]);
+          }
         }
-        emit(u, val[u], vr, va);
+        uint32_t pending = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          vr[u] = 0; va[u] = 0;
+          if (val[u]) {
+            uint64_t pay = 0;
+            bool full;
+            const bool hit = joint_match(P.J, b[u], tg[u], pay, full);
+            va[u] = (uint32_t)pay & P.J.amax;
+            vr[u] = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
+            if ((!hit && full) || (hit && (vr[u] == P.J.rmax || va[u] == P.J.amax))) pending |= 1u << u;
+          }
+        }
+        while (__any_sync(0xffffffffu, pending != 0)) {
+          if (pending) {
+            const int u = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint64_t c = u == 0 ? ck[0] : u == 1 ? ck[1] : u == 2 ? ck[2] : ck[3];
+            const uint64_t l = u == 0 ? ln[0] : u == 1 ? ln[1] : u == 2 ? ln[2] : ln[3];
+            const uint64_t t = u == 0 ? tg[0] : u == 1 ? tg[1] : u == 2 ? tg[2] : tg[3];
+            uint32_t r2, a2;
+            joint_full(P.J, c, l, t, r2, a2);
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q == u) { vr[q] = r2; va[q] = a2; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (val[u] && pal[u]) { vr[u] += vr[u]; va[u] += va[u]; }   // value(f) + value(r), f == r (Q2)
+          emit(half * 4 + u, val[u], vr[u], va[u]);
+        }
       }
     } else {
 #pragma unroll

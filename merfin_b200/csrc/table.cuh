@@ -85,12 +85,13 @@ __device__ __forceinline__ uint32_t mfn_oa_hash(uint64_t key) {
 __device__ __forceinline__ uint32_t mfn_oa_get(const OaTable &t, uint64_t key) {
   if (key == MFN_EMPTY64) return *t.special;
   uint32_t i = mfn_oa_hash(key) & t.mask;
-  while (true) {
+  for (uint32_t n = 0; n <= t.mask; n++) {          // bounded even if the table is full
     uint64_t cur = t.keys[i];
     if (cur == key) return t.vals[i];
     if (cur == MFN_EMPTY64) return 0;
     i = (i + 1) & t.mask;
   }
+  return 0;
 }
 
 // Levels 2 and 3 and the saturated-value excess: rare, kept out of line.

@@ -208,6 +208,16 @@ def test_score_paths_matches_oracle(ctx, golden_dir):
 
 
 # ---------------------------------------------------------------------------------- bigger / edge cases
+def _np_revcomp(x, k):
+    """Reverse complement of 2-bit packed k-mers (A=0 C=1 T=2 G=3: complement = xor 2)."""
+    x = x.astype(np.uint64) ^ np.uint64(0xAAAAAAAAAAAAAAAA)
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF),
+                  (16, 0x0000FFFF0000FFFF)):
+        x = ((x >> np.uint64(sh)) & np.uint64(m)) | ((x & np.uint64(m)) << np.uint64(sh))
+    x = (x >> np.uint64(32)) | (x << np.uint64(32))
+    return x >> np.uint64(64 - 2 * k)
+
+
 def _synthetic_case(k, total, seed, noncanonical=False):
     from merfin_b200 import synth
     recs = synth.make_assembly(total, 5, seed, dup_len=2000)
@@ -224,7 +234,10 @@ def _synthetic_case(k, total, seed, noncanonical=False):
     rk = ak[keep]
     rv = (ac[keep] * rng.poisson(12, size=keep.sum())).astype(np.uint32) + 1
     rv[::1000] = 5000 + rng.integers(0, 100000, size=len(rv[::1000])).astype(np.uint32)
-    extra = np.setdiff1d(rng.integers(0, 1 << (2 * k), size=len(ak) // 2, dtype=np.uint64), ak)
+    extra = rng.integers(0, (1 << (2 * k)) - 1, size=len(ak) // 2, dtype=np.uint64, endpoint=True)
+    if not noncanonical:            # error k-mers of a canonical read DB are canonical too
+        extra = np.minimum(extra, _np_revcomp(extra, k))
+    extra = np.setdiff1d(extra, ak)
     rk = np.concatenate([rk, extra]); rv = np.concatenate([rv, np.ones(len(extra), dtype=np.uint32)])
     if noncanonical:        # store the strand the assembly shows, split counts between strands
         fk, fc = np.unique(f, return_counts=True)
@@ -266,7 +279,7 @@ def test_hist_joint_histogram_2mbp(ctx, k, noncanon):
     recs, (ak, ac), (rk, rv) = _synthetic_case(k, 2_000_000, 100 + k, noncanon)
     R = api.MerylExactLookup.from_kmers(ctx, k, rk, rv)
     A = api.MerylExactLookup.from_kmers(ctx, k, ak, ac)
-    assert A.info.canonical == (0 if noncanon else 1)
+    assert A.info.canonical == (0 if noncanon else 1) and R.info.canonical == (0 if noncanon else 1)
     exp, per = _expected_pairs(recs, k, _ArrLookup(k, rk, rv), _ArrLookup(k, ak, ac))
     res = api.hist(ctx, R, A, recs, api.KModel(12.0))
     got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in res.pairs}
@@ -304,6 +317,7 @@ def test_joint_table_spill_and_saturation(ctx, monkeypatch):
     for k in (21, 31):
         n = 400000
         keys = np.unique(rng.integers(0, (1 << (2 * k)) - 1, size=n, dtype=np.uint64, endpoint=True))
+        keys = np.unique(np.minimum(keys, _np_revcomp(keys, k)))
         rk = keys[rng.random(len(keys)) < 0.8]
         ak = keys[rng.random(len(keys)) < 0.6]
         rv = rng.integers(1, 40, size=len(rk)).astype(np.uint32)
