@@ -281,7 +281,12 @@ extern "C" int mfn_table_load(mfn_ctx *ctx, const char *dir, uint32_t minV, uint
   for (size_t i = 0; i < idx.histValue.size(); i++)
     if (idx.histValue[i] >= minV && idx.histValue[i] <= maxV) keep += idx.histCount[i];
   mfn_table *t = nullptr;
-  MFN_TRY(mfn_table_alloc(ctx, idx.k, keep, &t));
+  MFN_TRY(mfn_table_alloc(ctx, idx.k, keep, &t, [&](uint32_t vmax) {       // from the value histogram
+    uint64_t c = 0;
+    for (size_t i = 0; i < idx.histValue.size(); i++)
+      if (idx.histValue[i] >= minV && idx.histValue[i] <= maxV && idx.histValue[i] - (minV - 1) > vmax) c += idx.histCount[i];
+    return c;
+  }));
   t->min_value = minV; t->max_value = maxV; t->value_offset = minV - 1;
   int st = meryl_stream_to_device(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
     return mfn_table_insert_device(t, dk, dv, n, minV, maxV, minV - 1, false);

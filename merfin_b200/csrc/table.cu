@@ -255,7 +255,8 @@ static void level_geometry(uint32_t k, uint64_t buckets, TableLevel &lv, uint32_
   tagbits = std::max(1u, bits_of(lv.D - 1));
 }
 
-int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out) {
+int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out,
+                    const std::function<uint64_t(uint32_t)> &count_big) {
   if (k < 1 || k > 32) { mfn_set_error("k=%u: this build supports 1 <= k <= 32 (64-bit k-mers)", k); return MFN_ERR_UNSUPPORTED; }
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_table *t = new mfn_table();
@@ -298,7 +299,9 @@ int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **o
   int st = MFN_OK;
   for (int l = 0; l < 2 && st == MFN_OK; l++) st = dalloc(&d.lv[l].slots, d.lv[l].buckets * 32, 0);
   OaTable *oas[2] = {&d.stash, &d.big};
-  uint64_t caps[2] = {next_pow2(std::max<uint64_t>(1 << 12, n / 1024)), next_pow2(std::max<uint64_t>(1 << 12, n / 256))};
+  // excess table for saturated values: sized exactly when the caller can count them
+  const uint64_t nbig = count_big ? count_big(d.vmax) : n / 64;
+  uint64_t caps[2] = {next_pow2(std::max<uint64_t>(1 << 12, n / 1024)), next_pow2(2 * nbig + 4096)};
   for (int i = 0; i < 2 && st == MFN_OK; i++) {
     oas[i]->mask = (uint32_t)(caps[i] - 1);
     st = dalloc((void **)&oas[i]->keys, caps[i] * 8, 0xff);
@@ -398,7 +401,11 @@ extern "C" int mfn_table_from_kmers(mfn_ctx *ctx, uint32_t k, const uint64_t *km
   uint64_t keep = 0;
   for (uint64_t i = 0; i < n; i++) { uint32_t v = values ? values[i] : 1u; keep += (v >= minV && v <= maxV); }
   mfn_table *t = nullptr;
-  MFN_TRY(mfn_table_alloc(ctx, k, keep, &t));
+  MFN_TRY(mfn_table_alloc(ctx, k, keep, &t, [&](uint32_t vmax) {
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; i++) { uint32_t v = values ? values[i] : 1u; c += (v >= minV && v <= maxV && v - (minV - 1) > vmax); }
+    return c;
+  }));
   t->min_value = minV; t->max_value = maxV; t->value_offset = minV - 1;
   const uint64_t CH = 1ull << 22;
   unsigned long long *dk = nullptr; uint32_t *dv = nullptr;

@@ -5,7 +5,9 @@
 
 #include <functional>
 
-int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out);
+// count_big(vmax): how many stored values exceed vmax (sizes the excess table); null -> a guess
+int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out,
+                    const std::function<uint64_t(uint32_t)> &count_big = nullptr);
 int mfn_table_insert_device(mfn_table *t, const unsigned long long *d_kmers, const uint32_t *d_values,
                             uint64_t n, uint32_t minV, uint32_t maxV, uint32_t voff, bool add);
 int mfn_table_finalize(mfn_table *t, bool counted);
