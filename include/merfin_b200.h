@@ -174,6 +174,17 @@ int  mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int in
                      mfn_seq_counts *per_seq /*[nseq] or NULL*/,
                      mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
 
+/* Layout of the flat buffer and host-side decoding of a copy of it (no GPU needed): lets a
+ * caller all-reduce with any transport and decode on any rank. */
+int  mfn_accum_layout(uint32_t nseq, uint32_t *header_words, uint32_t *dense_r, uint32_t *dense_a,
+                      uint64_t *nwords);
+int  mfn_accum_decode(const uint64_t *host_buf, uint32_t nseq, mfn_seq_counts *per_seq,
+                      mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+/* Global base range [g_begin, g_end) (records concatenated with one separator slot after
+ * each) whose windows shard `shard` of `nshards` scans. */
+int  mfn_shard_tiles(uint64_t total_bases, uint32_t nseq, uint32_t shard, uint32_t nshards,
+                     uint64_t *g_begin, uint64_t *g_end);
+
 /* ---- the hot path ---------------------------------------------------------- */
 
 /* -hist inner loop (merfin-histogram.C:54-91 + merfin-globals.C:101-110) over the

@@ -166,6 +166,54 @@ extern "C" int mfn_accum_device_buffer(const mfn_accum *a, void **dptr, uint64_t
   return MFN_OK;
 }
 
+// ---- accumulator layout (host side, no GPU needed) --------------------------------------------
+extern "C" int mfn_accum_layout(uint32_t nseq, uint32_t *header_words, uint32_t *dense_r, uint32_t *dense_a,
+                                uint64_t *nwords) {
+  if (header_words) *header_words = MFN_ACC_HEADER;
+  if (dense_r) *dense_r = MFN_DENSE_R;
+  if (dense_a) *dense_a = MFN_DENSE_A;
+  if (nwords) *nwords = MFN_ACC_HEADER + (uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2ull * nseq;
+  return MFN_OK;
+}
+
+extern "C" int mfn_shard_tiles(uint64_t total_bases, uint32_t nseq, uint32_t shard, uint32_t nshards,
+                               uint64_t *g_begin, uint64_t *g_end) {
+  if (nshards == 0 || shard >= nshards || !g_begin || !g_end) return MFN_ERR_INVALID;
+  uint64_t G = total_bases + nseq, ntiles = std::max<uint64_t>(1, ceil_div_u64(G, MFN_TILE)), b, e;
+  shard_tiles(ntiles, shard, nshards, b, e);
+  *g_begin = b * MFN_TILE; *g_end = std::min<uint64_t>(e * MFN_TILE, std::max<uint64_t>(G, 1));
+  if (shard + 1 == nshards) *g_end = G;
+  return MFN_OK;
+}
+
+// Decode a (possibly all-reduced) copy of the flat accumulator buffer.
+extern "C" int mfn_accum_decode(const uint64_t *h, uint32_t nseq, mfn_seq_counts *per_seq,
+                                mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!h || !npairs) return MFN_ERR_INVALID;
+  if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", (unsigned long long)h[2]); return MFN_ERR_CAPACITY; }
+  uint64_t n = 0;
+  bool full = false;
+  const uint64_t *d = h + MFN_ACC_HEADER;
+  for (uint32_t va = 0; va < MFN_DENSE_A; va++)
+    for (uint32_t vr = 0; vr < MFN_DENSE_R; vr++) {
+      uint64_t c = d[(uint64_t)va * MFN_DENSE_R + vr];
+      if (!c) continue;
+      if (pairs && n < cap) { pairs[n].v_read = vr; pairs[n].v_asm = va; pairs[n].count = c; } else full = true;
+      n++;
+    }
+  if (h[3]) {
+    if (pairs && n < cap) { pairs[n].v_read = 0xffffffffu; pairs[n].v_asm = 0xffffffffu; pairs[n].count = h[3]; } else full = true;
+    n++;
+  }
+  if (per_seq)
+    for (uint32_t i = 0; i < nseq; i++) {
+      per_seq[i].kasm = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i];
+      per_seq[i].kmissing = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i + 1];
+    }
+  *npairs = n;
+  return (pairs && full) ? MFN_ERR_CAPACITY : MFN_OK;
+}
+
 extern "C" int mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int include_sparse,
                                mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
   if (!ctx || !a || !npairs) return MFN_ERR_INVALID;
@@ -173,27 +221,19 @@ extern "C" int mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_den
   std::vector<unsigned long long> h(a->nwords);
   MFN_CUDA(cudaMemcpyAsync(h.data(), a->d_buf, a->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFN_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", h[2]); return MFN_ERR_CAPACITY; }
   uint64_t n = 0;
   bool full = false;
+  if (include_dense) {
+    int st = mfn_accum_decode((const uint64_t *)h.data(), a->nseq, per_seq, pairs, cap, &n);
+    if (st == MFN_ERR_CAPACITY && h[2]) return st;
+    full = (st == MFN_ERR_CAPACITY);
+  } else if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", h[2]); return MFN_ERR_CAPACITY; }
   auto push = [&](uint32_t vr, uint32_t va, uint64_t c) {
     if (pairs && n < cap) { pairs[n].v_read = vr; pairs[n].v_asm = va; pairs[n].count = c; } else full = true;
     n++;
   };
-  if (include_dense) {
-    const unsigned long long *d = h.data() + MFN_ACC_HEADER;
-    for (uint32_t va = 0; va < MFN_DENSE_A; va++)
-      for (uint32_t vr = 0; vr < MFN_DENSE_R; vr++)
-        if (d[(uint64_t)va * MFN_DENSE_R + vr]) push(vr, va, d[(uint64_t)va * MFN_DENSE_R + vr]);
-    if (per_seq)
-      for (uint32_t i = 0; i < a->nseq; i++) {
-        per_seq[i].kasm = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i];
-        per_seq[i].kmissing = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i + 1];
-      }
-    if (h[3]) push(0xffffffffu, 0xffffffffu, h[3]);
-  }
   if (include_sparse && h[1]) {
-    // rank-local: read the inserted-pair count from the device table itself, not the (possibly reduced) header
+    // rank-local side table of pairs outside the dense tier
     std::vector<unsigned long long> keys(MFN_SPARSE_CAP), counts(MFN_SPARSE_CAP);
     MFN_CUDA(cudaMemcpyAsync(keys.data(), a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MFN_CUDA(cudaMemcpyAsync(counts.data(), a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));

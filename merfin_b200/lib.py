@@ -103,6 +103,11 @@ SIGNATURES = {
     "mfn_accum_free": (None, [_P]),
     "mfn_accum_device_buffer": (C.c_int, [_P, _PP, C.POINTER(C.c_uint64)]),
     "mfn_accum_fetch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_accum_layout": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint64)]),
+    "mfn_accum_decode": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_shard_tiles": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64)]),
     "mfn_hist_resident": (C.c_int, [_P, _P, _P, _P, C.POINTER(KModel), C.c_uint32, C.c_uint32, _P]),
     "mfn_hist_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(KModel), C.c_uint32, C.c_uint32, _P]),
     "mfn_hist": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(KModel), _P, _P, C.c_uint64,
