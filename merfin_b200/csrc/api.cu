@@ -60,6 +60,12 @@ extern "C" int mfn_ctx_create(mfn_ctx **out, int device) {
   MFN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) MFN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   c->stream = c->own_stream;
+  // keep stream-ordered workspace (cudaMallocAsync) cached between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = c;
   return MFN_OK;
 }

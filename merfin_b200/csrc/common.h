@@ -142,4 +142,4 @@ struct mfn_accum {
 // tile geometry of the scan kernels
 #define MFN_TILE 2048               // window start positions per tile (multiple of 64)
 
-static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline __host__ __device__ uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

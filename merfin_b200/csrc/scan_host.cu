@@ -95,7 +95,11 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   unsigned long long *zmap = nullptr;
   MFN_TRY(build_zmap(ctx, km, &zmap, &P.zlen));
   P.zmap = zmap;
-  int st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));
+  int st;
+  if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0))
+    st = mfn_sweep_hist(ctx, reads, asm_, seq, km, P.tile_begin, P.tile_end, acc, zmap, P.zlen);
+  else
+    st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));
   if (zmap) cudaFreeAsync(zmap, ctx->stream);
   return st;
 }

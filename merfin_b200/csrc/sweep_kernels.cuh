@@ -1,0 +1,327 @@
+// Range-partitioned -hist scan ("sweep").
+//
+// A direct scan spends one random 128-byte HBM line per window, and the B200 sustains only
+// ~36.5e9 of those per second.  But the windows of a whole assembly hit
+// every line of the joint table many times over, so the random accesses can be traded for
+// streaming ones:
+//
+//   pass 1  k_sweep_scatter   every valid window -> h = mix(canonical k-mer); the top `bbits`
+//                             bits of h select a bin; (low bits of h, record id) is appended to
+//                             that bin.  A CTA sorts 8192 windows by bin in shared memory and
+//                             writes each bin's run with coalesced stores.
+//   pass 2  k_sweep_probe     bins are processed in order by the whole grid.  A bin maps to a
+//                             contiguous slice of the joint table (line = h / D is monotonic
+//                             in h) of ~20 MB, which stays L2-resident while the bin's ~3e6
+//                             windows probe it: each line comes from HBM once, every further
+//                             probe is an L2 hit (~200e9/s).
+//
+// DRAM traffic per window: 8 B written + 8 B read + (table bytes / windows) instead of 128 B.
+// Integer results are identical to the direct scan (same lookups, sums are order-free).
+#pragma once
+#include "scan_kernel.cuh"
+
+#define SW_THREADS 256
+#define SW_CHUNK_TILES 4
+#define SW_CHUNK (SW_CHUNK_TILES * MFN_TILE)      // 8192 windows per CTA round
+#define SW_MAX_BINS 2048
+#define SW_SLICE 4096                              // entries per probe work item (16 per thread)
+#define SW_NOSPACE 0xffffffffu
+
+struct SweepParams {
+  JointDev J;
+  const unsigned long long *seq2, *ok, *rec_start;
+  uint32_t nseq;
+  uint64_t tile_begin, tile_end;
+  uint32_t bbits, lowbits, nbins;
+  unsigned long long *entries;             // bin b: entries[b * cap .. b * cap + n_b); entry = rec << 32 | low
+  uint64_t cap;
+  unsigned long long *bin_count;           // [nbins] reserved entries (may exceed cap)
+  unsigned long long *bin_valid;           // [nbins] first reservation that did not fit (~0: none)
+  unsigned long long *over_h;              // windows whose bin was full: full h ...
+  uint32_t *over_rec;                      //   ... and record id
+  unsigned long long *over_n;
+  uint64_t over_cap;
+  unsigned long long *counter;             // work distribution (one per pass)
+  unsigned long long *acc;
+  PairTable sparse;
+  const unsigned long long *zmap;
+  uint32_t zlen;
+};
+
+// ------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------
+template <int UNUSED>
+__global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
+  uint32_t *s_low = (uint32_t *)sw_smem;                               // [SW_CHUNK]
+  uint32_t *s_meta = s_low + SW_CHUNK;                                 // [SW_CHUNK] bin | record delta << 12
+  uint32_t *s_cnt = s_meta + SW_CHUNK, *s_off = s_cnt + SW_MAX_BINS, *s_base = s_off + SW_MAX_BINS;
+  __shared__ uint32_t s_warp[SW_THREADS / 32];
+  __shared__ unsigned long long s_chunk;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t k = P.J.k;
+  const uint64_t kmask = P.J.kmask;
+  const uint64_t kbits = (1ull << k) - 1;
+  const uint64_t cmask = 0xaaaaaaaaaaaaaaaaull & kmask;
+  const uint64_t lowmask = (P.lowbits >= 64) ? ~0ull : ((1ull << P.lowbits) - 1);
+  const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, SW_CHUNK_TILES);
+  const uint32_t per_thread_bins = P.nbins / SW_THREADS;       // nbins is a multiple of 256
+
+  unsigned long long my_valid = 0;
+  uint32_t cur_rec = 0xffffffffu, n_ok0 = 0;
+  auto flush_rec = [&]() {
+    uint32_t a = n_ok0;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if ((tid & 31) == 0 && cur_rec < P.nseq && a)
+      atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * cur_rec], (unsigned long long)a);
+    n_ok0 = 0;
+  };
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_chunk = atomicAdd(P.counter, 1ull);
+    for (uint32_t i = tid; i < P.nbins; i += SW_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t chunk = s_chunk;
+    if (chunk >= nchunks) break;
+    const uint64_t tile0 = P.tile_begin + chunk * SW_CHUNK_TILES;
+
+    // record of the chunk's first window (uniform)
+    uint32_t r0;
+    {
+      const uint64_t gt = tile0 * MFN_TILE;
+      uint32_t a = 0, b = P.nseq;
+      while (a < b) { uint32_t m = (a + b + 1) >> 1; if (P.rec_start[m] <= gt) a = m; else b = m - 1; }
+      r0 = a;
+    }
+    if (r0 != cur_rec) { flush_rec(); cur_rec = r0; }
+
+    // ---- hash this thread's 32 windows; rank them inside their bins ------------------------
+    uint32_t low[SW_CHUNK_TILES * WPT], meta[SW_CHUNK_TILES * WPT];     // meta: bin | rank << 12 | rdelta << 25
+#pragma unroll
+    for (int q = 0; q < SW_CHUNK_TILES; q++) {
+      const uint64_t tile = tile0 + q;
+      const uint32_t j0 = tid * WPT;
+      const uint64_t g0 = tile * MFN_TILE + j0;
+      uint64_t lo = 0, hi = 0, okb = 0;
+      if (tile < P.tile_end) {
+        const uint64_t w = g0 >> 5, sh = (g0 & 31) * 2;
+        const uint64_t a = __ldg(&P.seq2[w]), b = __ldg(&P.seq2[w + 1]);
+        lo = sh ? ((a >> sh) | (b << (64 - sh))) : a;
+        hi = b >> sh;
+        const uint64_t wo = g0 >> 6, so = g0 & 63;
+        const uint64_t c = __ldg(&P.ok[wo]), d = __ldg(&P.ok[wo + 1]);
+        okb = so ? ((c >> so) | (d << (64 - so))) : c;
+      }
+      uint32_t rec = r0;
+      uint64_t next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull;
+#pragma unroll
+      for (int u = 0; u < WPT; u++) {
+        const int idx = q * WPT + u;
+        meta[idx] = 0xffffffffu;
+        low[idx] = 0;
+        if (((okb >> u) & kbits) != kbits) continue;
+        uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
+        x &= kmask;
+        const uint64_t r = x ^ cmask, f = mfn_revcomp(r, k);
+        const uint64_t h = mfn_mix(f < r ? f : r, P.J.seed, kmask, k);
+        const uint64_t g = g0 + u;
+        while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
+        my_valid++;
+        if (rec == r0) n_ok0++;
+        else atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec], 1ull);
+        const uint32_t bin = (uint32_t)(h >> P.lowbits);
+        const uint32_t rd = rec - r0;
+        if (rd > 126) {                                   // a chunk spanning > 126 records: side list
+          unsigned long long o = atomicAdd(P.over_n, 1ull);
+          if (o < P.over_cap) { P.over_h[o] = h; P.over_rec[o] = rec; } else atomicAdd(&P.acc[2], 1ull);
+          continue;
+        }
+        const uint32_t rank = atomicAdd(&s_cnt[bin], 1u);
+        low[idx] = (uint32_t)(h & lowmask);
+        meta[idx] = bin | (rank << 12) | (rd << 25);
+      }
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
+    {
+      uint32_t sum = 0;
+      const uint32_t b0 = tid * per_thread_bins;
+      for (uint32_t i = 0; i < per_thread_bins; i++) sum += s_cnt[b0 + i];
+      uint32_t incl = sum;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
+      if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (uint32_t w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
+      uint32_t run = wbase + incl - sum;
+      for (uint32_t i = 0; i < per_thread_bins; i++) {
+        const uint32_t c = s_cnt[b0 + i];
+        s_off[b0 + i] = run;
+        run += c;
+        uint32_t base = 0;
+        if (c) {
+          const unsigned long long g = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)c);
+          if (g + c > P.cap) { atomicMin(&P.bin_valid[b0 + i], g); base = SW_NOSPACE; }
+          else base = (uint32_t)g;
+        }
+        s_base[b0 + i] = base;
+      }
+    }
+    __syncthreads();
+
+    // ---- counting sort into shared memory --------------------------------------------------
+#pragma unroll
+    for (int idx = 0; idx < SW_CHUNK_TILES * WPT; idx++) {
+      const uint32_t m = meta[idx];
+      if (m == 0xffffffffu) continue;
+      const uint32_t bin = m & 0xfffu, rank = (m >> 12) & 0x1fffu, rd = m >> 25;
+      const uint32_t p = s_off[bin] + rank;
+      s_low[p] = low[idx];
+      s_meta[p] = bin | (rd << 12);
+    }
+    __syncthreads();
+
+    // ---- coalesced copy-out: consecutive threads write consecutive entries of a bin's run --
+    {
+      uint32_t total = 0;
+      const uint32_t last = P.nbins - 1;
+      total = s_off[last] + s_cnt[last];
+      for (uint32_t i = tid; i < total; i += SW_THREADS) {
+        const uint32_t m = s_meta[i];
+        const uint32_t bin = m & 0xfffu, rec = r0 + (m >> 12);
+        const uint32_t base = s_base[bin];
+        if (base != SW_NOSPACE) {
+          P.entries[(uint64_t)bin * P.cap + base + (i - s_off[bin])] = ((unsigned long long)rec << 32) | s_low[i];
+        } else {
+          unsigned long long o = atomicAdd(P.over_n, 1ull);
+          if (o < P.over_cap) { P.over_h[o] = ((uint64_t)bin << P.lowbits) | s_low[i]; P.over_rec[o] = rec; }
+          else atomicAdd(&P.acc[2], 1ull);                 // reported as MFN_ERR_CAPACITY at fetch
+        }
+      }
+    }
+  }
+  flush_rec();
+  for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xffffffffu, my_valid, o);
+  if ((tid & 31) == 0 && my_valid) atomicAdd(&P.acc[0], my_valid);
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2 (and the overflow list: OVER = true probes full h values from the side list)
+// ------------------------------------------------------------------------------------------
+template <bool OVER>
+__global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_constant__ SweepParams P) {
+  __shared__ uint32_t s_hist[SH_R * SH_A];
+  __shared__ unsigned long long s_item;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) s_hist[i] = 0;
+
+  const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
+  const uint64_t nitems = OVER ? ceil_div_u64(min(*P.over_n, (unsigned long long)P.over_cap), SW_SLICE)
+                               : (uint64_t)P.nbins * slices_per_bin;
+  const bool even_k = (P.J.k & 1u) == 0;
+
+  auto account = [&](uint64_t h, uint32_t rec, uint32_t vr, uint32_t va) {
+    if (even_k) {                                          // palindromes count twice (Q2)
+      const uint64_t c = mfn_unmix(h, P.J.seed, P.J.kmask, P.J.k);
+      if (c == mfn_revcomp(c, P.J.k)) { vr += vr; va += va; }
+    }
+    bool miss = (vr == 0);
+    if (vr != 0 && vr < P.zlen) miss = (__ldg(&P.zmap[vr >> 6]) >> (vr & 63)) & 1;
+    if (miss) atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec + 1], 1ull);
+    if (vr < SH_R && va < SH_A) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+    else if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
+    else sparse_add(P.sparse, P.acc, vr, va, 1ull);
+  };
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(P.counter, 1ull);
+    __syncthreads();
+    const uint64_t item = s_item;
+    if (item >= nitems) break;
+    uint64_t n, first;                 // entries [first, first + n) of this item
+    const unsigned long long *src;
+    uint64_t hbase = 0;
+    if (OVER) {
+      const uint64_t tot = min(*P.over_n, (unsigned long long)P.over_cap);
+      first = item * SW_SLICE; n = min((uint64_t)SW_SLICE, tot - first); src = P.over_h;
+    } else {
+      const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
+      const uint64_t cnt = min(min(P.bin_count[bin], P.bin_valid[bin]), (unsigned long long)P.cap);
+      if (s * SW_SLICE >= cnt) continue;
+      first = bin * P.cap + s * SW_SLICE; n = min((uint64_t)SW_SLICE, cnt - s * SW_SLICE); src = P.entries;
+      hbase = bin << P.lowbits;
+    }
+    // each thread: 4 batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
+#pragma unroll 1
+    for (uint32_t bt = 0; bt < SW_SLICE / (SW_THREADS * 4); bt++) {
+      const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
+      if (i0 >= n) break;                                  // later batches start even further
+      unsigned long long e[4];
+      if (i0 + 4 <= n && (((first + i0) & 3) == 0)) {
+        // streamed once: keep it from evicting the table slice
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + first + i0));
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[first + i0 + u] : 0;
+      }
+      uint64_t hh[4], ln[4], tg[4];
+      uint32_t rc[4], vr[4], va[4];
+      bool val[4];
+      Bucket b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        val[u] = i0 + u < n;
+        if (OVER) { hh[u] = e[u]; rc[u] = val[u] ? P.over_rec[first + i0 + u] : 0; }
+        else { hh[u] = hbase | (e[u] & 0xffffffffull); rc[u] = (uint32_t)(e[u] >> 32); }
+        if (val[u]) {
+          mfn_split(hh[u], P.J.D, P.J.magic, ln[u], tg[u]);
+          joint_load_sector(P.J, ln[u], (uint32_t)tg[u] & 3u, b[u]);
+        }
+      }
+      uint32_t pending = 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        vr[u] = 0; va[u] = 0;
+        if (val[u]) {
+          uint64_t pay = 0;
+          bool full;
+          const bool hit = joint_match(P.J, b[u], tg[u], pay, full);
+          va[u] = (uint32_t)pay & P.J.amax;
+          vr[u] = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
+          if ((!hit && full) || (hit && (vr[u] == P.J.rmax || va[u] == P.J.amax))) pending |= 1u << u;
+        }
+      }
+      while (__any_sync(0xffffffffu, pending != 0)) {
+        if (pending) {
+          const int u = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const uint64_t h = u == 0 ? hh[0] : u == 1 ? hh[1] : u == 2 ? hh[2] : hh[3];
+          const uint64_t l = u == 0 ? ln[0] : u == 1 ? ln[1] : u == 2 ? ln[2] : ln[3];
+          const uint64_t t = u == 0 ? tg[0] : u == 1 ? tg[1] : u == 2 ? tg[2] : tg[3];
+          uint32_t r2, a2;
+          joint_full(P.J, mfn_unmix(h, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);   // side tables are keyed by k-mer
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (q == u) { vr[q] = r2; va[q] = a2; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (val[u]) account(hh[u], rc[u], vr[u], va[u]);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {
+    uint32_t c = s_hist[i];
+    if (c) atomicAdd(&P.acc[MFN_ACC_HEADER + (i / SH_R) * MFN_DENSE_R + (i % SH_R)], (unsigned long long)c);
+  }
+}
+
+
+// k_sweep_probe<true> lives in its own translation unit (sweep_over.cu): ptxas 12.9 crashes when
+// two entries that share an out-of-line device function are compiled in one module.
+void mfn_sweep_launch_over(const SweepParams &P, int grid, cudaStream_t stream);

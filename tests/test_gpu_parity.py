@@ -347,3 +347,40 @@ def test_k_mismatch_is_an_error(ctx, golden_dir):
     with pytest.raises(MfnError):
         api.MerylExactLookup.load(ctx, "/nonexistent/db.meryl")
     R.close(); A.close()
+
+
+# ---------------------------------------------------------------------------------- sweep (range-partitioned scan)
+@pytest.mark.parametrize("k", [21, 16, 6])
+def test_sweep_equals_direct_scan(ctx, monkeypatch, k):
+    """The range-partitioned -hist scan gives the same joint histogram and per-record counters as
+    the direct scan (forced on here; it is chosen automatically for large batches)."""
+    from merfin_b200 import api
+    recs, (ak, ac), (rk, rv) = _synthetic_case(k, 1_500_000 if k > 6 else 300_000, 200 + k)
+    # many tiny records in one chunk (record-delta side list) and a long tail of records
+    rng = np.random.default_rng(k)
+    recs += [(f"t{i}", bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(k, 3 * k))).astype(np.uint8))) for i in range(400)]
+    R = api.MerylExactLookup.from_kmers(ctx, k, rk, rv)
+    A = api.MerylExactLookup.from_kmers(ctx, k, ak, ac)
+    R.fuse(A)
+    km = api.KModel(12.0, [0, 0, 1], [0.5, 0.6, 0.7])        # readK == 0 for v_read 1 and 2 too
+    monkeypatch.setenv("MFN_SWEEP", "0")
+    d = api.hist(ctx, R, A, recs, km)
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    s = api.hist(ctx, R, A, recs, km)
+    assert len(d.pairs) == len(s.pairs) and (d.pairs == s.pairs).all()
+    assert (d.per_seq == s.per_seq).all()
+    assert int(d.per_seq["kmissing"].sum()) > 0
+    exp, per = _expected_pairs(recs, k, _ArrLookup(k, rk, rv), _ArrLookup(k, ak, ac))
+    got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in s.pairs}
+    assert got == exp
+    assert [int(c["kasm"]) for c in s.per_seq] == [p[0] for p in per]
+    R.close(); A.close()
+
+
+def test_sweep_on_golden_files(ctx, golden_dir, monkeypatch):
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    for name, k, peak in SETS[:2]:
+        d, recs = _golden(golden_dir, name)
+        _hist_check(ctx, d, recs, k, peak, 0, 0xFFFFFFFF, None, "ref")
+    d, recs = _golden(golden_dir, "g1_k21")
+    _hist_check(ctx, d, recs, 21, 8.0, 0, 0xFFFFFFFF, os.path.join(d, "prob.csv"), "ref.prob")
