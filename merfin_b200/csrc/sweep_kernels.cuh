@@ -257,10 +257,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
       hbase = bin << P.lowbits;
     }
     // each thread: 4 batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
-#pragma unroll 1
-    for (uint32_t bt = 0; bt < SW_SLICE / (SW_THREADS * 4); bt++) {
+    const uint32_t nbatch = (uint32_t)ceil_div_u64(n, SW_THREADS * 4);     // uniform: every lane of a warp
+#pragma unroll 1                                                           // takes part in the warp votes below
+    for (uint32_t bt = 0; bt < nbatch; bt++) {
       const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
-      if (i0 >= n) break;                                  // later batches start even further
       unsigned long long e[4];
       if (i0 + 4 <= n && (((first + i0) & 3) == 0)) {
         // streamed once: keep it from evicting the table slice
