@@ -73,6 +73,29 @@ __device__ __forceinline__ bool joint_match(const JointDev &J, const Bucket &b, 
   return hit;
 }
 
+// Fast-path search of the home sector: hit and payload only (everything else goes to joint_full).
+// A stored slot always has a non-zero value field, so  slot == want | values  <=>  1 <= slot ^ want < 2^vb.
+__device__ __forceinline__ bool joint_match_fast(const JointDev &J, const Bucket &b, uint64_t tag, uint64_t &pay) {
+  const uint32_t vb = J.rbits + J.abits;
+  bool hit = false;
+  if (J.w64) {
+    const uint64_t want = tag << vb, lim = (1ull << vb) - 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint64_t d = (((uint64_t)b.w[2 * i + 1] << 32) | b.w[2 * i]) ^ want;
+      if (d - 1ull < lim) { hit = true; pay = d; }
+    }
+  } else {
+    const uint32_t want = (uint32_t)tag << vb, lim = (1u << vb) - 1u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t d = b.w[i] ^ want;
+      if (d - 1u < lim) { hit = true; pay = d; }
+    }
+  }
+  return hit;
+}
+
 __device__ __forceinline__ bool oa2_get(const OaTable2 &t, uint64_t key, uint32_t &a, uint32_t &b) {
   if (key == MFN_EMPTY64) { a = t.special[0]; b = t.special[1]; return (a | b) != 0; }
   uint32_t i = mfn_oa_hash(key) & t.mask;

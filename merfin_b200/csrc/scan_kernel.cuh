@@ -232,11 +232,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, (MODE & SCAN_JOINT) ? 2 : 1) k_s
           vr[u] = 0; va[u] = 0;
           if (val[u]) {
             uint64_t pay = 0;
-            bool full;
-            const bool hit = joint_match(P.J, b[u], tg[u], pay, full);
+            const bool hit = joint_match_fast(P.J, b[u], tg[u], pay);
             va[u] = (uint32_t)pay & P.J.amax;
             vr[u] = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
-            if ((!hit && full) || (hit && (vr[u] == P.J.rmax || va[u] == P.J.amax))) pending |= 1u << u;
+            if (!hit || vr[u] == P.J.rmax || va[u] == P.J.amax) pending |= 1u << u;
           }
         }
         while (__any_sync(0xffffffffu, pending != 0)) {

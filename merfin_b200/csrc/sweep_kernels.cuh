@@ -5,15 +5,16 @@
 // every line of the joint table many times over, so the random accesses can be traded for
 // streaming ones:
 //
-//   pass 1  k_sweep_scatter   every valid window -> h = mix(canonical k-mer); the top `bbits`
-//                             bits of h select a bin; (low bits of h, record id) is appended to
-//                             that bin.  A CTA sorts 8192 windows by bin in shared memory and
-//                             writes each bin's run with coalesced stores.
-//   pass 2  k_sweep_probe     bins are processed in order by the whole grid.  A bin maps to a
-//                             contiguous slice of the joint table (line = h / D is monotonic
-//                             in h) of ~20 MB, which stays L2-resident while the bin's ~3e6
-//                             windows probe it: each line comes from HBM once, every further
-//                             probe is an L2 hit (~200e9/s).
+//   pass 1  k_sweep_scatter   every valid window -> h = mix(canonical k-mer) -> (line, tag) of the
+//                             joint table.  Lines are grouped into bins of 2^lbits consecutive
+//                             lines; (line in bin, tag, record id) is appended to the window's
+//                             bin.  A CTA sorts 8192 windows by bin in shared memory and writes
+//                             each bin's run with coalesced stores.
+//   pass 2  k_sweep_probe     bins are processed in order by the whole grid.  A bin is a
+//                             contiguous slice of the joint table of <= 32 MB, which stays
+//                             L2-resident while the bin's windows probe it: each line comes from
+//                             HBM once, every further probe is an L2 hit.  No hashing, no
+//                             division here: the entry already holds line and tag.
 //
 // DRAM traffic per window: 8 B written + 8 B read + (table bytes / windows) instead of 128 B.
 // Integer results are identical to the direct scan (same lookups, sums are order-free).
@@ -32,16 +33,16 @@ struct SweepParams {
   const unsigned long long *seq2, *ok, *rec_start;
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
-  uint32_t bbits, lowbits, nbins;
-  unsigned long long *entries;             // bin b: entries[b * cap .. b * cap + n_b); entry = rec << 32 | low
+  uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low word = (line & L-1) << tbits | tag
+  unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b); entry = rec << 32 | low word
   uint64_t cap;
-  unsigned long long *bin_count;           // [nbins] reserved entries (may exceed cap)
-  unsigned long long *bin_valid;           // [nbins] first reservation that did not fit (~0: none)
-  unsigned long long *over_h;              // windows whose bin was full: full h ...
-  uint32_t *over_rec;                      //   ... and record id
+  unsigned long long *bin_count;             // [nbins_pad] reserved entries (may exceed cap)
+  unsigned long long *bin_valid;             // [nbins_pad] first reservation that did not fit (~0: none)
+  unsigned long long *over_lt;               // windows that found no room in their bin: line << 32 | tag ...
+  uint32_t *over_rec;                        //   ... and record id
   unsigned long long *over_n;
   uint64_t over_cap;
-  unsigned long long *counter;             // work distribution (one per pass)
+  unsigned long long *counter;               // work distribution (one per pass)
   unsigned long long *acc;
   PairTable sparse;
   const unsigned long long *zmap;
@@ -65,9 +66,9 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
   const uint64_t kmask = P.J.kmask;
   const uint64_t kbits = (1ull << k) - 1;
   const uint64_t cmask = 0xaaaaaaaaaaaaaaaaull & kmask;
-  const uint64_t lowmask = (P.lowbits >= 64) ? ~0ull : ((1ull << P.lowbits) - 1);
+  const uint32_t lmask = (1u << P.lbits) - 1u;
   const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, SW_CHUNK_TILES);
-  const uint32_t per_thread_bins = P.nbins / SW_THREADS;       // nbins is a multiple of 256
+  const uint32_t per_thread_bins = P.nbins_pad / SW_THREADS;
 
   unsigned long long my_valid = 0;
   uint32_t cur_rec = 0xffffffffu, n_ok0 = 0;
@@ -82,13 +83,13 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
   while (true) {
     __syncthreads();
     if (tid == 0) s_chunk = atomicAdd(P.counter, 1ull);
-    for (uint32_t i = tid; i < P.nbins; i += SW_THREADS) s_cnt[i] = 0;
+    for (uint32_t i = tid; i < P.nbins_pad; i += SW_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const uint64_t chunk = s_chunk;
     if (chunk >= nchunks) break;
     const uint64_t tile0 = P.tile_begin + chunk * SW_CHUNK_TILES;
 
-    // record of the chunk's first window (uniform)
+    // record of the chunk's first window (uniform); does the chunk stay inside it?
     uint32_t r0;
     {
       const uint64_t gt = tile0 * MFN_TILE;
@@ -97,14 +98,15 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
       r0 = a;
     }
     if (r0 != cur_rec) { flush_rec(); cur_rec = r0; }
+    const uint64_t r0_end = (r0 < P.nseq) ? P.rec_start[r0 + 1] : ~0ull;
+    const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
     // ---- hash this thread's 32 windows; rank them inside their bins ------------------------
     uint32_t low[SW_CHUNK_TILES * WPT], meta[SW_CHUNK_TILES * WPT];     // meta: bin | rank << 12 | rdelta << 25
 #pragma unroll
     for (int q = 0; q < SW_CHUNK_TILES; q++) {
       const uint64_t tile = tile0 + q;
-      const uint32_t j0 = tid * WPT;
-      const uint64_t g0 = tile * MFN_TILE + j0;
+      const uint64_t g0 = tile * MFN_TILE + tid * WPT;
       uint64_t lo = 0, hi = 0, okb = 0;
       if (tile < P.tile_end) {
         const uint64_t w = g0 >> 5, sh = (g0 & 31) * 2;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
       uint32_t rec = r0;
-      uint64_t next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull;
+      uint64_t next_start = r0_end;
 #pragma unroll
       for (int u = 0; u < WPT; u++) {
         const int idx = q * WPT + u;
@@ -124,23 +126,27 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
         low[idx] = 0;
         if (((okb >> u) & kbits) != kbits) continue;
         uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
-        x &= kmask;
-        const uint64_t r = x ^ cmask, f = mfn_revcomp(r, k);
-        const uint64_t h = mfn_mix(f < r ? f : r, P.J.seed, kmask, k);
-        const uint64_t g = g0 + u;
-        while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
+        x &= kmask;                                             // base g in the low 2 bits: reversed f
+        const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
+        uint64_t line, tag;
+        joint_locate(P.J, f < r ? f : r, line, tag);
+        uint32_t rd = 0;
+        if (!one_record) {
+          const uint64_t g = g0 + u;
+          while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
+          rd = rec - r0;
+        }
         my_valid++;
-        if (rec == r0) n_ok0++;
+        if (rd == 0) n_ok0++;
         else atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec], 1ull);
-        const uint32_t bin = (uint32_t)(h >> P.lowbits);
-        const uint32_t rd = rec - r0;
         if (rd > 126) {                                   // a chunk spanning > 126 records: side list
           unsigned long long o = atomicAdd(P.over_n, 1ull);
-          if (o < P.over_cap) { P.over_h[o] = h; P.over_rec[o] = rec; } else atomicAdd(&P.acc[2], 1ull);
+          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec; } else atomicAdd(&P.acc[2], 1ull);
           continue;
         }
+        const uint32_t bin = (uint32_t)(line >> P.lbits);
         const uint32_t rank = atomicAdd(&s_cnt[bin], 1u);
-        low[idx] = (uint32_t)(h & lowmask);
+        low[idx] = (((uint32_t)line & lmask) << P.tbits) | (uint32_t)tag;
         meta[idx] = bin | (rank << 12) | (rd << 25);
       }
     }
@@ -187,9 +193,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
 
     // ---- coalesced copy-out: consecutive threads write consecutive entries of a bin's run --
     {
-      uint32_t total = 0;
-      const uint32_t last = P.nbins - 1;
-      total = s_off[last] + s_cnt[last];
+      const uint32_t last = P.nbins_pad - 1;
+      const uint32_t total = s_off[last] + s_cnt[last];
       for (uint32_t i = tid; i < total; i += SW_THREADS) {
         const uint32_t m = s_meta[i];
         const uint32_t bin = m & 0xfffu, rec = r0 + (m >> 12);
@@ -198,8 +203,11 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
           P.entries[(uint64_t)bin * P.cap + base + (i - s_off[bin])] = ((unsigned long long)rec << 32) | s_low[i];
         } else {
           unsigned long long o = atomicAdd(P.over_n, 1ull);
-          if (o < P.over_cap) { P.over_h[o] = ((uint64_t)bin << P.lowbits) | s_low[i]; P.over_rec[o] = rec; }
-          else atomicAdd(&P.acc[2], 1ull);                 // reported as MFN_ERR_CAPACITY at fetch
+          const uint32_t lw = s_low[i];
+          if (o < P.over_cap) {
+            P.over_lt[o] = ((((uint64_t)bin << P.lbits) | (lw >> P.tbits)) << 32) | (lw & ((1u << P.tbits) - 1u));
+            P.over_rec[o] = rec;
+          } else atomicAdd(&P.acc[2], 1ull);               // reported as MFN_ERR_CAPACITY at fetch
         }
       }
     }
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
-// pass 2 (and the overflow list: OVER = true probes full h values from the side list)
+// pass 2 (and the overflow list: OVER = true probes (line, tag) pairs from the side list)
 // ------------------------------------------------------------------------------------------
 template <bool OVER>
 __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_constant__ SweepParams P) {
@@ -223,10 +231,11 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
   const uint64_t nitems = OVER ? ceil_div_u64(min(*P.over_n, (unsigned long long)P.over_cap), SW_SLICE)
                                : (uint64_t)P.nbins * slices_per_bin;
   const bool even_k = (P.J.k & 1u) == 0;
+  const uint32_t tmask = (1u << P.tbits) - 1u;
 
-  auto account = [&](uint64_t h, uint32_t rec, uint32_t vr, uint32_t va) {
+  auto account = [&](uint32_t line, uint32_t tag, uint32_t rec, uint32_t vr, uint32_t va) {
     if (even_k) {                                          // palindromes count twice (Q2)
-      const uint64_t c = mfn_unmix(h, P.J.seed, P.J.kmask, P.J.k);
+      const uint64_t c = mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k);
       if (c == mfn_revcomp(c, P.J.k)) { vr += vr; va += va; }
     }
     bool miss = (vr == 0);
@@ -245,24 +254,24 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     if (item >= nitems) break;
     uint64_t n, first;                 // entries [first, first + n) of this item
     const unsigned long long *src;
-    uint64_t hbase = 0;
+    uint32_t line0 = 0;
     if (OVER) {
       const uint64_t tot = min(*P.over_n, (unsigned long long)P.over_cap);
-      first = item * SW_SLICE; n = min((uint64_t)SW_SLICE, tot - first); src = P.over_h;
+      first = item * SW_SLICE; n = min((uint64_t)SW_SLICE, tot - first); src = P.over_lt;
     } else {
       const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
       const uint64_t cnt = min(min(P.bin_count[bin], P.bin_valid[bin]), (unsigned long long)P.cap);
       if (s * SW_SLICE >= cnt) continue;
       first = bin * P.cap + s * SW_SLICE; n = min((uint64_t)SW_SLICE, cnt - s * SW_SLICE); src = P.entries;
-      hbase = bin << P.lowbits;
+      line0 = (uint32_t)bin << P.lbits;
     }
-    // each thread: 4 batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
+    // each thread: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
     const uint32_t nbatch = (uint32_t)ceil_div_u64(n, SW_THREADS * 4);     // uniform: every lane of a warp
 #pragma unroll 1                                                           // takes part in the warp votes below
     for (uint32_t bt = 0; bt < nbatch; bt++) {
       const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
       unsigned long long e[4];
-      if (i0 + 4 <= n && (((first + i0) & 3) == 0)) {
+      if (i0 + 4 <= n) {
         // streamed once: keep it from evicting the table slice
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
                      : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + first + i0));
@@ -270,19 +279,18 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
 #pragma unroll
         for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[first + i0 + u] : 0;
       }
-      uint64_t hh[4], ln[4], tg[4];
-      uint32_t rc[4], vr[4], va[4];
+      uint32_t ln[4], tg[4], rc[4], vr[4], va[4];
       bool val[4];
       Bucket b[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         val[u] = i0 + u < n;
-        if (OVER) { hh[u] = e[u]; rc[u] = val[u] ? P.over_rec[first + i0 + u] : 0; }
-        else { hh[u] = hbase | (e[u] & 0xffffffffull); rc[u] = (uint32_t)(e[u] >> 32); }
-        if (val[u]) {
-          mfn_split(hh[u], P.J.D, P.J.magic, ln[u], tg[u]);
-          joint_load_sector(P.J, ln[u], (uint32_t)tg[u] & 3u, b[u]);
+        if (OVER) { ln[u] = (uint32_t)(e[u] >> 32); tg[u] = (uint32_t)e[u]; rc[u] = val[u] ? P.over_rec[first + i0 + u] : 0; }
+        else {
+          const uint32_t lw = (uint32_t)e[u];
+          ln[u] = line0 + (lw >> P.tbits); tg[u] = lw & tmask; rc[u] = (uint32_t)(e[u] >> 32);
         }
+        if (val[u]) joint_load_sector(P.J, ln[u], tg[u] & 3u, b[u]);
       }
       uint32_t pending = 0;
 #pragma unroll
@@ -290,28 +298,26 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
         vr[u] = 0; va[u] = 0;
         if (val[u]) {
           uint64_t pay = 0;
-          bool full;
-          const bool hit = joint_match(P.J, b[u], tg[u], pay, full);
+          const bool hit = joint_match_fast(P.J, b[u], tg[u], pay);
           va[u] = (uint32_t)pay & P.J.amax;
           vr[u] = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
-          if ((!hit && full) || (hit && (vr[u] == P.J.rmax || va[u] == P.J.amax))) pending |= 1u << u;
+          if (!hit || vr[u] == P.J.rmax || va[u] == P.J.amax) pending |= 1u << u;
         }
       }
       while (__any_sync(0xffffffffu, pending != 0)) {
         if (pending) {
           const int u = __ffs(pending) - 1;
           pending &= pending - 1;
-          const uint64_t h = u == 0 ? hh[0] : u == 1 ? hh[1] : u == 2 ? hh[2] : hh[3];
-          const uint64_t l = u == 0 ? ln[0] : u == 1 ? ln[1] : u == 2 ? ln[2] : ln[3];
-          const uint64_t t = u == 0 ? tg[0] : u == 1 ? tg[1] : u == 2 ? tg[2] : tg[3];
-          uint32_t r2, a2;
-          joint_full(P.J, mfn_unmix(h, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);   // side tables are keyed by k-mer
+          const uint32_t l = u == 0 ? ln[0] : u == 1 ? ln[1] : u == 2 ? ln[2] : ln[3];
+          const uint32_t t = u == 0 ? tg[0] : u == 1 ? tg[1] : u == 2 ? tg[2] : tg[3];
+          uint32_t r2, a2;                                   // side tables are keyed by k-mer
+          joint_full(P.J, mfn_unmix((uint64_t)l * P.J.D + t, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);
 #pragma unroll
           for (int q = 0; q < 4; q++) if (q == u) { vr[q] = r2; va[q] = a2; }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) if (val[u]) account(hh[u], rc[u], vr[u], va[u]);
+      for (int u = 0; u < 4; u++) if (val[u]) account(ln[u], tg[u], rc[u], vr[u], va[u]);
     }
   }
   __syncthreads();
@@ -320,7 +326,6 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     if (c) atomicAdd(&P.acc[MFN_ACC_HEADER + (i / SH_R) * MFN_DENSE_R + (i % SH_R)], (unsigned long long)c);
   }
 }
-
 
 // k_sweep_probe<true> lives in its own translation unit (sweep_over.cu): ptxas 12.9 crashes when
 // two entries that share an out-of-line device function are compiled in one module.

@@ -25,15 +25,24 @@ __device__ __forceinline__ void mfn_split(uint64_t h, uint64_t D, uint64_t magic
   bucket = q; tag = r;
 }
 
-__host__ __device__ __forceinline__ uint64_t mfn_revcomp(uint64_t f, uint32_t k) {
-  // complement every base (A=00 <-> T=10, C=01 <-> G=11), reverse the 2-bit groups, realign
-  uint64_t x = f ^ 0xaaaaaaaaaaaaaaaaull;
+// reverse the order of the 32 two-bit groups of x
+__host__ __device__ __forceinline__ uint64_t mfn_rev2(uint64_t x) {
+#ifdef __CUDA_ARCH__
+  // two BREVs reverse all 64 bits; then swap the two bits inside every group back
+  uint64_t y = ((uint64_t)__brev((uint32_t)x) << 32) | __brev((uint32_t)(x >> 32));
+  return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+#else
   x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
   x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
   x = ((x >> 8) & 0x00ff00ff00ff00ffull) | ((x & 0x00ff00ff00ff00ffull) << 8);
   x = ((x >> 16) & 0x0000ffff0000ffffull) | ((x & 0x0000ffff0000ffffull) << 16);
-  x = (x >> 32) | (x << 32);
-  return x >> (64 - 2 * k);
+  return (x >> 32) | (x << 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint64_t mfn_revcomp(uint64_t f, uint32_t k) {
+  // complement every base (A=00 <-> T=10, C=01 <-> G=11), reverse the 2-bit groups, realign
+  return mfn_rev2(f ^ 0xaaaaaaaaaaaaaaaaull) >> (64 - 2 * k);
 }
 
 // 32-byte bucket load: one LDG.256, read-only path, no L1 allocation (no reuse).
