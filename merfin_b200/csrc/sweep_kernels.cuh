@@ -246,6 +246,25 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     else sparse_add(P.sparse, P.acc, vr, va, 1ull);
   };
 
+  // per-warp queue of lookups that need more than the home sector: (line, tag, record)
+  __shared__ uint32_t s_q[SW_THREADS / 32][3][64];
+  const uint32_t lane = tid & 31, wid = tid >> 5;
+  uint32_t qn = 0;                                           // warp-uniform
+  auto drain = [&](bool all) {
+    while (qn >= 32 || (all && qn > 0)) {
+      const uint32_t take = qn < 32 ? qn : 32;
+      if (lane < take) {
+        const uint32_t i = qn - take + lane;
+        const uint32_t l = s_q[wid][0][i], t = s_q[wid][1][i], rec = s_q[wid][2][i];
+        uint32_t r2, a2;                                     // side tables are keyed by k-mer
+        joint_full(P.J, mfn_unmix((uint64_t)l * P.J.D + t, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);
+        account(l, t, rec, r2, a2);
+      }
+      qn -= take;
+      __syncwarp();
+    }
+  };
+
   while (true) {
     __syncthreads();
     if (tid == 0) s_item = atomicAdd(P.counter, 1ull);
@@ -279,7 +298,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
 #pragma unroll
         for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[first + i0 + u] : 0;
       }
-      uint32_t ln[4], tg[4], rc[4], vr[4], va[4];
+      uint32_t ln[4], tg[4], rc[4];
       bool val[4];
       Bucket b[4];
 #pragma unroll
@@ -292,34 +311,27 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
         }
         if (val[u]) joint_load_sector(P.J, ln[u], tg[u] & 3u, b[u]);
       }
-      uint32_t pending = 0;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        vr[u] = 0; va[u] = 0;
-        if (val[u]) {
-          uint64_t pay = 0;
-          const bool hit = joint_match_fast(P.J, b[u], tg[u], pay);
-          va[u] = (uint32_t)pay & P.J.amax;
-          vr[u] = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
-          if (!hit || vr[u] == P.J.rmax || va[u] == P.J.amax) pending |= 1u << u;
+        uint64_t pay = 0;
+        const bool hit = val[u] && joint_match_fast(P.J, b[u], tg[u], pay);
+        const uint32_t a1 = (uint32_t)pay & P.J.amax, r1 = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
+        // the few lookups the home sector cannot answer are queued per warp and finished 32 at a
+        // time with every lane busy, instead of dragging the whole warp through the slow path
+        const bool slow = val[u] && (!hit || r1 == P.J.rmax || a1 == P.J.amax);
+        if (val[u] && !slow) account(ln[u], tg[u], rc[u], r1, a1);
+        const uint32_t m = __ballot_sync(0xffffffffu, slow);
+        if (slow) {
+          const uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
+          s_q[wid][0][pos] = ln[u]; s_q[wid][1][pos] = tg[u]; s_q[wid][2][pos] = rc[u];
         }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) drain(false);
       }
-      while (__any_sync(0xffffffffu, pending != 0)) {
-        if (pending) {
-          const int u = __ffs(pending) - 1;
-          pending &= pending - 1;
-          const uint32_t l = u == 0 ? ln[0] : u == 1 ? ln[1] : u == 2 ? ln[2] : ln[3];
-          const uint32_t t = u == 0 ? tg[0] : u == 1 ? tg[1] : u == 2 ? tg[2] : tg[3];
-          uint32_t r2, a2;                                   // side tables are keyed by k-mer
-          joint_full(P.J, mfn_unmix((uint64_t)l * P.J.D + t, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);
-#pragma unroll
-          for (int q = 0; q < 4; q++) if (q == u) { vr[q] = r2; va[q] = a2; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) if (val[u]) account(ln[u], tg[u], rc[u], vr[u], va[u]);
     }
   }
+  drain(true);
   __syncthreads();
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {
     uint32_t c = s_hist[i];
