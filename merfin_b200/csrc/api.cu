@@ -144,6 +144,24 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
   MFN_TRY(scratch_seq(ctx, seq_off, nseq, &seq));
   const uint64_t tb = seq->ntiles * shard / nshards, te = seq->ntiles * (shard + 1) / nshards;
   const uint64_t pieces = std::max<uint64_t>(1, std::min<uint64_t>(16, (te - tb) / 8192));
+  if (reads->dev.k != asm_->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", reads->dev.k, asm_->dev.k); return MFN_ERR_K_MISMATCH; }
+  if (mfn_sweep_applicable(reads, asm_, te - tb)) {
+    // range-partitioned scan: scatter each piece as soon as it is packed (overlaps the H2D of
+    // the next piece), probe all bins once at the end
+    if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
+    unsigned long long *zmap = nullptr; uint32_t zlen = 0;
+    MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &zlen));
+    mfn_sweep *w = nullptr;
+    int st = mfn_sweep_begin(ctx, reads, seq, (te - tb) * MFN_TILE, acc, zmap, zlen, &w);
+    for (uint64_t p = 0; p < pieces && st == MFN_OK; p++) {
+      uint64_t a = tb + (te - tb) * p / pieces, b = tb + (te - tb) * (p + 1) / pieces;
+      st = mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128);
+      if (st == MFN_OK) st = mfn_sweep_scatter(ctx, w, a, b);
+    }
+    if (w) { int st2 = mfn_sweep_finish(ctx, w); if (st == MFN_OK) st = st2; }
+    if (zmap) cudaFreeAsync(zmap, ctx->stream);
+    return st;
+  }
   for (uint64_t p = 0; p < pieces; p++) {
     uint64_t a = tb + (te - tb) * p / pieces, b = tb + (te - tb) * (p + 1) / pieces;
     MFN_TRY(mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128));

@@ -66,7 +66,7 @@ static int launch_scan(mfn_ctx *ctx, ScanParams &P, bool dump, bool joint) {
 }
 
 // bitmap of read multiplicities whose readK is 0 under the -prob table (merfin-globals.C:93-97)
-static int build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen) {
+int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen) {
   *d_zmap = nullptr; *zlen = 0;
   if (!km || km->nprob == 0) return MFN_OK;
   uint32_t n = km->nprob + 1;                    // values 0 .. nprob
@@ -93,7 +93,7 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   P.tile_begin = tile_begin; P.tile_end = std::min(tile_end, seq->ntiles);
   P.acc = acc->d_buf; P.sparse = acc->sparse;
   unsigned long long *zmap = nullptr;
-  MFN_TRY(build_zmap(ctx, km, &zmap, &P.zlen));
+  MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &P.zlen));
   P.zmap = zmap;
   int st;
   if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0))

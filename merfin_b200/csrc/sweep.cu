@@ -32,51 +32,87 @@ bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntile
   return windows >= (1ull << 24) && windows * 4 >= R->joint->dev.nlines;
 }
 
-int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
-                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen) {
-  (void)km; (void)A;
-  if (tile_begin >= tile_end) return MFN_OK;
-  const JointDev &J = R->joint->dev;
+// A sweep over a sequence set: begin (workspace sized for `windows`), scatter any number of tile
+// ranges as their bases become resident, finish (probe every bin once).
+struct mfn_sweep {
   SweepParams P{};
+  unsigned long long *ctl = nullptr, *counters = nullptr;
+  uint32_t n_scatter = 0;
+};
+
+int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
+                    const unsigned long long *zmap, uint32_t zlen, mfn_sweep **out) {
+  const JointDev &J = R->joint->dev;
+  mfn_sweep *w = new mfn_sweep();
+  SweepParams &P = w->P;
   P.J = J;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
-  P.tile_begin = tile_begin; P.tile_end = tile_end;
-  if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins)) { mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
+  if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins)) { delete w; mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
   P.nbins_pad = (P.nbins + SW_THREADS - 1) / SW_THREADS * SW_THREADS;
-  const uint64_t windows = (tile_end - tile_begin) * MFN_TILE;
   P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;
   P.over_cap = std::max<uint64_t>(1 << 20, windows / 16);
   P.acc = acc->d_buf; P.sparse = acc->sparse; P.zmap = zmap; P.zlen = zlen;
-
-  // workspace (stream-ordered pool: reused across steps without cudaMalloc cost)
+  // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
-  unsigned long long *ctl = nullptr;
-  MFN_CUDA(cudaMallocAsync(&P.entries, ebytes, ctx->stream));
-  MFN_CUDA(cudaMallocAsync(&ctl, (2 * (size_t)P.nbins_pad + 4) * 8, ctx->stream));
-  MFN_CUDA(cudaMallocAsync(&P.over_lt, P.over_cap * 8, ctx->stream));
-  MFN_CUDA(cudaMallocAsync(&P.over_rec, P.over_cap * 4, ctx->stream));
-  P.bin_count = ctl; P.bin_valid = ctl + P.nbins_pad; P.over_n = ctl + 2 * P.nbins_pad;
-  unsigned long long *counters = ctl + 2 * P.nbins_pad + 1;       // [3]
-  MFN_CUDA(cudaMemsetAsync(ctl, 0, (2 * (size_t)P.nbins_pad + 4) * 8, ctx->stream));
+  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64;            // bins, side-list count, pass counters
+  cudaError_t e = cudaMallocAsync(&P.entries, ebytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&w->ctl, cwords * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&P.over_lt, P.over_cap * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&P.over_rec, P.over_cap * 4, ctx->stream);
+  if (e != cudaSuccess) { mfn_set_error("sweep workspace (%zu bytes): %s", ebytes, cudaGetErrorString(e)); delete w; return MFN_ERR_NOMEM; }
+  P.bin_count = w->ctl; P.bin_valid = w->ctl + P.nbins_pad; P.over_n = w->ctl + 2 * P.nbins_pad;
+  w->counters = w->ctl + 2 * P.nbins_pad + 1;
+  MFN_CUDA(cudaMemsetAsync(w->ctl, 0, cwords * 8, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(P.bin_valid, 0xff, (size_t)P.nbins_pad * 8, ctx->stream));
+  *out = w;
+  return MFN_OK;
+}
 
+int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end) {
+  if (tile_begin >= tile_end) return MFN_OK;
+  if (w->n_scatter >= 60) { mfn_set_error("sweep: too many scatter passes"); return MFN_ERR_INVALID; }
+  SweepParams P = w->P;
+  P.tile_begin = tile_begin; P.tile_end = tile_end;
   int per_sm = 0;
   const size_t sc_smem = (2 * (size_t)SW_CHUNK + 3 * (size_t)SW_MAX_BINS) * 4;
   MFN_CUDA(cudaFuncSetAttribute(k_sweep_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_scatter<0>, SW_THREADS, sc_smem);
-  P.counter = counters;
-  k_sweep_scatter<0><<<ctx->sm_count * std::max(per_sm, 1), SW_THREADS, sc_smem, ctx->stream>>>(P);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_probe<false>, SW_THREADS, 0);
-  P.counter = counters + 1;
-  k_sweep_probe<false><<<ctx->sm_count * std::max(per_sm, 1), SW_THREADS, 0, ctx->stream>>>(P);
-  P.counter = counters + 2;
-  mfn_sweep_launch_over(P, ctx->sm_count, ctx->stream);
-  ctx->launches += 3;
+  P.counter = w->counters + 2 + w->n_scatter++;
+  const uint64_t nchunks = ceil_div_u64(tile_end - tile_begin, SW_CHUNK_TILES);
+  const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks);
+  k_sweep_scatter<0><<<grid, SW_THREADS, sc_smem, ctx->stream>>>(P);
+  ctx->launches++;
   MFN_CUDA(cudaGetLastError());
-  // the side list must not have overflowed: checked lazily at fetch through the header
-  MFN_CUDA(cudaFreeAsync(P.entries, ctx->stream));
-  MFN_CUDA(cudaFreeAsync(ctl, ctx->stream));
-  MFN_CUDA(cudaFreeAsync(P.over_lt, ctx->stream));
-  MFN_CUDA(cudaFreeAsync(P.over_rec, ctx->stream));
   return MFN_OK;
+}
+
+int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
+  SweepParams P = w->P;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_probe<false>, SW_THREADS, 0);
+  P.counter = w->counters;
+  k_sweep_probe<false><<<ctx->sm_count * std::max(per_sm, 1), SW_THREADS, 0, ctx->stream>>>(P);
+  P.counter = w->counters + 1;
+  mfn_sweep_launch_over(P, ctx->sm_count, ctx->stream);
+  ctx->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  // a side list that overflowed is reported through the accumulator header (MFN_ERR_CAPACITY at fetch)
+  cudaFreeAsync(P.entries, ctx->stream);
+  cudaFreeAsync(w->ctl, ctx->stream);
+  cudaFreeAsync(P.over_lt, ctx->stream);
+  cudaFreeAsync(P.over_rec, ctx->stream);
+  delete w;
+  if (e != cudaSuccess) { mfn_set_error("sweep: %s", cudaGetErrorString(e)); return MFN_ERR_CUDA; }
+  return MFN_OK;
+}
+
+int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
+                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen) {
+  (void)km; (void)A;
+  if (tile_begin >= tile_end) return MFN_OK;
+  mfn_sweep *w = nullptr;
+  MFN_TRY(mfn_sweep_begin(ctx, R, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, &w));
+  int st = mfn_sweep_scatter(ctx, w, tile_begin, tile_end);
+  int st2 = mfn_sweep_finish(ctx, w);
+  return st != MFN_OK ? st : st2;
 }

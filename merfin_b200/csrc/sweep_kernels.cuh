@@ -164,17 +164,26 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
       uint32_t wbase = 0;
       for (uint32_t w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
       uint32_t run = wbase + incl - sum;
-      for (uint32_t i = 0; i < per_thread_bins; i++) {
-        const uint32_t c = s_cnt[b0 + i];
-        s_off[b0 + i] = run;
-        run += c;
-        uint32_t base = 0;
-        if (c) {
-          const unsigned long long g = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)c);
-          if (g + c > P.cap) { atomicMin(&P.bin_valid[b0 + i], g); base = SW_NOSPACE; }
-          else base = (uint32_t)g;
+      // reserve space in the global bins: all atomics of this thread in flight together
+      unsigned long long got[SW_MAX_BINS / SW_THREADS];
+#pragma unroll
+      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
+        got[i] = 0;
+        if (i < per_thread_bins) {
+          const uint32_t c = s_cnt[b0 + i];
+          if (c) got[i] = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)c);
         }
-        s_base[b0 + i] = base;
+      }
+#pragma unroll
+      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
+        if (i < per_thread_bins) {
+          const uint32_t c = s_cnt[b0 + i];
+          s_off[b0 + i] = run;
+          run += c;
+          uint32_t base = (uint32_t)got[i];
+          if (c && got[i] + c > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); base = SW_NOSPACE; }
+          s_base[b0 + i] = base;
+        }
       }
     }
     __syncthreads();
@@ -286,10 +295,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     }
     // each thread: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
     const uint32_t nbatch = (uint32_t)ceil_div_u64(n, SW_THREADS * 4);     // uniform: every lane of a warp
-#pragma unroll 1                                                           // takes part in the warp votes below
-    for (uint32_t bt = 0; bt < nbatch; bt++) {
+    auto load_entries = [&](uint32_t bt, unsigned long long (&e)[4]) {
       const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
-      unsigned long long e[4];
       if (i0 + 4 <= n) {
         // streamed once: keep it from evicting the table slice
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
@@ -298,6 +305,16 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
 #pragma unroll
         for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[first + i0 + u] : 0;
       }
+    };
+    unsigned long long enext[4];
+    load_entries(0, enext);
+#pragma unroll 1                                                           // (every lane takes part in the warp votes below)
+    for (uint32_t bt = 0; bt < nbatch; bt++) {
+      const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
+      unsigned long long e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) e[u] = enext[u];
+      if (bt + 1 < nbatch) load_entries(bt + 1, enext);        // in flight while this batch probes
       uint32_t ln[4], tg[4], rc[4];
       bool val[4];
       Bucket b[4];
