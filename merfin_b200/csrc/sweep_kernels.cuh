@@ -25,7 +25,7 @@
 #define SW_CHUNK_TILES 4
 #define SW_CHUNK (SW_CHUNK_TILES * MFN_TILE)      // 8192 windows per CTA round
 #define SW_MAX_BINS 2048
-#define SW_SLICE 4096                              // entries per probe work item (16 per thread)
+#define SW_SLICE 1024                              // entries per probe work item (one WARP: 32 per lane)
 #define SW_NOSPACE 0xffffffffu
 
 struct SweepParams {
@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
 // pass 2 (and the overflow list: OVER = true probes (line, tag) pairs from the side list)
 // ------------------------------------------------------------------------------------------
 template <bool OVER>
-__global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_constant__ SweepParams P) {
   __shared__ uint32_t s_hist[SH_R * SH_A];
-  __shared__ unsigned long long s_item;
   const uint32_t tid = threadIdx.x;
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) s_hist[i] = 0;
+  __syncthreads();
 
   const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
   const uint64_t nitems = OVER ? ceil_div_u64(min(*P.over_n, (unsigned long long)P.over_cap), SW_SLICE)
@@ -274,11 +274,11 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     }
   };
 
+  // work items are handed out per WARP (no CTA barrier in the loop)
   while (true) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(P.counter, 1ull);
-    __syncthreads();
-    const uint64_t item = s_item;
+    uint64_t item = 0;
+    if (lane == 0) item = atomicAdd(P.counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) break;
     uint64_t n, first;                 // entries [first, first + n) of this item
     const unsigned long long *src;
@@ -294,9 +294,9 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
       line0 = (uint32_t)bin << P.lbits;
     }
     // each thread: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
-    const uint32_t nbatch = (uint32_t)ceil_div_u64(n, SW_THREADS * 4);     // uniform: every lane of a warp
+    const uint32_t nbatch = (uint32_t)ceil_div_u64(n, 32 * 4);             // uniform: every lane of the warp
     auto load_entries = [&](uint32_t bt, unsigned long long (&e)[4]) {
-      const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
+      const uint64_t i0 = (uint64_t)bt * 32 * 4 + lane * 4;
       if (i0 + 4 <= n) {
         // streamed once: keep it from evicting the table slice
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_probe(const __grid_cons
     load_entries(0, enext);
 #pragma unroll 1                                                           // (every lane takes part in the warp votes below)
     for (uint32_t bt = 0; bt < nbatch; bt++) {
-      const uint64_t i0 = (uint64_t)bt * SW_THREADS * 4 + tid * 4;
+      const uint64_t i0 = (uint64_t)bt * 32 * 4 + lane * 4;
       unsigned long long e[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) e[u] = enext[u];
