@@ -1,0 +1,77 @@
+// Variant front-end of the merfin-compatible CLI (-filter / -polish / -better / -strict / -loose):
+// VCF loading, clustering of nearby variants, enumeration of allele combinations ("paths"),
+// replay of varMer::score from integer (v_read, v_asm) pairs, and the path selectors.
+//
+// Host-only control logic written against the behaviour of the reference (file:line in the
+// reference tree): vcfRecord.H:50-76, vcf.C:23-87 (genotype -> allele list), vcf.C:156-246
+// (clustering), merfin-variants.C:22-126 (path enumeration), :131-310 (per-cluster driver),
+// varMer.C:48-145 (score), :150-467 (selectors), :472-550 (output records), :553-659 (stats).
+// The k-mer probes themselves are NOT done here: a PathScorer (the GPU library) returns the
+// integer pairs for every window of every path.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/merfin_b200.h"
+
+namespace mfnv {
+
+enum Mode { FILTER = 4, POLISH = 5, BETTER = 6, STRICT = 7, LOOSE = 8 };   // merfin-globals.H:32-40
+
+struct VcfRecord {
+  std::string chr, id, ref, alts, filter, info, formats, samples;
+  uint32_t pos = 0;
+  double qual = 0.0;
+  std::vector<std::string> alt_list, sample_fields;
+  std::string save() const;                 // vcfRecord.H:78-99: the first ten columns, QUAL as %.1f
+};
+
+struct GtAllele {                           // vcf.H:37-50
+  const VcfRecord *record = nullptr;
+  uint32_t pos = 0, refLen = 0;
+  double qual = 0.0;
+  std::vector<std::string> alleles;         // [0] is the reference allele; may be EMPTY (Q10)
+};
+
+struct PosGT {                              // vcf.H:59-90: a cluster of nearby variants
+  std::string chr;
+  uint32_t rStart = 0, rEnd = 0;
+  std::vector<GtAllele *> gts;
+};
+
+struct VcfFile {
+  std::vector<std::string> headers;
+  std::vector<VcfRecord *> records;
+  std::vector<GtAllele *> alleles;          // owned
+  std::map<std::string, std::vector<PosGT *>> byChr;
+  uint64_t excluded = 0;
+  int numChr = 0;
+  ~VcfFile();
+  bool load(const std::string &path, std::string &err);              // vcf.C:93-151
+  void mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit);   // vcf.C:156-246
+};
+
+// paths: concatenated path strings + offsets (as mfn_score_paths takes them); the scorer fills one
+// (v_read, v_asm, valid) per base position (window start) of every path.
+typedef std::function<int(const std::string &paths, const std::vector<uint64_t> &off,
+                          std::vector<uint32_t> &v_read, std::vector<uint32_t> &v_asm,
+                          std::vector<uint8_t> &valid)> PathScorer;
+
+struct Options {
+  uint32_t k = 0, comb = 15;
+  Mode mode = POLISH;
+  mfn_kmodel km{};
+  bool debug = false;
+};
+
+// All clusters of one sequence record: returns the VCF text merfin appends to its output for this
+// record (processVariants' s->result) and, if opt.debug, the debug lines.  `varMerId` numbers
+// the debug lines across records.
+int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen, std::vector<PosGT *> &clusters,
+                     const Options &opt, const PathScorer &scorer, std::string &result, std::string *debug,
+                     uint64_t &varMerId);
+
+}  // namespace mfnv

@@ -137,3 +137,68 @@ def make_vcf(recs, nvar: int, seed: int, gts=("1/1", "0/1", "1|0", "1/2"),
             last_end = p + len(ref) - 1
             lines.append(f"{name}\t{p + 1}\t.\t{ref}\t{alt}\t30\tPASS\t.\tGT\t{gt}")
     return "\n".join(lines) + "\n"
+
+
+def plant_errors(truth_recs, n_per_rec: int, seed: int, false_per_rec: int = 0):
+    """Assembly = truth with planted SNV / small indel errors; returns (asm_recs, vcf_text).
+
+    The VCF proposes the corrections (REF = assembly allele, ALT = truth allele) with a mix of
+    genotypes, some records paired with a close neighbour (clusters), a few `0/0` and `./.`
+    records, and `false_per_rec` bogus SNVs per record that polishing should reject.
+    """
+    rng = np.random.default_rng(seed)
+    asm_recs, lines = [], ["##fileformat=VCFv4.2"]
+    body = []
+    for name, t in truth_recs:
+        t = t.copy()
+        L = len(t)
+        sites, p = [], 60
+        while len(sites) < n_per_rec and p < L - 80:
+            sites.append(p)
+            if rng.random() < 0.25 and p + 20 < L - 80:      # a close neighbour -> same cluster
+                sites.append(p + int(rng.integers(3, 13)))
+            p = sites[-1] + int(rng.integers(45, max(46, 2 * L // max(1, n_per_rec))))
+        out, edits, cur = [], [], 0                           # edits: (asm_pos, ref, alt)
+        alen = 0
+        for s in sites:
+            if s <= cur or not np.isin(t[s:s + 8] & 0xDF, _ACGT).all():
+                continue
+            out.append(t[cur:s]); alen += s - cur
+            kind = rng.random()
+            tb = chr(t[s] & 0xDF)
+            if kind < 0.6:                                     # SNV error in the assembly
+                eb = chr(_ACGT[(int(np.searchsorted(_ACGT, t[s] & 0xDF)) + int(rng.integers(1, 4))) % 4])
+                out.append(np.frombuffer(eb.encode(), dtype=np.uint8))
+                edits.append((alen, eb, tb)); alen += 1; cur = s + 1
+            elif kind < 0.8:                                   # assembly lost 1-3 bases after s
+                n = int(rng.integers(1, 4))
+                out.append(t[s:s + 1]); lost = (t[s + 1:s + 1 + n] & 0xDF).tobytes().decode()
+                edits.append((alen, tb, tb + lost)); alen += 1; cur = s + 1 + n
+            else:                                              # assembly gained 1-3 bases after s
+                ins = random_bases(int(rng.integers(1, 4)), rng)
+                out.append(t[s:s + 1]); out.append(ins)
+                edits.append((alen, tb + ins.tobytes().decode(), tb)); alen += 1 + len(ins); cur = s + 1
+        out.append(t[cur:])
+        a = np.concatenate(out) if out else t
+        asm_recs.append((name, a))
+        lines.append(f"##contig=<ID={name},length={len(a)}>")
+        recs = []
+        for pos, ref, alt in edits:
+            r = rng.random()
+            gt = "1/1" if r < 0.55 else "0/1" if r < 0.7 else "1|0" if r < 0.8 else "1/2" if r < 0.9 else "0/0" if r < 0.95 else "./."
+            alts = alt
+            if gt == "1/2":
+                alts = alt + "," + (alt + "A" if len(alt) < 4 else alt[:-1])
+            recs.append((pos, f"{name}\t{pos + 1}\t.\t{ref}\t{alts}\t{int(rng.integers(10, 60))}\tPASS\t.\tGT:DP\t{gt}:20"))
+        used = {pos for pos, _, _ in edits}
+        for _ in range(false_per_rec):
+            pos = int(rng.integers(30, len(a) - 30))
+            if any(abs(pos - u) < 3 for u in used) or (a[pos] & 0xDF) not in _ACGT:
+                continue
+            used.add(pos)
+            ref = chr(a[pos] & 0xDF)
+            alt = chr(_ACGT[(int(np.searchsorted(_ACGT, a[pos] & 0xDF)) + int(rng.integers(1, 4))) % 4])
+            recs.append((pos, f"{name}\t{pos + 1}\t.\t{ref}\t{alt}\t30\tPASS\t.\tGT\t1/1"))
+        body += [line for _, line in sorted(recs)]
+    lines.append("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE")
+    return asm_recs, "\n".join(lines + body) + "\n"

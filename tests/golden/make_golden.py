@@ -59,12 +59,16 @@ def make_set(name, k, total, nrec, seed, cov, peak, dup_len, extra=()):
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
-    recs = synth.make_assembly(total, nrec, seed, n_run=50 if total >= 4000 else 7,
-                               lower_run=100 if total >= 4000 else 11, dup_len=dup_len)
+    truth = synth.make_assembly(total, nrec, seed, n_run=50 if total >= 4000 else 7,
+                                lower_run=100 if total >= 4000 else 11, dup_len=dup_len)
+    recs = truth
+    if "variants" in extra:          # the assembly carries planted errors; the VCF proposes corrections
+        recs, vcf = synth.plant_errors(truth, 14, seed + 7, false_per_rec=5)
+        open(os.path.join(d, "calls.vcf"), "w").write(vcf)
     synth.write_fasta(os.path.join(d, "asm.fa"), recs, width=70)
     # a stretch of record 0 is never sequenced -> missing k-mers
-    skip = [(0, len(recs[0][1]) // 3, len(recs[0][1]) // 3 + 3 * k)]
-    reads = synth.simulate_reads(recs, cov, 150 if total >= 4000 else 40, 0.005, seed + 1, skip=skip)
+    skip = [(0, len(truth[0][1]) // 3, len(truth[0][1]) // 3 + 3 * k)]
+    reads = synth.simulate_reads(truth, cov, 150 if total >= 4000 else 40, 0.005, seed + 1, skip=skip)
     synth.write_fasta(os.path.join(d, "reads.fa"), reads, prefix="r")
     meryl_count(d, k, "reads.fa", "reads.meryl")
     meryl_count(d, k, "asm.fa", "asm.meryl")
@@ -103,6 +107,19 @@ def make_set(name, k, total, nrec, seed, cov, peak, dup_len, extra=()):
         p = run(base + ["-completeness", "-peak", str(peak), "-prob", "prob.csv"], d)
         open(os.path.join(d, "ref.prob.completeness"), "w").write(
             "\n".join(l for l in p.stderr.splitlines() if re.match(r"^(TOTAL|COMPLETENESS|thread)", l)) + "\n")
+    if "variants" in extra:
+        vbase = base + ["-vcf", "calls.vcf", "-peak", str(peak)]
+        for mode in ("polish", "filter", "better", "strict", "loose"):
+            run(vbase + ["-" + mode, "-output", "ref." + mode] + (["-debug"] if mode == "polish" else []), d)
+            produced = "ref.polish.polish.vcf" if mode == "polish" else f"ref.{mode}.filter.vcf"     # Q7
+            os.rename(os.path.join(d, produced), os.path.join(d, f"ref.{mode}.vcf"))
+        dbg = os.path.join(d, "ref.polish.00.debug.gz")
+        with gzip.open(dbg, "rb") as f, gzip.GzipFile(os.path.join(d, "ref.polish.debug.gz"), "wb", mtime=0) as g:
+            g.write(f.read())
+        os.remove(dbg)
+        # with a -prob table as well (prob weights enter the tie-break sums)
+        run(vbase + ["-polish", "-prob", "prob.csv", "-output", "ref.probpolish"], d)
+        os.rename(os.path.join(d, "ref.probpolish.polish.vcf"), os.path.join(d, "ref.probpolish.vcf"))
     # per-file .merylIndex files are never read on the sequential path; drop them to keep fixtures small
     for sub in ("reads.meryl", "asm.meryl"):
         for fn in os.listdir(os.path.join(d, sub)):
@@ -114,7 +131,7 @@ if __name__ == "__main__":
     if not (os.path.exists(MERFIN) and os.path.exists(MERYL)):
         raise SystemExit("build the reference first: make -C oracle ref")
     # G1: k=21, 2 records, N run + lowercase run + duplicated segment, 10x reads
-    make_set("g1_k21", 21, 12000, 2, 11, 10, 8, 300, extra=("min", "prob"))
+    make_set("g1_k21", 21, 12000, 2, 11, 10, 8, 300, extra=("min", "prob", "variants"))
     # G2: even k with palindromes (Q2), tiny
     make_set("g2_k6", 6, 1500, 2, 12, 6, 3, 40)
     # G3: k=31 (62-bit k-mers, 64-bit table slots)

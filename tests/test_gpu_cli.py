@@ -1,0 +1,81 @@
+"""The merfin-compatible CLI (merfin_b200/bin/merfin) on a B200 against the reference's golden
+outputs: same flags, byte-identical output files, same final summary block."""
+import gzip
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MERFIN = os.path.join(ROOT, "merfin_b200", "bin", "merfin")
+
+
+def _run(args, cwd):
+    p = subprocess.run([MERFIN] + args, cwd=cwd, capture_output=True, text=True, timeout=150)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stderr
+
+
+def _summary(stderr):
+    return "\n".join(l for l in stderr.splitlines() if re.match(r"^(K-mers|Missing QV|Merfin QV)", l)) + "\n"
+
+
+@pytest.mark.parametrize("name,peak", [("g1_k21", 8), ("g2_k6", 3), ("g3_k31", 6)])
+def test_cli_hist_dump_completeness(golden_dir, tmp_path, name, peak):
+    d = os.path.join(golden_dir, name)
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", str(peak)]
+    err = _run(base + ["-hist", "-output", "out.hist"], str(tmp_path))
+    assert open(tmp_path / "out.hist", "rb").read() == open(os.path.join(d, "ref.hist"), "rb").read()
+    assert _summary(err) == open(os.path.join(d, "ref.hist.summary")).read()
+    per = open(os.path.join(d, "ref.hist.perseq")).read()
+    assert per in err
+    _run(base + ["-dump", "-output", "out.dump"], str(tmp_path))
+    assert open(tmp_path / "out.dump", "rb").read() == gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
+    err = _run(base + ["-completeness"], str(tmp_path))
+    assert err.split("\n\n")[-1].startswith("TOTAL") or "TOTAL readK" in err
+    tail = [l for l in open(os.path.join(d, "ref.completeness")).read().splitlines() if not l.startswith("thread")]
+    for l in tail:
+        assert l in err
+    # without -seqmers the assembly k-mers are counted on the GPU (the reference shells out to meryl)
+    err = _run(base[:2] + base[4:] + ["-hist", "-output", "out2.hist"], str(tmp_path))
+    assert open(tmp_path / "out2.hist", "rb").read() == open(os.path.join(d, "ref.hist"), "rb").read()
+
+
+def test_cli_min_max_prob_skipmissing(golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "g1_k21")
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl")]
+    err = _run(base + ["-hist", "-peak", "1", "-min", "3", "-output", "a.hist"], str(tmp_path))
+    assert open(tmp_path / "a.hist", "rb").read() == open(os.path.join(d, "ref.min3.hist"), "rb").read()
+    assert _summary(err) == open(os.path.join(d, "ref.min3.hist.summary")).read()
+    err = _run(base + ["-hist", "-peak", "8", "-min", "2", "-max", "12", "-output", "b.hist"], str(tmp_path))
+    assert open(tmp_path / "b.hist", "rb").read() == open(os.path.join(d, "ref.min2max12.hist"), "rb").read()
+    err = _run(base + ["-hist", "-peak", "8", "-prob", os.path.join(d, "prob.csv"), "-output", "c.hist"], str(tmp_path))
+    assert open(tmp_path / "c.hist", "rb").read() == open(os.path.join(d, "ref.prob.hist"), "rb").read()
+    assert _summary(err) == open(os.path.join(d, "ref.prob.hist.summary")).read()
+    _run(base + ["-dump", "-peak", "8", "-skipMissing", "-output", "none.dump"], str(tmp_path))
+    assert not os.path.exists(tmp_path / "none.dump")          # Q9: -skipMissing writes no file at all
+
+
+@pytest.mark.parametrize("mode", ["polish", "filter", "better", "strict", "loose"])
+def test_cli_variant_modes(golden_dir, tmp_path, mode):
+    d = os.path.join(golden_dir, "g1_k21")
+    args = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", "8", "-vcf", os.path.join(d, "calls.vcf"),
+            "-" + mode, "-output", "out"]
+    if mode == "polish":
+        args.append("-debug")
+    _run(args, str(tmp_path))
+    produced = "out.polish.vcf" if mode == "polish" else "out.filter.vcf"      # Q7
+    assert open(tmp_path / produced).read() == open(os.path.join(d, f"ref.{mode}.vcf")).read()
+    if mode == "polish":
+        assert gzip.open(tmp_path / "out.00.debug.gz", "rt").read() == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
+
+
+def test_cli_usage_errors(tmp_path):
+    p = subprocess.run([MERFIN, "-hist"], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert "No input sequences (-sequence) supplied." in p.stderr and "No read meryl database (-readmers) supplied." in p.stderr

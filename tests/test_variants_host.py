@@ -1,0 +1,52 @@
+"""Host-side variant logic of the product (VCF parsing, clustering, path enumeration, score replay,
+selectors: merfin_b200/csrc/host/variants.cpp) against the reference's golden VCFs, with the CPU
+oracle standing in for the GPU probes (tests/variant_harness.cpp).  Runs without a GPU."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "build", "variant_harness")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    srcs = [os.path.join(ROOT, "tests", "variant_harness.cpp"),
+            os.path.join(ROOT, "merfin_b200", "csrc", "host", "variants.cpp"),
+            os.path.join(ROOT, "merfin_b200", "csrc", "host", "fasta.cpp"),
+            os.path.join(ROOT, "oracle", "mfn_oracle.c")]
+    so_dir = os.path.join(ROOT, "merfin_b200")
+    os.makedirs(os.path.dirname(HARNESS), exist_ok=True)
+    obj = os.path.join(ROOT, "build", "mfn_oracle_h.o")
+    subprocess.check_call(["gcc", "-O2", "-w", "-std=gnu11", "-c", srcs[3], "-o", obj])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-w", "-o", HARNESS, *srcs[:3], obj,
+                           "-L" + so_dir, "-lmerfin_b200", "-Wl,-rpath," + so_dir, "-lm"])
+    return HARNESS
+
+
+def _run(harness, d, mode, peak, *extra, cwd=None):
+    p = subprocess.run([harness, os.path.join(d, "asm.fa"), os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"),
+                        os.path.join(d, "calls.vcf"), mode, str(peak), *extra], capture_output=True, text=True, cwd=cwd)
+    assert p.returncode == 0, p.stderr
+    return p.stdout
+
+
+@pytest.mark.parametrize("mode", ["polish", "filter", "better", "strict", "loose"])
+def test_variant_modes_match_reference(harness, golden_dir, mode):
+    d = os.path.join(golden_dir, "g1_k21")
+    assert _run(harness, d, mode, 8) == open(os.path.join(d, f"ref.{mode}.vcf")).read()
+
+
+def test_polish_with_prob_table(harness, golden_dir):
+    d = os.path.join(golden_dir, "g1_k21")
+    assert _run(harness, d, "polish", 8, os.path.join(d, "prob.csv")) == open(os.path.join(d, "ref.probpolish.vcf")).read()
+
+
+def test_polish_debug_log_matches_reference(harness, golden_dir, tmp_path):
+    """Per-path numM, min/max/median/avg |k*| and the delta sum, for every candidate path."""
+    d = os.path.join(golden_dir, "g1_k21")
+    _run(harness, d, "polish", 8, "--debug", cwd=str(tmp_path))
+    got = open(tmp_path / "harness.debug").read()
+    assert got == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
