@@ -149,10 +149,10 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
     // range-partitioned scan: scatter each piece as soon as it is packed (overlaps the H2D of
     // the next piece), probe all bins once at the end
     if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
-    unsigned long long *zmap = nullptr; uint32_t zlen = 0;
-    MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &zlen));
+    unsigned long long *zmap = nullptr; uint32_t zlen = 0, zhi = 0;
+    MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &zlen, &zhi));
     mfn_sweep *w = nullptr;
-    int st = mfn_sweep_begin(ctx, reads, seq, (te - tb) * MFN_TILE, acc, zmap, zlen, &w);
+    int st = mfn_sweep_begin(ctx, reads, seq, (te - tb) * MFN_TILE, acc, zmap, zlen, zhi, &w);
     for (uint64_t p = 0; p < pieces && st == MFN_OK; p++) {
       uint64_t a = tb + (te - tb) * p / pieces, b = tb + (te - tb) * (p + 1) / pieces;
       st = mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128);

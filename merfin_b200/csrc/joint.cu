@@ -140,12 +140,26 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
   if (!(load > 0.05 && load < 0.99)) load = 0.70;
   for (int w64 = 0; w64 < 2; w64++) {
     const int slots = w64 ? 16 : 32;
-    J.nlines = std::max<uint64_t>(16, (uint64_t)std::ceil(n / (slots * load)));
+    // lines wanted for this load; the divisor actually used is the largest D' = d << t <= D with
+    // d in {3, 5, 9, 15} (steps of at most 1.25x), so the table is never fuller than asked
+    const uint64_t want_lines = std::max<uint64_t>(16, (uint64_t)std::ceil(n / (slots * load)));
     unsigned __int128 space = (unsigned __int128)1 << (2 * k);
-    unsigned __int128 D = (space + J.nlines - 1) / J.nlines;
-    if (D >> 64) D = ((unsigned __int128)1 << 64) - 1;
-    J.D = std::max<uint64_t>(1, (uint64_t)D);
-    J.magic = (J.D == 1) ? ~0ull : (uint64_t)((((unsigned __int128)1) << 64) / J.D);
+    unsigned __int128 D = space / want_lines;
+    if (D >> 63) D = ((unsigned __int128)1 << 63);
+    static const uint32_t FS[4][3] = {{3, 0xAAAAAAABu, 1}, {5, 0xCCCCCCCDu, 2}, {9, 0x38E38E39u, 1}, {15, 0x88888889u, 3}};
+    const uint32_t tmin = 2 * k > 32 ? 2 * k - 32 : 0;                    // h >> t must fit 32 bits
+    int bf = 0; uint32_t bt = tmin;
+    uint64_t best = 0;
+    for (int f = 0; f < 4; f++)
+      for (uint32_t t = tmin; t < 60; t++) {
+        const uint64_t cand = (uint64_t)FS[f][0] << t;
+        if ((unsigned __int128)cand > D) break;
+        if (cand > best) { best = cand; bf = f; bt = t; }
+      }
+    if (best == 0) best = (uint64_t)FS[0][0] << tmin;                     // more lines wanted than the geometry allows
+    J.fs_d = FS[bf][0]; J.fs_m = FS[bf][1]; J.fs_s = FS[bf][2]; J.fs_t = bt;
+    J.D = best;
+    J.nlines = (uint64_t)((space + J.D - 1) / J.D);
     const uint32_t T = std::max(1u, bits_of(J.D - 1));
     J.w64 = w64;
     if (!w64) {

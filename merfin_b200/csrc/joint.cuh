@@ -29,7 +29,10 @@ struct JointStats { unsigned long long n_home, n_spill, n_stash, n_big, errors; 
 
 struct JointDev {
   void    *lines;
-  uint64_t nlines, D, magic, seed, kmask;
+  uint64_t nlines, D, seed, kmask;
+  // D = fs_d << fs_t with fs_d in {3, 5, 9, 15}: h / D is a shift and an exact 32-bit
+  // multiply-high division by the small odd factor (fs_m, fs_s), no 64-bit divide in the probe path
+  uint32_t fs_t, fs_d, fs_m, fs_s;
   uint32_t k, w64;
   uint32_t rbits, abits;       // value field widths
   uint32_t rmax, amax;         // saturated field values (field masks)
@@ -37,8 +40,18 @@ struct JointDev {
   JointStats *stats;
 };
 
+// h -> (line, tag) with line = h / D, tag = h % D for D = d << t (h >> t always fits 32 bits)
+__device__ __forceinline__ void joint_split(uint64_t h, uint32_t t, uint32_t d, uint32_t m, uint32_t s,
+                                            uint64_t &line, uint64_t &tag) {
+  const uint32_t x = (uint32_t)(h >> t);
+  const uint32_t q = __umulhi(x, m) >> s;            // x / d, exact for every 32-bit x
+  const uint32_t rem = x - q * d;
+  line = q;
+  tag = ((uint64_t)rem << t) | (h & ((1ull << t) - 1ull));
+}
+
 __device__ __forceinline__ void joint_locate(const JointDev &J, uint64_t c, uint64_t &line, uint64_t &tag) {
-  mfn_split(mfn_mix(c, J.seed, J.kmask, J.k), J.D, J.magic, line, tag);
+  joint_split(mfn_mix(c, J.seed, J.kmask, J.k), J.fs_t, J.fs_d, J.fs_m, J.fs_s, line, tag);
 }
 
 __device__ __forceinline__ void joint_load_sector(const JointDev &J, uint64_t line, uint32_t sector, Bucket &b) {

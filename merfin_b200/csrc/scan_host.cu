@@ -66,14 +66,14 @@ static int launch_scan(mfn_ctx *ctx, ScanParams &P, bool dump, bool joint) {
 }
 
 // bitmap of read multiplicities whose readK is 0 under the -prob table (merfin-globals.C:93-97)
-int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen) {
-  *d_zmap = nullptr; *zlen = 0;
+int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen, uint32_t *zhi) {
+  *d_zmap = nullptr; *zlen = 0; *zhi = 0;
   if (!km || km->nprob == 0) return MFN_OK;
   uint32_t n = km->nprob + 1;                    // values 0 .. nprob
   std::vector<unsigned long long> bits((n + 63) / 64, 0);
   bits[0] |= 1;                                  // v == 0
   for (uint32_t v = 1; v <= km->nprob; v++)
-    if (km->probK[v - 1] == 0) bits[v >> 6] |= 1ull << (v & 63);
+    if (km->probK[v - 1] == 0) { bits[v >> 6] |= 1ull << (v & 63); *zhi = v; }
   MFN_CUDA(cudaMallocAsync(d_zmap, bits.size() * 8, ctx->stream));
   MFN_CUDA(cudaMemcpyAsync(*d_zmap, bits.data(), bits.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   MFN_CUDA(cudaStreamSynchronize(ctx->stream));  // 'bits' is a local
@@ -93,11 +93,12 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   P.tile_begin = tile_begin; P.tile_end = std::min(tile_end, seq->ntiles);
   P.acc = acc->d_buf; P.sparse = acc->sparse;
   unsigned long long *zmap = nullptr;
-  MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &P.zlen));
+  uint32_t zhi = 0;
+  MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &P.zlen, &zhi));
   P.zmap = zmap;
   int st;
   if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0))
-    st = mfn_sweep_hist(ctx, reads, asm_, seq, km, P.tile_begin, P.tile_end, acc, zmap, P.zlen);
+    st = mfn_sweep_hist(ctx, reads, asm_, seq, km, P.tile_begin, P.tile_end, acc, zmap, P.zlen, zhi);
   else
     st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));
   if (zmap) cudaFreeAsync(zmap, ctx->stream);

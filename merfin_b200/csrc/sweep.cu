@@ -41,7 +41,8 @@ struct mfn_sweep {
 };
 
 int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
-                    const unsigned long long *zmap, uint32_t zlen, mfn_sweep **out) {
+                    const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out) {
+  if (seq->nseq >= 0x7fffffffu) { mfn_set_error("sweep: too many records"); return MFN_ERR_UNSUPPORTED; }
   const JointDev &J = R->joint->dev;
   mfn_sweep *w = new mfn_sweep();
   SweepParams &P = w->P;
@@ -51,7 +52,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
   P.nbins_pad = (P.nbins + SW_THREADS - 1) / SW_THREADS * SW_THREADS;
   P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;
   P.over_cap = std::max<uint64_t>(1 << 20, windows / 16);
-  P.acc = acc->d_buf; P.sparse = acc->sparse; P.zmap = zmap; P.zlen = zlen;
+  P.acc = acc->d_buf; P.sparse = acc->sparse; P.zmap = zmap; P.zlen = zlen; P.zhi = zhi;
   // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
   const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64;            // bins, side-list count, pass counters
@@ -73,14 +74,23 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   if (w->n_scatter >= 60) { mfn_set_error("sweep: too many scatter passes"); return MFN_ERR_INVALID; }
   SweepParams P = w->P;
   P.tile_begin = tile_begin; P.tile_end = tile_end;
-  int per_sm = 0;
-  const size_t sc_smem = (2 * (size_t)SW_CHUNK + 3 * (size_t)SW_MAX_BINS) * 4;
-  MFN_CUDA(cudaFuncSetAttribute(k_sweep_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_scatter<0>, SW_THREADS, sc_smem);
+  const size_t sc_smem = (size_t)SW_CHUNK * 8 + (size_t)SW_MAX_BINS * 12;
   P.counter = w->counters + 2 + w->n_scatter++;
   const uint64_t nchunks = ceil_div_u64(tile_end - tile_begin, SW_CHUNK_TILES);
-  const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks);
-  k_sweep_scatter<0><<<grid, SW_THREADS, sc_smem, ctx->stream>>>(P);
+  // the mer size is a compile-time constant for the common k (shifts and masks fold away)
+  auto launch = [&](auto kernel) -> int {
+    int per_sm = 0;
+    MFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SW_THREADS, sc_smem);
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks);
+    kernel<<<grid, SW_THREADS, sc_smem, ctx->stream>>>(P);
+    return MFN_OK;
+  };
+  switch (P.J.k) {
+    case 21: MFN_TRY(launch(k_sweep_scatter<21>)); break;
+    case 31: MFN_TRY(launch(k_sweep_scatter<31>)); break;
+    default: MFN_TRY(launch(k_sweep_scatter<0>)); break;
+  }
   ctx->launches++;
   MFN_CUDA(cudaGetLastError());
   return MFN_OK;
@@ -88,10 +98,9 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
 
 int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
   SweepParams P = w->P;
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_probe<false>, SW_THREADS, 0);
   P.counter = w->counters;
-  k_sweep_probe<false><<<ctx->sm_count * std::max(per_sm, 1), SW_THREADS, 0, ctx->stream>>>(P);
+  if (P.J.w64) mfn_sweep_launch_probe64(P, ctx->sm_count, ctx->stream);
+  else mfn_sweep_launch_probe32(P, ctx->sm_count, ctx->stream);
   P.counter = w->counters + 1;
   mfn_sweep_launch_over(P, ctx->sm_count, ctx->stream);
   ctx->launches += 2;
@@ -107,11 +116,12 @@ int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
 }
 
 int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
-                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen) {
+                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen,
+                   uint32_t zhi) {
   (void)km; (void)A;
   if (tile_begin >= tile_end) return MFN_OK;
   mfn_sweep *w = nullptr;
-  MFN_TRY(mfn_sweep_begin(ctx, R, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, &w));
+  MFN_TRY(mfn_sweep_begin(ctx, R, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, zhi, &w));
   int st = mfn_sweep_scatter(ctx, w, tile_begin, tile_end);
   int st2 = mfn_sweep_finish(ctx, w);
   return st != MFN_OK ? st : st2;

@@ -18,15 +18,22 @@
 //
 // DRAM traffic per window: 8 B written + 8 B read + (table bytes / windows) instead of 128 B.
 // Integer results are identical to the direct scan (same lookups, sums are order-free).
+//
+// Entry (8 bytes):  bits 0..31   (line in bin) << tbits | tag
+//                   bits 32..62  record id
+//                   bit  63      the k-mer is its own reverse complement: counts twice (Q2)
 #pragma once
 #include "scan_kernel.cuh"
 
 #define SW_THREADS 256
 #define SW_CHUNK_TILES 4
 #define SW_CHUNK (SW_CHUNK_TILES * MFN_TILE)      // 8192 windows per CTA round
+#define SW_NW (SW_CHUNK_TILES * WPT)              // windows per thread per round
 #define SW_MAX_BINS 2048
-#define SW_SLICE 1024                              // entries per probe work item (one WARP: 32 per lane)
+#define SW_SLICE 4096                              // entries per probe work item (one WARP)
+#define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
 #define SW_NOSPACE 0xffffffffu
+#define SW_MAX_RD 126u                             // record delta inside one chunk that fits the staging word
 
 struct SweepParams {
   JointDev J;
@@ -34,12 +41,12 @@ struct SweepParams {
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
   uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low word = (line & L-1) << tbits | tag
-  unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b); entry = rec << 32 | low word
+  unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b)
   uint64_t cap;
   unsigned long long *bin_count;             // [nbins_pad] reserved entries (may exceed cap)
   unsigned long long *bin_valid;             // [nbins_pad] first reservation that did not fit (~0: none)
   unsigned long long *over_lt;               // windows that found no room in their bin: line << 32 | tag ...
-  uint32_t *over_rec;                        //   ... and record id
+  uint32_t *over_rec;                        //   ... and record id (bit 31: counts twice)
   unsigned long long *over_n;
   uint64_t over_cap;
   unsigned long long *counter;               // work distribution (one per pass)
@@ -47,43 +54,48 @@ struct SweepParams {
   PairTable sparse;
   const unsigned long long *zmap;
   uint32_t zlen;
+  uint32_t zhi;                              // largest multiplicity v >= 1 with readK(v) == 0 under -prob (0: none)
 };
 
 // ------------------------------------------------------------------------------------------
-// pass 1
+// pass 1.  KK: mer size known at compile time (0 = read it from the table)
 // ------------------------------------------------------------------------------------------
-template <int UNUSED>
+template <int KK>
 __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
-  uint32_t *s_low = (uint32_t *)sw_smem;                               // [SW_CHUNK]
-  uint32_t *s_meta = s_low + SW_CHUNK;                                 // [SW_CHUNK] bin | record delta << 12
-  uint32_t *s_cnt = s_meta + SW_CHUNK, *s_off = s_cnt + SW_MAX_BINS, *s_base = s_off + SW_MAX_BINS;
+  unsigned long long *s_ent = (unsigned long long *)sw_smem;           // [SW_CHUNK] entries sorted by bin
+  unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of sorted position 0 of the bin's run
+  uint32_t *s_off = (uint32_t *)(s_dst + SW_MAX_BINS);                 // [SW_MAX_BINS] counts, then exclusive offsets
   __shared__ uint32_t s_warp[SW_THREADS / 32];
   __shared__ unsigned long long s_chunk;
+  __shared__ uint32_t s_total;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t k = P.J.k;
-  const uint64_t kmask = P.J.kmask;
+  const uint32_t k = KK ? (uint32_t)KK : P.J.k;
+  const uint64_t kmask = KK ? (KK == 32 ? ~0ull : ((1ull << (2 * (KK & 31))) - 1ull)) : P.J.kmask;
   const uint64_t kbits = (1ull << k) - 1;
   const uint64_t cmask = 0xaaaaaaaaaaaaaaaaull & kmask;
+  const uint64_t need = (1ull << (WPT + k - 1)) - 1;                   // validity bits behind a thread's 8 windows
+  const bool even_k = (k & 1u) == 0;
   const uint32_t lmask = (1u << P.lbits) - 1u;
   const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, SW_CHUNK_TILES);
   const uint32_t per_thread_bins = P.nbins_pad / SW_THREADS;
+  unsigned long long *const rec_acc = P.acc + MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A;
 
   unsigned long long my_valid = 0;
   uint32_t cur_rec = 0xffffffffu, n_ok0 = 0;
   auto flush_rec = [&]() {
     uint32_t a = n_ok0;
     for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if ((tid & 31) == 0 && cur_rec < P.nseq && a)
-      atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * cur_rec], (unsigned long long)a);
+    if ((tid & 31) == 0 && cur_rec < P.nseq && a) atomicAdd(&rec_acc[2 * cur_rec], (unsigned long long)a);
+    my_valid += n_ok0;
     n_ok0 = 0;
   };
 
   while (true) {
     __syncthreads();
     if (tid == 0) s_chunk = atomicAdd(P.counter, 1ull);
-    for (uint32_t i = tid; i < P.nbins_pad; i += SW_THREADS) s_cnt[i] = 0;
+    for (uint32_t i = tid; i < P.nbins_pad; i += SW_THREADS) s_off[i] = 0;
     __syncthreads();
     const uint64_t chunk = s_chunk;
     if (chunk >= nchunks) break;
@@ -102,7 +114,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
     const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
     // ---- hash this thread's 32 windows; rank them inside their bins ------------------------
-    uint32_t low[SW_CHUNK_TILES * WPT], meta[SW_CHUNK_TILES * WPT];     // meta: bin | rank << 12 | rdelta << 25
+    // meta: bin (0..10) | rank in bin (11..23) | record delta (24..30) | counts twice (31)
+    uint32_t low[SW_NW], meta[SW_NW];
 #pragma unroll
     for (int q = 0; q < SW_CHUNK_TILES; q++) {
       const uint64_t tile = tile0 + q;
@@ -117,46 +130,61 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
         const uint64_t c = __ldg(&P.ok[wo]), d = __ldg(&P.ok[wo + 1]);
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
+      const bool allok = (okb & need) == need;
+      // forward k-mer (first base most significant, kmers-tiny.H:82): bit-reversal for the first
+      // window, then one base shifted in per window; the stream-order slice x gives the reverse
+      // complement for free (x ^ cmask)
+      uint64_t F = mfn_rev2(lo & kmask) >> (64 - 2 * k);
       uint32_t rec = r0;
       uint64_t next_start = r0_end;
 #pragma unroll
       for (int u = 0; u < WPT; u++) {
         const int idx = q * WPT + u;
+        uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
+        x &= kmask;                                             // base g in the low 2 bits
+        if (u) F = ((F << 2) | (x >> (2 * k - 2))) & kmask;
         meta[idx] = 0xffffffffu;
         low[idx] = 0;
-        if (((okb >> u) & kbits) != kbits) continue;
-        uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
-        x &= kmask;                                             // base g in the low 2 bits: reversed f
-        const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
+        if (!(allok || ((okb >> u) & kbits) == kbits)) continue;
+        const uint64_t r = x ^ cmask;
+        const uint32_t twice = (even_k && F == r) ? 0x80000000u : 0u;
         uint64_t line, tag;
-        joint_locate(P.J, f < r ? f : r, line, tag);
+        joint_split(mfn_mix(F < r ? F : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
         uint32_t rd = 0;
         if (!one_record) {
           const uint64_t g = g0 + u;
           while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
           rd = rec - r0;
         }
-        my_valid++;
         if (rd == 0) n_ok0++;
-        else atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec], 1ull);
-        if (rd > 126) {                                   // a chunk spanning > 126 records: side list
+        else { atomicAdd(&rec_acc[2 * rec], 1ull); my_valid++; }
+        if (rd > SW_MAX_RD) {                             // a chunk spanning > 126 records: side list
           unsigned long long o = atomicAdd(P.over_n, 1ull);
-          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec; } else atomicAdd(&P.acc[2], 1ull);
+          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec | twice; } else atomicAdd(&P.acc[2], 1ull);
           continue;
         }
-        const uint32_t bin = (uint32_t)(line >> P.lbits);
-        const uint32_t rank = atomicAdd(&s_cnt[bin], 1u);
+        const uint32_t bin = (uint32_t)line >> P.lbits;
+        const uint32_t rank = atomicAdd(&s_off[bin], 1u);
         low[idx] = (((uint32_t)line & lmask) << P.tbits) | (uint32_t)tag;
-        meta[idx] = bin | (rank << 12) | (rd << 25);
+        meta[idx] = bin | (rank << 11) | (rd << 24) | twice;
       }
     }
     __syncthreads();
 
     // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
     {
+      uint32_t cnt[SW_MAX_BINS / SW_THREADS];
       uint32_t sum = 0;
       const uint32_t b0 = tid * per_thread_bins;
-      for (uint32_t i = 0; i < per_thread_bins; i++) sum += s_cnt[b0 + i];
+#pragma unroll
+      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) { cnt[i] = i < per_thread_bins ? s_off[b0 + i] : 0; sum += cnt[i]; }
+      // all atomics of this thread in flight together
+      unsigned long long got[SW_MAX_BINS / SW_THREADS];
+#pragma unroll
+      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
+        got[i] = 0;
+        if (cnt[i]) got[i] = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)cnt[i]);
+      }
       uint32_t incl = sum;
       for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
       if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
@@ -164,55 +192,43 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
       uint32_t wbase = 0;
       for (uint32_t w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
       uint32_t run = wbase + incl - sum;
-      // reserve space in the global bins: all atomics of this thread in flight together
-      unsigned long long got[SW_MAX_BINS / SW_THREADS];
-#pragma unroll
-      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
-        got[i] = 0;
-        if (i < per_thread_bins) {
-          const uint32_t c = s_cnt[b0 + i];
-          if (c) got[i] = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)c);
-        }
-      }
 #pragma unroll
       for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
         if (i < per_thread_bins) {
-          const uint32_t c = s_cnt[b0 + i];
           s_off[b0 + i] = run;
-          run += c;
-          uint32_t base = (uint32_t)got[i];
-          if (c && got[i] + c > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); base = SW_NOSPACE; }
-          s_base[b0 + i] = base;
+          unsigned long long dst = (unsigned long long)(b0 + i) * P.cap + got[i] - run;
+          if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst = ~0ull; }
+          s_dst[b0 + i] = dst;
+          run += cnt[i];
         }
       }
+      if (tid == SW_THREADS - 1) s_total = run;
     }
     __syncthreads();
 
     // ---- counting sort into shared memory --------------------------------------------------
 #pragma unroll
-    for (int idx = 0; idx < SW_CHUNK_TILES * WPT; idx++) {
+    for (int idx = 0; idx < SW_NW; idx++) {
       const uint32_t m = meta[idx];
       if (m == 0xffffffffu) continue;
-      const uint32_t bin = m & 0xfffu, rank = (m >> 12) & 0x1fffu, rd = m >> 25;
-      const uint32_t p = s_off[bin] + rank;
-      s_low[p] = low[idx];
-      s_meta[p] = bin | (rd << 12);
+      const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & 0x1fffu);
+      s_ent[p] = ((unsigned long long)(m & 0xff0007ffu) << 32) | low[idx];
     }
     __syncthreads();
 
     // ---- coalesced copy-out: consecutive threads write consecutive entries of a bin's run --
     {
-      const uint32_t last = P.nbins_pad - 1;
-      const uint32_t total = s_off[last] + s_cnt[last];
+      const uint32_t total = s_total;
       for (uint32_t i = tid; i < total; i += SW_THREADS) {
-        const uint32_t m = s_meta[i];
-        const uint32_t bin = m & 0xfffu, rec = r0 + (m >> 12);
-        const uint32_t base = s_base[bin];
-        if (base != SW_NOSPACE) {
-          P.entries[(uint64_t)bin * P.cap + base + (i - s_off[bin])] = ((unsigned long long)rec << 32) | s_low[i];
+        const unsigned long long e = s_ent[i];
+        const uint32_t hs = (uint32_t)(e >> 32), lw = (uint32_t)e;
+        const uint32_t bin = hs & 0x7ffu;
+        const uint32_t rec = (r0 + ((hs >> 24) & 0x7fu)) | (hs & 0x80000000u);
+        const unsigned long long dst = s_dst[bin];
+        if (dst != ~0ull) {
+          P.entries[dst + i] = ((unsigned long long)rec << 32) | lw;
         } else {
           unsigned long long o = atomicAdd(P.over_n, 1ull);
-          const uint32_t lw = s_low[i];
           if (o < P.over_cap) {
             P.over_lt[o] = ((((uint64_t)bin << P.lbits) | (lw >> P.tbits)) << 32) | (lw & ((1u << P.tbits) - 1u));
             P.over_rec[o] = rec;
@@ -227,52 +243,58 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
-// pass 2 (and the overflow list: OVER = true probes (line, tag) pairs from the side list)
+// pass 2
 // ------------------------------------------------------------------------------------------
-template <bool OVER>
+
+// Everything the home sector alone does not settle (spilled or absent k-mer, saturated value,
+// v_read == 0, pair outside the shared-memory tier, k-mer that counts twice): complete lookup and
+// the general accumulation, as in k_scan.
+__device__ __forceinline__ void sweep_slow(const SweepParams &P, uint32_t *s_hist, uint32_t line, uint32_t tag,
+                                           uint32_t rec_flag) {
+  uint32_t vr, va;                                       // side tables are keyed by k-mer
+  joint_full(P.J, mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k), line, tag, vr, va);
+  if (rec_flag & 0x80000000u) { vr += vr; va += va; }    // value(f) + value(r), f == r (Q2)
+  const uint32_t rec = rec_flag & 0x7fffffffu;
+  bool miss = (vr == 0);
+  if (vr != 0 && vr < P.zlen) miss = (__ldg(&P.zmap[vr >> 6]) >> (vr & 63)) & 1;
+  if (miss) atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec + 1], 1ull);
+  if (vr < SH_R && va < SH_A) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+  else if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
+  else sparse_add(P.sparse, P.acc, vr, va, 1ull);
+}
+
+// 32-byte home sector -> slot payload (both value fields), or ~0 when the tag is not in it.
+// A stored slot is  tag << vb | values  with values != 0, so  slot - (tag << vb) - 1 < 2^vb - 1
+// exactly for the matching slot; the minimum over the 8 slots finds it (VIADDMNMX / VIMNMX3).
+__device__ __forceinline__ uint32_t sweep_match32(const Bucket &b, uint32_t nwant, uint32_t lim) {
+  const uint32_t m0 = min(b.w[0] + nwant, b.w[1] + nwant), m1 = min(b.w[2] + nwant, b.w[3] + nwant);
+  const uint32_t m2 = min(b.w[4] + nwant, b.w[5] + nwant), m3 = min(b.w[6] + nwant, b.w[7] + nwant);
+  const uint32_t m = min(min(m0, m1), min(m2, m3));
+  return m < lim ? m + 1u : 0xffffffffu;
+}
+
+template <bool W64>
 __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_constant__ SweepParams P) {
   __shared__ uint32_t s_hist[SH_R * SH_A];
-  const uint32_t tid = threadIdx.x;
+  __shared__ unsigned long long s_q[SW_THREADS / 32][SW_QCAP];    // per-warp queue of slow lookups
+  __shared__ uint32_t s_qn[SW_THREADS / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) s_hist[i] = 0;
+  if (tid < SW_THREADS / 32) s_qn[tid] = 0;
   __syncthreads();
 
   const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
-  const uint64_t nitems = OVER ? ceil_div_u64(min(*P.over_n, (unsigned long long)P.over_cap), SW_SLICE)
-                               : (uint64_t)P.nbins * slices_per_bin;
-  const bool even_k = (P.J.k & 1u) == 0;
-  const uint32_t tmask = (1u << P.tbits) - 1u;
-
-  auto account = [&](uint32_t line, uint32_t tag, uint32_t rec, uint32_t vr, uint32_t va) {
-    if (even_k) {                                          // palindromes count twice (Q2)
-      const uint64_t c = mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k);
-      if (c == mfn_revcomp(c, P.J.k)) { vr += vr; va += va; }
-    }
-    bool miss = (vr == 0);
-    if (vr != 0 && vr < P.zlen) miss = (__ldg(&P.zmap[vr >> 6]) >> (vr & 63)) & 1;
-    if (miss) atomicAdd(&P.acc[MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A + 2 * rec + 1], 1ull);
-    if (vr < SH_R && va < SH_A) atomicAdd(&s_hist[va * SH_R + vr], 1u);
-    else if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
-    else sparse_add(P.sparse, P.acc, vr, va, 1ull);
-  };
-
-  // per-warp queue of lookups that need more than the home sector: (line, tag, record)
-  __shared__ uint32_t s_q[SW_THREADS / 32][3][64];
-  const uint32_t lane = tid & 31, wid = tid >> 5;
-  uint32_t qn = 0;                                           // warp-uniform
-  auto drain = [&](bool all) {
-    while (qn >= 32 || (all && qn > 0)) {
-      const uint32_t take = qn < 32 ? qn : 32;
-      if (lane < take) {
-        const uint32_t i = qn - take + lane;
-        const uint32_t l = s_q[wid][0][i], t = s_q[wid][1][i], rec = s_q[wid][2][i];
-        uint32_t r2, a2;                                     // side tables are keyed by k-mer
-        joint_full(P.J, mfn_unmix((uint64_t)l * P.J.D + t, P.J.seed, P.J.kmask, P.J.k), l, t, r2, a2);
-        account(l, t, rec, r2, a2);
-      }
-      qn -= take;
-      __syncwarp();
-    }
-  };
+  const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
+  const uint32_t tbits = P.tbits, tmask = (1u << tbits) - 1u;
+  const uint32_t vb = P.J.rbits + P.J.abits, abits = P.J.abits, amax = P.J.amax;
+  const uint32_t lim = (1u << (vb & 31)) - 1u;                        // 32-bit slots: vb <= 31
+  const uint32_t wmask = tmask << (vb & 31);
+  // pairs the fast path takes: rlo <= v_read < min(rmax, SH_R), v_asm < min(amax, SH_A); everything
+  // else (v_read == 0 or zeroed by -prob, saturated fields, big values) goes to the queue
+  const uint32_t rlo = P.zhi + 1u;
+  const uint32_t rhi = min(P.J.rmax, SH_R), rspan = rhi > rlo ? rhi - rlo : 0u;
+  const uint32_t alim = min(amax, SH_A);
+  unsigned long long *const q = s_q[wid];
 
   // work items are handed out per WARP (no CTA barrier in the loop)
   while (true) {
@@ -280,75 +302,91 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
     if (lane == 0) item = atomicAdd(P.counter, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) break;
-    uint64_t n, first;                 // entries [first, first + n) of this item
-    const unsigned long long *src;
-    uint32_t line0 = 0;
-    if (OVER) {
-      const uint64_t tot = min(*P.over_n, (unsigned long long)P.over_cap);
-      first = item * SW_SLICE; n = min((uint64_t)SW_SLICE, tot - first); src = P.over_lt;
-    } else {
-      const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
-      const uint64_t cnt = min(min(P.bin_count[bin], P.bin_valid[bin]), (unsigned long long)P.cap);
-      if (s * SW_SLICE >= cnt) continue;
-      first = bin * P.cap + s * SW_SLICE; n = min((uint64_t)SW_SLICE, cnt - s * SW_SLICE); src = P.entries;
-      line0 = (uint32_t)bin << P.lbits;
-    }
-    // each thread: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
-    const uint32_t nbatch = (uint32_t)ceil_div_u64(n, 32 * 4);             // uniform: every lane of the warp
+    const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
+    const uint64_t cnt = min(min(P.bin_count[bin], P.bin_valid[bin]), (unsigned long long)P.cap);
+    if (s * SW_SLICE >= cnt) continue;
+    const unsigned long long *src = P.entries + bin * P.cap + s * SW_SLICE;
+    const uint32_t n = (uint32_t)min((uint64_t)SW_SLICE, cnt - s * SW_SLICE);
+    const uint32_t line0 = (uint32_t)bin << P.lbits;
+    const char *slice = (const char *)P.J.lines + (uint64_t)line0 * 128;
+
+    // each lane: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
+    const uint32_t nbatch = (n + 127u) >> 7;                                // uniform
     auto load_entries = [&](uint32_t bt, unsigned long long (&e)[4]) {
-      const uint64_t i0 = (uint64_t)bt * 32 * 4 + lane * 4;
+      const uint32_t i0 = bt * 128u + lane * 4u;
       if (i0 + 4 <= n) {
         // streamed once: keep it from evicting the table slice
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + first + i0));
+                     : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + i0));
       } else {
 #pragma unroll
-        for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[first + i0 + u] : 0;
+        for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[i0 + u] : ~0ull;      // ~0: no entry
       }
     };
     unsigned long long enext[4];
     load_entries(0, enext);
-#pragma unroll 1                                                           // (every lane takes part in the warp votes below)
+#pragma unroll 1
     for (uint32_t bt = 0; bt < nbatch; bt++) {
-      const uint64_t i0 = (uint64_t)bt * 32 * 4 + lane * 4;
       unsigned long long e[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) e[u] = enext[u];
       if (bt + 1 < nbatch) load_entries(bt + 1, enext);        // in flight while this batch probes
-      uint32_t ln[4], tg[4], rc[4];
-      bool val[4];
       Bucket b[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        val[u] = i0 + u < n;
-        if (OVER) { ln[u] = (uint32_t)(e[u] >> 32); tg[u] = (uint32_t)e[u]; rc[u] = val[u] ? P.over_rec[first + i0 + u] : 0; }
-        else {
-          const uint32_t lw = (uint32_t)e[u];
-          ln[u] = line0 + (lw >> P.tbits); tg[u] = lw & tmask; rc[u] = (uint32_t)(e[u] >> 32);
-        }
-        if (val[u]) joint_load_sector(P.J, ln[u], tg[u] & 3u, b[u]);
+        const uint32_t lw = (uint32_t)e[u];
+        const uint32_t sector = ((lw >> tbits) << 2) | (lw & 3u);
+        const char *p = slice + (uint64_t)sector * 32;
+        if (e[u] != ~0ull)
+          asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(b[u].w[0]), "=r"(b[u].w[1]), "=r"(b[u].w[2]), "=r"(b[u].w[3]),
+                         "=r"(b[u].w[4]), "=r"(b[u].w[5]), "=r"(b[u].w[6]), "=r"(b[u].w[7]) : "l"(p));
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        uint64_t pay = 0;
-        const bool hit = val[u] && joint_match_fast(P.J, b[u], tg[u], pay);
-        const uint32_t a1 = (uint32_t)pay & P.J.amax, r1 = (uint32_t)(pay >> P.J.abits) & P.J.rmax;
-        // the few lookups the home sector cannot answer are queued per warp and finished 32 at a
-        // time with every lane busy, instead of dragging the whole warp through the slow path
-        const bool slow = val[u] && (!hit || r1 == P.J.rmax || a1 == P.J.amax);
-        if (val[u] && !slow) account(ln[u], tg[u], rc[u], r1, a1);
-        const uint32_t m = __ballot_sync(0xffffffffu, slow);
-        if (slow) {
-          const uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
-          s_q[wid][0][pos] = ln[u]; s_q[wid][1][pos] = tg[u]; s_q[wid][2][pos] = rc[u];
+        if (e[u] == ~0ull) continue;
+        const uint32_t lw = (uint32_t)e[u], hw = (uint32_t)(e[u] >> 32);
+        bool fast = false;
+        uint32_t vr = 0, va = 0;
+        if (!W64) {
+          const uint32_t pay = sweep_match32(b[u], ~((lw << vb) & wmask), lim);
+          vr = pay >> abits; va = pay & amax;
+          fast = pay != 0xffffffffu && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
+        } else {
+          // 64-bit slots (4 per sector): same test on 64-bit words
+          const uint64_t nwant = ~((uint64_t)(lw & tmask) << vb), lim64 = (1ull << vb) - 1ull;
+          uint64_t pay = ~0ull;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint64_t d = (((uint64_t)b[u].w[2 * i + 1] << 32) | b[u].w[2 * i]) + nwant;
+            if (d < lim64) pay = d + 1ull;
+          }
+          const uint64_t r64 = pay >> abits;
+          vr = (uint32_t)r64; va = (uint32_t)pay & amax;
+          fast = pay != ~0ull && r64 < rhi && vr >= rlo && va < alim && (int32_t)hw >= 0;
         }
-        qn += __popc(m);
+        if (fast) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+        else q[atomicAdd(&s_qn[wid], 1u)] = e[u];
+      }
+      // the few lookups the home sector cannot settle are finished 32 at a time with every lane
+      // busy, instead of dragging the whole warp through the slow path once per entry
+      __syncwarp();
+      uint32_t qn = *(volatile uint32_t *)&s_qn[wid];
+      const uint32_t thr = (bt + 1 == nbatch) ? 1u : 32u;      // the queue is emptied before the bin changes
+      while (qn >= thr) {
+        const uint32_t take = min(qn, 32u);
+        if (lane < take) {
+          const unsigned long long x = q[qn - take + lane];
+          const uint32_t lw = (uint32_t)x;
+          sweep_slow(P, s_hist, line0 + (lw >> tbits), lw & tmask, (uint32_t)(x >> 32));
+        }
+        qn -= take;
         __syncwarp();
-        if (qn >= 32) drain(false);
+        if (lane == 0) s_qn[wid] = qn;
+        __syncwarp();
       }
     }
   }
-  drain(true);
   __syncthreads();
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {
     uint32_t c = s_hist[i];
@@ -356,6 +394,28 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
   }
 }
 
-// k_sweep_probe<true> lives in its own translation unit (sweep_over.cu): ptxas 12.9 crashes when
-// two entries that share an out-of-line device function are compiled in one module.
+// Windows that found no room in their bin (or whose chunk spanned too many records): probed
+// from the side list, one complete lookup each.  Normally empty.
+template <int UNUSED>
+__global__ void __launch_bounds__(SW_THREADS) k_sweep_over(const __grid_constant__ SweepParams P) {
+  __shared__ uint32_t s_hist[SH_R * SH_A];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const uint64_t n = min(*P.over_n, (unsigned long long)P.over_cap);
+  for (uint64_t i = blockIdx.x * (uint64_t)SW_THREADS + tid; i < n; i += (uint64_t)gridDim.x * SW_THREADS) {
+    const unsigned long long lt = P.over_lt[i];
+    sweep_slow(P, s_hist, (uint32_t)(lt >> 32), (uint32_t)lt, P.over_rec[i]);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {
+    uint32_t c = s_hist[i];
+    if (c) atomicAdd(&P.acc[MFN_ACC_HEADER + (i / SH_R) * MFN_DENSE_R + (i % SH_R)], (unsigned long long)c);
+  }
+}
+
+// One translation unit per probe entry (sweep_probe32.cu, sweep_probe64.cu, sweep_over.cu): ptxas
+// 12.9 crashes when two entries that share an out-of-line device function are compiled in one module.
+void mfn_sweep_launch_probe32(const SweepParams &P, int sm_count, cudaStream_t stream);
+void mfn_sweep_launch_probe64(const SweepParams &P, int sm_count, cudaStream_t stream);
 void mfn_sweep_launch_over(const SweepParams &P, int grid, cudaStream_t stream);

@@ -55,10 +55,11 @@ void mfn_joint_free(mfn_joint *j);
 // ---- range-partitioned -hist scan (sweep.cu) --------------------------------------------------
 bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles);
 int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
-                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen);
+                   uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen,
+                   uint32_t zhi);
 struct mfn_sweep;
 int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
-                    const unsigned long long *zmap, uint32_t zlen, mfn_sweep **out);
+                    const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out);
 int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end);
 int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w);
-int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen);
+int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen, uint32_t *zhi);
