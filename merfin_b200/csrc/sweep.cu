@@ -49,10 +49,15 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
   P.J = J;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
   if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins)) { delete w; mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
-  P.nbins_pad = (P.nbins + SW_THREADS - 1) / SW_THREADS * SW_THREADS;
+  P.nbins_pad = (P.nbins + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
   P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;
   P.over_cap = std::max<uint64_t>(1 << 20, windows / 16);
   P.acc = acc->d_buf; P.sparse = acc->sparse; P.zmap = zmap; P.zlen = zlen; P.zhi = zhi;
+  {
+    const uint32_t vb = (J.rbits + J.abits) & 31u;
+    P.pr_lim = (1u << vb) - 1u;
+    P.pr_wmask = ((1u << P.tbits) - 1u) << vb;
+  }
   // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
   const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64;            // bins, side-list count, pass counters
@@ -81,9 +86,9 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   auto launch = [&](auto kernel) -> int {
     int per_sm = 0;
     MFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SW_THREADS, sc_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SC_THREADS, sc_smem);
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks);
-    kernel<<<grid, SW_THREADS, sc_smem, ctx->stream>>>(P);
+    kernel<<<grid, SC_THREADS, sc_smem, ctx->stream>>>(P);
     return MFN_OK;
   };
   switch (P.J.k) {

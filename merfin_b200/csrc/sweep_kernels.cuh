@@ -28,9 +28,11 @@
 #define SW_THREADS 256
 #define SW_CHUNK_TILES 4
 #define SW_CHUNK (SW_CHUNK_TILES * MFN_TILE)      // 8192 windows per CTA round
-#define SW_NW (SW_CHUNK_TILES * WPT)              // windows per thread per round
+#define SC_THREADS 512                             // scatter CTA: two 2048-window tiles side by side, two rounds
+#define SC_TPT (SW_CHUNK / SC_THREADS / WPT)       // 8-window groups per thread per chunk
+#define SC_NW (SC_TPT * WPT)                       // windows per thread per chunk
 #define SW_MAX_BINS 2048
-#define SW_SLICE 4096                              // entries per probe work item (one WARP)
+#define SW_SLICE 1024                              // entries per probe work item (one WARP)
 #define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
 #define SW_NOSPACE 0xffffffffu
 #define SW_MAX_RD 126u                             // record delta inside one chunk that fits the staging word
@@ -55,22 +57,24 @@ struct SweepParams {
   const unsigned long long *zmap;
   uint32_t zlen;
   uint32_t zhi;                              // largest multiplicity v >= 1 with readK(v) == 0 under -prob (0: none)
+  uint32_t pr_lim, pr_wmask;                 // 32-bit slots: 2^vb - 1 and the tag field mask (vb = value bits)
 };
 
 // ------------------------------------------------------------------------------------------
 // pass 1.  KK: mer size known at compile time (0 = read it from the table)
 // ------------------------------------------------------------------------------------------
 template <int KK>
-__global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
   unsigned long long *s_ent = (unsigned long long *)sw_smem;           // [SW_CHUNK] entries sorted by bin
-  unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of sorted position 0 of the bin's run
+  unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of the chunk's sorted position 0, per bin
   uint32_t *s_off = (uint32_t *)(s_dst + SW_MAX_BINS);                 // [SW_MAX_BINS] counts, then exclusive offsets
-  __shared__ uint32_t s_warp[SW_THREADS / 32];
+  __shared__ uint32_t s_warp[SC_THREADS / 32];
   __shared__ unsigned long long s_chunk;
   __shared__ uint32_t s_total;
 
   const uint32_t tid = threadIdx.x;
+  const uint32_t grp = tid / (MFN_TILE / WPT), t8 = tid % (MFN_TILE / WPT);   // tile of the round, window group in it
   const uint32_t k = KK ? (uint32_t)KK : P.J.k;
   const uint64_t kmask = KK ? (KK == 32 ? ~0ull : ((1ull << (2 * (KK & 31))) - 1ull)) : P.J.kmask;
   const uint64_t kbits = (1ull << k) - 1;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
   const bool even_k = (k & 1u) == 0;
   const uint32_t lmask = (1u << P.lbits) - 1u;
   const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, SW_CHUNK_TILES);
-  const uint32_t per_thread_bins = P.nbins_pad / SW_THREADS;
+  const uint32_t per_thread_bins = P.nbins_pad / SC_THREADS;
   unsigned long long *const rec_acc = P.acc + MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A;
 
   unsigned long long my_valid = 0;
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
   while (true) {
     __syncthreads();
     if (tid == 0) s_chunk = atomicAdd(P.counter, 1ull);
-    for (uint32_t i = tid; i < P.nbins_pad; i += SW_THREADS) s_off[i] = 0;
+    for (uint32_t i = tid; i < P.nbins_pad; i += SC_THREADS) s_off[i] = 0;
     __syncthreads();
     const uint64_t chunk = s_chunk;
     if (chunk >= nchunks) break;
@@ -113,13 +117,13 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
     const uint64_t r0_end = (r0 < P.nseq) ? P.rec_start[r0 + 1] : ~0ull;
     const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
-    // ---- hash this thread's 32 windows; rank them inside their bins ------------------------
+    // ---- hash this thread's windows; rank them inside their bins ---------------------------
     // meta: bin (0..10) | rank in bin (11..23) | record delta (24..30) | counts twice (31)
-    uint32_t low[SW_NW], meta[SW_NW];
+    uint32_t low[SC_NW], meta[SC_NW];
 #pragma unroll
-    for (int q = 0; q < SW_CHUNK_TILES; q++) {
-      const uint64_t tile = tile0 + q;
-      const uint64_t g0 = tile * MFN_TILE + tid * WPT;
+    for (int q = 0; q < SC_TPT; q++) {
+      const uint64_t tile = tile0 + q * (SC_THREADS / (MFN_TILE / WPT)) + grp;
+      const uint64_t g0 = tile * MFN_TILE + t8 * WPT;
       uint64_t lo = 0, hi = 0, okb = 0;
       if (tile < P.tile_end) {
         const uint64_t w = g0 >> 5, sh = (g0 & 31) * 2;
@@ -130,13 +134,43 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
         const uint64_t c = __ldg(&P.ok[wo]), d = __ldg(&P.ok[wo + 1]);
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
-      const bool allok = (okb & need) == need;
+      // which of the 8 windows are valid (kmers-iterator.H:93-95): all of them almost always
+      uint32_t vmask = 0xffu;
+      if ((okb & need) != need) {
+        vmask = 0;
+#pragma unroll
+        for (int u = 0; u < WPT; u++) if (((okb >> u) & kbits) == kbits) vmask |= 1u << u;
+      }
+      // record of each window: the chunk's first record almost always (delta 0)
+      uint64_t rdpack = 0;                                       // 7 bits per window
+      if (one_record || vmask == 0) n_ok0 += __popc(vmask);
+      else {
+        uint32_t rec = r0;
+        uint64_t next_start = r0_end;
+        for (int u = 0; u < WPT; u++) {
+          if (!((vmask >> u) & 1u)) continue;
+          const uint64_t g = g0 + u;
+          while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
+          const uint32_t rd = rec - r0;
+          if (rd == 0) { n_ok0++; continue; }
+          atomicAdd(&rec_acc[2 * rec], 1ull);
+          my_valid++;
+          if (rd <= SW_MAX_RD) { rdpack |= (uint64_t)rd << (7 * u); continue; }
+          // a chunk spanning > 126 records: this window goes to the side list
+          vmask &= ~(1u << u);
+          const uint64_t x = (u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo) & kmask;
+          const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
+          uint64_t line, tag;
+          joint_split(mfn_mix(f < r ? f : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
+          unsigned long long o = atomicAdd(P.over_n, 1ull);
+          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec | ((even_k && f == r) ? 0x80000000u : 0u); }
+          else atomicAdd(&P.acc[2], 1ull);
+        }
+      }
       // forward k-mer (first base most significant, kmers-tiny.H:82): bit-reversal for the first
       // window, then one base shifted in per window; the stream-order slice x gives the reverse
       // complement for free (x ^ cmask)
       uint64_t F = mfn_rev2(lo & kmask) >> (64 - 2 * k);
-      uint32_t rec = r0;
-      uint64_t next_start = r0_end;
 #pragma unroll
       for (int u = 0; u < WPT; u++) {
         const int idx = q * WPT + u;
@@ -144,44 +178,31 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
         x &= kmask;                                             // base g in the low 2 bits
         if (u) F = ((F << 2) | (x >> (2 * k - 2))) & kmask;
         meta[idx] = 0xffffffffu;
-        low[idx] = 0;
-        if (!(allok || ((okb >> u) & kbits) == kbits)) continue;
+        if (!((vmask >> u) & 1u)) continue;
         const uint64_t r = x ^ cmask;
         const uint32_t twice = (even_k && F == r) ? 0x80000000u : 0u;
         uint64_t line, tag;
         joint_split(mfn_mix(F < r ? F : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
-        uint32_t rd = 0;
-        if (!one_record) {
-          const uint64_t g = g0 + u;
-          while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
-          rd = rec - r0;
-        }
-        if (rd == 0) n_ok0++;
-        else { atomicAdd(&rec_acc[2 * rec], 1ull); my_valid++; }
-        if (rd > SW_MAX_RD) {                             // a chunk spanning > 126 records: side list
-          unsigned long long o = atomicAdd(P.over_n, 1ull);
-          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec | twice; } else atomicAdd(&P.acc[2], 1ull);
-          continue;
-        }
         const uint32_t bin = (uint32_t)line >> P.lbits;
         const uint32_t rank = atomicAdd(&s_off[bin], 1u);
         low[idx] = (((uint32_t)line & lmask) << P.tbits) | (uint32_t)tag;
-        meta[idx] = bin | (rank << 11) | (rd << 24) | twice;
+        meta[idx] = bin | (rank << 11) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << 24) | twice;
       }
     }
     __syncthreads();
 
     // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
     {
-      uint32_t cnt[SW_MAX_BINS / SW_THREADS];
+      constexpr uint32_t BPT = SW_MAX_BINS / SC_THREADS;
+      uint32_t cnt[BPT];
       uint32_t sum = 0;
       const uint32_t b0 = tid * per_thread_bins;
 #pragma unroll
-      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) { cnt[i] = i < per_thread_bins ? s_off[b0 + i] : 0; sum += cnt[i]; }
+      for (uint32_t i = 0; i < BPT; i++) { cnt[i] = i < per_thread_bins ? s_off[b0 + i] : 0; sum += cnt[i]; }
       // all atomics of this thread in flight together
-      unsigned long long got[SW_MAX_BINS / SW_THREADS];
+      unsigned long long got[BPT];
 #pragma unroll
-      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
+      for (uint32_t i = 0; i < BPT; i++) {
         got[i] = 0;
         if (cnt[i]) got[i] = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)cnt[i]);
       }
@@ -193,22 +214,23 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
       for (uint32_t w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
       uint32_t run = wbase + incl - sum;
 #pragma unroll
-      for (uint32_t i = 0; i < SW_MAX_BINS / SW_THREADS; i++) {
+      for (uint32_t i = 0; i < BPT; i++) {
         if (i < per_thread_bins) {
           s_off[b0 + i] = run;
-          unsigned long long dst = (unsigned long long)(b0 + i) * P.cap + got[i] - run;
-          if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst = ~0ull; }
+          // bit 63: the run does not fit its bin (its windows go to the side list)
+          unsigned long long dst = ((unsigned long long)(b0 + i) * P.cap + got[i] - run) & 0x7fffffffffffffffull;
+          if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst |= 1ull << 63; }
           s_dst[b0 + i] = dst;
           run += cnt[i];
         }
       }
-      if (tid == SW_THREADS - 1) s_total = run;
+      if (tid == SC_THREADS - 1) s_total = run;
     }
     __syncthreads();
 
     // ---- counting sort into shared memory --------------------------------------------------
 #pragma unroll
-    for (int idx = 0; idx < SW_NW; idx++) {
+    for (int idx = 0; idx < SC_NW; idx++) {
       const uint32_t m = meta[idx];
       if (m == 0xffffffffu) continue;
       const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & 0x1fffu);
@@ -219,14 +241,15 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_scatter(const __grid_co
     // ---- coalesced copy-out: consecutive threads write consecutive entries of a bin's run --
     {
       const uint32_t total = s_total;
-      for (uint32_t i = tid; i < total; i += SW_THREADS) {
+#pragma unroll 4
+      for (uint32_t i = tid; i < total; i += SC_THREADS) {
         const unsigned long long e = s_ent[i];
         const uint32_t hs = (uint32_t)(e >> 32), lw = (uint32_t)e;
         const uint32_t bin = hs & 0x7ffu;
         const uint32_t rec = (r0 + ((hs >> 24) & 0x7fu)) | (hs & 0x80000000u);
         const unsigned long long dst = s_dst[bin];
-        if (dst != ~0ull) {
-          P.entries[dst + i] = ((unsigned long long)rec << 32) | lw;
+        if ((long long)dst >= 0) {
+          P.entries[(dst + i) & 0x7fffffffffffffffull] = ((unsigned long long)rec << 32) | lw;
         } else {
           unsigned long long o = atomicAdd(P.over_n, 1ull);
           if (o < P.over_cap) {
@@ -287,14 +310,39 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
   const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
   const uint32_t tbits = P.tbits, tmask = (1u << tbits) - 1u;
   const uint32_t vb = P.J.rbits + P.J.abits, abits = P.J.abits, amax = P.J.amax;
-  const uint32_t lim = (1u << (vb & 31)) - 1u;                        // 32-bit slots: vb <= 31
-  const uint32_t wmask = tmask << (vb & 31);
   // pairs the fast path takes: rlo <= v_read < min(rmax, SH_R), v_asm < min(amax, SH_A); everything
   // else (v_read == 0 or zeroed by -prob, saturated fields, big values) goes to the queue
   const uint32_t rlo = P.zhi + 1u;
   const uint32_t rhi = min(P.J.rmax, SH_R), rspan = rhi > rlo ? rhi - rlo : 0u;
   const uint32_t alim = min(amax, SH_A);
   unsigned long long *const q = s_q[wid];
+  uint32_t *const qn_p = &s_qn[wid];
+
+  // one entry whose home sector is in registers
+  auto settle = [&](unsigned long long e, const Bucket &b) {
+    const uint32_t lw = (uint32_t)e, hw = (uint32_t)(e >> 32);
+    bool fast;
+    uint32_t vr, va;
+    if (!W64) {
+      const uint32_t pay = sweep_match32(b, ~((lw << vb) & P.pr_wmask), P.pr_lim);
+      vr = pay >> abits; va = pay & amax;
+      fast = pay != 0xffffffffu && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
+    } else {
+      // 64-bit slots (4 per sector): same test on 64-bit words
+      const uint64_t nwant = ~((uint64_t)(lw & tmask) << vb), lim64 = (1ull << vb) - 1ull;
+      uint64_t pay = ~0ull;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint64_t d = (((uint64_t)b.w[2 * i + 1] << 32) | b.w[2 * i]) + nwant;
+        if (d < lim64) pay = d + 1ull;
+      }
+      const uint64_t r64 = pay >> abits;
+      vr = (uint32_t)r64; va = (uint32_t)pay & amax;
+      fast = pay != ~0ull && r64 < rhi && vr >= rlo && va < alim && (int32_t)hw >= 0;
+    }
+    if (fast) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+    else q[atomicAdd(qn_p, 1u)] = e;
+  };
 
   // work items are handed out per WARP (no CTA barrier in the loop)
   while (true) {
@@ -310,69 +358,23 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
     const uint32_t line0 = (uint32_t)bin << P.lbits;
     const char *slice = (const char *)P.J.lines + (uint64_t)line0 * 128;
 
-    // each lane: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced)
-    const uint32_t nbatch = (n + 127u) >> 7;                                // uniform
+    // each lane: batches of 4 consecutive entries (32 B per lane, 1 KB per warp, coalesced);
+    // full batches first, then one partial batch
+    const uint32_t nfull = n >> 7;                                          // uniform
     auto load_entries = [&](uint32_t bt, unsigned long long (&e)[4]) {
-      const uint32_t i0 = bt * 128u + lane * 4u;
-      if (i0 + 4 <= n) {
-        // streamed once: keep it from evicting the table slice
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + i0));
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; u++) e[u] = (i0 + u < n) ? src[i0 + u] : ~0ull;      // ~0: no entry
-      }
+      // streamed once: keep it from evicting the table slice
+      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
+                   : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + bt * 128u + lane * 4u));
     };
-    unsigned long long enext[4];
-    load_entries(0, enext);
-#pragma unroll 1
-    for (uint32_t bt = 0; bt < nbatch; bt++) {
-      unsigned long long e[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) e[u] = enext[u];
-      if (bt + 1 < nbatch) load_entries(bt + 1, enext);        // in flight while this batch probes
-      Bucket b[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t lw = (uint32_t)e[u];
-        const uint32_t sector = ((lw >> tbits) << 2) | (lw & 3u);
-        const char *p = slice + (uint64_t)sector * 32;
-        if (e[u] != ~0ull)
-          asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(b[u].w[0]), "=r"(b[u].w[1]), "=r"(b[u].w[2]), "=r"(b[u].w[3]),
-                         "=r"(b[u].w[4]), "=r"(b[u].w[5]), "=r"(b[u].w[6]), "=r"(b[u].w[7]) : "l"(p));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (e[u] == ~0ull) continue;
-        const uint32_t lw = (uint32_t)e[u], hw = (uint32_t)(e[u] >> 32);
-        bool fast = false;
-        uint32_t vr = 0, va = 0;
-        if (!W64) {
-          const uint32_t pay = sweep_match32(b[u], ~((lw << vb) & wmask), lim);
-          vr = pay >> abits; va = pay & amax;
-          fast = pay != 0xffffffffu && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
-        } else {
-          // 64-bit slots (4 per sector): same test on 64-bit words
-          const uint64_t nwant = ~((uint64_t)(lw & tmask) << vb), lim64 = (1ull << vb) - 1ull;
-          uint64_t pay = ~0ull;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const uint64_t d = (((uint64_t)b[u].w[2 * i + 1] << 32) | b[u].w[2 * i]) + nwant;
-            if (d < lim64) pay = d + 1ull;
-          }
-          const uint64_t r64 = pay >> abits;
-          vr = (uint32_t)r64; va = (uint32_t)pay & amax;
-          fast = pay != ~0ull && r64 < rhi && vr >= rlo && va < alim && (int32_t)hw >= 0;
-        }
-        if (fast) atomicAdd(&s_hist[va * SH_R + vr], 1u);
-        else q[atomicAdd(&s_qn[wid], 1u)] = e[u];
-      }
-      // the few lookups the home sector cannot settle are finished 32 at a time with every lane
-      // busy, instead of dragging the whole warp through the slow path once per entry
+    auto sector_of = [&](unsigned long long e) {
+      const uint32_t lw = (uint32_t)e;
+      return slice + (uint64_t)(((lw >> tbits) << 2) | (lw & 3u)) * 32;
+    };
+    // the few lookups the home sector cannot settle are finished 32 at a time with every lane
+    // busy, instead of dragging the whole warp through the slow path once per entry
+    auto drain = [&](uint32_t thr) {
       __syncwarp();
-      uint32_t qn = *(volatile uint32_t *)&s_qn[wid];
-      const uint32_t thr = (bt + 1 == nbatch) ? 1u : 32u;      // the queue is emptied before the bin changes
+      uint32_t qn = *(volatile uint32_t *)qn_p;
       while (qn >= thr) {
         const uint32_t take = min(qn, 32u);
         if (lane < take) {
@@ -382,10 +384,33 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
         }
         qn -= take;
         __syncwarp();
-        if (lane == 0) s_qn[wid] = qn;
+        if (lane == 0) *qn_p = qn;
         __syncwarp();
       }
+    };
+    unsigned long long enext[4];
+    if (nfull) load_entries(0, enext);
+#pragma unroll 1
+    for (uint32_t bt = 0; bt < nfull; bt++) {
+      unsigned long long e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) e[u] = enext[u];
+      if (bt + 1 < nfull) load_entries(bt + 1, enext);         // in flight while this batch probes
+      Bucket b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) mfn_load_bucket(sector_of(e[u]), 0, b[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) settle(e[u], b[u]);
+      drain(32u);
     }
+    // the tail: < 128 entries, one per lane per round
+    for (uint32_t i = (nfull << 7) + lane; i < n; i += 32) {
+      const unsigned long long e = src[i];
+      Bucket b;
+      mfn_load_bucket(sector_of(e), 0, b);
+      settle(e, b);
+    }
+    drain(1u);                                                 // the queue is emptied before the bin changes
   }
   __syncthreads();
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {
