@@ -58,6 +58,7 @@ extern "C" int mfn_ctx_create(mfn_ctx **out, int device) {
   c->sm_count = prop.multiProcessorCount;
   MFN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   MFN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  MFN_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) MFN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   c->stream = c->own_stream;
   // keep stream-ordered workspace (cudaMallocAsync) cached between calls
@@ -76,11 +77,12 @@ extern "C" void mfn_ctx_destroy(mfn_ctx *c) {
   cudaDeviceSynchronize();
   mfn_seq_free(c->scratch_seq);
   mfn_accum_free(c->scratch_acc);
-  for (int i = 0; i < 2; i++) cudaFree(c->d_ascii[i]);
+  for (int i = 0; i < MFN_STAGE_BUFS; i++) cudaFree(c->d_ascii[i]);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
+  cudaStreamDestroy(c->pack_stream);
   delete c;
 }
 
@@ -120,9 +122,12 @@ static int scratch_seq(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn
   bool reuse = s && s->nseq == nseq;
   for (uint32_t i = 0; reuse && i <= nseq; i++) reuse = s->rec_start[i] == (seq_off[i] - seq_off[0]) + i;
   if (reuse) {
+    // the packed arrays belong to the pack stream; scans of the previous call may still read them
     uint64_t gpad = (s->ntiles + 1) * MFN_TILE + 256;
-    MFN_CUDA(cudaMemsetAsync(s->d_seq2, 0, (gpad / 32 + 8) * 8, ctx->stream));
-    MFN_CUDA(cudaMemsetAsync(s->d_ok, 0, (gpad / 64 + 8) * 8, ctx->stream));
+    MFN_CUDA(cudaEventRecord(ctx->ev[MFN_STAGE_BUFS + 2], ctx->stream));
+    MFN_CUDA(cudaStreamWaitEvent(ctx->pack_stream, ctx->ev[MFN_STAGE_BUFS + 2], 0));
+    MFN_CUDA(cudaMemsetAsync(s->d_seq2, 0, (gpad / 32 + 8) * 8, ctx->pack_stream));
+    MFN_CUDA(cudaMemsetAsync(s->d_ok, 0, (gpad / 64 + 8) * 8, ctx->pack_stream));
   } else {
     mfn_seq_free(s);
     ctx->scratch_seq = nullptr;
@@ -146,19 +151,29 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
   const uint64_t pieces = std::max<uint64_t>(1, std::min<uint64_t>(16, (te - tb) / 8192));
   if (reads->dev.k != asm_->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", reads->dev.k, asm_->dev.k); return MFN_ERR_K_MISMATCH; }
   if (mfn_sweep_applicable(reads, asm_, te - tb)) {
-    // range-partitioned scan: scatter each piece as soon as it is packed (overlaps the H2D of
-    // the next piece), probe all bins once at the end
+    // Range-partitioned scan.  The shard is cut into sub-sweeps of ~2^30 windows: each scatters its
+    // pieces as soon as they are packed and then probes its bins, so the probe pass of one
+    // sub-sweep runs under the H2D copy of the next and only the last one is exposed.
     if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
     unsigned long long *zmap = nullptr; uint32_t zlen = 0, zhi = 0;
     MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &zlen, &zhi));
-    mfn_sweep *w = nullptr;
-    int st = mfn_sweep_begin(ctx, reads, seq, (te - tb) * MFN_TILE, acc, zmap, zlen, zhi, &w);
-    for (uint64_t p = 0; p < pieces && st == MFN_OK; p++) {
-      uint64_t a = tb + (te - tb) * p / pieces, b = tb + (te - tb) * (p + 1) / pieces;
-      st = mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128);
-      if (st == MFN_OK) st = mfn_sweep_scatter(ctx, w, a, b);
+    const char *env = getenv("MFN_SUBSWEEPS");
+    uint64_t nsw = env ? (uint64_t)atoll(env) : (((te - tb) * MFN_TILE + (1ull << 29)) >> 30);
+    nsw = std::max<uint64_t>(1, std::min<uint64_t>(nsw, 16));
+    int st = MFN_OK;
+    for (uint64_t sw = 0; sw < nsw && st == MFN_OK; sw++) {
+      const uint64_t sa = tb + (te - tb) * sw / nsw, sb = tb + (te - tb) * (sw + 1) / nsw;
+      if (sa >= sb) continue;
+      const uint64_t np = std::max<uint64_t>(1, std::min<uint64_t>(8, (sb - sa) / 16384));
+      mfn_sweep *w = nullptr;
+      st = mfn_sweep_begin(ctx, reads, seq, (sb - sa) * MFN_TILE, acc, zmap, zlen, zhi, &w);
+      for (uint64_t p = 0; p < np && st == MFN_OK; p++) {
+        uint64_t a = sa + (sb - sa) * p / np, b = sa + (sb - sa) * (p + 1) / np;
+        st = mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128);
+        if (st == MFN_OK) st = mfn_sweep_scatter(ctx, w, a, b);
+      }
+      if (w) { int st2 = mfn_sweep_finish(ctx, w); if (st == MFN_OK) st = st2; }
     }
-    if (w) { int st2 = mfn_sweep_finish(ctx, w); if (st == MFN_OK) st = st2; }
     if (zmap) cudaFreeAsync(zmap, ctx->stream);
     return st;
   }

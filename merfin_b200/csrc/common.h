@@ -75,17 +75,21 @@ struct DevTable {
   TableStats *stats;
 };
 
+#define MFN_STAGE_BUFS 4              // ring of 64 MB ASCII staging buffers for host-buffer calls
+
 struct mfn_ctx {
   int          device = 0;
   cudaStream_t stream = nullptr;       // stream in use
   cudaStream_t own_stream = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;    // H2D of the ASCII staging buffers
+  cudaStream_t pack_stream = nullptr;    // k_pack: the only writer of a sequence set's packed arrays
+  cudaEvent_t  ev[MFN_STAGE_BUFS + 3] = {};   // [b]: pack kernel that last read staging buffer b; then copy / pack / order
   int          sm_count = 0;
   std::atomic<uint64_t> launches{0};
   // staging for host-buffer calls
-  char  *d_ascii[2] = {nullptr, nullptr};
+  char  *d_ascii[MFN_STAGE_BUFS] = {};
   size_t ascii_cap = 0;
+  int    stage_next = 0;
   void  *h_pinned = nullptr;
   size_t pinned_cap = 0;
   struct mfn_seq   *scratch_seq = nullptr;

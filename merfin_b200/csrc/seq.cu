@@ -69,24 +69,30 @@ int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq 
   if (e == cudaSuccess) e = cudaMalloc(&s->d_rec_start, br);
   if (e != cudaSuccess) { mfn_set_error("cudaMalloc(sequence): %s", cudaGetErrorString(e)); mfn_seq_free(s); return MFN_ERR_NOMEM; }
   s->device_bytes = b2 + bo + br;
-  MFN_CUDA(cudaMemsetAsync(s->d_seq2, 0, b2, ctx->stream));
-  MFN_CUDA(cudaMemsetAsync(s->d_ok, 0, bo, ctx->stream));
-  MFN_CUDA(cudaMemcpyAsync(s->d_rec_start, s->rec_start.data(), br, cudaMemcpyHostToDevice, ctx->stream));
+  // the packed arrays are only ever written on the pack stream (see mfn_seq_pack_range)
+  MFN_CUDA(cudaMemsetAsync(s->d_seq2, 0, b2, ctx->pack_stream));
+  MFN_CUDA(cudaMemsetAsync(s->d_ok, 0, bo, ctx->pack_stream));
+  MFN_CUDA(cudaMemcpyAsync(s->d_rec_start, s->rec_start.data(), br, cudaMemcpyHostToDevice, ctx->pack_stream));
+  MFN_CUDA(cudaEventRecord(ctx->ev[MFN_STAGE_BUFS + 1], ctx->pack_stream));
+  MFN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[MFN_STAGE_BUFS + 1], 0));
   *out = s;
   return MFN_OK;
 }
 
 static int ensure_staging(mfn_ctx *ctx, size_t bytes) {
   if (ctx->ascii_cap >= bytes) return MFN_OK;
-  for (int i = 0; i < 2; i++) { cudaFree(ctx->d_ascii[i]); ctx->d_ascii[i] = nullptr; }
+  for (int i = 0; i < MFN_STAGE_BUFS; i++) { cudaFree(ctx->d_ascii[i]); ctx->d_ascii[i] = nullptr; }
   ctx->ascii_cap = 0;
-  for (int i = 0; i < 2; i++) MFN_CUDA(cudaMalloc(&ctx->d_ascii[i], bytes));
+  for (int i = 0; i < MFN_STAGE_BUFS; i++) MFN_CUDA(cudaMalloc(&ctx->d_ascii[i], bytes));
   ctx->ascii_cap = bytes;
   return MFN_OK;
 }
 
 // Upload and pack the source bytes that back global positions [g_begin, g_end).
-// H2D runs on the copy stream in chunks, double-buffered against the pack kernel.
+// Three streams: H2D of 64 MB chunks into a ring of staging buffers (copy stream), k_pack of each
+// chunk (pack stream), and the caller's compute stream, which is made to wait for the packed
+// range at the end.  Neither uploads nor packing wait for scan kernels queued on the compute
+// stream, so a caller that alternates pack_range / scan overlaps the next upload with the scan.
 int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end) {
   mfn_ctx *ctx = s->ctx;
   if (s->nseq == 0 || g_begin >= g_end) return MFN_OK;
@@ -98,16 +104,16 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
   if (sa >= sb) return MFN_OK;
   const size_t CH = 64ull << 20;
   MFN_TRY(ensure_staging(ctx, CH));
-  int buf = 0;
-  MFN_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));          // arrays zeroed / earlier work queued
-  MFN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2], 0));
-  for (uint64_t o = sa; o < sb; o += CH, buf ^= 1) {
+  cudaEvent_t ev_copy = ctx->ev[MFN_STAGE_BUFS], ev_pack = ctx->ev[MFN_STAGE_BUFS + 1];
+  for (uint64_t o = sa; o < sb; o += CH) {
+    const int buf = ctx->stage_next;
+    ctx->stage_next = (ctx->stage_next + 1) % MFN_STAGE_BUFS;
     uint64_t e = std::min<uint64_t>(sb, o + CH);
     // the pack kernel that last read this buffer must be done before we overwrite it
     MFN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[buf], 0));
     MFN_CUDA(cudaMemcpyAsync(ctx->d_ascii[buf], bases + o, e - o, cudaMemcpyHostToDevice, ctx->copy_stream));
-    MFN_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream));
-    MFN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+    MFN_CUDA(cudaEventRecord(ev_copy, ctx->copy_stream));
+    MFN_CUDA(cudaStreamWaitEvent(ctx->pack_stream, ev_copy, 0));
     // global words touched by source bytes [o, e)
     // g of a source byte x: x + r(x) where r is the record holding source byte x
     auto g_of_src = [&](uint64_t x) {
@@ -121,12 +127,14 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
     };
     uint64_t w0 = g_of_src(o) / 64, w1 = g_of_src(e - 1) / 64 + 1;
     uint64_t nw = w1 - w0;
-    k_pack<<<(unsigned)ceil_div_u64(nw, 256), 256, 0, ctx->stream>>>(
+    k_pack<<<(unsigned)ceil_div_u64(nw, 256), 256, 0, ctx->pack_stream>>>(
         (const unsigned char *)ctx->d_ascii[buf], o, e, s->d_rec_start, s->nseq, w0, w1, s->d_seq2, s->d_ok);
     ctx->launches++;
-    MFN_CUDA(cudaEventRecord(ctx->ev[buf], ctx->stream));
+    MFN_CUDA(cudaEventRecord(ctx->ev[buf], ctx->pack_stream));
   }
   MFN_CUDA(cudaGetLastError());
+  MFN_CUDA(cudaEventRecord(ev_pack, ctx->pack_stream));
+  MFN_CUDA(cudaStreamWaitEvent(ctx->stream, ev_pack, 0));
   return MFN_OK;
 }
 
