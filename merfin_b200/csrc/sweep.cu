@@ -48,6 +48,10 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
   SweepParams &P = w->P;
   P.J = J;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
+  {
+    const uint64_t gpad = (seq->ntiles + 1) * MFN_TILE + 256;            // as allocated by mfn_seq_alloc
+    P.seq_words = gpad / 32 + 8; P.ok_words = gpad / 64 + 8;
+  }
   if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins)) { delete w; mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
   P.nbins_pad = (P.nbins + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
   P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;

@@ -31,6 +31,8 @@
 #define SC_THREADS 512                             // scatter CTA: two 2048-window tiles side by side, two rounds
 #define SC_TPT (SW_CHUNK / SC_THREADS / WPT)       // 8-window groups per thread per chunk
 #define SC_NW (SC_TPT * WPT)                       // windows per thread per chunk
+#define SC_SEQ_WORDS (SW_CHUNK / 32 + 2)           // staged 2-bit words of a chunk (2064 B)
+#define SC_OK_WORDS (SW_CHUNK / 64 + 2)            // staged validity words (1040 B)
 #define SW_MAX_BINS 2048
 #define SW_SLICE 1024                              // entries per probe work item (one WARP)
 #define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
@@ -40,6 +42,7 @@
 struct SweepParams {
   JointDev J;
   const unsigned long long *seq2, *ok, *rec_start;
+  uint64_t seq_words, ok_words;              // allocated length of seq2 / ok (TMA copies are clamped to it)
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
   uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low word = (line & L-1) << tbits | tag
@@ -70,8 +73,12 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
   unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of the chunk's sorted position 0, per bin
   uint32_t *s_off = (uint32_t *)(s_dst + SW_MAX_BINS);                 // [SW_MAX_BINS] counts, then exclusive offsets
   __shared__ uint32_t s_warp[SC_THREADS / 32];
-  __shared__ unsigned long long s_chunk;
+  __shared__ unsigned long long s_chunk[2];
   __shared__ uint32_t s_total;
+  // the chunk's 2-bit words and validity bits (incl. a 64-base halo), staged by TMA one chunk ahead
+  __shared__ __align__(16) unsigned long long s_seq[2][SC_SEQ_WORDS];
+  __shared__ __align__(16) unsigned long long s_ok[2][SC_OK_WORDS];
+  __shared__ __align__(8) unsigned long long s_bar[2];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t grp = tid / (MFN_TILE / WPT), t8 = tid % (MFN_TILE / WPT);   // tile of the round, window group in it
@@ -87,7 +94,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
   unsigned long long *const rec_acc = P.acc + MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A;
 
   unsigned long long my_valid = 0;
-  uint32_t cur_rec = 0xffffffffu, n_ok0 = 0;
+  uint32_t cur_rec = 0, n_ok0 = 0;                           // record of the current chunk's first window
+  uint64_t cur_end = P.nseq ? P.rec_start[1] : ~0ull;        // chunks arrive in increasing order: the record only moves forward
   auto flush_rec = [&]() {
     uint32_t a = n_ok0;
     for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
@@ -96,25 +104,48 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
     n_ok0 = 0;
   };
 
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s_chunk = atomicAdd(P.counter, 1ull);
+  // thread 0 claims chunks two rounds ahead and starts the TMA of the next chunk's sequence one
+  // round ahead, so neither the atomic's round trip nor the loads sit on a round's critical path
+  auto stage = [&](unsigned long long c, int buf) {
+    s_chunk[buf] = c;
+    if (c >= nchunks) return;
+    const uint64_t t0 = P.tile_begin + c * SW_CHUNK_TILES;
+    const uint64_t w2 = t0 * (MFN_TILE / 32), wo = t0 * (MFN_TILE / 64);
+    const uint32_t n2 = (uint32_t)min((uint64_t)SC_SEQ_WORDS, P.seq_words - w2) & ~1u;     // multiples of 16 bytes
+    const uint32_t no = (uint32_t)min((uint64_t)SC_OK_WORDS, P.ok_words - wo) & ~1u;
+    mbar_expect_tx(&s_bar[buf], (n2 + no) * 8);
+    tma_load_1d(s_seq[buf], P.seq2 + w2, n2 * 8, &s_bar[buf]);
+    tma_load_1d(s_ok[buf], P.ok + wo, no * 8, &s_bar[buf]);
+  };
+  unsigned long long pre = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage(atomicAdd(P.counter, 1ull), 0);
+    pre = atomicAdd(P.counter, 1ull);
+  }
+
+  for (uint32_t it = 0;; it++) {
+    const int buf = it & 1;
     for (uint32_t i = tid; i < P.nbins_pad; i += SC_THREADS) s_off[i] = 0;
-    __syncthreads();
-    const uint64_t chunk = s_chunk;
+    __syncthreads();                                         // s_chunk[buf], the zeroed counters; everyone is done with the other buffer
+    const uint64_t chunk = s_chunk[buf];
     if (chunk >= nchunks) break;
+    if (tid == 0) { stage(pre, buf ^ 1); pre = atomicAdd(P.counter, 1ull); }
     const uint64_t tile0 = P.tile_begin + chunk * SW_CHUNK_TILES;
 
     // record of the chunk's first window (uniform); does the chunk stay inside it?
-    uint32_t r0;
     {
       const uint64_t gt = tile0 * MFN_TILE;
-      uint32_t a = 0, b = P.nseq;
-      while (a < b) { uint32_t m = (a + b + 1) >> 1; if (P.rec_start[m] <= gt) a = m; else b = m - 1; }
-      r0 = a;
+      if (gt >= cur_end) {
+        flush_rec();
+        while (gt >= cur_end) { cur_rec++; cur_end = (cur_rec < P.nseq) ? P.rec_start[cur_rec + 1] : ~0ull; }
+      }
     }
-    if (r0 != cur_rec) { flush_rec(); cur_rec = r0; }
-    const uint64_t r0_end = (r0 < P.nseq) ? P.rec_start[r0 + 1] : ~0ull;
+    const uint32_t r0 = cur_rec;
+    const uint64_t r0_end = cur_end;
+    mbar_wait(&s_bar[buf], (it >> 1) & 1);
     const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
     // ---- hash this thread's windows; rank them inside their bins ---------------------------
@@ -126,12 +157,13 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
       const uint64_t g0 = tile * MFN_TILE + t8 * WPT;
       uint64_t lo = 0, hi = 0, okb = 0;
       if (tile < P.tile_end) {
-        const uint64_t w = g0 >> 5, sh = (g0 & 31) * 2;
-        const uint64_t a = __ldg(&P.seq2[w]), b = __ldg(&P.seq2[w + 1]);
+        const uint32_t j0 = (uint32_t)(tile - tile0) * MFN_TILE + t8 * WPT;      // position in the staged chunk
+        const uint32_t w = j0 >> 5, sh = (j0 & 31) * 2;
+        const uint64_t a = s_seq[buf][w], b = s_seq[buf][w + 1];
         lo = sh ? ((a >> sh) | (b << (64 - sh))) : a;
         hi = b >> sh;
-        const uint64_t wo = g0 >> 6, so = g0 & 63;
-        const uint64_t c = __ldg(&P.ok[wo]), d = __ldg(&P.ok[wo + 1]);
+        const uint32_t wo = j0 >> 6, so = j0 & 63;
+        const uint64_t c = s_ok[buf][wo], d = s_ok[buf][wo + 1];
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
       // which of the 8 windows are valid (kmers-iterator.H:93-95): all of them almost always
@@ -192,15 +224,15 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
     __syncthreads();
 
     // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
+    constexpr uint32_t BPT = SW_MAX_BINS / SC_THREADS;
+    const uint32_t b0 = tid * per_thread_bins;
+    uint32_t cnt[BPT];
+    unsigned long long got[BPT];
     {
-      constexpr uint32_t BPT = SW_MAX_BINS / SC_THREADS;
-      uint32_t cnt[BPT];
       uint32_t sum = 0;
-      const uint32_t b0 = tid * per_thread_bins;
 #pragma unroll
       for (uint32_t i = 0; i < BPT; i++) { cnt[i] = i < per_thread_bins ? s_off[b0 + i] : 0; sum += cnt[i]; }
-      // all atomics of this thread in flight together
-      unsigned long long got[BPT];
+      // all atomics of this thread in flight together; their results are first needed after the sort
 #pragma unroll
       for (uint32_t i = 0; i < BPT; i++) {
         got[i] = 0;
@@ -215,26 +247,29 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
       uint32_t run = wbase + incl - sum;
 #pragma unroll
       for (uint32_t i = 0; i < BPT; i++) {
-        if (i < per_thread_bins) {
-          s_off[b0 + i] = run;
-          // bit 63: the run does not fit its bin (its windows go to the side list)
-          unsigned long long dst = ((unsigned long long)(b0 + i) * P.cap + got[i] - run) & 0x7fffffffffffffffull;
-          if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst |= 1ull << 63; }
-          s_dst[b0 + i] = dst;
-          run += cnt[i];
-        }
+        if (i < per_thread_bins) { s_off[b0 + i] = run; run += cnt[i]; }
       }
       if (tid == SC_THREADS - 1) s_total = run;
     }
     __syncthreads();
 
-    // ---- counting sort into shared memory --------------------------------------------------
+    // ---- counting sort into shared memory (the reservations are still in flight) -----------
 #pragma unroll
     for (int idx = 0; idx < SC_NW; idx++) {
       const uint32_t m = meta[idx];
       if (m == 0xffffffffu) continue;
       const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & 0x1fffu);
       s_ent[p] = ((unsigned long long)(m & 0xff0007ffu) << 32) | low[idx];
+    }
+    // where each bin's run goes: global index of the chunk's sorted position 0
+#pragma unroll
+    for (uint32_t i = 0; i < BPT; i++) {
+      if (i < per_thread_bins) {
+        // bit 63: the run does not fit its bin (its windows go to the side list)
+        unsigned long long dst = ((unsigned long long)(b0 + i) * P.cap + got[i] - s_off[b0 + i]) & 0x7fffffffffffffffull;
+        if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst |= 1ull << 63; }
+        s_dst[b0 + i] = dst;
+      }
     }
     __syncthreads();
 
