@@ -258,6 +258,12 @@ int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const
 /* ---- timing hooks for benchmarks -------------------------------------------- */
 /* Number of kernels this library launched on the ctx since creation. */
 uint64_t mfn_ctx_launch_count(const mfn_ctx *ctx);
+/* Per-pass device times of the range-partitioned -hist scan.  After mfn_ctx_time_passes(ctx, 1)
+ * every scan brackets its passes with CUDA events on the launch stream; mfn_ctx_pass_times
+ * synchronises and returns the summed milliseconds of pass 1 (scatter) and pass 2 (probe) and
+ * the number of scans measured since the last call. */
+int  mfn_ctx_time_passes(mfn_ctx *ctx, int enable);
+int  mfn_ctx_pass_times(mfn_ctx *ctx, double *scatter_ms, double *probe_ms, uint32_t *nscans);
 
 #ifdef __cplusplus
 }

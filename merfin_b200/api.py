@@ -37,6 +37,16 @@ class Context:
     def launches(self) -> int:
         return int(self._lib.mfn_ctx_launch_count(self.h))
 
+    def time_passes(self, enable: bool = True):
+        """Bracket the passes of every range-partitioned -hist scan with CUDA events."""
+        L.check(self._lib.mfn_ctx_time_passes(self.h, 1 if enable else 0))
+
+    def pass_times(self):
+        """(scatter ms, probe ms, scans) summed over the scans since the last call."""
+        a, b, n = C.c_double(), C.c_double(), C.c_uint32()
+        L.check(self._lib.mfn_ctx_pass_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def close(self):
         if self.h:
             self._lib.mfn_ctx_destroy(self.h)

@@ -80,6 +80,7 @@ extern "C" void mfn_ctx_destroy(mfn_ctx *c) {
   for (int i = 0; i < MFN_STAGE_BUFS; i++) cudaFree(c->d_ascii[i]);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->pass_ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->pack_stream);
@@ -101,6 +102,43 @@ extern "C" int mfn_ctx_sync(mfn_ctx *c) {
 }
 
 extern "C" uint64_t mfn_ctx_launch_count(const mfn_ctx *c) { return c ? c->launches.load() : 0; }
+
+extern "C" int mfn_ctx_time_passes(mfn_ctx *c, int enable) {
+  if (!c) return MFN_ERR_INVALID;
+  c->time_passes = enable != 0;
+  c->pass_ev_used = 0;
+  return MFN_OK;
+}
+
+// next timing event of the ctx (grown on demand), recorded on the launch stream
+cudaEvent_t mfn_ctx_mark(mfn_ctx *c) {
+  if (c->pass_ev_used == c->pass_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    c->pass_ev.push_back(e);
+  }
+  cudaEvent_t e = c->pass_ev[c->pass_ev_used++];
+  cudaEventRecord(e, c->stream);
+  return e;
+}
+
+extern "C" int mfn_ctx_pass_times(mfn_ctx *c, double *scatter_ms, double *probe_ms, uint32_t *nscans) {
+  if (!c) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaStreamSynchronize(c->stream));
+  double a = 0, b = 0;
+  uint32_t n = 0;
+  for (size_t i = 0; i + 2 < c->pass_ev_used; i += 3) {
+    float t1 = 0, t2 = 0;
+    if (cudaEventElapsedTime(&t1, c->pass_ev[i], c->pass_ev[i + 1]) != cudaSuccess) break;
+    if (cudaEventElapsedTime(&t2, c->pass_ev[i + 1], c->pass_ev[i + 2]) != cudaSuccess) break;
+    a += t1; b += t2; n++;
+  }
+  c->pass_ev_used = 0;
+  if (scatter_ms) *scatter_ms = a;
+  if (probe_ms) *probe_ms = b;
+  if (nscans) *nscans = n;
+  return MFN_OK;
+}
 
 extern "C" int mfn_host_alloc(void **p, size_t bytes) {
   if (!p) return MFN_ERR_INVALID;

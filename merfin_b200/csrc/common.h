@@ -92,6 +92,10 @@ struct mfn_ctx {
   int    stage_next = 0;
   void  *h_pinned = nullptr;
   size_t pinned_cap = 0;
+  // optional per-pass timing of the sweep (mfn_ctx_time_passes)
+  bool time_passes = false;
+  std::vector<cudaEvent_t> pass_ev;      // triples: before scatter, between, after probe
+  size_t pass_ev_used = 0;
   struct mfn_seq   *scratch_seq = nullptr;
   struct mfn_accum *scratch_acc = nullptr;
 };

@@ -131,7 +131,10 @@ int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const m
   if (tile_begin >= tile_end) return MFN_OK;
   mfn_sweep *w = nullptr;
   MFN_TRY(mfn_sweep_begin(ctx, R, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, zhi, &w));
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   int st = mfn_sweep_scatter(ctx, w, tile_begin, tile_end);
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   int st2 = mfn_sweep_finish(ctx, w);
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   return st != MFN_OK ? st : st2;
 }

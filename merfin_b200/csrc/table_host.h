@@ -57,6 +57,7 @@ bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntile
 int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
                    uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen,
                    uint32_t zhi);
+cudaEvent_t mfn_ctx_mark(mfn_ctx *c);
 struct mfn_sweep;
 int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out);

@@ -370,6 +370,11 @@ def test_sweep_equals_direct_scan(ctx, monkeypatch, k):
     assert len(d.pairs) == len(s.pairs) and (d.pairs == s.pairs).all()
     assert (d.per_seq == s.per_seq).all()
     assert int(d.per_seq["kmissing"].sum()) > 0
+    # the host-buffer path cut into several sub-sweeps (probe of one under the upload of the next)
+    monkeypatch.setenv("MFN_SUBSWEEPS", "3")
+    s3 = api.hist(ctx, R, A, recs, km)
+    monkeypatch.delenv("MFN_SUBSWEEPS")
+    assert len(d.pairs) == len(s3.pairs) and (d.pairs == s3.pairs).all() and (d.per_seq == s3.per_seq).all()
     exp, per = _expected_pairs(recs, k, _ArrLookup(k, rk, rv), _ArrLookup(k, ak, ac))
     got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in s.pairs}
     assert got == exp
