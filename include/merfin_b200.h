@@ -255,9 +255,22 @@ double mfn_getKmetric(double readK, double asmK);                  /* merfin-glo
 int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const mfn_kmodel *km,
                              double *total, double *undr);
 
+/* ---- host-side packing (no device needed) -------------------------------------- */
+/* Pack global positions [g_begin, g_end) (multiples of 64) of a sequence set into the device
+ * layout: 2 bits per base, (ascii >> 1) & 3 (kmers-tiny.H:69-83), and one validity bit per base
+ * (ACGTacgt, kmers-iterator.H:97-102).  rec_start[r] = seq_off[r] - seq_off[0] + r (one separator
+ * slot after every record), nseq + 1 entries.  seq2_out / ok_out receive (g_end - g_begin) / 32
+ * resp. / 64 words.  Used by mfn_hist_host's host packing lane; thread-safe on disjoint ranges. */
+void mfn_pack_host_range(const char *bases, const uint64_t *rec_start, uint32_t nseq, uint64_t g_begin,
+                         uint64_t g_end, uint64_t *seq2_out, uint64_t *ok_out);
+const char *mfn_pack_host_isa(void);       /* "avx2" or "scalar" */
+
 /* ---- timing hooks for benchmarks -------------------------------------------- */
 /* Number of kernels this library launched on the ctx since creation. */
 uint64_t mfn_ctx_launch_count(const mfn_ctx *ctx);
+/* Bytes of sequence data the host-buffer calls copied host -> device on this ctx since creation
+ * (raw ASCII of the upload lane + packed words of the host packing lane). */
+uint64_t mfn_ctx_h2d_bytes(const mfn_ctx *ctx);
 /* Per-pass device times of the range-partitioned -hist scan.  After mfn_ctx_time_passes(ctx, 1)
  * every scan brackets its passes with CUDA events on the launch stream; mfn_ctx_pass_times
  * synchronises and returns the summed milliseconds of pass 1 (scatter) and pass 2 (probe) and

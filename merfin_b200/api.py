@@ -37,6 +37,10 @@ class Context:
     def launches(self) -> int:
         return int(self._lib.mfn_ctx_launch_count(self.h))
 
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self._lib.mfn_ctx_h2d_bytes(self.h))
+
     def time_passes(self, enable: bool = True):
         """Bracket the passes of every range-partitioned -hist scan with CUDA events."""
         L.check(self._lib.mfn_ctx_time_passes(self.h, 1 if enable else 0))

@@ -75,6 +75,7 @@ extern "C" void mfn_ctx_destroy(mfn_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  mfn_ingest_free(c->ingest);
   mfn_seq_free(c->scratch_seq);
   mfn_accum_free(c->scratch_acc);
   for (int i = 0; i < MFN_STAGE_BUFS; i++) cudaFree(c->d_ascii[i]);
@@ -102,6 +103,8 @@ extern "C" int mfn_ctx_sync(mfn_ctx *c) {
 }
 
 extern "C" uint64_t mfn_ctx_launch_count(const mfn_ctx *c) { return c ? c->launches.load() : 0; }
+
+extern "C" uint64_t mfn_ctx_h2d_bytes(const mfn_ctx *c) { return c ? c->h2d_bytes.load() : 0; }
 
 extern "C" int mfn_ctx_time_passes(mfn_ctx *c, int enable) {
   if (!c) return MFN_ERR_INVALID;
@@ -189,29 +192,45 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
   const uint64_t pieces = std::max<uint64_t>(1, std::min<uint64_t>(16, (te - tb) / 8192));
   if (reads->dev.k != asm_->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", reads->dev.k, asm_->dev.k); return MFN_ERR_K_MISMATCH; }
   if (mfn_sweep_applicable(reads, asm_, te - tb)) {
-    // Range-partitioned scan.  The shard is cut into sub-sweeps of ~2^30 windows: each scatters its
+    // Range-partitioned scan.  The shard is cut into sub-sweeps of ~1.5e9 windows: each scatters its
     // pieces as soon as they are packed and then probes its bins, so the probe pass of one
-    // sub-sweep runs under the H2D copy of the next and only the last one is exposed.
+    // sub-sweep runs under the ingest of the next and only the last one is exposed (every extra
+    // sub-sweep streams the table once more, which is why there are few of them).
     if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
     unsigned long long *zmap = nullptr; uint32_t zlen = 0, zhi = 0;
     MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &zlen, &zhi));
     const char *env = getenv("MFN_SUBSWEEPS");
-    uint64_t nsw = env ? (uint64_t)atoll(env) : (((te - tb) * MFN_TILE + (1ull << 29)) >> 30);
+    uint64_t nsw = env ? (uint64_t)atoll(env) : ((te - tb) * MFN_TILE + 750000000ull) / 1500000000ull;
     nsw = std::max<uint64_t>(1, std::min<uint64_t>(nsw, 16));
-    int st = MFN_OK;
+    // pieces of <= 32768 tiles (64 MB of ASCII); two ingest lanes fill them (ingest.cu): raw upload
+    // + k_pack, and host-packed words
+    const uint64_t piece_tiles = std::max<uint64_t>(1024, std::min<uint64_t>(32768, ceil_div_u64(te - tb, 8 * nsw)));
+    uint32_t np = 0;
+    int st = mfn_ingest_begin(ctx, seq, bases + seq_off[0], tb, te, piece_tiles, &np);
+    nsw = std::min<uint64_t>(nsw, std::max<uint32_t>(np, 1));
+    std::vector<char> waited(np, 0);
+    auto wait_piece = [&](uint32_t i) -> int {
+      if (i >= np || waited[i]) return MFN_OK;
+      waited[i] = 1;
+      return mfn_ingest_wait(ctx, i);
+    };
     for (uint64_t sw = 0; sw < nsw && st == MFN_OK; sw++) {
-      const uint64_t sa = tb + (te - tb) * sw / nsw, sb = tb + (te - tb) * (sw + 1) / nsw;
-      if (sa >= sb) continue;
-      const uint64_t np = std::max<uint64_t>(1, std::min<uint64_t>(8, (sb - sa) / 16384));
+      const uint32_t pa = (uint32_t)(np * sw / nsw), pb = (uint32_t)(np * (sw + 1) / nsw);
+      if (pa >= pb) continue;
+      const uint64_t sa = tb + (uint64_t)pa * piece_tiles, sb = std::min(te, tb + (uint64_t)pb * piece_tiles);
       mfn_sweep *w = nullptr;
       st = mfn_sweep_begin(ctx, reads, seq, (sb - sa) * MFN_TILE, acc, zmap, zlen, zhi, &w);
-      for (uint64_t p = 0; p < np && st == MFN_OK; p++) {
-        uint64_t a = sa + (sb - sa) * p / np, b = sa + (sb - sa) * (p + 1) / np;
-        st = mfn_seq_pack_range(seq, bases + seq_off[0], a * MFN_TILE, b * MFN_TILE + 128);
+      for (uint32_t p = pa; p < pb && st == MFN_OK; p++) {
+        // lane G runs a few pieces ahead of the scan; the windows of a piece read k-1 bases of the next one
+        st = mfn_ingest_feed(ctx, p + 3);
+        if (st == MFN_OK) st = wait_piece(p);
+        if (st == MFN_OK) st = wait_piece(p + 1);
+        const uint64_t a = tb + (uint64_t)p * piece_tiles, b = std::min(te, a + piece_tiles);
         if (st == MFN_OK) st = mfn_sweep_scatter(ctx, w, a, b);
       }
       if (w) { int st2 = mfn_sweep_finish(ctx, w); if (st == MFN_OK) st = st2; }
     }
+    mfn_ingest_end(ctx);
     if (zmap) cudaFreeAsync(zmap, ctx->stream);
     return st;
   }

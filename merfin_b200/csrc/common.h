@@ -86,6 +86,7 @@ struct mfn_ctx {
   cudaEvent_t  ev[MFN_STAGE_BUFS + 3] = {};   // [b]: pack kernel that last read staging buffer b; then copy / pack / order
   int          sm_count = 0;
   std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> h2d_bytes{0};    // bytes of sequence data copied host -> device by host-buffer calls
   // staging for host-buffer calls
   char  *d_ascii[MFN_STAGE_BUFS] = {};
   size_t ascii_cap = 0;
@@ -96,6 +97,7 @@ struct mfn_ctx {
   bool time_passes = false;
   std::vector<cudaEvent_t> pass_ev;      // triples: before scatter, between, after probe
   size_t pass_ev_used = 0;
+  struct mfn_ingest *ingest = nullptr;   // host packing lane of the host-buffer -hist path (ingest.cu)
   struct mfn_seq   *scratch_seq = nullptr;
   struct mfn_accum *scratch_acc = nullptr;
 };

@@ -1,0 +1,158 @@
+// Host-side packing of ASCII bases into the device layout of mfn_seq (seq.cu): 2 bits per base
+// ((ascii >> 1) & 3, kmers-tiny.H:69-83) + 1 validity bit per base (ACGTacgt, kmers-iterator.H:97-102),
+// in GLOBAL coordinates (one separator slot after every record).
+//
+// Why on the host at all: the host-buffer entry points are bound by the PCIe copy of 1 byte per
+// base.  A packed piece is 0.375 bytes per base, so pieces packed by idle host cores cross the
+// link 2.7x cheaper; mfn_hist_host runs both lanes side by side (api.cu).
+//
+// Plain C++ (compiled by g++, not nvcc); the 32-base inner kernel uses AVX2 when the CPU has it
+// (runtime dispatch), a scalar loop otherwise.  Bit-identical to k_pack by construction; the GPU
+// parity test packs the same records both ways and compares the arrays.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <immintrin.h>
+
+// 32 bases at p -> (2-bit codes, base i at bits 2i; validity mask, base i at bit i); invalid bases have code 0
+static inline void pack32_scalar(const unsigned char *p, uint64_t *codes, uint32_t *okmask) {
+  uint64_t c = 0;
+  uint32_t m = 0;
+  for (int i = 0; i < 32; i++) {
+    const unsigned u = p[i] | 0x20u;
+    if (u == 'a' || u == 'c' || u == 'g' || u == 't') {
+      c |= (uint64_t)((p[i] >> 1) & 3u) << (2 * i);
+      m |= 1u << i;
+    }
+  }
+  *codes = c;
+  *okmask = m;
+}
+
+__attribute__((target("avx2"))) static inline void pack32_avx2(const unsigned char *p, uint64_t *codes, uint32_t *okmask) {
+  const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+  const __m256i u = _mm256_or_si256(v, _mm256_set1_epi8(0x20));
+  // expected byte for each low nibble: 1 -> 'a', 3 -> 'c', 7 -> 'g', 4 -> 't', anything else never matches
+  const __m256i lut = _mm256_setr_epi8((char)0xff, 'a', (char)0xff, 'c', 't', (char)0xff, (char)0xff, 'g', (char)0xff, (char)0xff,
+                                       (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, 'a',
+                                       (char)0xff, 'c', 't', (char)0xff, (char)0xff, 'g', (char)0xff, (char)0xff, (char)0xff,
+                                       (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff);
+  const __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(u, _mm256_set1_epi8(0x0f)));
+  const __m256i ok = _mm256_cmpeq_epi8(want, u);
+  *okmask = (uint32_t)_mm256_movemask_epi8(ok);
+  // codes 0..3 per byte, zero where invalid
+  __m256i c = _mm256_and_si256(_mm256_srli_epi16(v, 1), _mm256_set1_epi8(3));
+  c = _mm256_and_si256(c, ok);
+  // pairs of bytes -> 4 bits (c0 + 4 c1), pairs of those -> 8 bits (x0 + 16 x1): one byte per 32-bit lane
+  const __m256i x = _mm256_maddubs_epi16(c, _mm256_set1_epi16(0x0401));
+  const __m256i y = _mm256_madd_epi16(x, _mm256_set1_epi32(0x00100001));
+  // gather the 8 low bytes of the 8 lanes
+  const __m256i z = _mm256_shuffle_epi8(y, _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                            0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+  const uint32_t lo = (uint32_t)_mm256_extract_epi32(z, 0), hi = (uint32_t)_mm256_extract_epi32(z, 4);
+  *codes = ((uint64_t)hi << 32) | lo;
+}
+
+// OR `n` (<= 32) bases starting at global position g into the word arrays (which hold zeros there)
+static inline void deposit(uint64_t *seq2, uint64_t *ok, uint64_t g, uint64_t codes, uint32_t okmask) {
+  const uint64_t w = g >> 5, sh = (g & 31) * 2;
+  seq2[w] |= codes << sh;
+  if (sh) { const uint64_t hi = codes >> (64 - sh); if (hi) seq2[w + 1] |= hi; }     // never touch a word we put nothing in:
+  const uint64_t wo = g >> 6, so = g & 63;                                          // it may belong to another thread
+  ok[wo] |= (uint64_t)okmask << so;
+  if (so > 32) { const uint64_t hi = (uint64_t)okmask >> (64 - so); if (hi) ok[wo + 1] |= hi; }
+}
+
+// One record segment [a, b) of global positions whose first source byte is p.
+template <class PACK32>
+static inline __attribute__((always_inline)) void pack_segment(PACK32 pack32, const unsigned char *p, uint64_t a, uint64_t b,
+                                                               uint64_t *s2, uint64_t *so) {
+  uint64_t g = a;
+  // peel up to the next 64-aligned global position, then whole words are stored without
+  // read-modify-write (the range was zeroed, and nothing else lands in these words)
+  if ((g & 63) && g + 32 <= b) {
+    const uint64_t n = std::min<uint64_t>(64 - (g & 63), 32);
+    unsigned char tmp[32];
+    memset(tmp, 0, sizeof tmp);
+    memcpy(tmp, p, n);
+    uint64_t codes;
+    uint32_t okm;
+    pack32(tmp, &codes, &okm);
+    deposit(s2, so, g, codes, okm);
+    g += n; p += n;
+    if ((g & 63) && g + 32 <= b) {                 // the peel was capped at 32 bases: one more block reaches the boundary
+      const uint64_t m = 64 - (g & 63);
+      memset(tmp, 0, sizeof tmp);
+      memcpy(tmp, p, m);
+      pack32(tmp, &codes, &okm);
+      deposit(s2, so, g, codes, okm);
+      g += m; p += m;
+    }
+  }
+  if ((g & 63) == 0) {
+    for (; g + 64 <= b; g += 64, p += 64) {
+      uint64_t c0, c1;
+      uint32_t m0, m1;
+      pack32(p, &c0, &m0);
+      pack32(p + 32, &c1, &m1);
+      s2[g >> 5] = c0;
+      s2[(g >> 5) + 1] = c1;
+      so[g >> 6] = ((uint64_t)m1 << 32) | m0;
+    }
+  }
+  for (; g + 32 <= b; g += 32, p += 32) {
+    uint64_t codes;
+    uint32_t okm;
+    pack32(p, &codes, &okm);
+    deposit(s2, so, g, codes, okm);
+  }
+  if (g < b) {
+    unsigned char tmp[32];
+    memset(tmp, 0, sizeof tmp);
+    memcpy(tmp, p, b - g);
+    uint64_t codes;
+    uint32_t okm;
+    pack32(tmp, &codes, &okm);
+    deposit(s2, so, g, codes, okm);
+  }
+}
+static void pack_segment_scalar(const unsigned char *p, uint64_t a, uint64_t b, uint64_t *s2, uint64_t *so) {
+  pack_segment(pack32_scalar, p, a, b, s2, so);
+}
+__attribute__((target("avx2"))) static void pack_segment_avx2(const unsigned char *p, uint64_t a, uint64_t b, uint64_t *s2, uint64_t *so) {
+  pack_segment(pack32_avx2, p, a, b, s2, so);
+}
+typedef void (*segment_fn)(const unsigned char *, uint64_t, uint64_t, uint64_t *, uint64_t *);
+static segment_fn pick_segment() {
+  __builtin_cpu_init();
+  return __builtin_cpu_supports("avx2") ? pack_segment_avx2 : pack_segment_scalar;
+}
+
+// Pack global positions [g_begin, g_end) (both multiples of 64) of a sequence set into
+// seq2_out / ok_out, whose word 0 is global word g_begin/32 resp. g_begin/64.  rec_start[r] is the
+// global coordinate of record r's first base (nseq + 1 entries, rec_start[r] = source offset + r);
+// `bases` is the caller's concatenated ASCII.  Words are fully written (zeros where nothing is).
+extern "C" void mfn_pack_host_range(const char *bases, const uint64_t *rec_start, uint32_t nseq, uint64_t g_begin,
+                                    uint64_t g_end, uint64_t *seq2_out, uint64_t *ok_out) {
+  static const segment_fn segment = pick_segment();
+  if (g_end <= g_begin) return;
+  memset(seq2_out, 0, (g_end - g_begin) / 32 * 8);
+  memset(ok_out, 0, (g_end - g_begin) / 64 * 8);
+  if (nseq == 0) return;
+  // first record that ends after g_begin
+  uint32_t r = (uint32_t)(std::upper_bound(rec_start, rec_start + nseq + 1, g_begin) - rec_start);
+  r = r ? r - 1 : 0;
+  uint64_t *const s2 = seq2_out - g_begin / 32, *const so = ok_out - g_begin / 64;      // index by global word
+  const unsigned char *src = (const unsigned char *)bases;
+  for (; r < nseq && rec_start[r] < g_end; r++) {
+    // bases of record r occupy [rec_start[r], rec_start[r+1] - 1); the last slot is the separator
+    const uint64_t a = std::max(rec_start[r], g_begin), b = std::min(rec_start[r + 1] - 1, g_end);
+    if (a < b) segment(src + (a - r), a, b, s2, so);           // a - r: source byte of global position a
+  }
+}
+
+// Which inner kernel this CPU gets (for logs and tests).
+extern "C" const char *mfn_pack_host_isa(void) {
+  __builtin_cpu_init();
+  return __builtin_cpu_supports("avx2") ? "avx2" : "scalar";
+}

@@ -93,7 +93,7 @@ static int ensure_staging(mfn_ctx *ctx, size_t bytes) {
 // chunk (pack stream), and the caller's compute stream, which is made to wait for the packed
 // range at the end.  Neither uploads nor packing wait for scan kernels queued on the compute
 // stream, so a caller that alternates pack_range / scan overlaps the next upload with the scan.
-int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end) {
+int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end, cudaEvent_t done) {
   mfn_ctx *ctx = s->ctx;
   if (s->nseq == 0 || g_begin >= g_end) return MFN_OK;
   g_end = std::min(g_end, s->G);
@@ -112,6 +112,7 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
     // the pack kernel that last read this buffer must be done before we overwrite it
     MFN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[buf], 0));
     MFN_CUDA(cudaMemcpyAsync(ctx->d_ascii[buf], bases + o, e - o, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->h2d_bytes += e - o;
     MFN_CUDA(cudaEventRecord(ev_copy, ctx->copy_stream));
     MFN_CUDA(cudaStreamWaitEvent(ctx->pack_stream, ev_copy, 0));
     // global words touched by source bytes [o, e)
@@ -133,6 +134,7 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
     MFN_CUDA(cudaEventRecord(ctx->ev[buf], ctx->pack_stream));
   }
   MFN_CUDA(cudaGetLastError());
+  if (done) { MFN_CUDA(cudaEventRecord(done, ctx->pack_stream)); return MFN_OK; }
   MFN_CUDA(cudaEventRecord(ev_pack, ctx->pack_stream));
   MFN_CUDA(cudaStreamWaitEvent(ctx->stream, ev_pack, 0));
   return MFN_OK;

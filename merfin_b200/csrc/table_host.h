@@ -34,7 +34,17 @@ int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
 
 // ---- sequences ------------------------------------------------------------------
 int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out);
-int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end);
+// done == nullptr: the compute stream is made to wait for the packed range; otherwise `done` is
+// recorded on the pack stream instead and the caller orders its own streams
+int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end, cudaEvent_t done = nullptr);
+// hybrid ingest (ingest.cu)
+struct mfn_ingest;
+int mfn_ingest_begin(mfn_ctx *ctx, mfn_seq *seq, const char *bases, uint64_t tile_begin, uint64_t tile_end,
+                     uint64_t piece_tiles, uint32_t *npieces);
+int mfn_ingest_feed(mfn_ctx *ctx, uint32_t upto);
+int mfn_ingest_wait(mfn_ctx *ctx, uint32_t piece);
+void mfn_ingest_end(mfn_ctx *ctx);
+void mfn_ingest_free(mfn_ingest *I);
 // -hist scan of tiles [tile_begin, tile_end) of a resident sequence set
 int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
                    const mfn_kmodel *km, uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc);

@@ -124,6 +124,9 @@ SIGNATURES = {
     "mfn_completeness_report": (C.c_int, [_P, C.c_uint64, C.POINTER(KModel), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double)]),
     "mfn_ctx_launch_count": (C.c_uint64, [_P]),
+    "mfn_ctx_h2d_bytes": (C.c_uint64, [_P]),
+    "mfn_pack_host_range": (None, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P]),
+    "mfn_pack_host_isa": (C.c_char_p, []),
     "mfn_ctx_time_passes": (C.c_int, [_P, C.c_int]),
     "mfn_ctx_pass_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
 }

@@ -389,3 +389,36 @@ def test_sweep_on_golden_files(ctx, golden_dir, monkeypatch):
         _hist_check(ctx, d, recs, k, peak, 0, 0xFFFFFFFF, None, "ref")
     d, recs = _golden(golden_dir, "g1_k21")
     _hist_check(ctx, d, recs, 21, 8.0, 0, 0xFFFFFFFF, os.path.join(d, "prob.csv"), "ref.prob")
+
+
+def test_host_packing_lane_equals_device_packing(ctx, monkeypatch):
+    """mfn_hist over host buffers with half of the pieces packed by the host threads (ingest.cu,
+    host_pack.cpp) and half uploaded raw gives exactly the result of the all-device path."""
+    from merfin_b200 import api
+    k = 21
+    rng = np.random.default_rng(77)
+    recs = []
+    for i, n in enumerate([3_000_001, 2_500_000, 17, 4_000_003, 1_999_999]):      # ~11.5 Mbp: 6 pieces of 1024 tiles
+        b = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+        b[rng.integers(0, n, size=max(1, n // 5000))] = ord("N")
+        if n > 1000:
+            b[100:200] |= 0x20                                                       # a lowercase run
+        recs.append((f"r{i}", b.tobytes()))
+    seq = api.SeqSet(ctx, recs)
+    A = api.MerylExactLookup.count_sequence(ctx, k, seq)
+    R = api.MerylExactLookup.synth_reads(ctx, A, 15.0, 1_000_000, 5)
+    R.fuse(A)
+    km = api.KModel(15.0)
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    monkeypatch.setenv("MFN_HOST_PACK_SHARE", "0")
+    d = api.hist(ctx, R, A, recs, km)
+    monkeypatch.setenv("MFN_HOST_PACK_SHARE", "0.5")
+    monkeypatch.setenv("MFN_HOST_PACK_THREADS", "3")
+    h = api.hist(ctx, R, A, recs, km)
+    monkeypatch.setenv("MFN_HOST_PACK_SHARE", "0.9")
+    monkeypatch.setenv("MFN_SUBSWEEPS", "2")
+    h2 = api.hist(ctx, R, A, recs, km)
+    for x in (h, h2):
+        assert len(d.pairs) == len(x.pairs) and (d.pairs == x.pairs).all() and (d.per_seq == x.per_seq).all()
+    assert int(d.per_seq["kasm"].sum()) > 11_000_000
+    seq.close(); R.close(); A.close()
