@@ -336,7 +336,7 @@ extern "C" int mfn_completeness(mfn_ctx *ctx, const char *reads_dir, const char 
   mfn_accum *acc = nullptr;
   if (st == MFN_OK) st = mfn_accum_create(ctx, 0, &acc);
   if (st == MFN_OK)
-    st = meryl_stream_to_device(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
+    st = meryl_stream(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
       int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
       k_join<<<grid, 256, 0, ctx->stream>>>(A->dev, dk, dv, n, acc->d_buf, acc->sparse);
       ctx->launches++;

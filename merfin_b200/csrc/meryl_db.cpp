@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <mutex>
+#include <atomic>
+#include <map>
 #include <thread>
 
 #include <sys/stat.h>
@@ -288,7 +290,7 @@ extern "C" int mfn_table_load(mfn_ctx *ctx, const char *dir, uint32_t minV, uint
     return c;
   }));
   t->min_value = minV; t->max_value = maxV; t->value_offset = minV - 1;
-  int st = meryl_stream_to_device(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
+  int st = meryl_stream(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
     return mfn_table_insert_device(t, dk, dv, n, minV, maxV, minV - 1, false);
   });
   if (st == MFN_OK) st = mfn_table_finalize(t, false);
@@ -354,32 +356,50 @@ struct BitWriter {
 
 extern "C" int mfn_meryl_write(const char *dir, uint32_t k, const uint64_t *kmers, const uint32_t *values, uint64_t n) {
   if (!dir || k < 4 || k > 32 || (n && (!kmers || !values))) { mfn_set_error("mfn_meryl_write: need 4 <= k <= 32"); return MFN_ERR_INVALID; }
-  std::vector<uint64_t> order(n);
-  for (uint64_t i = 0; i < n; i++) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return kmers[a] < kmers[b]; });
-  for (uint64_t i = 1; i < n; i++)
-    if (kmers[order[i]] == kmers[order[i - 1]]) { mfn_set_error("mfn_meryl_write: duplicate k-mer"); return MFN_ERR_INVALID; }
-
   const uint32_t filesBits = 6;
   uint32_t blocksBits = 0;
   while (blocksBits < 16 && (n >> (filesBits + blocksBits)) > 8192) blocksBits++;
   if (2 * k < filesBits + blocksBits + 1) blocksBits = 2 * k - filesBits - 1;
   const uint32_t prefixSize = filesBits + blocksBits, suffixSize = 2 * k - prefixSize;
 
+  // bucket the pairs by data file (top 6 bits), then every file is sorted and written on its own
+  // thread: the 64 files are independent
+  struct KV { uint64_t k; uint32_t v; };
+  std::vector<uint64_t> fstart(65, 0);
+  for (uint64_t i = 0; i < n; i++) fstart[(kmers[i] >> (2 * k - filesBits)) + 1]++;
+  for (int f = 0; f < 64; f++) fstart[f + 1] += fstart[f];
+  std::vector<KV> kv(n);
+  {
+    std::vector<uint64_t> fill(fstart.begin(), fstart.end() - 1);
+    for (uint64_t i = 0; i < n; i++) kv[fill[kmers[i] >> (2 * k - filesBits)]++] = {kmers[i], values[i]};
+  }
   mkdir(dir, 0777);
   MerylIndex idx; idx.dir = dir; idx.numFilesBits = filesBits;
-  uint64_t i = 0;
-  for (uint32_t f = 0; f < 64; f++) {
+  std::vector<int> fstatus(64, MFN_OK);
+  std::vector<std::map<uint32_t, uint64_t>> fhist(64);
+  auto write_file = [&](uint32_t f) {
+    KV *seg = kv.data() + fstart[f];
+    const uint64_t m = fstart[f + 1] - fstart[f];
+    std::sort(seg, seg + m, [](const KV &a, const KV &b) { return a.k < b.k; });
+    for (uint64_t i = 1; i < m; i++) if (seg[i].k == seg[i - 1].k) { fstatus[f] = MFN_ERR_INVALID; return; }
+    {
+      // value histogram of this file (small values dominate: count them in a flat array)
+      std::vector<uint64_t> small(1 << 16, 0);
+      auto &big = fhist[f];
+      for (uint64_t i = 0; i < m; i++) { if (seg[i].v < small.size()) small[seg[i].v]++; else big[seg[i].v]++; }
+      for (uint32_t v = 0; v < small.size(); v++) if (small[v]) big[v] += small[v];
+    }
     FILE *D = fopen(meryl_file_name(idx, f, false).c_str(), "wb");
     FILE *I = fopen(meryl_file_name(idx, f, true).c_str(), "wb");
-    if (!D || !I) { if (D) fclose(D); if (I) fclose(I); mfn_set_error("cannot write under '%s'", dir); return MFN_ERR_IO; }
+    if (!D || !I) { if (D) fclose(D); if (I) fclose(I); fstatus[f] = MFN_ERR_IO; return; }
     std::vector<uint64_t> index((size_t)3 << blocksBits);
     for (uint64_t b = 0; b < (1ull << blocksBits); b++) { index[3 * b] = 0; index[3 * b + 1] = ~0ull; index[3 * b + 2] = 0; }
     bool ok = true;
-    while (ok && i < n && (kmers[order[i]] >> (2 * k - filesBits)) == f) {
-      uint64_t prefix = suffixSize >= 64 ? 0 : kmers[order[i]] >> suffixSize;
+    uint64_t i = 0;
+    while (ok && i < m) {
+      uint64_t prefix = suffixSize >= 64 ? 0 : seg[i].k >> suffixSize;
       uint64_t j = i;
-      while (j < n && (suffixSize >= 64 ? 0 : kmers[order[j]] >> suffixSize) == prefix) j++;
+      while (j < m && (suffixSize >= 64 ? 0 : seg[j].k >> suffixSize) == prefix) j++;
       uint64_t nk = j - i;
       uint32_t unaryBits = 0; uint64_t unarySum = 1;
       while (unarySum < nk) { unaryBits++; unarySum <<= 1; }
@@ -395,13 +415,13 @@ extern "C" int mfn_meryl_write(const char *dir, uint32_t k, const uint64_t *kmer
       const uint64_t smask = suffixSize >= 64 ? ~0ull : ((1ull << suffixSize) - 1);
       uint64_t last = 0;
       for (uint64_t x = i; x < j; x++) {
-        uint64_t suf = kmers[order[x]] & smask;
+        uint64_t suf = seg[x].k & smask;
         uint64_t hi = binaryBits >= 64 ? 0 : suf >> binaryBits;
         w.unary(hi - last);
         w.binary(binaryBits, suf);
         last = hi;
       }
-      for (uint64_t x = i; x < j; x++) w.binary(32, values[order[x]]);
+      for (uint64_t x = i; x < j; x++) w.binary(32, seg[x].v);
       uint64_t blk = prefix & ((1ull << blocksBits) - 1);
       index[3 * blk] = prefix; index[3 * blk + 1] = (uint64_t)ftell(D); index[3 * blk + 2] = nk;
       ok = w.dump(D);
@@ -409,25 +429,31 @@ extern "C" int mfn_meryl_write(const char *dir, uint32_t k, const uint64_t *kmer
     }
     ok = ok && fwrite(index.data(), 8, index.size(), I) == index.size();
     fclose(D); fclose(I);
-    if (!ok) { mfn_set_error("short write under '%s'", dir); return MFN_ERR_IO; }
+    if (!ok) fstatus[f] = MFN_ERR_IO;
+  };
+  {
+    const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::atomic<uint32_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; t++)
+      th.emplace_back([&]() { for (uint32_t f; (f = next++) < 64;) write_file(f); });
+    for (auto &t : th) t.join();
+  }
+  for (int f = 0; f < 64; f++) {
+    if (fstatus[f] == MFN_ERR_INVALID) { mfn_set_error("mfn_meryl_write: duplicate k-mer"); return MFN_ERR_INVALID; }
+    if (fstatus[f] != MFN_OK) { mfn_set_error("cannot write under '%s'", dir); return MFN_ERR_IO; }
   }
 
   // master index with the value histogram (the reference sizes its table from it)
-  std::vector<uint32_t> sorted(n);
-  for (uint64_t x = 0; x < n; x++) sorted[x] = values[x];
-  std::sort(sorted.begin(), sorted.end());
-  uint64_t numUnique = 0, numTotal = 0, distinctValues = 0;
-  for (uint64_t x = 0; x < n; x++) { numTotal += sorted[x]; numUnique += sorted[x] == 1; if (x == 0 || sorted[x] != sorted[x - 1]) distinctValues++; }
+  std::map<uint32_t, uint64_t> hist;
+  for (auto &h : fhist) for (auto &e : h) hist[e.first] += e.second;
+  uint64_t numUnique = 0, numTotal = 0;
+  for (auto &e : hist) { numTotal += (uint64_t)e.first * e.second; if (e.first == 1) numUnique = e.second; }
   BitWriter m(32 * 1024);
   m.binary(64, MAGIC_INDEX_1); m.binary(64, MAGIC_INDEX_V3);
   m.binary(32, prefixSize); m.binary(32, suffixSize); m.binary(32, filesBits); m.binary(32, blocksBits); m.binary(32, 0);
-  m.binary(64, numUnique); m.binary(64, n); m.binary(64, numTotal); m.binary(64, distinctValues);
-  for (uint64_t x = 0; x < n;) {
-    uint64_t y = x;
-    while (y < n && sorted[y] == sorted[x]) y++;
-    m.binary(64, sorted[x]); m.binary(64, y - x);
-    x = y;
-  }
+  m.binary(64, numUnique); m.binary(64, n); m.binary(64, numTotal); m.binary(64, (uint64_t)hist.size());
+  for (auto &e : hist) { m.binary(64, e.first); m.binary(64, e.second); }
   FILE *M = fopen((std::string(dir) + "/merylIndex").c_str(), "wb");
   if (!M) { mfn_set_error("cannot write '%s/merylIndex'", dir); return MFN_ERR_IO; }
   bool ok = m.dump(M);

@@ -1,5 +1,7 @@
 // Table construction, batch lookup and export kernels.
 #include "table.cuh"
+
+#include <cub/cub.cuh>
 #include "table_host.h"
 
 #include <algorithm>
@@ -467,13 +469,19 @@ extern "C" int mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmer
   int st = MFN_OK;
   if (n > cap) st = MFN_ERR_CAPACITY;
   else if (n) {
-    std::vector<uint64_t> hk(n); std::vector<uint32_t> hv(n);
-    cudaMemcpy(hk.data(), dk, n * 8, cudaMemcpyDeviceToHost);
-    cudaMemcpy(hv.data(), dv, n * 4, cudaMemcpyDeviceToHost);
-    std::vector<uint64_t> idx(n);
-    for (uint64_t i = 0; i < n; i++) idx[i] = i;
-    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
-    for (uint64_t i = 0; i < n; i++) { kmers[i] = hk[idx[i]]; values[i] = hv[idx[i]]; }
+    // ascending by k-mer (the order `meryl print` lists a database in): device radix sort, then
+    // straight into the caller's arrays.  Infrastructure for tests / generators, not the hot path.
+    unsigned long long *dk2 = nullptr; uint32_t *dv2 = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc(&dk2, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dv2, n * 4);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dk2, dv, dv2, (int64_t)n, 0, 64, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dk2, dv, dv2, (int64_t)n, 0, 64, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(kmers, dk2, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, dv2, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dk2); cudaFree(dv2); cudaFree(tmp);
+    if (e != cudaSuccess) { mfn_set_error("export: %s", cudaGetErrorString(e)); st = MFN_ERR_CUDA; }
   }
   *n_out = n;
   cudaFree(dk); cudaFree(dv); cudaFree(dn);

@@ -32,6 +32,17 @@ int meryl_decode_file(const MerylIndex &idx, uint32_t file,
 int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
                            const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn);
 
+// The same with the decode on the device (meryl_gpu.cu): the file images are uploaded as they are
+// on disk and one thread per meryl block decodes its chain of codes.
+int meryl_stream_to_device_gpu(mfn_ctx *ctx, const MerylIndex &idx,
+                               const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn);
+// the decoder in use: the device one unless MFN_HOST_DECODE=1
+inline int meryl_stream(mfn_ctx *ctx, const MerylIndex &idx,
+                        const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn) {
+  const char *env = getenv("MFN_HOST_DECODE");
+  return (env && atoi(env)) ? meryl_stream_to_device(ctx, idx, fn) : meryl_stream_to_device_gpu(ctx, idx, fn);
+}
+
 // ---- sequences ------------------------------------------------------------------
 int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out);
 // done == nullptr: the compute stream is made to wait for the packed range; otherwise `done` is

@@ -422,3 +422,41 @@ def test_host_packing_lane_equals_device_packing(ctx, monkeypatch):
         assert len(d.pairs) == len(x.pairs) and (d.pairs == x.pairs).all() and (d.per_seq == x.per_seq).all()
     assert int(d.per_seq["kasm"].sum()) > 11_000_000
     seq.close(); R.close(); A.close()
+
+
+@pytest.mark.parametrize("name", ["g1_k21", "g2_k6", "g3_k31"])
+def test_gpu_decode_equals_host_decode(ctx, golden_dir, monkeypatch, name):
+    """The device decoder of the on-disk meryl blocks (meryl_gpu.cu: one thread per block walks the
+    unary/binary chain) yields exactly the (k-mer, value) pairs of the host decoder, which the
+    CPU tests pin to `meryl print`."""
+    from merfin_b200 import api
+    for db in ("reads.meryl", "asm.meryl"):
+        path = os.path.join(golden_dir, name, db)
+        monkeypatch.setenv("MFN_HOST_DECODE", "1")
+        H = api.MerylExactLookup.load(ctx, path)
+        monkeypatch.delenv("MFN_HOST_DECODE")
+        G = api.MerylExactLookup.load(ctx, path)
+        hk, hv = H.export()
+        gk, gv = G.export()
+        ho, go = np.argsort(hk), np.argsort(gk)
+        assert len(hk) == len(gk) > 0
+        assert (hk[ho] == gk[go]).all() and (hv[ho] == gv[go]).all()
+        H.close(); G.close()
+
+
+def test_gpu_decode_written_database(ctx, tmp_path):
+    """A larger database with many blocks per file, written by mfn_meryl_write (which the
+    reference reads back in the CPU tests), decoded on the device."""
+    from merfin_b200 import api
+    k = 21
+    rng = np.random.default_rng(11)
+    km = np.unique(rng.integers(0, 1 << 42, size=3_000_000, dtype=np.uint64))
+    vv = rng.integers(1, 70000, size=len(km), dtype=np.uint32)
+    vv[::1000] = 0xFFFFFFF0                                   # values that need the excess table
+    d = str(tmp_path / "w.meryl")
+    api.meryl_write(d, k, km, vv)
+    T = api.MerylExactLookup.load(ctx, d)
+    gk, gv = T.export()
+    o = np.argsort(gk)
+    assert (gk[o] == km).all() and (gv[o] == vv).all()
+    T.close()

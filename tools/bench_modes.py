@@ -136,6 +136,21 @@ def main():
                     km, vv = t.export()
                     api.meryl_write(os.path.join(d, name), k, km, vv)
                 wsec = time.time() - t0
+                # table load from disk: device decode (default) vs host decode
+                loads = {}
+                for label, envv in (("gpu_decode", None), ("host_decode", "1"), ("gpu_decode_again", None)):
+                    if envv:
+                        os.environ["MFN_HOST_DECODE"] = envv
+                    else:
+                        os.environ.pop("MFN_HOST_DECODE", None)
+                    t0 = time.time()
+                    T = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
+                    ctx.sync()
+                    loads[label] = time.time() - t0
+                    T.close()
+                os.environ.pop("MFN_HOST_DECODE", None)
+                emit({"mode": "mfn_table_load (reads.meryl from disk -> HBM table, wall clock)", **tinfo, "read_kmers": int(R.nKmers()),
+                      "seconds": loads, "kmers_per_s": {k_: R.nKmers() / v for k_, v in loads.items()}})
                 t0 = time.time()
                 tot, undr, _pairs = api.completeness(ctx, os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), api.KModel(B.PEAK))
                 dt = time.time() - t0
