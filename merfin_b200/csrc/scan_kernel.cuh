@@ -25,7 +25,7 @@
 #define SEQ_WORDS (MFN_TILE / 32 + 2)      // 66 words = 528 B
 #define OK_WORDS (MFN_TILE / 64 + 2)       // 34 words = 272 B
 #define SH_R 512u                          // shared-memory tier of the joint histogram
-#define SH_A 8u
+#define SH_A 16u
 #define SCAN_DUMP 1
 #define SCAN_JOINT 2
 

@@ -356,12 +356,13 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
   // one entry whose home sector is in registers
   auto settle = [&](unsigned long long e, const Bucket &b) {
     const uint32_t lw = (uint32_t)e, hw = (uint32_t)(e >> 32);
-    bool fast;
+    bool fast, settled;                           // settled: the home sector holds the k-mer
     uint32_t vr, va;
     if (!W64) {
       const uint32_t pay = sweep_match32(b, ~((lw << vb) & P.pr_wmask), P.pr_lim);
       vr = pay >> abits; va = pay & amax;
-      fast = pay != 0xffffffffu && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
+      settled = pay != 0xffffffffu;
+      fast = settled && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
     } else {
       // 64-bit slots (4 per sector): same test on 64-bit words
       const uint64_t nwant = ~((uint64_t)(lw & tmask) << vb), lim64 = (1ull << vb) - 1ull;
@@ -373,9 +374,12 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
       }
       const uint64_t r64 = pay >> abits;
       vr = (uint32_t)r64; va = (uint32_t)pay & amax;
-      fast = pay != ~0ull && r64 < rhi && vr >= rlo && va < alim && (int32_t)hw >= 0;
+      settled = pay != ~0ull && r64 < P.J.rmax;
+      fast = settled && r64 < rhi && vr >= rlo && va < alim && (int32_t)hw >= 0;
     }
     if (fast) atomicAdd(&s_hist[va * SH_R + vr], 1u);
+    else if (settled && vr >= rlo && vr < min(P.J.rmax, MFN_DENSE_R) && va < min(amax, MFN_DENSE_A) && (int32_t)hw >= 0)
+      atomicAdd(&P.acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);   // found, just outside the shared-memory tier: global tier, fire and forget
     else q[atomicAdd(qn_p, 1u)] = e;
   };
 
