@@ -97,7 +97,7 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &P.zlen, &zhi));
   P.zmap = zmap;
   int st;
-  if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0))
+  if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0, seq->nseq))
     st = mfn_sweep_hist(ctx, reads, asm_, seq, km, P.tile_begin, P.tile_end, acc, zmap, P.zlen, zhi);
   else
     st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));

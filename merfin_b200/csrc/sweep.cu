@@ -6,26 +6,33 @@
 // ------------------------------------------------------------------------------------------
 static uint32_t bits_of(uint64_t x) { uint32_t n = 0; while (x) { n++; x >>= 1; } return n; }
 
-// bins of 2^lbits lines: slice <= 16 MB (32 MB if that is what it takes to stay <= 2048 bins);
-// the entry's low word holds (line in bin) << tbits | tag, so lbits + tbits <= 32
-static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, uint32_t &nbins) {
+// bins of 2^lbits lines: slice <= 16 MB (32 MB if that is what it takes to stay <= 2048 bins).
+// The entry's low part holds (line in bin) << tbits | tag: 32 bits when that fits (narrow entries),
+// else up to 52 bits for tables with 64-bit slots (wide entries, fewer bits left for the record).
+static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, uint32_t &nbins, uint32_t &lowbits) {
   tbits = std::max(1u, bits_of(J.D - 1));
-  if (tbits >= 31 || J.nlines >= (1ull << 32)) return false;
-  for (uint32_t lb : {17u, 18u}) {
-    lbits = std::min(lb, 32u - tbits);
-    nbins = (uint32_t)ceil_div_u64(J.nlines, 1ull << lbits);
-    if (nbins <= SW_MAX_BINS) return true;
+  if (J.nlines >= (1ull << 32)) return false;
+  for (int wide = 0; wide < 2; wide++) {
+    const uint32_t room = wide ? 52u : 32u;
+    if (wide && !J.w64) break;
+    if (tbits + 1 > room) continue;
+    for (uint32_t lb : {17u, 18u}) {
+      lbits = std::min(lb, room - tbits);
+      nbins = (uint32_t)ceil_div_u64(J.nlines, 1ull << lbits);
+      if (nbins <= SW_MAX_BINS) { lowbits = wide ? lbits + tbits : 32u; return true; }
+    }
   }
   return false;
 }
 
 // Can (and should) this scan use the sweep?
-bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles) {
+bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, uint32_t nseq) {
   const char *env = getenv("MFN_SWEEP");
   if (env && atoi(env) == 0) return false;
   if (!R->joint || R->joint->asm_ != A) return false;
-  uint32_t lbits, tbits, nbins;
-  if (!sweep_geometry(R->joint->dev, lbits, tbits, nbins)) return false;
+  uint32_t lbits, tbits, nbins, lowbits;
+  if (!sweep_geometry(R->joint->dev, lbits, tbits, nbins, lowbits)) return false;
+  if ((uint64_t)nseq + 1 >= (1ull << (63 - lowbits))) return false;       // record ids must fit the entry
   if (env && atoi(env) == 1) return true;
   // worth it when the windows revisit the table lines: >= 1 window per 4 lines, and a big batch
   const uint64_t windows = ntiles * MFN_TILE;
@@ -42,7 +49,7 @@ struct mfn_sweep {
 
 int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out) {
-  if (seq->nseq >= 0x7fffffffu) { mfn_set_error("sweep: too many records"); return MFN_ERR_UNSUPPORTED; }
+
   const JointDev &J = R->joint->dev;
   mfn_sweep *w = new mfn_sweep();
   SweepParams &P = w->P;
@@ -52,7 +59,8 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
     const uint64_t gpad = (seq->ntiles + 1) * MFN_TILE + 256;            // as allocated by mfn_seq_alloc
     P.seq_words = gpad / 32 + 8; P.ok_words = gpad / 64 + 8;
   }
-  if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins)) { delete w; mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
+  if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins, P.lowbits)) { delete w; mfn_set_error("sweep: table geometry not supported"); return MFN_ERR_UNSUPPORTED; }
+  if ((uint64_t)seq->nseq + 1 >= (1ull << (63 - P.lowbits))) { delete w; mfn_set_error("sweep: %u records do not fit the entry", seq->nseq); return MFN_ERR_UNSUPPORTED; }
   P.nbins_pad = (P.nbins + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
   P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;
   P.over_cap = std::max<uint64_t>(1 << 20, windows / 16);
@@ -95,10 +103,17 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
     kernel<<<grid, SC_THREADS, sc_smem, ctx->stream>>>(P);
     return MFN_OK;
   };
-  switch (P.J.k) {
-    case 21: MFN_TRY(launch(k_sweep_scatter<21>)); break;
-    case 31: MFN_TRY(launch(k_sweep_scatter<31>)); break;
-    default: MFN_TRY(launch(k_sweep_scatter<0>)); break;
+  if (P.lowbits > 32) {
+    switch (P.J.k) {
+      case 31: MFN_TRY(launch(k_sweep_scatter<31, true>)); break;
+      default: MFN_TRY(launch(k_sweep_scatter<0, true>)); break;
+    }
+  } else {
+    switch (P.J.k) {
+      case 21: MFN_TRY(launch(k_sweep_scatter<21, false>)); break;
+      case 31: MFN_TRY(launch(k_sweep_scatter<31, false>)); break;
+      default: MFN_TRY(launch(k_sweep_scatter<0, false>)); break;
+    }
   }
   ctx->launches++;
   MFN_CUDA(cudaGetLastError());

@@ -19,9 +19,12 @@
 // DRAM traffic per window: 8 B written + 8 B read + (table bytes / windows) instead of 128 B.
 // Integer results are identical to the direct scan (same lookups, sums are order-free).
 //
-// Entry (8 bytes):  bits 0..31   (line in bin) << tbits | tag
-//                   bits 32..62  record id
-//                   bit  63      the k-mer is its own reverse complement: counts twice (Q2)
+// Entry (8 bytes):  bits 0..lowbits-1   (line in bin) << tbits | tag
+//                   bits lowbits..62   record id
+//                   bit  63            the k-mer is its own reverse complement: counts twice (Q2)
+// lowbits = 32 ("narrow") whenever line-in-bin and tag fit 32 bits (k = 21 at any table size);
+// wide tags (k = 31: 34-46 bits) use lowbits = lbits + tbits <= 52 and leave fewer bits for the
+// record id (the scan falls back to k_scan when the records do not fit).
 #pragma once
 #include "scan_kernel.cuh"
 
@@ -45,12 +48,13 @@ struct SweepParams {
   uint64_t seq_words, ok_words;              // allocated length of seq2 / ok (TMA copies are clamped to it)
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
-  uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low word = (line & L-1) << tbits | tag
+  uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low part = (line & L-1) << tbits | tag
+  uint32_t lowbits;                          // width of the low part: 32 (narrow) or lbits + tbits (wide)
   unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b)
   uint64_t cap;
   unsigned long long *bin_count;             // [nbins_pad] reserved entries (may exceed cap)
   unsigned long long *bin_valid;             // [nbins_pad] first reservation that did not fit (~0: none)
-  unsigned long long *over_lt;               // windows that found no room in their bin: line << 32 | tag ...
+  unsigned long long *over_lt;               // windows that found no room in their bin: h = line * D + tag ...
   uint32_t *over_rec;                        //   ... and record id (bit 31: counts twice)
   unsigned long long *over_n;
   uint64_t over_cap;
@@ -66,8 +70,9 @@ struct SweepParams {
 // ------------------------------------------------------------------------------------------
 // pass 1.  KK: mer size known at compile time (0 = read it from the table)
 // ------------------------------------------------------------------------------------------
-template <int KK>
-__global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+template <int KK, bool WIDE>
+__global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+  typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type low_t;
   extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
   unsigned long long *s_ent = (unsigned long long *)sw_smem;           // [SW_CHUNK] entries sorted by bin
   unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of the chunk's sorted position 0, per bin
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
 
     // ---- hash this thread's windows; rank them inside their bins ---------------------------
     // meta: bin (0..10) | rank in bin (11..23) | record delta (24..30) | counts twice (31)
-    uint32_t low[SC_NW], meta[SC_NW];
+    low_t low[SC_NW];
+    uint32_t meta[SC_NW];
 #pragma unroll
     for (int q = 0; q < SC_TPT; q++) {
       const uint64_t tile = tile0 + q * (SC_THREADS / (MFN_TILE / WPT)) + grp;
@@ -187,15 +193,16 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
           if (rd == 0) { n_ok0++; continue; }
           atomicAdd(&rec_acc[2 * rec], 1ull);
           my_valid++;
-          if (rd <= SW_MAX_RD) { rdpack |= (uint64_t)rd << (7 * u); continue; }
-          // a chunk spanning > 126 records: this window goes to the side list
+          if (!WIDE && rd <= SW_MAX_RD) { rdpack |= (uint64_t)rd << (7 * u); continue; }
+          // a chunk spanning > 126 records (wide entries: any record but the chunk's first): this
+          // window goes to the side list
           vmask &= ~(1u << u);
           const uint64_t x = (u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo) & kmask;
           const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
           uint64_t line, tag;
           joint_split(mfn_mix(f < r ? f : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
           unsigned long long o = atomicAdd(P.over_n, 1ull);
-          if (o < P.over_cap) { P.over_lt[o] = (line << 32) | tag; P.over_rec[o] = rec | ((even_k && f == r) ? 0x80000000u : 0u); }
+          if (o < P.over_cap) { P.over_lt[o] = line * P.J.D + tag; P.over_rec[o] = rec | ((even_k && f == r) ? 0x80000000u : 0u); }
           else atomicAdd(&P.acc[2], 1ull);
         }
       }
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
         joint_split(mfn_mix(F < r ? F : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
         const uint32_t bin = (uint32_t)line >> P.lbits;
         const uint32_t rank = atomicAdd(&s_off[bin], 1u);
-        low[idx] = (((uint32_t)line & lmask) << P.tbits) | (uint32_t)tag;
+        low[idx] = (low_t)((((uint64_t)((uint32_t)line & lmask)) << P.tbits) | tag);
         meta[idx] = bin | (rank << 11) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << 24) | twice;
       }
     }
@@ -259,7 +266,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
       const uint32_t m = meta[idx];
       if (m == 0xffffffffu) continue;
       const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & 0x1fffu);
-      s_ent[p] = ((unsigned long long)(m & 0xff0007ffu) << 32) | low[idx];
+      // staged: narrow = meta without the rank << 32 | low; wide = twice (63) | bin (52..62) | low (0..51)
+      if (WIDE) s_ent[p] = ((unsigned long long)(m & 0x80000000u) << 32) | ((unsigned long long)(m & 0x7ffu) << 52) | low[idx];
+      else s_ent[p] = ((unsigned long long)(m & 0xff0007ffu) << 32) | low[idx];
     }
     // where each bin's run goes: global index of the chunk's sorted position 0
 #pragma unroll
@@ -279,16 +288,28 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
 #pragma unroll 4
       for (uint32_t i = tid; i < total; i += SC_THREADS) {
         const unsigned long long e = s_ent[i];
-        const uint32_t hs = (uint32_t)(e >> 32), lw = (uint32_t)e;
-        const uint32_t bin = hs & 0x7ffu;
-        const uint32_t rec = (r0 + ((hs >> 24) & 0x7fu)) | (hs & 0x80000000u);
+        uint32_t bin, rec;
+        unsigned long long lowpart, out;
+        if (WIDE) {
+          bin = (uint32_t)(e >> 52) & 0x7ffu;
+          lowpart = e & 0x000fffffffffffffull;
+          rec = r0 | ((uint32_t)(e >> 32) & 0x80000000u);
+          out = lowpart | ((unsigned long long)r0 << P.lowbits) | (e & 0x8000000000000000ull);
+        } else {
+          const uint32_t hs = (uint32_t)(e >> 32);
+          bin = hs & 0x7ffu;
+          lowpart = (uint32_t)e;
+          rec = (r0 + ((hs >> 24) & 0x7fu)) | (hs & 0x80000000u);
+          out = ((unsigned long long)rec << 32) | lowpart;
+        }
         const unsigned long long dst = s_dst[bin];
         if ((long long)dst >= 0) {
-          P.entries[(dst + i) & 0x7fffffffffffffffull] = ((unsigned long long)rec << 32) | lw;
+          P.entries[(dst + i) & 0x7fffffffffffffffull] = out;
         } else {
           unsigned long long o = atomicAdd(P.over_n, 1ull);
           if (o < P.over_cap) {
-            P.over_lt[o] = ((((uint64_t)bin << P.lbits) | (lw >> P.tbits)) << 32) | (lw & ((1u << P.tbits) - 1u));
+            const uint64_t line = ((uint64_t)bin << P.lbits) | (lowpart >> P.tbits);
+            P.over_lt[o] = line * P.J.D + (lowpart & ((1ull << P.tbits) - 1ull));
             P.over_rec[o] = rec;
           } else atomicAdd(&P.acc[2], 1ull);               // reported as MFN_ERR_CAPACITY at fetch
         }
@@ -307,7 +328,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_sweep_scatter(const __grid_co
 // Everything the home sector alone does not settle (spilled or absent k-mer, saturated value,
 // v_read == 0, pair outside the shared-memory tier, k-mer that counts twice): complete lookup and
 // the general accumulation, as in k_scan.
-__device__ __forceinline__ void sweep_slow(const SweepParams &P, uint32_t *s_hist, uint32_t line, uint32_t tag,
+__device__ __forceinline__ void sweep_slow(const SweepParams &P, uint32_t *s_hist, uint32_t line, uint64_t tag,
                                            uint32_t rec_flag) {
   uint32_t vr, va;                                       // side tables are keyed by k-mer
   joint_full(P.J, mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k), line, tag, vr, va);
@@ -343,7 +364,13 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
 
   const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
   const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
-  const uint32_t tbits = P.tbits, tmask = (1u << tbits) - 1u;
+  const uint32_t tbits = P.tbits;
+  const uint64_t tmask64 = (1ull << tbits) - 1ull;
+  // entry fields (W64 tables may use wide entries: the low part is lowbits wide, the record above it)
+  const uint32_t lowbits = W64 ? P.lowbits : 32u;
+  const uint64_t lowmask = (1ull << lowbits) - 1ull;
+  const uint32_t recmask = (uint32_t)((1ull << (63 - lowbits)) - 1ull);
+  auto recflag_of = [&](unsigned long long e) { return ((uint32_t)(e >> lowbits) & recmask) | ((uint32_t)(e >> 32) & 0x80000000u); };
   const uint32_t vb = P.J.rbits + P.J.abits, abits = P.J.abits, amax = P.J.amax;
   // pairs the fast path takes: rlo <= v_read < min(rmax, SH_R), v_asm < min(amax, SH_A); everything
   // else (v_read == 0 or zeroed by -prob, saturated fields, big values) goes to the queue
@@ -355,7 +382,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
 
   // one entry whose home sector is in registers
   auto settle = [&](unsigned long long e, const Bucket &b) {
-    const uint32_t lw = (uint32_t)e, hw = (uint32_t)(e >> 32);
+    const uint32_t lw = (uint32_t)e, hw = (uint32_t)(e >> 32);   // bit 31 of hw: counts twice
     bool fast, settled;                           // settled: the home sector holds the k-mer
     uint32_t vr, va;
     if (!W64) {
@@ -365,7 +392,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
       fast = settled && (vr - rlo) < rspan && va < alim && (int32_t)hw >= 0;
     } else {
       // 64-bit slots (4 per sector): same test on 64-bit words
-      const uint64_t nwant = ~((uint64_t)(lw & tmask) << vb), lim64 = (1ull << vb) - 1ull;
+      const uint64_t nwant = ~(((e & lowmask) & tmask64) << vb), lim64 = (1ull << vb) - 1ull;
       uint64_t pay = ~0ull;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -406,6 +433,10 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
                    : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + bt * 128u + lane * 4u));
     };
     auto sector_of = [&](unsigned long long e) {
+      if (W64) {
+        const uint64_t lp = e & lowmask;
+        return slice + (((lp >> tbits) << 2) | (lp & 3u)) * 32;
+      }
       const uint32_t lw = (uint32_t)e;
       return slice + (uint64_t)(((lw >> tbits) << 2) | (lw & 3u)) * 32;
     };
@@ -418,8 +449,8 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
         const uint32_t take = min(qn, 32u);
         if (lane < take) {
           const unsigned long long x = q[qn - take + lane];
-          const uint32_t lw = (uint32_t)x;
-          sweep_slow(P, s_hist, line0 + (lw >> tbits), lw & tmask, (uint32_t)(x >> 32));
+          const uint64_t lp = x & lowmask;
+          sweep_slow(P, s_hist, line0 + (uint32_t)(lp >> tbits), lp & tmask64, recflag_of(x));
         }
         qn -= take;
         __syncwarp();
@@ -468,8 +499,9 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_over(const __grid_constant
   __syncthreads();
   const uint64_t n = min(*P.over_n, (unsigned long long)P.over_cap);
   for (uint64_t i = blockIdx.x * (uint64_t)SW_THREADS + tid; i < n; i += (uint64_t)gridDim.x * SW_THREADS) {
-    const unsigned long long lt = P.over_lt[i];
-    sweep_slow(P, s_hist, (uint32_t)(lt >> 32), (uint32_t)lt, P.over_rec[i]);
+    uint64_t line, tag;
+    joint_split(P.over_lt[i], P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
+    sweep_slow(P, s_hist, (uint32_t)line, tag, P.over_rec[i]);
   }
   __syncthreads();
   for (uint32_t i = tid; i < SH_R * SH_A; i += SW_THREADS) {

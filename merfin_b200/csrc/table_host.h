@@ -74,7 +74,7 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
 void mfn_joint_free(mfn_joint *j);
 
 // ---- range-partitioned -hist scan (sweep.cu) --------------------------------------------------
-bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles);
+bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, uint32_t nseq);
 int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
                    uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen,
                    uint32_t zhi);

@@ -350,7 +350,7 @@ def test_k_mismatch_is_an_error(ctx, golden_dir):
 
 
 # ---------------------------------------------------------------------------------- sweep (range-partitioned scan)
-@pytest.mark.parametrize("k", [21, 16, 6])
+@pytest.mark.parametrize("k", [21, 16, 6, 31])
 def test_sweep_equals_direct_scan(ctx, monkeypatch, k):
     """The range-partitioned -hist scan gives the same joint histogram and per-record counters as
     the direct scan (forced on here; it is chosen automatically for large batches)."""
