@@ -460,3 +460,67 @@ def test_gpu_decode_written_database(ctx, tmp_path):
     o = np.argsort(gk)
     assert (gk[o] == km).all() and (gv[o] == vv).all()
     T.close()
+
+
+def _run_reference_hist(workdir, args):
+    import subprocess
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "merfin")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/merfin not built (reference sources absent)")
+    p = subprocess.run([ref] + args, cwd=workdir, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stderr
+
+
+@pytest.mark.parametrize("k,mn,prob", [(21, 0, False), (21, 2, True), (31, 0, False)])
+def test_midsize_hist_against_reference_binary(ctx, tmp_path, monkeypatch, k, mn, prob):
+    """12 Mbp through every fast path at once (host-buffer call, both ingest lanes, sub-sweeps,
+    range-partitioned scan, device decode of the databases) against the UNMODIFIED reference
+    binary run here on the same FASTA and the same on-disk meryl databases: -hist file byte for
+    byte, missing / found counts exactly, the printed QV lines as printed."""
+    from merfin_b200 import api, synth
+    recs = [(n, b.tobytes()) for n, b in synth.make_assembly(12_000_000, 7, 100 + k, dup_len=5000)]
+    seq = api.SeqSet(ctx, recs)
+    A0 = api.MerylExactLookup.count_sequence(ctx, k, seq)
+    R0 = api.MerylExactLookup.synth_reads(ctx, A0, 12.0, 4_000_000, 9)
+    d = str(tmp_path)
+    with open(os.path.join(d, "asm.fa"), "wb") as f:
+        for n, b in recs:
+            f.write(b">" + n.encode() + b" some description\n")
+            for i in range(0, len(b), 100000):
+                f.write(b[i:i + 100000] + b"\n")
+    for t, name in ((A0, "asm.meryl"), (R0, "reads.meryl")):
+        km_, vv_ = t.export()
+        api.meryl_write(os.path.join(d, name), k, km_, vv_)
+    seq.close(); A0.close(); R0.close()
+    args = ["-hist", "-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl", "-peak", "12",
+            "-threads", "8", "-memory", "32", "-output", "ref.hist"]
+    probfile = None
+    if prob:
+        probfile = os.path.join(d, "prob.csv")
+        with open(probfile, "w") as f:      # readK 0 for multiplicities 1-2, then K = round(v/12) with decreasing confidence
+            for v in range(1, 120):
+                f.write("%d,%.3f\n" % (0 if v <= 2 else max(1, round(v / 12)), max(0.05, 1.0 - v / 150)))
+        args += ["-prob", "prob.csv"]
+    if mn:
+        args += ["-min", str(mn)]
+    err = _run_reference_hist(d, args)
+    want_file = open(os.path.join(d, "ref.hist"), "rb").read()
+    import re
+    want_summary = "\n".join(l for l in err.splitlines() if re.match(r"^(K-mers|Missing QV|Merfin QV)", l)) + "\n"
+
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"), mn, 0xFFFFFFFF)
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    R.fuse(A)
+    km = api.KModel.load_Kmetric(12.0, probfile)
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    monkeypatch.setenv("MFN_SUBSWEEPS", "2")
+    monkeypatch.setenv("MFN_HOST_PACK_SHARE", "0.5")
+    monkeypatch.setenv("MFN_HOST_PACK_THREADS", "4")
+    res = api.hist(ctx, R, A, recs, km)
+    assert res.file_text() == want_file
+    assert res.summary_text() == want_summary
+    monkeypatch.setenv("MFN_SWEEP", "0")
+    res2 = api.hist(ctx, R, A, recs, km)
+    assert (res.pairs == res2.pairs).all() and (res.per_seq == res2.per_seq).all()
+    R.close(); A.close()
