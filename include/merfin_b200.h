@@ -251,6 +251,13 @@ int  mfn_hist_format(const uint64_t *undr, uint32_t n_undr, const uint64_t *over
 void mfn_getK(const mfn_kmodel *km, uint32_t v_read, uint32_t v_asm,
               double *readK, double *asmK, double *prob);          /* merfin-globals.C:66-98   */
 double mfn_getKmetric(double readK, double asmK);                  /* merfin-globals.H:248-261 */
+/* -dump text of one record (merfin-dump.C:87-93, outputDump): "%s\t%lu\t%.2f\t%.2f\t%.2f\n" for
+ * every valid position whose (readK, asmK, k*) are not all zero, written to file descriptor fd
+ * in position order; fd < 0 only counts (what -skipMissing does, merfin-dump.C:34-38).  The
+ * arrays are the record's slices of mfn_dump's output.  Formatting runs on `threads` host threads
+ * (0 = all cores).  counts receives the record's kasm / kmissing (merfin-dump.C:58-66). */
+int  mfn_dump_write(int fd, const char *ident, uint64_t n, const uint32_t *v_read, const uint32_t *v_asm,
+                    const uint8_t *valid, const mfn_kmodel *km, int threads, mfn_seq_counts *counts);
 /* -completeness sums from the joint histogram of raw values. */
 int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const mfn_kmodel *km,
                              double *total, double *undr);

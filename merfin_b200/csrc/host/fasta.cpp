@@ -1,5 +1,8 @@
 #include "fasta.h"
 
+#include <immintrin.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -35,6 +38,33 @@ bool slurp_file(const std::string &path, std::vector<char> &data, std::string &e
 
 static inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
 
+// Append the non-whitespace bytes of [p, p + n) to `bases`.  A sequence line is normally free of
+// whitespace, so blocks of 32 bytes without any byte <= ' ' are copied as they are (AVX2 when the
+// CPU has it); anything else goes through the per-byte filter.
+__attribute__((target("avx2"))) static size_t clean_prefix_avx2(const char *p, size_t n) {
+  size_t i = 0;
+  const __m256i lim = _mm256_set1_epi8(0x21);
+  for (; i + 32 <= n; i += 32) {
+    const __m256i v = _mm256_loadu_si256((const __m256i *)(p + i));
+    // bytes 0x00..0x20 (and none of 0x80..0xff, which compare as negative: checked below)
+    const __m256i low = _mm256_cmpgt_epi8(lim, v);
+    if (_mm256_movemask_epi8(low)) break;
+  }
+  return i;
+}
+static void append_bases(std::vector<char> &bases, const char *p, size_t n) {
+  static const bool avx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2"));
+  size_t i = 0;
+  while (i < n) {
+    if (avx2 && n - i >= 32) {
+      const size_t c = clean_prefix_avx2(p + i, n - i);
+      if (c) { bases.insert(bases.end(), p + i, p + i + c); i += c; continue; }
+    }
+    const size_t e = std::min(n, i + 32);
+    for (; i < e; i++) if (!is_space(p[i])) bases.push_back(p[i]);
+  }
+}
+
 bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
   std::vector<char> data;
   if (!slurp_file(path, data, err)) return false;
@@ -62,8 +92,13 @@ bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
         size_t e = nl ? (size_t)(nl - data.data()) : N;
         // a marker inside the line ends the record there
         size_t stop = e;
-        for (size_t q = p; q < e; q++) if (data[q] == '>' || data[q] == '@') { stop = q; break; }
-        for (size_t q = p; q < stop; q++) if (!is_space(data[q])) out.bases.push_back(data[q]);
+        {
+          const char *m1 = (const char *)memchr(data.data() + p, '>', e - p);
+          if (m1) stop = (size_t)(m1 - data.data());
+          const char *m2 = (const char *)memchr(data.data() + p, '@', stop - p);
+          if (m2) stop = (size_t)(m2 - data.data());
+        }
+        append_bases(out.bases, data.data() + p, stop - p);
         p = stop;
         if (stop == e && p < N) p++;                     // consume the newline
       }

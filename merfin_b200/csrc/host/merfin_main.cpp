@@ -22,6 +22,7 @@ struct Globals {
   double peak = 0;
   uint64_t minV = 0, maxV = ~0ull;
   uint32_t comb = 15;
+  uint32_t threads = 0;          // host threads for the -dump formatter (0 = all cores)
   int report = OP_NONE, device = 0;
   bool nosplit = false, skipMissing = false, debug = false, nofuse = false;
   std::vector<uint32_t> probK;
@@ -43,7 +44,7 @@ static void usage(const char *argv0, const std::vector<std::string> &err) {
   fprintf(stderr, "         -output   <output>        \n\n");
   fprintf(stderr, "  Report types: -hist, -dump [-skipMissing], -completeness, -filter, -polish, -better, -strict, -loose\n");
   fprintf(stderr, "  Options:      -seqmers <seq.meryl>  -min m  -max m  -comb N  -nosplit  -debug\n");
-  fprintf(stderr, "                -threads t  -memory m   (accepted for compatibility; the work runs on the GPU)\n");
+  fprintf(stderr, "                -threads t  (host threads of the -dump formatter)   -memory m   (accepted for compatibility)\n");
   fprintf(stderr, "                -device d   CUDA device to use (default 0)\n");
   fprintf(stderr, "  This is the B200 build of merfin's k-mer evaluation; flags and outputs follow merfin.\n\n");
   for (const std::string &e : err) fputs(e.c_str(), stderr);
@@ -108,7 +109,7 @@ int main(int argc, char **argv) {
     else if (is("-output")) G.outName = next();
     else if (is("-min")) G.minV = strtoull(next(), nullptr, 10);
     else if (is("-max")) G.maxV = strtoull(next(), nullptr, 10);
-    else if (is("-threads")) next();
+    else if (is("-threads")) G.threads = (uint32_t)strtoul(next(), nullptr, 10);
     else if (is("-memory")) next();
     else if (is("-device")) G.device = atoi(next());
     else if (is("-nofuse")) G.nofuse = true;
@@ -249,21 +250,13 @@ int main(int argc, char **argv) {
     uint64_t totMissing = 0, totAsm = 0;
     for (size_t i = 0; i < S.nseq(); i++) {
       if (!G.skipMissing && !F) { F = fopen(G.outName, "w"); if (!F) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; } }
-      uint64_t kasm = 0, kmiss = 0;
-      for (uint64_t p = S.off[i]; p < S.off[i + 1]; p++) {
-        if (!ok[p]) continue;
-        double readK, asmK, prob;
-        mfn_getK(&km, vr[p], va[p], &readK, &asmK, &prob);
-        kasm++;
-        if (readK == 0) kmiss++;
-        if (!G.skipMissing) {
-          double ks = mfn_getKmetric(readK, asmK);
-          if (readK != 0.0 || asmK != 0.0 || ks != 0.0)
-            fprintf(F, "%s\t%lu\t%.2f\t%.2f\t%.2f\n", S.ident[i].c_str(), (unsigned long)(p - S.off[i]), readK, asmK, ks);
-        }
-      }
-      totMissing += kmiss; totAsm += kasm;
-      fprintf(stderr, "%s\t%lu\t%lu\t%lu\n", S.ident[i].c_str(), (unsigned long)kmiss, (unsigned long)totMissing, (unsigned long)totAsm);
+      // lines of this record, formatted on all host threads and written in position order
+      mfn_seq_counts c{};
+      const uint64_t a = S.off[i], n = S.off[i + 1] - S.off[i];
+      if (F) fflush(F);
+      if (mfn_dump_write(F ? fileno(F) : -1, S.ident[i].c_str(), n, vr.data() + a, va.data() + a, ok.data() + a, &km, (int)G.threads, &c) != MFN_OK) die("-dump");
+      totMissing += c.kmissing; totAsm += c.kasm;
+      fprintf(stderr, "%s\t%lu\t%lu\t%lu\n", S.ident[i].c_str(), (unsigned long)c.kmissing, (unsigned long)totMissing, (unsigned long)totAsm);
     }
     if (F) fclose(F);
   }

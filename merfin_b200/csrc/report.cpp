@@ -116,3 +116,92 @@ extern "C" int mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npa
   *total = t; *undr = u;
   return MFN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// -dump text (merfin-dump.C:87-93): "%s\t%lu\t%.2f\t%.2f\t%.2f\n" of (readK, asmK, k*) for every
+// valid window whose three numbers are not all zero.  The reference formats every line with
+// fprintf in its single writer thread; here the positions are cut into chunks that worker threads
+// format side by side (the three %.2f fields depend only on the integer pair, so each thread keeps
+// the formatted tail of every pair it has seen), and the chunks are written in order.
+// ---------------------------------------------------------------------------------------------
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <unordered_map>
+
+namespace {
+struct DumpChunk { std::string text; uint64_t kasm = 0, kmiss = 0; };
+
+void format_chunk(const char *ident, size_t ident_len, uint64_t p0, uint64_t p1, const uint32_t *vr, const uint32_t *va,
+                  const uint8_t *ok, const mfn_kmodel *km, bool want_text, DumpChunk &out) {
+  std::unordered_map<uint64_t, std::string> tails;        // pair -> "\t%.2f\t%.2f\t%.2f\n", empty string = line suppressed
+  std::unordered_map<uint64_t, bool> miss;
+  out.text.clear();
+  if (want_text) out.text.reserve((size_t)(p1 - p0) * (ident_len + 28));
+  char num[24];
+  for (uint64_t p = p0; p < p1; p++) {
+    if (!ok[p]) continue;
+    const uint64_t key = ((uint64_t)vr[p] << 32) | va[p];
+    auto it = tails.find(key);
+    if (it == tails.end()) {
+      double readK, asmK, prob;
+      mfn_getK(km, vr[p], va[p], &readK, &asmK, &prob);
+      const double ks = mfn_getKmetric(readK, asmK);
+      char buf[128];
+      int n = 0;
+      if (readK != 0.0 || asmK != 0.0 || ks != 0.0) n = snprintf(buf, sizeof buf, "\t%.2f\t%.2f\t%.2f\n", readK, asmK, ks);
+      it = tails.emplace(key, std::string(buf, (size_t)n)).first;
+      miss[key] = (readK == 0);
+    }
+    out.kasm++;
+    if (miss[key]) out.kmiss++;
+    if (!want_text || it->second.empty()) continue;
+    out.text.append(ident, ident_len);
+    out.text.push_back('\t');
+    uint64_t v = p;                                     // position inside the record, as decimal
+    int d = 0;
+    do { num[d++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (d) out.text.push_back(num[--d]);
+    out.text.append(it->second);
+  }
+}
+}  // namespace
+
+// Format one record's -dump lines into file descriptor fd (fd < 0: count only, as -skipMissing does)
+// with up to `threads` worker threads.  v_read / v_asm / valid are the record's slices of mfn_dump's
+// output (index = position in the record).  Returns the record's kasm / kmissing in *counts.
+extern "C" int mfn_dump_write(int fd, const char *ident, uint64_t n, const uint32_t *v_read, const uint32_t *v_asm,
+                              const uint8_t *valid, const mfn_kmodel *km, int threads, mfn_seq_counts *counts) {
+  if (!ident || (n && (!v_read || !v_asm || !valid))) return MFN_ERR_INVALID;
+  const size_t il = strlen(ident);
+  const uint64_t CH = 1 << 20;
+  const uint64_t nch = (n + CH - 1) / CH;
+  unsigned T = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
+  T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(T, nch));
+  uint64_t kasm = 0, kmiss = 0;
+  std::vector<DumpChunk> round(T);
+  for (uint64_t c0 = 0; c0 < nch; c0 += T) {
+    const unsigned m = (unsigned)std::min<uint64_t>(T, nch - c0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < m; t++)
+      th.emplace_back([&, t]() {
+        const uint64_t a = (c0 + t) * CH, b = std::min(n, a + CH);
+        format_chunk(ident, il, a, b, v_read, v_asm, valid, km, fd >= 0, round[t]);
+      });
+    for (auto &x : th) x.join();
+    for (unsigned t = 0; t < m; t++) {
+      kasm += round[t].kasm; kmiss += round[t].kmiss;
+      const char *p = round[t].text.data();
+      size_t left = fd >= 0 ? round[t].text.size() : 0;
+      while (left) {
+        const ssize_t w = write(fd, p, left);
+        if (w <= 0) { mfn_set_error("-dump: write failed"); return MFN_ERR_IO; }
+        p += w; left -= (size_t)w;
+      }
+    }
+  }
+  if (counts) { counts->kasm = kasm; counts->kmissing = kmiss; }
+  return MFN_OK;
+}

@@ -125,6 +125,7 @@ SIGNATURES = {
                                           C.POINTER(C.c_double)]),
     "mfn_ctx_launch_count": (C.c_uint64, [_P]),
     "mfn_ctx_h2d_bytes": (C.c_uint64, [_P]),
+    "mfn_dump_write": (C.c_int, [C.c_int, C.c_char_p, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "mfn_pack_host_range": (None, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P]),
     "mfn_pack_host_isa": (C.c_char_p, []),
     "mfn_ctx_time_passes": (C.c_int, [_P, C.c_int]),
