@@ -270,6 +270,9 @@ def main():
     torch.cuda.empty_cache()
     asm_np = asm_host.numpy()
 
+    # the host packing lane of mfn_hist_host uses the host cores: split them between the ranks of this box
+    if "MFN_HOST_PACK_THREADS" not in os.environ and world > 1:
+        os.environ["MFN_HOST_PACK_THREADS"] = str(max(1, ((os.cpu_count() or 2) - 2) // world))
     ctx = api.Context(local)
     # a non-default torch stream: our kernels, torch's events and NCCL are all ordered on it
     stream = torch.cuda.Stream(device=dev)
