@@ -8,7 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/merfin_b200.h"
@@ -288,23 +292,54 @@ int main(int argc, char **argv) {
     };
     std::string outPath = std::string(G.outName) + (G.report == OP_POLISH ? ".polish.vcf" : ".filter.vcf");   // merfin-variants.C:324-327 (Q7)
     FILE *O = nullptr, *D = nullptr;
+    // Records are independent: path enumeration and selection run on host threads (one record
+    // per task, like the reference's sweatShop workers), the device call is one at a time, and
+    // the results are written in record order, so the output does not depend on the thread count.
+    std::mutex gpu_mu;
+    mfnv::PathScorer locked_scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, std::vector<uint32_t> &vr,
+                                         std::vector<uint32_t> &va, std::vector<uint8_t> &ok) -> int {
+      std::lock_guard<std::mutex> lk(gpu_mu);
+      return scorer(paths, off, vr, va, ok);
+    };
+    const size_t nrec = S.nseq();
+    std::vector<std::string> results(nrec), dbgs(nrec);
+    std::vector<int> status(nrec, 0);
+    unsigned nthreads = G.threads ? G.threads : std::max(1u, std::thread::hardware_concurrency());
+    if (G.debug) nthreads = 1;                                   // debug records carry a running id
+    nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, nrec));
     uint64_t varMerId = 0;
-    for (size_t i = 0; i < S.nseq(); i++) {
-      auto it = vcf.byChr.find(S.ident[i]);
-      std::string result, dbg;
-      if (it != vcf.byChr.end()) {
-        if (mfnv::process_sequence(S.ident[i], S.seq(i), S.length(i), it->second, opt, scorer, result, G.debug ? &dbg : nullptr, varMerId) != 0) return 1;
-      }
+    {
+      // biggest records first (they bound the makespan)
+      std::vector<size_t> order(nrec);
+      for (size_t i = 0; i < nrec; i++) order[i] = i;
+      if (nthreads > 1) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return S.length(a) > S.length(b); });
+      std::atomic<size_t> next{0};
+      auto worker = [&]() {
+        for (size_t j; (j = next++) < nrec;) {
+          const size_t i = order[j];
+          auto it = vcf.byChr.find(S.ident[i]);
+          if (it == vcf.byChr.end()) continue;
+          uint64_t localId = 0;
+          status[i] = mfnv::process_sequence(S.ident[i], S.seq(i), S.length(i), it->second, opt, locked_scorer, results[i],
+                                             G.debug ? &dbgs[i] : nullptr, nthreads == 1 ? varMerId : localId);
+        }
+      };
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nthreads; t++) th.emplace_back(worker);
+      worker();
+      for (auto &t : th) t.join();
+    }
+    for (size_t i = 0; i < nrec; i++) {
+      if (status[i] != 0) return 1;
       if (!O) {                                                  // outputVariants: header once, then every record's result
         O = fopen(outPath.c_str(), "w");
         if (!O) { fprintf(stderr, "cannot write '%s'\n", outPath.c_str()); return 1; }
         for (const std::string &h : vcf.headers) fprintf(O, "%s\n", h.c_str());
       }
-      fputs(result.c_str(), O);
-      fflush(O);
-      if (G.debug && !dbg.empty()) {
+      fputs(results[i].c_str(), O);
+      if (G.debug && !dbgs[i].empty()) {
         if (!D) { std::string cmd = "gzip -1c > '" + std::string(G.outName) + ".00.debug.gz'"; D = popen(cmd.c_str(), "w"); }
-        if (D) fputs(dbg.c_str(), D);
+        if (D) fputs(dbgs[i].c_str(), D);
       }
     }
     if (O) fclose(O);
