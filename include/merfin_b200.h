@@ -229,6 +229,12 @@ int  mfn_score_paths(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_
  * assembly DB value; result = joint histogram of (raw v_read, raw v_asm). */
 int  mfn_completeness(mfn_ctx *ctx, const char *reads_dir, const char *asm_dir,
                       mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+/* The same, one shard at a time for multi-GPU runs: data files [64 s/n, 64 (s+1)/n) of the read
+ * database (the grain of the reference's OpenMP loop, merfin-completeness.C:65) are joined with an
+ * assembly table loaded RAW (mfn_table_load(..., 0, UINT32_MAX)) into acc; the caller
+ * sum-all-reduces the accumulator buffers (mfn_accum_device_buffer) and fetches the pairs. */
+int  mfn_completeness_shard(mfn_ctx *ctx, const char *reads_dir, const mfn_table *asm_raw,
+                            uint32_t shard, uint32_t nshards, mfn_accum *acc);
 
 /* ---- host replay of the K* arithmetic (bit-exact doubles) ------------------ */
 

@@ -325,23 +325,35 @@ __global__ void __launch_bounds__(256) k_join(DevTable A, const unsigned long lo
   }
 }
 
+// One shard of -completeness: data files [64 s / n, 64 (s+1) / n) of the read database (the unit
+// the reference's OpenMP loop hands out, merfin-completeness.C:65) are streamed and joined with the
+// RAW assembly table into `acc`; ranks sum-all-reduce the accumulator buffers afterwards.
+extern "C" int mfn_completeness_shard(mfn_ctx *ctx, const char *reads_dir, const mfn_table *asm_raw, uint32_t shard,
+                                      uint32_t nshards, mfn_accum *acc) {
+  if (!ctx || !reads_dir || !asm_raw || !acc || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  if (asm_raw->value_offset != 0) { mfn_set_error("-completeness joins raw values: load the assembly table with minV = 0"); return MFN_ERR_INVALID; }
+  MerylIndex idx;
+  MFN_TRY(meryl_open(reads_dir, idx));
+  if (idx.k != asm_raw->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", idx.k, asm_raw->dev.k); return MFN_ERR_K_MISMATCH; }
+  const uint32_t nfiles = 1u << idx.numFilesBits;
+  const uint32_t fb = (uint32_t)((uint64_t)nfiles * shard / nshards), fe = (uint32_t)((uint64_t)nfiles * (shard + 1) / nshards);
+  if (fb >= fe) return MFN_OK;
+  return meryl_stream(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
+    int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
+    k_join<<<grid, 256, 0, ctx->stream>>>(asm_raw->dev, dk, dv, n, acc->d_buf, acc->sparse);
+    ctx->launches++;
+    return cudaGetLastError() == cudaSuccess ? MFN_OK : MFN_ERR_CUDA;
+  }, fb, fe);
+}
+
 extern "C" int mfn_completeness(mfn_ctx *ctx, const char *reads_dir, const char *asm_dir,
                                 mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
   if (!ctx || !reads_dir || !asm_dir || !npairs) return MFN_ERR_INVALID;
   mfn_table *A = nullptr;
   MFN_TRY(mfn_table_load(ctx, asm_dir, 0, 0xffffffffu, &A));      // raw values: offset 0
-  MerylIndex idx;
-  int st = meryl_open(reads_dir, idx);
-  if (st == MFN_OK && idx.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", idx.k, A->dev.k); st = MFN_ERR_K_MISMATCH; }
   mfn_accum *acc = nullptr;
-  if (st == MFN_OK) st = mfn_accum_create(ctx, 0, &acc);
-  if (st == MFN_OK)
-    st = meryl_stream(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
-      int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
-      k_join<<<grid, 256, 0, ctx->stream>>>(A->dev, dk, dv, n, acc->d_buf, acc->sparse);
-      ctx->launches++;
-      return cudaGetLastError() == cudaSuccess ? MFN_OK : MFN_ERR_CUDA;
-    });
+  int st = mfn_accum_create(ctx, 0, &acc);
+  if (st == MFN_OK) st = mfn_completeness_shard(ctx, reads_dir, A, 0, 1, acc);
   if (st == MFN_OK) st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs, cap, npairs);
   mfn_accum_free(acc);
   mfn_table_free(A);

@@ -201,9 +201,10 @@ int meryl_decode_file(const MerylIndex &idx, uint32_t file,
 }
 
 int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
-                           const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn) {
+                           const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
+                           uint32_t file_begin, uint32_t file_end) {
   if (idx.k > 32) { mfn_set_error("k=%u: this build supports k <= 32", idx.k); return MFN_ERR_UNSUPPORTED; }
-  const uint32_t nfiles = 1u << idx.numFilesBits;
+  const uint32_t nfiles = std::min(file_end, 1u << idx.numFilesBits);      // data files [file_begin, nfiles)
   const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   const uint64_t CH = 1ull << 22;                 // entries per device chunk
   unsigned long long *dk = nullptr; uint32_t *dv = nullptr;
@@ -225,7 +226,7 @@ int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
     return s;
   };
   // decode a group of files in parallel, then feed them to the device in file order
-  for (uint32_t f0 = 0; f0 < nfiles && status == MFN_OK; f0 += nthreads) {
+  for (uint32_t f0 = file_begin; f0 < nfiles && status == MFN_OK; f0 += nthreads) {
     uint32_t f1 = std::min(nfiles, f0 + nthreads);
     std::vector<std::vector<uint64_t>> K(f1 - f0);
     std::vector<std::vector<uint32_t>> V(f1 - f0);

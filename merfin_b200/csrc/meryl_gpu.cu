@@ -201,10 +201,11 @@ struct Group {
 // Files are read straight into one of two pinned staging buffers by a few reader threads while
 // the device works on the other one: read, upload, decode and the consumer overlap.
 int meryl_stream_to_device_gpu(mfn_ctx *ctx, const MerylIndex &idx,
-                               const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn) {
+                               const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
+                               uint32_t file_begin, uint32_t file_end) {
   if (idx.k > 32) { mfn_set_error("k=%u: this build supports k <= 32", idx.k); return MFN_ERR_UNSUPPORTED; }
   MFN_CUDA(cudaSetDevice(ctx->device));
-  const uint32_t nfiles = 1u << idx.numFilesBits;
+  const uint32_t nfiles = std::min(file_end, 1u << idx.numFilesBits);      // data files [file_begin, nfiles)
   const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   const bool dbg = getenv("MFN_LOAD_DEBUG") != nullptr;
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -214,11 +215,11 @@ int meryl_stream_to_device_gpu(mfn_ctx *ctx, const MerylIndex &idx,
 
   // groups of whole files of at most ~1 GiB (a single bigger file is its own group)
   std::vector<size_t> fwords(nfiles, 0);
-  for (uint32_t f = 0; f < nfiles; f++)
+  for (uint32_t f = file_begin; f < nfiles; f++)
     if (!file_words(meryl_file_name(idx, f, false), fwords[f])) { mfn_set_error("cannot read '%s'", meryl_file_name(idx, f, false).c_str()); return MFN_ERR_IO; }
   const size_t GROUP_WORDS = (size_t)1 << 25;               // 256 MiB of file image per group
   std::vector<Group> groups;
-  for (uint32_t f = 0; f < nfiles;) {
+  for (uint32_t f = file_begin; f < nfiles;) {
     Group g; g.f0 = f;
     while (f < nfiles && (f == g.f0 || g.words + fwords[f] <= GROUP_WORDS)) { g.word0.push_back(g.words); g.words += fwords[f]; f++; }
     g.f1 = f;

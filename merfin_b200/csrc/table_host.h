@@ -30,17 +30,21 @@ int meryl_decode_file(const MerylIndex &idx, uint32_t file,
 // Stream a whole database to the device in chunks; fn(d_kmers, d_values, n) is called per chunk
 // on ctx->stream with device arrays that stay valid until the next call.
 int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
-                           const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn);
+                           const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
+                           uint32_t file_begin = 0, uint32_t file_end = 0xffffffffu);
 
 // The same with the decode on the device (meryl_gpu.cu): the file images are uploaded as they are
 // on disk and one thread per meryl block decodes its chain of codes.
 int meryl_stream_to_device_gpu(mfn_ctx *ctx, const MerylIndex &idx,
-                               const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn);
+                               const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
+                               uint32_t file_begin = 0, uint32_t file_end = 0xffffffffu);
 // the decoder in use: the device one unless MFN_HOST_DECODE=1
 inline int meryl_stream(mfn_ctx *ctx, const MerylIndex &idx,
-                        const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn) {
+                        const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
+                        uint32_t file_begin = 0, uint32_t file_end = 0xffffffffu) {
   const char *env = getenv("MFN_HOST_DECODE");
-  return (env && atoi(env)) ? meryl_stream_to_device(ctx, idx, fn) : meryl_stream_to_device_gpu(ctx, idx, fn);
+  return (env && atoi(env)) ? meryl_stream_to_device(ctx, idx, fn, file_begin, file_end)
+                            : meryl_stream_to_device_gpu(ctx, idx, fn, file_begin, file_end);
 }
 
 // ---- sequences ------------------------------------------------------------------

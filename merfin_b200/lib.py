@@ -116,6 +116,7 @@ SIGNATURES = {
     "mfn_dump": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
     "mfn_score_paths": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
     "mfn_completeness": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_completeness_shard": (C.c_int, [_P, C.c_char_p, _P, C.c_uint32, C.c_uint32, _P]),
     "mfn_hist_report": (C.c_int, [_P, C.c_uint64, C.POINTER(KModel), C.c_uint32, _P, _P, C.c_uint32,
                                   C.POINTER(HistSummary)]),
     "mfn_hist_format": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -524,3 +524,21 @@ def test_midsize_hist_against_reference_binary(ctx, tmp_path, monkeypatch, k, mn
     res2 = api.hist(ctx, R, A, recs, km)
     assert (res.pairs == res2.pairs).all() and (res.per_seq == res2.per_seq).all()
     R.close(); A.close()
+
+
+def test_completeness_shards_sum_to_the_whole(ctx, golden_dir):
+    """-completeness cut into shards of read-database files (what N ranks do before the all-reduce)
+    accumulates exactly the joint histogram of the single-call version."""
+    import ctypes as C
+    from merfin_b200 import api, lib as L
+    lib = L.load()
+    d = os.path.join(golden_dir, "g1_k21")
+    _, _, whole = api.completeness(ctx, os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), api.KModel(8.0))
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))          # raw values
+    acc = api.Accum(ctx, 0)
+    for s in range(3):
+        L.check(lib.mfn_completeness_shard(ctx.h, os.path.join(d, "reads.meryl").encode(), A.h, s, 3, acc.h))
+    _, pairs = acc.fetch()
+    key = lambda p: sorted((int(x["v_read"]), int(x["v_asm"]), int(x["count"])) for x in p)
+    assert key(pairs) == key(whole) and len(pairs) > 3
+    acc.close(); A.close()
