@@ -34,6 +34,9 @@ bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntile
   if (!sweep_geometry(R->joint->dev, lbits, tbits, nbins, lowbits)) return false;
   if ((uint64_t)nseq + 1 >= (1ull << (63 - lowbits))) return false;       // record ids must fit the entry
   if (env && atoi(env) == 1) return true;
+  // wide entries have no room for a record delta: windows of a chunk that are not in the chunk's
+  // first record take the side list, which is only acceptable when records are long
+  if (lowbits > 32 && ntiles * MFN_TILE < (uint64_t)nseq * 16 * SW_CHUNK) return false;
   // worth it when the windows revisit the table lines: >= 1 window per 4 lines, and a big batch
   const uint64_t windows = ntiles * MFN_TILE;
   return windows >= (1ull << 24) && windows * 4 >= R->joint->dev.nlines;
