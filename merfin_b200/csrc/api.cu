@@ -251,6 +251,19 @@ extern "C" int mfn_hist(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *a
   if (!acc) { MFN_TRY(mfn_accum_create(ctx, nseq, &acc)); ctx->scratch_acc = acc; }
   else MFN_TRY(mfn_accum_reset(ctx, acc));
   MFN_TRY(mfn_hist_host(ctx, reads, asm_, bases, seq_off, nseq, km, 0, 1, acc));
+  // The range-partitioned scan sizes its bins for k-mers that spread over the table; a batch
+  // dominated by a handful of k-mers (one bin taking a large share of all windows) can run out of
+  // side-list room, which the accumulator header records.  Redo such a batch with the direct scan.
+  unsigned long long lost = 0;
+  MFN_CUDA(cudaMemcpyAsync(&lost, acc->d_buf + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (lost && !ctx->no_sweep) {
+    ctx->no_sweep = true;
+    int st2 = mfn_accum_reset(ctx, acc);
+    if (st2 == MFN_OK) st2 = mfn_hist_host(ctx, reads, asm_, bases, seq_off, nseq, km, 0, 1, acc);
+    ctx->no_sweep = false;
+    if (st2 != MFN_OK) return st2;
+  }
   uint32_t keep = acc->nseq;
   acc->nseq = nseq;                      // fetch exactly the caller's records
   int st = mfn_accum_fetch(ctx, acc, 1, 1, per_seq, pairs, cap, npairs);

@@ -27,6 +27,7 @@ static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, 
 
 // Can (and should) this scan use the sweep?
 bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, uint32_t nseq) {
+  if (R->ctx && R->ctx->no_sweep) return false;
   const char *env = getenv("MFN_SWEEP");
   if (env && atoi(env) == 0) return false;
   if (!R->joint || R->joint->asm_ != A) return false;

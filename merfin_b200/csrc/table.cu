@@ -162,10 +162,19 @@ template <bool W64>
 __global__ void __launch_bounds__(256) k_count_seq(DevTable t, const unsigned long long *seq2,
                                                    const unsigned long long *ok, uint64_t G) {
   InsertCounts cnt = {0, 0, 0, 0, 0};
-  for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t f, r;
-    if (!mfn_window(seq2, ok, g, t.k, t.kmask, f, r)) continue;
-    mfn_insert<W64, true>(t, f < r ? f : r, 1u, cnt);
+  // Adjacent windows of homopolymers and short tandem repeats are the same k-mer: the lanes of a
+  // warp that hold equal k-mers elect one to insert their sum, so a megabase satellite costs
+  // 1/32 of the increments (and of the contention on its slot).  The loop bound is warp-uniform.
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t g0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); g0 < G; g0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = g0 + lane;
+    uint64_t f = 0, r = 0;
+    const bool valid = g < G && mfn_window(seq2, ok, g, t.k, t.kmask, f, r);
+    const uint64_t c = f < r ? f : r;
+    const uint32_t have = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const uint32_t peers = __match_any_sync(have, c);
+    if ((uint32_t)(__ffs(peers) - 1) == lane) mfn_insert<W64, true>(t, c, (uint32_t)__popc(peers), cnt);
   }
   mfn_flush_counts(t, cnt);
 }

@@ -542,3 +542,25 @@ def test_completeness_shards_sum_to_the_whole(ctx, golden_dir):
     key = lambda p: sorted((int(x["v_read"]), int(x["v_asm"]), int(x["count"])) for x in p)
     assert key(pairs) == key(whole) and len(pairs) > 3
     acc.close(); A.close()
+
+
+def test_sweep_overflow_falls_back_to_the_direct_scan(ctx, monkeypatch):
+    """A batch dominated by one k-mer (5 Mbp of poly-A) sends nearly every window to a single
+    bin; the range-partitioned scan runs out of room there and mfn_hist redoes the batch with the
+    direct scan instead of failing."""
+    from merfin_b200 import api
+    rng = np.random.default_rng(4)
+    rnd = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1_000_000).tobytes()
+    recs = [("polyA", b"A" * 5_000_000), ("rnd", rnd), ("polyA2", b"a" * 1_000_000)]
+    seq = api.SeqSet(ctx, recs)
+    A = api.MerylExactLookup.count_sequence(ctx, 21, seq)
+    R = api.MerylExactLookup.synth_reads(ctx, A, 10.0, 100_000, 3)
+    R.fuse(A)
+    km = api.KModel(10.0)
+    monkeypatch.setenv("MFN_SWEEP", "0")
+    d = api.hist(ctx, R, A, recs, km)
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    s = api.hist(ctx, R, A, recs, km)
+    assert len(d.pairs) == len(s.pairs) and (d.pairs == s.pairs).all() and (d.per_seq == s.per_seq).all()
+    assert int(s.per_seq["kasm"][0]) == 5_000_000 - 20
+    seq.close(); R.close(); A.close()
