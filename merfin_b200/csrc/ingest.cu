@@ -36,6 +36,7 @@ struct mfn_ingest {
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   bool stop = false;
+  bool abort = false;                                     // the current call is being abandoned (error path)
   // current call
   mfn_seq *seq = nullptr;
   const char *bases = nullptr;
@@ -72,12 +73,13 @@ static void ingest_worker(mfn_ingest *I) {
     IngestPiece &P = I->pieces[task.first];
     I->active++;
     // the staging buffer is free once the upload of the piece that used it last has completed
-    while (!P.buf_ready && !I->stop) {
+    while (!P.buf_ready && !I->stop && !I->abort) {
       if (P.prev < 0) { P.buf_ready = true; break; }
       if (!P.buf_checking) {
         P.buf_checking = true;
         IngestPiece &Q = I->pieces[P.prev];
-        I->cv_done.wait(lk, [&] { return Q.uploaded || I->stop || I->error; });
+        I->cv_done.wait(lk, [&] { return Q.uploaded || I->stop || I->abort || I->error; });
+        if (I->stop || I->abort) break;
         cudaEvent_t ev = Q.done;
         lk.unlock();
         cudaEventSynchronize(ev);
@@ -85,10 +87,11 @@ static void ingest_worker(mfn_ingest *I) {
         P.buf_ready = true;
         I->cv_done.notify_all();
       } else {
-        I->cv_done.wait(lk, [&] { return P.buf_ready || I->stop; });
+        I->cv_done.wait(lk, [&] { return P.buf_ready || I->stop || I->abort; });
       }
     }
     if (I->stop) return;
+    if (I->abort) { I->active--; I->cv_done.notify_all(); continue; }
     lk.unlock();
     const uint64_t a = P.g_begin + (uint64_t)task.second * I->sub, b = std::min(P.g_end, a + I->sub);
     unsigned long long *s2 = I->h_stage[P.buf], *so = s2 + I->stage_positions / 32;
@@ -268,8 +271,11 @@ void mfn_ingest_end(mfn_ctx *ctx) {
   {
     // nothing of this call may still run on the workers (also the way out after an error)
     std::unique_lock<std::mutex> lk(I->mu);
+    const bool unfinished = !I->tasks.empty();
     I->tasks.clear();
+    if (unfinished) { I->abort = true; I->cv_done.notify_all(); }
     I->cv_done.wait(lk, [&] { return I->active == 0; });
+    I->abort = false;
   }
   if (!I->bytes_c || I->busy_c <= 0 || I->workers.empty()) return;
   // Balance the lanes.  Host packing rate rc = bytes / (busy time / threads); the link carries
