@@ -2,6 +2,8 @@
 // cited against the reference line it reproduces.
 #include "variants.h"
 
+#include <thread>
+
 #include "fasta.h"
 
 #include <algorithm>
@@ -65,36 +67,70 @@ static GtAllele *make_allele(const VcfRecord *r) {
   return g;
 }
 
+// vcf.C:93-151.  Lines are independent, so they are parsed on host threads (contiguous ranges of
+// lines per thread) and appended in file order afterwards: the order inside byChr is what the
+// reference's (unstable) sort starts from, so it must be the file order.
 bool VcfFile::load(const std::string &path, std::string &err) {
   std::vector<char> data;
   if (!slurp_file(path, data, err)) return false;
-  size_t p = 0, N = data.size();
-  while (p < N) {
+  const size_t N = data.size();
+  std::vector<size_t> starts;                       // first byte of every line
+  for (size_t p = 0; p < N;) {
+    starts.push_back(p);
     const char *nl = (const char *)memchr(data.data() + p, '\n', N - p);
-    size_t e = nl ? (size_t)(nl - data.data()) : N;
-    std::string line(data.data() + p, e - p);
-    p = e + 1;
-    while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
-    if (line.empty()) continue;
-    if (line[0] == '#') {
-      headers.push_back(line);
-      if (line.compare(0, 12, "##contig=<ID") == 0) numChr++;
-      continue;
-    }
-    std::vector<std::string> w = split(line, "\t");
-    if (w.size() < 10) { excluded++; continue; }                                    // vcfRecord.H:53-56
-    VcfRecord *r = new VcfRecord();
-    r->chr = w[0]; r->pos = (uint32_t)strtoul(w[1].c_str(), nullptr, 10); r->id = w[2]; r->ref = w[3]; r->alts = w[4];
-    r->qual = strtod(w[5].c_str(), nullptr); r->filter = w[6]; r->info = w[7]; r->formats = w[8]; r->samples = w[9];
-    r->alt_list = split(r->alts, ",");
-    r->sample_fields = split(r->samples, ":");
-    records.push_back(r);
-    GtAllele *g = make_allele(r);
-    alleles.push_back(g);
-    PosGT *pg = new PosGT();
-    pg->chr = r->chr; pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
-    byChr[r->chr].push_back(pg);
+    p = nl ? (size_t)(nl - data.data()) + 1 : N;
   }
+  starts.push_back(N);
+  const size_t nlines = starts.size() - 1;
+  struct Item { std::string header; VcfRecord *r = nullptr; GtAllele *g = nullptr; PosGT *pg = nullptr; bool excluded = false; };
+  unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (nlines < 20000) T = 1;
+  if (const char *env = getenv("MFN_VCF_THREADS")) T = (unsigned)std::max(1, atoi(env));     // (tests force the threaded path on small files)
+  T = (unsigned)std::max<size_t>(1, std::min<size_t>(T, nlines));
+  std::vector<std::vector<Item>> parts(T);
+  auto parse = [&](unsigned t) {
+    const size_t l0 = nlines * t / T, l1 = nlines * (t + 1) / T;
+    std::vector<Item> &out = parts[t];
+    out.reserve(l1 - l0);
+    for (size_t l = l0; l < l1; l++) {
+      size_t p = starts[l], e = starts[l + 1];
+      while (e > p && (data[e - 1] == '\r' || data[e - 1] == '\n')) e--;
+      if (e == p) continue;
+      std::string line(data.data() + p, e - p);
+      Item it;
+      if (line[0] == '#') { it.header = std::move(line); out.push_back(std::move(it)); continue; }
+      std::vector<std::string> w = split(line, "\t");
+      if (w.size() < 10) { it.excluded = true; out.push_back(std::move(it)); continue; }   // vcfRecord.H:53-56
+      VcfRecord *r = new VcfRecord();
+      r->chr = w[0]; r->pos = (uint32_t)strtoul(w[1].c_str(), nullptr, 10); r->id = w[2]; r->ref = w[3]; r->alts = w[4];
+      r->qual = strtod(w[5].c_str(), nullptr); r->filter = w[6]; r->info = w[7]; r->formats = w[8]; r->samples = w[9];
+      r->alt_list = split(r->alts, ",");
+      r->sample_fields = split(r->samples, ":");
+      GtAllele *g = make_allele(r);
+      PosGT *pg = new PosGT();
+      pg->chr = r->chr; pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
+      it.r = r; it.g = g; it.pg = pg;
+      out.push_back(std::move(it));
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back(parse, t);
+    parse(0);
+    for (auto &x : th) x.join();
+  }
+  for (auto &part : parts)
+    for (Item &it : part) {
+      if (it.excluded) { excluded++; continue; }
+      if (!it.r) {
+        if (it.header.compare(0, 12, "##contig=<ID") == 0) numChr++;
+        headers.push_back(std::move(it.header));
+        continue;
+      }
+      records.push_back(it.r);
+      alleles.push_back(it.g);
+      byChr[it.r->chr].push_back(it.pg);
+    }
   return true;
 }
 

@@ -50,3 +50,12 @@ def test_polish_debug_log_matches_reference(harness, golden_dir, tmp_path):
     _run(harness, d, "polish", 8, "--debug", cwd=str(tmp_path))
     got = open(tmp_path / "harness.debug").read()
     assert got == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
+
+
+def test_threaded_vcf_parse_keeps_file_order(harness, golden_dir, monkeypatch):
+    """The VCF is parsed on several host threads; clustering starts from the file order (the
+    reference's sort is not stable), so the output must not depend on the thread count."""
+    d = os.path.join(golden_dir, "g1_k21")
+    monkeypatch.setenv("MFN_VCF_THREADS", "5")
+    assert _run(harness, d, "polish", 8) == open(os.path.join(d, "ref.polish.vcf")).read()
+    assert _run(harness, d, "filter", 8) == open(os.path.join(d, "ref.filter.vcf")).read()
