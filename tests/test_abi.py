@@ -118,3 +118,20 @@ def test_meryl_writer_roundtrip(tmp_path):
             assert len(lines) == len(kmers)
             assert [O.kmer_from_string(a) for a, _ in lines] == [int(x) for x in kmers]
             assert [int(b) for _, b in lines] == [int(x) for x in values]
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/merfin_b200.h is a C header (no C++): a C99 -pedantic translation unit that uses
+    the -hist entry points compiles and links against the library (examples/hist_example.c); run
+    without a GPU it must fail with the library's own 'no device' error, not crash."""
+    import subprocess
+    exe = str(tmp_path / "hist_example")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "hist_example.c"), "-L" + os.path.join(ROOT, "merfin_b200"),
+                           "-lmerfin_b200", "-Wl,-rpath," + os.path.join(ROOT, "merfin_b200"), "-o", exe])
+    import torch
+    if not torch.cuda.is_available():
+        g = os.path.join(ROOT, "tests", "golden", "g1_k21")
+        p = subprocess.run([exe, os.path.join(g, "reads.meryl"), os.path.join(g, "asm.meryl"), "8", "ACGT" * 10],
+                           capture_output=True, text=True)
+        assert p.returncode == 1 and "no usable CUDA device" in p.stderr
