@@ -11,6 +11,7 @@
 // parity test packs the same records both ways and compares the arrays.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
 
@@ -123,10 +124,12 @@ __attribute__((target("avx2"))) static void pack_segment_avx2(const unsigned cha
   pack_segment(pack32_avx2, p, a, b, s2, so);
 }
 typedef void (*segment_fn)(const unsigned char *, uint64_t, uint64_t, uint64_t *, uint64_t *);
-static segment_fn pick_segment() {
+static bool use_avx2() {
   __builtin_cpu_init();
-  return __builtin_cpu_supports("avx2") ? pack_segment_avx2 : pack_segment_scalar;
+  const char *env = getenv("MFN_PACK_SCALAR");           // tests compare the two kernels
+  return __builtin_cpu_supports("avx2") && !(env && atoi(env));
 }
+static segment_fn pick_segment() { return use_avx2() ? pack_segment_avx2 : pack_segment_scalar; }
 
 // Pack global positions [g_begin, g_end) (both multiples of 64) of a sequence set into
 // seq2_out / ok_out, whose word 0 is global word g_begin/32 resp. g_begin/64.  rec_start[r] is the
@@ -152,7 +155,4 @@ extern "C" void mfn_pack_host_range(const char *bases, const uint64_t *rec_start
 }
 
 // Which inner kernel this CPU gets (for logs and tests).
-extern "C" const char *mfn_pack_host_isa(void) {
-  __builtin_cpu_init();
-  return __builtin_cpu_supports("avx2") ? "avx2" : "scalar";
-}
+extern "C" const char *mfn_pack_host_isa(void) { return use_avx2() ? "avx2" : "scalar"; }

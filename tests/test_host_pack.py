@@ -45,3 +45,35 @@ def test_pack_host_range_matches_definition(seed, lens):
                                 C.c_void_p(gotok.ctypes.data + a // 64 * 8))
     assert (got2 == want2).all()
     assert (gotok == wantok).all()
+
+
+def test_scalar_and_avx2_kernels_agree(tmp_path):
+    """The packer picks its 32-base kernel once per process; run the same input through a child
+    process with the scalar kernel forced and compare the packed words."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %r)
+from merfin_b200 import lib as L
+lib = L.load()
+rng = np.random.default_rng(21)
+b = rng.choice(np.frombuffer(b"ACGTacgtNn-*", dtype=np.uint8), size=200_003)
+rs = np.array([0, 70_001, 70_001 + 130_002 + 1], dtype=np.uint64)
+G = (int(rs[-1]) + 2047) // 2048 * 2048
+s2 = np.zeros(G // 32, dtype=np.uint64); ok = np.zeros(G // 64, dtype=np.uint64)
+lib.mfn_pack_host_range(C.c_void_p(b.ctypes.data), C.c_void_p(rs.ctypes.data), 2, C.c_uint64(0), C.c_uint64(G),
+                        C.c_void_p(s2.ctypes.data), C.c_void_p(ok.ctypes.data))
+sys.stdout.write(lib.mfn_pack_host_isa().decode() + " " + str(int(s2.sum() & np.uint64(0xffffffffffff))) + " " + str(int(np.bitwise_xor.reduce(s2))) + " " + str(int(np.bitwise_xor.reduce(ok))))
+""" % root
+    outs = {}
+    for scalar in ("0", "1"):
+        env = dict(os.environ, MFN_PACK_SCALAR=scalar)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        isa, *digest = p.stdout.split()
+        outs[scalar] = (isa, digest)
+    assert outs["1"][0] == "scalar"
+    assert outs["0"][1] == outs["1"][1]
