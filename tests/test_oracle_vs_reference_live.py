@@ -89,3 +89,28 @@ def test_oracle_equals_reference_on_fresh_input(tmp_path, k, total, nrec, cov, p
     _, _, t, u = O.completeness(S, A, km)
     tail = ("TOTAL readK:   %15.2f\nTOTAL undrcpy:    %15.5f\nCOMPLETENESS:             %0.5f\n" % (t, u, 1.0 - u / t))
     assert tail in err_c
+
+
+@pytest.mark.parametrize("k,n", [(21, 200_000), (31, 50_000), (12, 30_000)])
+def test_reference_meryl_reads_databases_written_by_the_library(tmp_path, k, n):
+    """mfn_meryl_write (the generator side of the benchmarks) produces databases the unmodified
+    reference tool lists exactly: same k-mers, same values, same order."""
+    from merfin_b200 import api
+    rng = np.random.default_rng(k)
+    km = np.unique(rng.integers(0, (1 << (2 * k)) - 1, size=n, dtype=np.uint64, endpoint=True))
+    vv = rng.integers(1, 3000, size=len(km), dtype=np.uint32)
+    vv[::500] = rng.integers(70000, 4_000_000, size=len(vv[::500]), dtype=np.uint32)
+    d = os.path.join(str(tmp_path), "w.meryl")
+    api.meryl_write(d, k, km, vv)
+    p = subprocess.run([MERYL, "threads=1", "print", d], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.split("\n")[:-1]
+    assert len(lines) == len(km)
+    dec = "ACTG"                                            # kmers-tiny.H:69-83: A=0 C=1 T=2 G=3
+    def text(x):
+        return "".join(dec[(int(x) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+    idx = rng.integers(0, len(km), size=2000)
+    for i in idx:                                           # spot-check the text form, then every value and the order
+        assert lines[i] == "%s\t%d" % (text(km[i]), vv[i])
+    got_v = np.array([int(l.split("\t")[1]) for l in lines], dtype=np.uint32)
+    assert (got_v == vv).all()
