@@ -137,6 +137,20 @@ int  mfn_joint_lookup(mfn_ctx *ctx, const mfn_table *reads, const uint64_t *kmer
 int  mfn_meryl_write(const char *meryl_dir, uint32_t k, const uint64_t *kmers,
                      const uint32_t *values, uint64_t n);
 
+/* ---- meryl database header (merylFileReader's constructor, kmers-reader.C:128-205, and the
+ * statistics block of a v03 master index, kmers-histogram.C:170-200); host only, no GPU work. */
+typedef struct {
+  uint32_t  k, version;               /* mer size; master-index format 1..3          */
+  uint32_t  prefix_bits, suffix_bits; /* split of the 2k bits                        */
+  uint32_t  files, blocks_per_file;   /* 2^numFilesBits, 2^numBlocksBits             */
+  uint32_t  multiset, hist_len;       /* flags bit 0; value-histogram entries (v03)  */
+  uint64_t  n_unique, n_distinct, n_total;   /* v03 only, else 0                     */
+} mfn_meryl_info_t;
+int  mfn_meryl_info(const char *meryl_dir, mfn_meryl_info_t *info);
+/* The stored value histogram (value, number of distinct k-mers with it), ascending value;
+ * MFN_ERR_CAPACITY with *n = entries needed when cap is too small. */
+int  mfn_meryl_histogram(const char *meryl_dir, uint64_t *values, uint64_t *counts, uint64_t cap, uint64_t *n);
+
 /* ---- sequences: replaces dnaSeq + kmerIterator::nextBase ------------------
  * kmers-iterator.H:93-160.  bases = concatenated ASCII records, record i is
  * bases[seq_off[i] .. seq_off[i+1]).  Any byte outside ACGTacgt breaks windows;

@@ -438,6 +438,26 @@ def completeness_text(total: float, undr: float) -> str:
             % (total, undr, 1.0 - undr / total))
 
 
+def meryl_info(path: str) -> dict:
+    """Header of a meryl database (mfn_meryl_info): k, layout and the v03 statistics."""
+    info = L.MerylInfo()
+    L.check(L.load().mfn_meryl_info(path.encode(), C.byref(info)))
+    return {f: int(getattr(info, f)) for f, _ in L.MerylInfo._fields_}
+
+
+def meryl_histogram(path: str):
+    """(values, counts) of the stored value histogram (mfn_meryl_histogram)."""
+    lib = L.load()
+    n = C.c_uint64(0)
+    st = lib.mfn_meryl_histogram(path.encode(), None, None, 0, C.byref(n))
+    if st not in (0, L.MFN_ERR_CAPACITY):
+        L.check(st)
+    v = np.zeros(n.value, dtype=np.uint64)
+    c = np.zeros(n.value, dtype=np.uint64)
+    L.check(lib.mfn_meryl_histogram(path.encode(), _ptr(v), _ptr(c), n.value, C.byref(n)))
+    return v, c
+
+
 def meryl_write(path: str, k: int, kmers, values):
     km = np.ascontiguousarray(kmers, dtype=np.uint64)
     vv = np.ascontiguousarray(values, dtype=np.uint32)

@@ -152,12 +152,35 @@ int main(int argc, char **argv) {
 
   // ---- -completeness streams both databases (merfin-completeness.C:48-144) ----------------------
   if (G.report == OP_COMPL) {
-    if (!G.seqDBname) { fprintf(stderr, "-completeness needs -seqmers in this build.\n"); return 1; }
     fprintf(stderr, "-- Compute completeness.\n");
     std::vector<mfn_pair_count> pairs(1 << 20);
     uint64_t np = 0;
-    int st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np);
-    if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np); }
+    int st;
+    if (G.seqDBname) {
+      st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np);
+      if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np); }
+    } else {
+      // the reference builds <sequence>.meryl with "meryl count" first (merfin-globals.C:168-189) and
+      // streams that; here the assembly k-mers are counted on the GPU and joined in place
+      mfn_meryl_info_t mi;
+      if (mfn_meryl_info(G.readDBname, &mi) != MFN_OK) die("-readmers");
+      fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", mi.k, G.seqName);
+      SeqSet S;
+      std::string e;
+      if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
+      mfn_seq *seq = nullptr;
+      mfn_table *A = nullptr;
+      mfn_accum *acc = nullptr;
+      if (mfn_seq_create(ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq) != MFN_OK) die("-sequence");
+      if (mfn_table_count_seq(ctx, mi.k, seq, &A) != MFN_OK) die("counting -sequence");
+      mfn_seq_free(seq);
+      st = mfn_accum_create(ctx, 0, &acc);
+      if (st == MFN_OK) st = mfn_completeness_shard(ctx, G.readDBname, A, 0, 1, acc);
+      if (st == MFN_OK) st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs.data(), pairs.size(), &np);
+      if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs.data(), pairs.size(), &np); }
+      mfn_accum_free(acc);
+      mfn_table_free(A);
+    }
     if (st != MFN_OK) die("completeness");
     double total = 0, undr = 0;
     mfn_completeness_report(pairs.data(), np, &km, &total, &undr);

@@ -355,6 +355,29 @@ struct BitWriter {
 
 }  // namespace
 
+extern "C" int mfn_meryl_info(const char *dir, mfn_meryl_info_t *info) {
+  if (!dir || !info) return MFN_ERR_INVALID;
+  MerylIndex idx;
+  MFN_TRY(meryl_open(dir, idx));
+  memset(info, 0, sizeof(*info));
+  info->k = idx.k; info->version = idx.version;
+  info->prefix_bits = idx.prefixSize; info->suffix_bits = idx.suffixSize;
+  info->files = 1u << idx.numFilesBits; info->blocks_per_file = 1u << idx.numBlocksBits;
+  info->multiset = idx.flags & 1u; info->hist_len = (uint32_t)idx.histValue.size();
+  info->n_unique = idx.numUnique; info->n_distinct = idx.numDistinct; info->n_total = idx.numTotal;
+  return MFN_OK;
+}
+
+extern "C" int mfn_meryl_histogram(const char *dir, uint64_t *values, uint64_t *counts, uint64_t cap, uint64_t *n) {
+  if (!dir || !n) return MFN_ERR_INVALID;
+  MerylIndex idx;
+  MFN_TRY(meryl_open(dir, idx));
+  *n = idx.histValue.size();
+  if (*n > cap || (*n && (!values || !counts))) return MFN_ERR_CAPACITY;
+  for (uint64_t i = 0; i < *n; i++) { values[i] = idx.histValue[i]; counts[i] = idx.histCount[i]; }
+  return MFN_OK;
+}
+
 extern "C" int mfn_meryl_write(const char *dir, uint32_t k, const uint64_t *kmers, const uint32_t *values, uint64_t n) {
   if (!dir || k < 4 || k > 32 || (n && (!kmers || !values))) { mfn_set_error("mfn_meryl_write: need 4 <= k <= 32"); return MFN_ERR_INVALID; }
   const uint32_t filesBits = 6;

@@ -48,6 +48,12 @@ class JointInfo(C.Structure):
                 ("lines", C.c_uint64), ("device_bytes", C.c_uint64)]
 
 
+class MerylInfo(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("version", C.c_uint32), ("prefix_bits", C.c_uint32), ("suffix_bits", C.c_uint32),
+                ("files", C.c_uint32), ("blocks_per_file", C.c_uint32), ("multiset", C.c_uint32), ("hist_len", C.c_uint32),
+                ("n_unique", C.c_uint64), ("n_distinct", C.c_uint64), ("n_total", C.c_uint64)]
+
+
 class KModel(C.Structure):
     _fields_ = [("peak", C.c_double), ("nprob", C.c_uint32),
                 ("probK", C.POINTER(C.c_uint32)), ("probP", C.POINTER(C.c_double))]
@@ -95,6 +101,8 @@ SIGNATURES = {
     "mfn_joint_info": (C.c_int, [_P, C.POINTER(JointInfo)]),
     "mfn_joint_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "mfn_meryl_write": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, C.c_uint64]),
+    "mfn_meryl_info": (C.c_int, [C.c_char_p, C.POINTER(MerylInfo)]),
+    "mfn_meryl_histogram": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_seq_create": (C.c_int, [_P, _P, _P, C.c_uint32, _PP]),
     "mfn_seq_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "mfn_seq_free": (None, [_P]),

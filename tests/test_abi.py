@@ -120,6 +120,34 @@ def test_meryl_writer_roundtrip(tmp_path):
             assert [int(b) for _, b in lines] == [int(x) for x in values]
 
 
+@pytest.mark.parametrize("name,k", [("g1_k21", 21), ("g2_k6", 6), ("g3_k31", 31)])
+def test_meryl_info_matches_the_reference_listing(golden_dir, name, k):
+    """mfn_meryl_info / mfn_meryl_histogram (host only) against the reference's `meryl print` of the
+    same databases (committed as *.print.gz): k, distinct / unique / total and the value histogram."""
+    import gzip
+    from merfin_b200 import api
+    for db in ("reads", "asm"):
+        d = os.path.join(golden_dir, name, db + ".meryl")
+        vals = np.array([int(l.split()[1]) for l in gzip.open(os.path.join(golden_dir, name, db + ".print.gz"), "rt")], dtype=np.uint64)
+        info = api.meryl_info(d)
+        assert info["k"] == k and info["prefix_bits"] + info["suffix_bits"] == 2 * k
+        assert info["version"] == 3 and info["files"] == 64 and info["multiset"] == 0
+        assert info["n_distinct"] == len(vals)
+        assert info["n_unique"] == int((vals == 1).sum())
+        assert info["n_total"] == int(vals.sum())
+        hv, hc = api.meryl_histogram(d)
+        uv, uc = np.unique(vals, return_counts=True)
+        assert info["hist_len"] == len(uv)
+        assert (hv == uv).all() and (hc == uc.astype(np.uint64)).all()
+
+
+def test_meryl_info_errors(tmp_path):
+    info = L.MerylInfo()
+    assert L.load().mfn_meryl_info(str(tmp_path).encode(), C.byref(info)) == L.MFN_ERR_IO
+    assert b"doesn't appear to be a meryl database" in L.load().mfn_last_error()
+    assert L.load().mfn_meryl_info(None, C.byref(info)) == L.MFN_ERR_INVALID
+
+
 def test_header_is_plain_c_and_example_links(tmp_path):
     """include/merfin_b200.h is a C header (no C++): a C99 -pedantic translation unit that uses
     the -hist entry points compiles and links against the library (examples/hist_example.c); run

@@ -42,6 +42,9 @@ def test_cli_hist_dump_completeness(golden_dir, tmp_path, name, peak):
     # without -seqmers the assembly k-mers are counted on the GPU (the reference shells out to meryl)
     err = _run(base[:2] + base[4:] + ["-hist", "-output", "out2.hist"], str(tmp_path))
     assert open(tmp_path / "out2.hist", "rb").read() == open(os.path.join(d, "ref.hist"), "rb").read()
+    err = _run(base[:2] + base[4:] + ["-completeness"], str(tmp_path))      # likewise for -completeness
+    for l in tail:
+        assert l in err
 
 
 def test_cli_min_max_prob_skipmissing(golden_dir, tmp_path):

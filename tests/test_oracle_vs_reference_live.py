@@ -114,3 +114,10 @@ def test_reference_meryl_reads_databases_written_by_the_library(tmp_path, k, n):
         assert lines[i] == "%s\t%d" % (text(km[i]), vv[i])
     got_v = np.array([int(l.split("\t")[1]) for l in lines], dtype=np.uint32)
     assert (got_v == vv).all()
+    # the statistics block the writer stored is the one the reference reports, and mfn_meryl_info reads it back
+    p = subprocess.run([MERYL, "statistics", d], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    stats = {w: int(n) for w, n in re.findall(r"^\s+(unique|distinct|present)\s+(\d+)", p.stdout, re.M)}
+    info = api.meryl_info(d)
+    assert stats == {"unique": info["n_unique"], "distinct": info["n_distinct"], "present": info["n_total"]}
+    assert info["n_distinct"] == len(km) and info["n_total"] == int(vv.astype(np.uint64).sum())
