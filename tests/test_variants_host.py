@@ -59,3 +59,46 @@ def test_threaded_vcf_parse_keeps_file_order(harness, golden_dir, monkeypatch):
     monkeypatch.setenv("MFN_VCF_THREADS", "5")
     assert _run(harness, d, "polish", 8) == open(os.path.join(d, "ref.polish.vcf")).read()
     assert _run(harness, d, "filter", 8) == open(os.path.join(d, "ref.filter.vcf")).read()
+
+
+MERFIN = os.path.join(ROOT, "oracle", "_ref", "merfin")
+MERYL = os.path.join(ROOT, "oracle", "_ref", "meryl")
+
+LIVE = [  # k, bases per record, records, edits per record, bogus SNVs per record, peak, extra reference flags
+    (21, 30000, 3, 150, 20, 10.0, []),
+    (15, 20000, 2, 200, 30, 8.0, ["-comb", "3"]),
+    (31, 25000, 2, 120, 10, 12.0, ["-nosplit"]),
+    (18, 20000, 4, 100, 10, 9.0, ["-comb", "6", "-nosplit"]),
+]
+
+
+@pytest.mark.skipif(not (os.path.exists(MERFIN) and os.path.exists(MERYL)), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("k,length,nrec,nedit,nfalse,peak,flags", LIVE)
+def test_variant_modes_against_reference_on_fresh_input(harness, tmp_path, k, length, nrec, nedit, nfalse, peak, flags):
+    """All five selectors against the unmodified reference run NOW (one thread, so its output order is
+    the file order) on a fresh assembly with planted errors and a VCF of proposed corrections: mixed
+    genotypes, clustered neighbours, multi-allelic records, 0/0 and ./. records, bogus SNVs;
+    -comb / -nosplit change how clusters are split."""
+    from merfin_b200 import synth
+    d = str(tmp_path)
+    truth = synth.make_assembly(length * nrec, nrec, 4000 + k, n_run=15, lower_run=30, dup_len=1500)
+    asm, vcf = synth.plant_errors(truth, nedit, 77 + k, false_per_rec=nfalse)
+    synth.write_fasta(os.path.join(d, "asm.fa"), asm, width=70)
+    open(os.path.join(d, "calls.vcf"), "w").write(vcf)
+    reads = synth.simulate_reads(truth, 12, 120, 0.005, 5000 + k)
+    synth.write_fasta(os.path.join(d, "reads.fa"), reads, prefix="r")
+    for fa, db in (("reads.fa", "reads.meryl"), ("asm.fa", "asm.meryl")):
+        p = subprocess.run([MERYL, "threads=1", "count", f"k={k}", "memory=1", fa, "output", db], cwd=d, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+    hflags = [f.replace("-comb", "--comb").replace("-nosplit", "--nosplit") for f in flags]
+    nrecords = 0
+    for mode in ("polish", "filter", "better", "strict", "loose"):
+        p = subprocess.run([MERFIN, "-" + mode, "-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl",
+                            "-vcf", "calls.vcf", "-peak", str(peak), "-threads", "1", "-memory", "4", "-output", "ref." + mode] + flags,
+                           cwd=d, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        want = open(os.path.join(d, "ref.%s.%s.vcf" % (mode, "polish" if mode == "polish" else "filter"))).read()
+        got = _run(harness, d, mode, peak, *hflags)
+        assert got == want, mode
+        nrecords += sum(1 for l in want.splitlines() if not l.startswith("#"))
+    assert nrecords > 100                       # the comparison is not vacuous

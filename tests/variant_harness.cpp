@@ -2,7 +2,7 @@
 // the CPU oracle as the path scorer, so the host-side control logic (VCF parsing, clustering,
 // path enumeration, selectors) can be checked against the reference's golden VCFs without a GPU.
 // Test infrastructure only.
-//   variant_harness <asm.fa> <reads.meryl> <asm.meryl> <calls.vcf> <mode> <peak> [prob.csv] [--debug]
+//   variant_harness <asm.fa> <reads.meryl> <asm.meryl> <calls.vcf> <mode> <peak> [prob.csv] [--debug] [--comb N] [--nosplit]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,9 +25,12 @@ int main(int argc, char **argv) {
   if (!vcf.load(argv[4], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
   std::string mode = argv[5];
   std::vector<uint32_t> pk; std::vector<double> pp;
-  bool debug = false;
+  bool debug = false, nosplit = false;
+  uint32_t comb = 15;
   for (int a = 7; a < argc; a++) {
     if (!strcmp(argv[a], "--debug")) { debug = true; continue; }
+    if (!strcmp(argv[a], "--nosplit")) { nosplit = true; continue; }
+    if (!strcmp(argv[a], "--comb") && a + 1 < argc) { comb = (uint32_t)atoi(argv[++a]); continue; }
     FILE *F = fopen(argv[a], "r"); char line[256];
     while (F && fgets(line, sizeof line, F)) {
       unsigned k; double p; char extra;
@@ -36,10 +39,10 @@ int main(int argc, char **argv) {
     if (F) fclose(F);
   }
   mfnv::Options opt;
-  opt.k = rd->k; opt.comb = 15; opt.debug = debug;
+  opt.k = rd->k; opt.comb = comb; opt.debug = debug;
   opt.km = mfn_kmodel{atof(argv[6]), (uint32_t)pk.size(), pk.data(), pp.data()};
   opt.mode = mode == "polish" ? mfnv::POLISH : mode == "better" ? mfnv::BETTER : mode == "strict" ? mfnv::STRICT : mode == "loose" ? mfnv::LOOSE : mfnv::FILTER;
-  vcf.mergeChrPosGT(opt.k, opt.comb, false);
+  vcf.mergeChrPosGT(opt.k, opt.comb, nosplit);
   mfnv::PathScorer scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, std::vector<uint32_t> &vr,
                                 std::vector<uint32_t> &va, std::vector<uint8_t> &ok) -> int {
     vr.assign(paths.size() + 1, 0); va.assign(paths.size() + 1, 0); ok.assign(paths.size() + 1, 0);
