@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MERFIN = os.path.join(ROOT, "merfin_b200", "bin", "merfin")
+MERFIN = os.environ.get("MFN_TEST_CLI", os.path.join(ROOT, "merfin_b200", "bin", "merfin"))
 
 
 def _run(args, cwd):
@@ -82,3 +82,41 @@ def test_cli_usage_errors(tmp_path):
     p = subprocess.run([MERFIN, "-hist"], capture_output=True, text=True)
     assert p.returncode == 1
     assert "No input sequences (-sequence) supplied." in p.stderr and "No read meryl database (-readmers) supplied." in p.stderr
+
+
+def test_cli_reads_databases_made_by_meryl_set_operations(tmp_path, monkeypatch):
+    """Read databases in the wild are `meryl union-sum` of per-run counts, often filtered with
+    `greater-than`: written by meryl's streaming writer, with sparse prefixes.  Built here with the
+    unmodified reference tools (oracle/_ref, when it travelled to the box); -hist through the CLI with
+    the device decoder and with the host decoder must equal the reference's file and summary."""
+    ref_merfin = os.path.join(ROOT, "oracle", "_ref", "merfin")
+    ref_meryl = os.path.join(ROOT, "oracle", "_ref", "meryl")
+    if not (os.path.exists(ref_merfin) and os.path.exists(ref_meryl)):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    from merfin_b200 import synth
+    d = str(tmp_path)
+    k = 21
+
+    def ref(cmd):
+        p = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        return p.stderr
+
+    truth = synth.make_assembly(1_500_000, 4, 11, n_run=50, lower_run=100, dup_len=20000)
+    synth.write_fasta(os.path.join(d, "asm.fa"), truth, width=80)
+    for i in range(3):
+        synth.write_fasta(os.path.join(d, "r%d.fa" % i), synth.simulate_reads(truth, 5, 150, 0.01, 100 + i), prefix="r")
+        ref([ref_meryl, "threads=4", "count", f"k={k}", "memory=2", "r%d.fa" % i, "output", "r%d.meryl" % i])
+    ref([ref_meryl, "threads=4", "count", f"k={k}", "memory=2", "asm.fa", "output", "asm.meryl"])
+    ref([ref_meryl, "threads=4", "union-sum", "r0.meryl", "r1.meryl", "r2.meryl", "output", "union.meryl"])
+    ref([ref_meryl, "threads=4", "greater-than", "1", "union.meryl", "output", "solid.meryl"])
+    for db in ("union.meryl", "solid.meryl"):
+        base = ["-hist", "-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", db, "-peak", "14"]
+        err = ref([ref_merfin] + base + ["-threads", "4", "-memory", "8", "-output", "ref.hist"])
+        want, want_summary = open(os.path.join(d, "ref.hist"), "rb").read(), _summary(err)
+        assert len(want) > 20 and "Merfin QV*" in want_summary
+        for host_decode in ("0", "1"):
+            monkeypatch.setenv("MFN_HOST_DECODE", host_decode)
+            err = _run(base + ["-output", "ours.hist"], d)
+            assert open(os.path.join(d, "ours.hist"), "rb").read() == want, (db, host_decode)
+            assert _summary(err) == want_summary, (db, host_decode)

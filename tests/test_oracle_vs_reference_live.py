@@ -121,3 +121,36 @@ def test_reference_meryl_reads_databases_written_by_the_library(tmp_path, k, n):
     info = api.meryl_info(d)
     assert stats == {"unique": info["n_unique"], "distinct": info["n_distinct"], "present": info["n_total"]}
     assert info["n_distinct"] == len(km) and info["n_total"] == int(vv.astype(np.uint64).sum())
+
+
+def test_oracle_decodes_databases_made_by_meryl_set_operations(tmp_path):
+    """Read databases in the wild are usually `meryl union-sum` of per-run counts, written by meryl's
+    streaming writer (kmers-writer-stream.C) rather than the block writer `count` uses, and filtered
+    ones (`greater-than`) have sparse prefixes.  The oracle's decoder against `meryl print` of each,
+    and mfn_meryl_info against `meryl statistics`."""
+    from merfin_b200 import synth, api
+    d = str(tmp_path)
+    k = 21
+    t1 = synth.make_assembly(60000, 3, 1, n_run=10, lower_run=20, dup_len=500)
+    t2 = synth.make_assembly(50000, 2, 2, n_run=10, lower_run=20, dup_len=500)
+    synth.write_fasta(os.path.join(d, "a.fa"), t1)
+    synth.write_fasta(os.path.join(d, "b.fa"), t2 + t1[:1])
+    for fa, db in (("a.fa", "a.meryl"), ("b.fa", "b.meryl")):
+        _run([MERYL, "threads=2", "count", f"k={k}", "memory=1", fa, "output", db], d)
+    _run([MERYL, "threads=2", "union-sum", "a.meryl", "b.meryl", "output", "u.meryl"], d)
+    _run([MERYL, "threads=1", "greater-than", "1", "u.meryl", "output", "g.meryl"], d)
+    _run([MERYL, "threads=1", "intersect-min", "a.meryl", "b.meryl", "output", "i.meryl"], d)
+    dec = "ACTG"
+    for db in ("u.meryl", "g.meryl", "i.meryl"):
+        p = subprocess.run([MERYL, "threads=1", "print", os.path.join(d, db)], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        lines = p.stdout.splitlines()
+        D = O.DB(os.path.join(d, db))
+        assert D.n == len(lines) > 1000, db
+        want_v = np.array([int(l.split()[1]) for l in lines], dtype=np.uint32)
+        assert (D.val == want_v).all(), db
+        for i in np.random.default_rng(1).integers(0, D.n, size=500):
+            x = int(D.lo[i])
+            assert "".join(dec[(x >> (2 * (k - 1 - j))) & 3] for j in range(k)) == lines[i].split()[0]
+        info = api.meryl_info(os.path.join(d, db))
+        assert info["k"] == k and info["n_distinct"] == D.n and info["n_total"] == int(want_v.astype(np.uint64).sum())
