@@ -120,53 +120,194 @@ extern "C" int mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npa
 // ---------------------------------------------------------------------------------------------
 // -dump text (merfin-dump.C:87-93): "%s\t%lu\t%.2f\t%.2f\t%.2f\n" of (readK, asmK, k*) for every
 // valid window whose three numbers are not all zero.  The reference formats every line with
-// fprintf in its single writer thread; here the positions are cut into chunks that worker threads
-// format side by side (the three %.2f fields depend only on the integer pair, so each thread keeps
-// the formatted tail of every pair it has seen), and the chunks are written in order.
+// fprintf in its single writer thread.  Here:
+//   * the three %.2f fields depend only on the integer pair, so the formatted tail of a pair is
+//     computed once and kept in a table shared by all threads and all calls with the same K* model;
+//   * positions are cut into chunks that worker threads format side by side into reusable buffers
+//     (decimal position kept as digits and incremented, fixed-width copies), while the calling
+//     thread writes finished chunks in order.
 // ---------------------------------------------------------------------------------------------
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
 
 namespace {
-struct DumpChunk { std::string text; uint64_t kasm = 0, kmiss = 0; };
 
-void format_chunk(const char *ident, size_t ident_len, uint64_t p0, uint64_t p1, const uint32_t *vr, const uint32_t *va,
-                  const uint8_t *ok, const mfn_kmodel *km, bool want_text, DumpChunk &out) {
-  std::unordered_map<uint64_t, std::string> tails;        // pair -> "\t%.2f\t%.2f\t%.2f\n", empty string = line suppressed
-  std::unordered_map<uint64_t, bool> miss;
-  out.text.clear();
-  if (want_text) out.text.reserve((size_t)(p1 - p0) * (ident_len + 28));
-  char num[24];
-  for (uint64_t p = p0; p < p1; p++) {
-    if (!ok[p]) continue;
-    const uint64_t key = ((uint64_t)vr[p] << 32) | va[p];
-    auto it = tails.find(key);
-    if (it == tails.end()) {
-      double readK, asmK, prob;
-      mfn_getK(km, vr[p], va[p], &readK, &asmK, &prob);
-      const double ks = mfn_getKmetric(readK, asmK);
-      char buf[128];
-      int n = 0;
-      if (readK != 0.0 || asmK != 0.0 || ks != 0.0) n = snprintf(buf, sizeof buf, "\t%.2f\t%.2f\t%.2f\n", readK, asmK, ks);
-      it = tails.emplace(key, std::string(buf, (size_t)n)).first;
-      miss[key] = (readK == 0);
-    }
-    out.kasm++;
-    if (miss[key]) out.kmiss++;
-    if (!want_text || it->second.empty()) continue;
-    out.text.append(ident, ident_len);
-    out.text.push_back('\t');
-    uint64_t v = p;                                     // position inside the record, as decimal
-    int d = 0;
-    do { num[d++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (d) out.text.push_back(num[--d]);
-    out.text.append(it->second);
-  }
+constexpr uint32_t TAIL_R = 2048, TAIL_A = 32;            // pairs kept in the shared table: v_read < TAIL_R, v_asm < TAIL_A
+constexpr uint32_t TAIL_MAX = 60;                         // longest tail kept inline
+constexpr uint64_t DUMP_CHUNK = 1 << 17;                  // positions per formatter task
+
+struct Tail {                                             // 64 bytes
+  std::atomic<uint8_t> state{0};                          // 0 empty, 1 being filled, 2 ready
+  uint8_t len = 0;                                        // 0: the line is suppressed (all three numbers zero)
+  uint8_t miss = 0;                                       // readK == 0
+  char s[TAIL_MAX + 1];
+};
+
+struct LongTail { std::string s; bool miss = false; };
+
+// "\t%.2f\t%.2f\t%.2f\n" of one pair; returns the length snprintf wanted
+int make_tail(const mfn_kmodel *km, uint32_t vr, uint32_t va, char *buf, size_t cap, bool *miss) {
+  double readK, asmK, prob;
+  mfn_getK(km, vr, va, &readK, &asmK, &prob);
+  const double ks = mfn_getKmetric(readK, asmK);
+  *miss = (readK == 0);
+  if (readK == 0.0 && asmK == 0.0 && ks == 0.0) { buf[0] = 0; return 0; }
+  return snprintf(buf, cap, "\t%.2f\t%.2f\t%.2f\n", readK, asmK, ks);
 }
+
+struct TailTable {
+  double peak = 0;
+  std::vector<uint32_t> probK;
+  std::vector<double> probP;
+  std::unique_ptr<Tail[]> t{new Tail[(size_t)TAIL_R * TAIL_A]};
+  bool same_model(const mfn_kmodel *km) const {
+    if (memcmp(&peak, &km->peak, sizeof peak) != 0 || probK.size() != km->nprob) return false;
+    return !km->nprob || (memcmp(probK.data(), km->probK, km->nprob * sizeof(uint32_t)) == 0 &&
+                          memcmp(probP.data(), km->probP, km->nprob * sizeof(double)) == 0);
+  }
+};
+
+// the table of the K* model in use (a call with another model installs a fresh one; calls still
+// running keep theirs alive through the shared_ptr)
+std::shared_ptr<TailTable> tail_table(const mfn_kmodel *km) {
+  static std::mutex mu;
+  static std::shared_ptr<TailTable> cur;
+  std::lock_guard<std::mutex> g(mu);
+  if (!cur || !cur->same_model(km)) {
+    cur = std::make_shared<TailTable>();
+    cur->peak = km->peak;
+    if (km->nprob) { cur->probK.assign(km->probK, km->probK + km->nprob); cur->probP.assign(km->probP, km->probP + km->nprob); }
+  }
+  return cur;
+}
+
+// reusable text buffers (a fresh 6 MB allocation per chunk would spend its time in page faults)
+struct BufferPool {
+  std::mutex mu;
+  std::vector<std::vector<char>> free_;
+  std::vector<char> get() {
+    std::lock_guard<std::mutex> g(mu);
+    if (free_.empty()) return {};
+    std::vector<char> b = std::move(free_.back());
+    free_.pop_back();
+    return b;
+  }
+  void put(std::vector<char> &&b) {
+    std::lock_guard<std::mutex> g(mu);
+    if (free_.size() < 64) free_.push_back(std::move(b));
+  }
+};
+BufferPool &pool() { static BufferPool P; return P; }
+
+struct DumpChunk { std::vector<char> text; size_t len = 0; uint64_t kasm = 0, kmiss = 0; };
+
+struct ChunkFormatter {
+  const mfn_kmodel *km;
+  TailTable *table;
+  std::unordered_map<uint64_t, LongTail> rare;            // pairs outside the shared table, or with a long tail
+  Tail scratch;
+
+  // tail text + flags of a pair
+  // (inl: the text lives in a Tail, so a fixed 32-byte copy may read past its end)
+  inline void lookup(uint32_t vr, uint32_t va, const char *&s, uint32_t &len, bool &miss, bool &inl) {
+    inl = true;
+    if (vr < TAIL_R && va < TAIL_A) {
+      Tail &e = table->t[(size_t)va * TAIL_R + vr];
+      uint8_t st = e.state.load(std::memory_order_acquire);
+      if (st == 2) {
+        if (e.len <= TAIL_MAX) { s = e.s; len = e.len; miss = e.miss; return; }
+      } else {
+        char buf[256];
+        bool m;
+        const int n = make_tail(km, vr, va, buf, sizeof buf, &m);
+        uint8_t expect = 0;
+        if (st == 0 && e.state.compare_exchange_strong(expect, 1, std::memory_order_acq_rel)) {
+          e.miss = m;
+          e.len = n <= (int)TAIL_MAX ? (uint8_t)n : (uint8_t)255;       // 255: too long, kept per thread
+          if (n <= (int)TAIL_MAX) memcpy(e.s, buf, (size_t)n + 1);
+          e.state.store(2, std::memory_order_release);
+          if (n <= (int)TAIL_MAX) { s = e.s; len = (uint32_t)n; miss = m; return; }
+        } else if (n <= (int)TAIL_MAX) {
+          // another thread is filling the entry right now: use a private copy this once
+          scratch.len = (uint8_t)n; scratch.miss = m;
+          memcpy(scratch.s, buf, (size_t)n + 1);
+          s = scratch.s; len = (uint32_t)n; miss = m;
+          return;
+        }
+      }
+    }
+    inl = false;
+    const uint64_t key = ((uint64_t)vr << 32) | va;
+    auto it = rare.find(key);
+    if (it == rare.end()) {
+      std::string buf(64, '\0');
+      bool m;
+      int n = make_tail(km, vr, va, &buf[0], buf.size(), &m);
+      if (n >= (int)buf.size()) { buf.assign((size_t)n + 1, '\0'); n = make_tail(km, vr, va, &buf[0], buf.size(), &m); }
+      buf.resize((size_t)n);
+      it = rare.emplace(key, LongTail{std::move(buf), m}).first;
+    }
+    s = it->second.s.data(); len = (uint32_t)it->second.s.size(); miss = it->second.miss;
+  }
+
+  void run(const char *ident, size_t il, uint64_t p0, uint64_t p1, const uint32_t *vr, const uint32_t *va, const uint8_t *ok,
+           bool want_text, DumpChunk &out) {
+    out.len = 0; out.kasm = 0; out.kmiss = 0;
+    const size_t slack = il + 64 + 256;                   // one line with a short tail, plus the over-copies below
+    if (want_text && out.text.size() < (size_t)(p1 - p0) * (il + 36) + slack) out.text.resize((size_t)(p1 - p0) * (il + 36) + slack);
+    char *base = out.text.data(), *w = base, *lim = base + out.text.size();
+    char idbuf[64] = {0};                                 // short names are copied with a fixed width
+    const bool short_id = il <= 32;
+    if (short_id) memcpy(idbuf, ident, il);
+    // decimal digits of the position, right-aligned so that the last digit is dig[31]
+    char dig[64] = {0};
+    uint32_t nd = 0;
+    uint64_t cur = 0;
+    bool have_cur = false;
+    uint64_t kasm = 0, kmiss = 0;
+    for (uint64_t p = p0; p < p1; p++) {
+      if (!ok[p]) continue;
+      const char *ts; uint32_t tl; bool miss, inl;
+      lookup(vr[p], va[p], ts, tl, miss, inl);
+      kasm++;
+      kmiss += miss;
+      if (!want_text || tl == 0) continue;
+      if (have_cur && p == cur + 1) {                     // next position: increment the digits
+        int i = 31;
+        while (dig[i] == '9') { dig[i] = '0'; i--; if (31 - i == (int)nd) { dig[i] = '0'; nd++; } }
+        dig[i]++;
+      } else {
+        uint64_t v = p;
+        nd = 0;
+        do { dig[31 - nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+      }
+      cur = p; have_cur = true;
+      if ((size_t)(lim - w) < il + tl + slack) {          // rare: long tails
+        const size_t used = (size_t)(w - base);
+        out.text.resize(out.text.size() * 2 + il + tl + slack);
+        base = out.text.data(); w = base + used; lim = base + out.text.size();
+      }
+      if (short_id) memcpy(w, idbuf, 32); else memcpy(w, ident, il);
+      w += il;
+      *w++ = '\t';
+      memcpy(w, dig + 32 - nd, 20);                       // nd <= 20; what follows the digits is overwritten
+      w += nd;
+      if (inl && tl <= 32) memcpy(w, ts, 32); else memcpy(w, ts, tl);
+      w += tl;
+    }
+    out.len = (size_t)(w - base);
+    out.kasm = kasm; out.kmiss = kmiss;
+  }
+};
+
 }  // namespace
 
 // Format one record's -dump lines into file descriptor fd (fd < 0: count only, as -skipMissing does)
@@ -174,34 +315,87 @@ void format_chunk(const char *ident, size_t ident_len, uint64_t p0, uint64_t p1,
 // output (index = position in the record).  Returns the record's kasm / kmissing in *counts.
 extern "C" int mfn_dump_write(int fd, const char *ident, uint64_t n, const uint32_t *v_read, const uint32_t *v_asm,
                               const uint8_t *valid, const mfn_kmodel *km, int threads, mfn_seq_counts *counts) {
-  if (!ident || (n && (!v_read || !v_asm || !valid))) return MFN_ERR_INVALID;
+  if (!ident || !km || (n && (!v_read || !v_asm || !valid))) return MFN_ERR_INVALID;
   const size_t il = strlen(ident);
-  const uint64_t CH = 1 << 20;
+  const uint64_t CH = DUMP_CHUNK;
   const uint64_t nch = (n + CH - 1) / CH;
   unsigned T = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
   T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(T, nch));
+  const bool want_text = fd >= 0;
+  std::shared_ptr<TailTable> table = tail_table(km);
   uint64_t kasm = 0, kmiss = 0;
-  std::vector<DumpChunk> round(T);
-  for (uint64_t c0 = 0; c0 < nch; c0 += T) {
-    const unsigned m = (unsigned)std::min<uint64_t>(T, nch - c0);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < m; t++)
-      th.emplace_back([&, t]() {
-        const uint64_t a = (c0 + t) * CH, b = std::min(n, a + CH);
-        format_chunk(ident, il, a, b, v_read, v_asm, valid, km, fd >= 0, round[t]);
-      });
-    for (auto &x : th) x.join();
-    for (unsigned t = 0; t < m; t++) {
-      kasm += round[t].kasm; kmiss += round[t].kmiss;
-      const char *p = round[t].text.data();
-      size_t left = fd >= 0 ? round[t].text.size() : 0;
-      while (left) {
-        const ssize_t w = write(fd, p, left);
-        if (w <= 0) { mfn_set_error("-dump: write failed"); return MFN_ERR_IO; }
-        p += w; left -= (size_t)w;
-      }
+  auto write_all = [&](const char *p, size_t left) -> bool {
+    while (left) {
+      const ssize_t w = write(fd, p, left);
+      if (w <= 0) { mfn_set_error("-dump: write failed"); return false; }
+      p += w; left -= (size_t)w;
     }
+    return true;
+  };
+
+  if (T == 1) {                                            // small records: no threads
+    ChunkFormatter F{km, table.get()};
+    DumpChunk c;
+    c.text = pool().get();
+    bool ok = true;
+    for (uint64_t i = 0; i < nch && ok; i++) {
+      F.run(ident, il, i * CH, std::min(n, (i + 1) * CH), v_read, v_asm, valid, want_text, c);
+      kasm += c.kasm; kmiss += c.kmiss;
+      if (want_text) ok = write_all(c.text.data(), c.len);
+    }
+    pool().put(std::move(c.text));
+    if (!ok) return MFN_ERR_IO;
+    if (counts) { counts->kasm = kasm; counts->kmissing = kmiss; }
+    return MFN_OK;
   }
+
+  // chunk c is formatted by worker c % T into slot c % (2 T); the caller writes the chunks in order
+  // and hands the slots back, so every worker formats one chunk ahead of the writer
+  const unsigned NS = 2 * T;
+  std::vector<DumpChunk> slot(NS);
+  for (auto &s : slot) s.text = pool().get();
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<uint8_t> ready(nch, 0);
+  uint64_t written = 0;                                    // chunks below this are written: their slots are free
+  bool failed = false;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; t++)
+    th.emplace_back([&, t]() {
+      ChunkFormatter F{km, table.get()};
+      for (uint64_t c = t; c < nch; c += T) {
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return failed || c < written + NS; });          // slot c % NS is free
+          if (failed) return;
+        }
+        F.run(ident, il, c * CH, std::min(n, (c + 1) * CH), v_read, v_asm, valid, want_text, slot[c % NS]);
+        {
+          std::lock_guard<std::mutex> g(mu);
+          ready[c] = 1;
+        }
+        cv.notify_all();
+      }
+    });
+  for (uint64_t c = 0; c < nch; c++) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return ready[c] != 0; });
+    }
+    DumpChunk &d = slot[c % NS];
+    kasm += d.kasm; kmiss += d.kmiss;
+    const bool ok = !want_text || write_all(d.text.data(), d.len);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      written = c + 1;
+      if (!ok) failed = true;
+    }
+    cv.notify_all();
+    if (!ok) break;
+  }
+  for (auto &x : th) x.join();
+  for (auto &s : slot) pool().put(std::move(s.text));
+  if (failed) return MFN_ERR_IO;
   if (counts) { counts->kasm = kasm; counts->kmissing = kmiss; }
   return MFN_OK;
 }
