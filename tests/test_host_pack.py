@@ -77,3 +77,55 @@ sys.stdout.write(lib.mfn_pack_host_isa().decode() + " " + str(int(s2.sum() & np.
         outs[scalar] = (isa, digest)
     assert outs["1"][0] == "scalar"
     assert outs["0"][1] == outs["1"][1]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_pack_host_range_block_boundaries(seed):
+    """No up-front memset: whole 64-position blocks are stored outright, the rest is zeroed and OR-ed.
+    Record lengths around the block size, runs of empty / one-base records sharing a block, random
+    64-aligned cuts, output arrays pre-filled with garbage."""
+    from merfin_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(100 + seed)
+    pool = [0, 0, 1, 1, 2, 5, 30, 31, 32, 33, 61, 62, 63, 64, 65, 66, 126, 127, 128, 129, 191, 192, 193, 255, 256, 257, 1000, 4096, 4097]
+    lens = [int(rng.choice(pool)) for _ in range(int(rng.integers(1, 120)))]
+    if seed % 3 == 0:
+        lens.insert(int(rng.integers(0, len(lens))), 70_000)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    recs = [rng.choice(alphabet, size=n) for n in lens]
+    bases = np.concatenate(recs + [np.zeros(1, dtype=np.uint8)])
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    rec_start = (off + np.arange(len(lens) + 1, dtype=np.uint64)).astype(np.uint64)
+    Gp = (int(rec_start[-1]) + 2047) // 2048 * 2048 + (2048 if seed % 2 else 0)      # sometimes a tail of pure padding
+    want2, wantok = _expected(recs, rec_start, Gp)
+    cuts = sorted({0, Gp} | {int(x) // 64 * 64 for x in rng.integers(0, Gp, size=int(rng.integers(0, 12)))})
+    got2 = np.full(Gp // 32, 0xdeadbeefdeadbeef, dtype=np.uint64)
+    gotok = np.full(Gp // 64, 0xdeadbeefdeadbeef, dtype=np.uint64)
+    order = list(zip(cuts[:-1], cuts[1:]))
+    rng.shuffle(order)                                  # ranges are independent: any order
+    for a, b in order:
+        lib.mfn_pack_host_range(C.c_void_p(bases.ctypes.data), C.c_void_p(rec_start.ctypes.data), len(lens),
+                                C.c_uint64(a), C.c_uint64(b), C.c_void_p(got2.ctypes.data + a // 32 * 8),
+                                C.c_void_p(gotok.ctypes.data + a // 64 * 8))
+    assert (got2 == want2).all()
+    assert (gotok == wantok).all()
+
+
+def test_packer_under_address_sanitizer(tmp_path):
+    """host_pack.cpp built with ASan+UBSan and driven by tests/pack_sanitize_harness.cpp: every piece is
+    packed into its own exact-size allocation from an exact-size source (no access outside either), and
+    compared with a per-base loop; both the AVX2 and the scalar kernel."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pk_asan")
+    b = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        os.path.join(root, "merfin_b200", "csrc", "host_pack.cpp"), os.path.join(root, "tests", "pack_sanitize_harness.cpp"),
+                        "-o", exe], capture_output=True, text=True)
+    if b.returncode != 0 and ("cannot find -l" in b.stderr or "libasan" in b.stderr):
+        pytest.skip("sanitizer runtime not installed")
+    assert b.returncode == 0, b.stderr[-2000:]
+    for scalar in ("0", "1"):
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, MFN_PACK_SCALAR=scalar))
+        assert p.returncode == 0 and p.stdout.strip() == "ok", (scalar, p.stdout[-500:], p.stderr[-3000:])
