@@ -6,6 +6,11 @@
 #include <cstdio>
 #include <cstring>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 static bool ends_with(const std::string &s, const char *suf) {
   size_t n = strlen(suf);
   return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
@@ -38,39 +43,47 @@ bool slurp_file(const std::string &path, std::vector<char> &data, std::string &e
 
 static inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
 
-// Append the non-whitespace bytes of [p, p + n) to `bases`.  A sequence line is normally free of
-// whitespace, so blocks of 32 bytes without any byte <= ' ' are copied as they are (AVX2 when the
-// CPU has it); anything else goes through the per-byte filter.
-__attribute__((target("avx2"))) static size_t clean_prefix_avx2(const char *p, size_t n) {
-  size_t i = 0;
-  const __m256i lim = _mm256_set1_epi8(0x21);
-  for (; i + 32 <= n; i += 32) {
-    const __m256i v = _mm256_loadu_si256((const __m256i *)(p + i));
-    // bytes 0x00..0x20 (and none of 0x80..0xff, which compare as negative: checked below)
-    const __m256i low = _mm256_cmpgt_epi8(lim, v);
-    if (_mm256_movemask_epi8(low)) break;
-  }
-  return i;
+// Copy a FASTA body starting at p (input ends at e) to dst, dropping whitespace, until a record
+// marker ('>' or '@', anywhere) or the end of the input.  Returns the input position reached; dst is
+// advanced.  dst must have room for every remaining input byte plus 32 (blocks are stored whole and
+// the write pointer then moves by the bytes kept).
+static inline const char *copy_body_scalar(const char *p, const char *e, char *&dst) {
+  char *d = dst;
+  for (; p < e && *p != '>' && *p != '@'; p++) if (!is_space(*p)) *d++ = *p;
+  dst = d;
+  return p;
 }
-static void append_bases(std::vector<char> &bases, const char *p, size_t n) {
-  static const bool avx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2"));
-  size_t i = 0;
-  while (i < n) {
-    if (avx2 && n - i >= 32) {
-      const size_t c = clean_prefix_avx2(p + i, n - i);
-      if (c) { bases.insert(bases.end(), p + i, p + i + c); i += c; continue; }
-    }
-    const size_t e = std::min(n, i + 32);
-    for (; i < e; i++) if (!is_space(p[i])) bases.push_back(p[i]);
+__attribute__((target("avx2"))) static const char *copy_body_avx2(const char *p, const char *e, char *&dst) {
+  char *d = dst;
+  const __m256i lim = _mm256_set1_epi8(0x21), gt = _mm256_set1_epi8('>'), at = _mm256_set1_epi8('@');
+  while (p + 32 <= e) {
+    const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+    _mm256_storeu_si256((__m256i *)d, v);
+    // bytes that need a look: 0x00..0x20 (and 0x80..0xff, which compare as negative), '>' and '@'
+    const __m256i sp = _mm256_or_si256(_mm256_cmpgt_epi8(lim, v), _mm256_or_si256(_mm256_cmpeq_epi8(v, gt), _mm256_cmpeq_epi8(v, at)));
+    const uint32_t m = (uint32_t)_mm256_movemask_epi8(sp);
+    if (m == 0) { p += 32; d += 32; continue; }
+    const uint32_t n = (uint32_t)__builtin_ctz(m);
+    p += n; d += n;                                    // the bytes before it are in place
+    const char c = *p;
+    if (c == '>' || c == '@') { dst = d; return p; }
+    if (!is_space(c)) *d++ = c;
+    p++;
   }
+  dst = d;
+  return copy_body_scalar(p, e, dst);
+}
+static const char *copy_body(const char *p, const char *e, char *&dst) {
+  static const bool avx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2"));
+  return avx2 ? copy_body_avx2(p, e, dst) : copy_body_scalar(p, e, dst);
 }
 
-bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
-  std::vector<char> data;
-  if (!slurp_file(path, data, err)) return false;
+// The records of a whole file image [data, data + N).
+static void parse_records(const char *data, size_t N, SeqSet &out) {
   out.ident.clear(); out.off.assign(1, 0); out.bases.clear();
-  out.bases.reserve(data.size());
-  const size_t N = data.size();
+  out.bases.resize(N + 64);                             // every base is an input byte; + room for whole-block stores
+  char *const base = out.bases.data();
+  char *dst = base;
   size_t p = 0;
   while (p < N) {
     while (p < N && is_space(data[p])) p++;
@@ -78,34 +91,21 @@ bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
     const char mark = data[p];
     if (mark != '>' && mark != '@') break;              // not at a record start: stop, like the reference
     size_t h0 = ++p;
-    while (p < N && data[p] != '\n') p++;
+    const char *nl = (const char *)memchr(data + p, '\n', N - p);
+    p = nl ? (size_t)(nl - data) : N;
     size_t h1 = p;
     while (h0 < h1 && is_space(data[h0])) h0++;          // ident = first word of the header
     size_t he = h0;
     while (he < h1 && !is_space(data[he]) && (unsigned char)data[he] > 32 && (unsigned char)data[he] < 127) he++;
-    out.ident.emplace_back(data.data() + h0, he - h0);
+    out.ident.emplace_back(data + h0, he - h0);
     if (p < N) p++;
     if (mark == '>') {
       // body: everything up to the next '>' or '@' (anywhere), whitespace dropped
-      while (p < N && data[p] != '>' && data[p] != '@') {
-        const char *nl = (const char *)memchr(data.data() + p, '\n', N - p);
-        size_t e = nl ? (size_t)(nl - data.data()) : N;
-        // a marker inside the line ends the record there
-        size_t stop = e;
-        {
-          const char *m1 = (const char *)memchr(data.data() + p, '>', e - p);
-          if (m1) stop = (size_t)(m1 - data.data());
-          const char *m2 = (const char *)memchr(data.data() + p, '@', stop - p);
-          if (m2) stop = (size_t)(m2 - data.data());
-        }
-        append_bases(out.bases, data.data() + p, stop - p);
-        p = stop;
-        if (stop == e && p < N) p++;                     // consume the newline
-      }
+      p = (size_t)(copy_body(data + p, data + N, dst) - data);
     } else {
       // FASTQ: one sequence line, '+' line, one quality line
       while (p < N && is_space(data[p])) p++;
-      while (p < N && data[p] != '\n') { if (!is_space(data[p])) out.bases.push_back(data[p]); p++; }
+      while (p < N && data[p] != '\n') { if (!is_space(data[p])) *dst++ = data[p]; p++; }
       while (p < N && is_space(data[p])) p++;
       if (p < N && data[p] == '+') {
         while (p < N && data[p] != '\n') p++;
@@ -113,7 +113,31 @@ bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
         while (p < N && data[p] != '\n') p++;
       }
     }
-    out.off.push_back(out.bases.size());
+    out.off.push_back((uint64_t)(dst - base));
   }
+  out.bases.resize((size_t)(dst - base));
+}
+
+bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
+  // plain files are parsed straight from a read-only mapping; compressed ones from the decompressor's output
+  if (!ends_with(path, ".gz") && !ends_with(path, ".bz2") && !ends_with(path, ".xz")) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "cannot open '" + path + "'"; return false; }
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        parse_records((const char *)m, (size_t)st.st_size, out);
+        munmap(m, (size_t)st.st_size);
+        close(fd);
+        return true;
+      }
+    }
+    close(fd);
+  }
+  std::vector<char> data;
+  if (!slurp_file(path, data, err)) return false;
+  parse_records(data.data(), data.size(), out);
   return true;
 }
