@@ -17,16 +17,25 @@
 namespace mfnv {
 
 // strings.C:188-249: runs of separators collapse, empty words do not exist
-static std::vector<std::string> split(const std::string &s, const char *seps) {
-  std::vector<std::string> out;
-  size_t i = 0, n = s.size();
+typedef std::pair<const char *, size_t> Span;
+static void split_spans(const char *s, size_t n, const char *seps, std::vector<Span> &out) {
+  out.clear();
+  size_t i = 0;
   while (i < n) {
     while (i < n && strchr(seps, s[i])) i++;
     size_t j = i;
     while (j < n && !strchr(seps, s[j])) j++;
-    if (j > i) out.emplace_back(s, i, j - i);
+    if (j > i) out.emplace_back(s + i, j - i);
     i = j;
   }
+}
+static std::vector<std::string> split(const std::string &s, const char *seps) {
+  std::vector<Span> sp;
+  sp.reserve(8);
+  split_spans(s.data(), s.size(), seps, sp);
+  std::vector<std::string> out;
+  out.reserve(sp.size());
+  for (const Span &w : sp) out.emplace_back(w.first, w.second);
   return out;
 }
 
@@ -52,14 +61,29 @@ static GtAllele *make_allele(const VcfRecord *r) {
   g->qual = r->qual;
   const std::string &gt = r->sample_fields.empty() ? std::string() : r->sample_fields[0];
   if (gt.compare(0, 3, "./.") == 0 || gt.compare(0, 3, "0/0") == 0) return g;      // no alleles at all (Q10)
+  g->alleles.reserve(3);
   g->alleles.push_back(r->ref);
-  std::vector<int> used;
-  for (const std::string &tok : split(gt, "|/")) {
-    long idx = strtol(tok.c_str(), nullptr, 10);
+  int used[8];                                        // ALT column entries taken so far (a sample names a handful at most)
+  size_t nused = 0;
+  std::vector<int> used_more;
+  const char *p = gt.data(), *const e = p + gt.size();
+  while (p < e) {
+    while (p < e && (*p == '|' || *p == '/')) p++;
+    const char *q = p;
+    while (q < e && *q != '|' && *q != '/') q++;
+    if (q == p) break;
+    char tok[24];
+    const size_t tl = std::min<size_t>((size_t)(q - p), sizeof tok - 1);
+    memcpy(tok, p, tl);
+    tok[tl] = 0;
+    p = q;
+    long idx = strtol(tok, nullptr, 10);
     if (idx <= 0) continue;
     if ((size_t)idx > r->alt_list.size()) continue;
-    if (std::find(used.begin(), used.end(), (int)idx) != used.end()) continue;      // same ALT column entry again
-    used.push_back((int)idx);
+    bool seen = std::find(used, used + nused, (int)idx) != used + nused ||
+                std::find(used_more.begin(), used_more.end(), (int)idx) != used_more.end();
+    if (seen) continue;                                                             // same ALT column entry again
+    if (nused < 8) used[nused++] = (int)idx; else used_more.push_back((int)idx);
     const std::string &hap = r->alt_list[idx - 1];
     if (hap == r->ref) continue;
     g->alleles.push_back(hap);
@@ -92,20 +116,30 @@ bool VcfFile::load(const std::string &path, std::string &err) {
     const size_t l0 = nlines * t / T, l1 = nlines * (t + 1) / T;
     std::vector<Item> &out = parts[t];
     out.reserve(l1 - l0);
+    std::vector<Span> w, sub;                        // reused for every line of this thread
+    w.reserve(16); sub.reserve(8);
     for (size_t l = l0; l < l1; l++) {
       size_t p = starts[l], e = starts[l + 1];
       while (e > p && (data[e - 1] == '\r' || data[e - 1] == '\n')) e--;
       if (e == p) continue;
-      std::string line(data.data() + p, e - p);
+      const char *line = data.data() + p;
+      const size_t len = e - p;
       Item it;
-      if (line[0] == '#') { it.header = std::move(line); out.push_back(std::move(it)); continue; }
-      std::vector<std::string> w = split(line, "\t");
+      if (line[0] == '#') { it.header.assign(line, len); out.push_back(std::move(it)); continue; }
+      split_spans(line, len, "\t", w);
       if (w.size() < 10) { it.excluded = true; out.push_back(std::move(it)); continue; }   // vcfRecord.H:53-56
+      auto str = [&](int i) { return std::string(w[i].first, w[i].second); };
       VcfRecord *r = new VcfRecord();
-      r->chr = w[0]; r->pos = (uint32_t)strtoul(w[1].c_str(), nullptr, 10); r->id = w[2]; r->ref = w[3]; r->alts = w[4];
-      r->qual = strtod(w[5].c_str(), nullptr); r->filter = w[6]; r->info = w[7]; r->formats = w[8]; r->samples = w[9];
-      r->alt_list = split(r->alts, ",");
-      r->sample_fields = split(r->samples, ":");
+      char num[64];
+      auto cstr = [&](int i) { const size_t n = std::min<size_t>(w[i].second, sizeof num - 1); memcpy(num, w[i].first, n); num[n] = 0; return num; };
+      r->chr = str(0); r->pos = (uint32_t)strtoul(cstr(1), nullptr, 10); r->id = str(2); r->ref = str(3); r->alts = str(4);
+      r->qual = strtod(cstr(5), nullptr); r->filter = str(6); r->info = str(7); r->formats = str(8); r->samples = str(9);
+      split_spans(r->alts.data(), r->alts.size(), ",", sub);
+      r->alt_list.reserve(sub.size());
+      for (const Span &x : sub) r->alt_list.emplace_back(x.first, x.second);
+      split_spans(r->samples.data(), r->samples.size(), ":", sub);
+      r->sample_fields.reserve(sub.size());
+      for (const Span &x : sub) r->sample_fields.emplace_back(x.first, x.second);
       GtAllele *g = make_allele(r);
       PosGT *pg = new PosGT();
       pg->chr = r->chr; pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
