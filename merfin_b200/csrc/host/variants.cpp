@@ -29,16 +29,6 @@ static void split_spans(const char *s, size_t n, const char *seps, std::vector<S
     i = j;
   }
 }
-static std::vector<std::string> split(const std::string &s, const char *seps) {
-  std::vector<Span> sp;
-  sp.reserve(8);
-  split_spans(s.data(), s.size(), seps, sp);
-  std::vector<std::string> out;
-  out.reserve(sp.size());
-  for (const Span &w : sp) out.emplace_back(w.first, w.second);
-  return out;
-}
-
 std::string VcfRecord::save() const {
   char num[64];
   snprintf(num, sizeof num, "%.1f", qual);
