@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../../include/merfin_b200.h"
+#include "dump_driver.h"
 #include "fasta.h"
 #include "variants.h"
 
@@ -269,22 +270,15 @@ int main(int argc, char **argv) {
   // ---- -dump (merfin-dump.C) ---------------------------------------------------------------------
   if (G.report == OP_DUMP) {
     fprintf(stderr, "-- Dump per-base k* metric to '%s'.\n", G.outName);
-    const uint64_t N = S.bases.size();
-    std::vector<uint32_t> vr(N + 1), va(N + 1);
-    std::vector<uint8_t> ok(N + 1);
-    if (mfn_dump(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), vr.data(), va.data(), ok.data()) != MFN_OK) die("-dump");
+    // records go through the GPU in batches while the previous batch is formatted on the host threads
+    // and written in position order (host/dump_driver.cpp)
     FILE *F = nullptr;
-    uint64_t totMissing = 0, totAsm = 0;
-    for (size_t i = 0; i < S.nseq(); i++) {
-      if (!G.skipMissing && !F) { F = fopen(G.outName, "w"); if (!F) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; } }
-      // lines of this record, formatted on all host threads and written in position order
-      mfn_seq_counts c{};
-      const uint64_t a = S.off[i], n = S.off[i + 1] - S.off[i];
-      if (F) fflush(F);
-      if (mfn_dump_write(F ? fileno(F) : -1, S.ident[i].c_str(), n, vr.data() + a, va.data() + a, ok.data() + a, &km, (int)G.threads, &c) != MFN_OK) die("-dump");
-      totMissing += c.kmissing; totAsm += c.kasm;
-      fprintf(stderr, "%s\t%lu\t%lu\t%lu\n", S.ident[i].c_str(), (unsigned long)c.kmissing, (unsigned long)totMissing, (unsigned long)totAsm);
-    }
+    if (!G.skipMissing && S.nseq() > 0) { F = fopen(G.outName, "w"); if (!F) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; } }
+    DumpBatchFn pairs = [&](const char *bases, const uint64_t *off, uint32_t nrec, uint32_t *vr, uint32_t *va, uint8_t *ok) {
+      return mfn_dump(ctx, R, A, bases, off, nrec, vr, va, ok);
+    };
+    std::string derr;
+    if (dump_records(S, &km, F ? fileno(F) : -1, (int)G.threads, 0, pairs, stderr, &derr) != MFN_OK) { fprintf(stderr, "-dump: %s\n", derr.c_str()); return 1; }
     if (F) fclose(F);
   }
 

@@ -117,3 +117,34 @@ def test_dump_formatter_under_sanitizers(tmp_path):
         assert b.returncode == 0, b.stderr[-2000:]
         p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
         assert p.returncode == 0 and p.stdout.strip().endswith("ok"), (name, p.stdout[-500:], p.stderr[-3000:])
+
+
+def test_cli_dump_driver_batches_match_reference_files(tmp_path, golden_dir):
+    """The CLI's -dump driver (csrc/host/dump_driver.cpp) with the CPU oracle standing in for mfn_dump:
+    whatever the batch size (one batch, one record per batch, a few records per batch) and thread count,
+    the file is the reference's ref.dump byte for byte and the per-record log lines are ref.dump.perseq."""
+    import gzip
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dump_driver_harness")
+    obj = str(tmp_path / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-w", "-std=gnu11", "-c", os.path.join(root, "oracle", "mfn_oracle.c"), "-o", obj])
+    so_dir = os.path.join(root, "merfin_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-pthread", "-o", exe, os.path.join(root, "tests", "dump_driver_harness.cpp"),
+                           os.path.join(root, "merfin_b200", "csrc", "host", "dump_driver.cpp"),
+                           os.path.join(root, "merfin_b200", "csrc", "host", "fasta.cpp"), obj,
+                           "-L" + so_dir, "-lmerfin_b200", "-Wl,-rpath," + so_dir, "-lm"])
+    for name, peak in (("g1_k21", 8), ("g2_k6", 3), ("g3_k31", 6)):
+        d = os.path.join(golden_dir, name)
+        want = gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
+        want_per = open(os.path.join(d, "ref.dump.perseq")).read()
+        ncalls = set()
+        for batch, threads in ((0, 0), (1, 1), (7000, 3), (20000, 2), (10**9, 4)):
+            out, per = str(tmp_path / "o.dump"), str(tmp_path / "o.perseq")
+            p = subprocess.run([exe, os.path.join(d, "asm.fa"), os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), str(peak),
+                                out, per, str(batch), str(threads)], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            assert open(out, "rb").read() == want, (name, batch)
+            assert open(per).read() == want_per, (name, batch)
+            ncalls.add(int(p.stdout))
+        assert len(ncalls) > 1                       # the batch sizes above really produced different batchings

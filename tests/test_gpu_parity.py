@@ -564,3 +564,21 @@ def test_sweep_overflow_falls_back_to_the_direct_scan(ctx, monkeypatch):
     assert len(d.pairs) == len(s.pairs) and (d.pairs == s.pairs).all() and (d.per_seq == s.per_seq).all()
     assert int(s.per_seq["kasm"][0]) == 5_000_000 - 20
     seq.close(); R.close(); A.close()
+
+
+def test_cli_dump_in_batches(golden_dir, tmp_path):
+    """The CLI's -dump with one record per batch (MFN_DUMP_BATCH=1): every batch after the first is
+    computed on a worker thread while the previous one is formatted (host/dump_driver.cpp); same file
+    as the reference's.  (Kept last: it is the only GPU test of the multi-batch path.)"""
+    import gzip
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    merfin = os.path.join(root, "merfin_b200", "bin", "merfin")
+    for name, peak in (("g1_k21", 8), ("g3_k31", 6)):
+        d = os.path.join(golden_dir, name)
+        args = [merfin, "-dump", "-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+                "-readmers", os.path.join(d, "reads.meryl"), "-peak", str(peak), "-output", "b.dump"]
+        p = subprocess.run(args, cwd=str(tmp_path), capture_output=True, text=True, timeout=150, env=dict(os.environ, MFN_DUMP_BATCH="1"))
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert open(tmp_path / "b.dump", "rb").read() == gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
+        assert open(os.path.join(d, "ref.dump.perseq")).read() in p.stderr
