@@ -312,6 +312,7 @@ static void score(VarMer &vm, const Options &opt, const uint32_t *vr, const uint
     uint32_t numM = 0, idx = 0;
     std::vector<double> ks, dks;
     const size_t nwin = L >= k ? L - k + 1 : 0;
+    if (opt.mode != FILTER) { ks.reserve(nwin); dks.reserve(nwin); }
     for (size_t w = 0; w < nwin; w++) {
       double readK = 0, asmK = 0;
       if (ok[base + w]) mfn_getK(&opt.km, vr[base + w], va[base + w], &readK, &asmK, &prob);
@@ -332,7 +333,7 @@ static void score(VarMer &vm, const Options &opt, const uint32_t *vr, const uint
       dks.push_back(oD - nD);
       idx++;
     }
-    vm.numMs.push_back(numM); vm.kstrs.push_back(ks); vm.dkstrs.push_back(dks);
+    vm.numMs.push_back(numM); vm.kstrs.push_back(std::move(ks)); vm.dkstrs.push_back(std::move(dks));
   }
 }
 
