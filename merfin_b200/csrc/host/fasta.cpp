@@ -120,21 +120,19 @@ static void parse_records(const char *data, size_t N, SeqSet &out) {
 
 bool load_sequences(const std::string &path, SeqSet &out, std::string &err) {
   // plain files are parsed straight from a read-only mapping; compressed ones from the decompressor's output
-  if (!ends_with(path, ".gz") && !ends_with(path, ".bz2") && !ends_with(path, ".xz")) {
+  struct stat st;
+  if (!ends_with(path, ".gz") && !ends_with(path, ".bz2") && !ends_with(path, ".xz") &&
+      stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {       // (pipes and devices are read once, below)
     const int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) { err = "cannot open '" + path + "'"; return false; }
-    struct stat st;
-    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
-      void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-      if (m != MAP_FAILED) {
-        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
-        parse_records((const char *)m, (size_t)st.st_size, out);
-        munmap(m, (size_t)st.st_size);
-        close(fd);
-        return true;
-      }
-    }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
+    if (m != MAP_FAILED) {
+      madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+      parse_records((const char *)m, (size_t)st.st_size, out);
+      munmap(m, (size_t)st.st_size);
+      return true;
+    }
   }
   std::vector<char> data;
   if (!slurp_file(path, data, err)) return false;
