@@ -8,7 +8,7 @@ random extra records crowded near record starts / ends and near each other (over
 duplicate positions, multi-allelic, lower-case REF, odd genotypes), sorted by position; all five
 selectors with varying k / -comb / -nosplit.
 
-    python tools/fuzz_variants.py FIRST_SEED LAST_SEED [workdir]
+    python tests/fuzz_variants.py FIRST_SEED LAST_SEED [workdir]
 
 Round 1: seeds 1-55 x 5 modes, no difference (tests/test_variants_host.py runs one seed of it).
 """

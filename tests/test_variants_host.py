@@ -107,10 +107,10 @@ def test_variant_modes_against_reference_on_fresh_input(harness, tmp_path, k, le
 @pytest.mark.skipif(not (os.path.exists(MERFIN) and os.path.exists(MERYL)), reason="oracle/_ref not built (reference sources absent)")
 @pytest.mark.parametrize("seed,k,flags", [(13, 15, ("-comb", "4", "-nosplit")), (30, 21, ())])
 def test_adversarial_vcf_against_reference(harness, tmp_path, seed, k, flags):
-    """One seed of tools/fuzz_variants.py per case: records crowded at record ends and on top of each
+    """One seed of tests/fuzz_variants.py per case: records crowded at record ends and on top of each
     other, overlapping REF spans, duplicate positions, multi-allelic and lower-case REF, odd genotypes."""
     import sys
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import fuzz_variants
     res = fuzz_variants.run(seed, k=k, flags=flags, nvar=60, L=4000, work=str(tmp_path))
     assert all(v.startswith("ok ") for v in res.values()), res
