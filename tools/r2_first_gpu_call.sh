@@ -7,6 +7,7 @@ cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out/r2_first
 mkdir -p $O
 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
+MFN_TEST_EXTRA_K=1 python -m pytest tests/test_gpu_parity.py -q -k "test_sweep_equals_direct_scan" > $O/pytest_extra_k.log 2>&1; echo "extra k (32, 11) rc=$?" | tee -a $O/summary.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/summary.txt
 # headline, with the ingest lanes' own report (new host packer: expect a higher host share than 0.69)
 MFN_INGEST_DEBUG=1 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; tail -1 $O/bench.json | tee -a $O/summary.txt
