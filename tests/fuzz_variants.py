@@ -10,7 +10,7 @@ selectors with varying k / -comb / -nosplit.
 
     python tests/fuzz_variants.py FIRST_SEED LAST_SEED [workdir]
 
-Round 1: seeds 1-55 x 5 modes, no difference (tests/test_variants_host.py runs one seed of it).
+Round 1: seeds 1-89 x 5 modes, no difference (tests/test_variants_host.py runs one seed of it).
 """
 import os
 import subprocess
