@@ -29,9 +29,20 @@
 #include "scan_kernel.cuh"
 
 #define SW_THREADS 256
+// The scatter CTA's shape can be overridden at compile time for experiments (`make exp` builds
+// libmerfin_b200_exp.so with 16384-window chunks in one 1024-thread CTA per SM; MFN_LIB selects it).
+#ifndef SW_CHUNK_TILES
 #define SW_CHUNK_TILES 4
+#endif
 #define SW_CHUNK (SW_CHUNK_TILES * MFN_TILE)      // 8192 windows per CTA round
+#ifndef SC_THREADS
 #define SC_THREADS 512                             // scatter CTA: two 2048-window tiles side by side, two rounds
+#endif
+#define SC_RANK_BITS (SW_CHUNK_TILES <= 4 ? 13 : 14)                 // rank of a window inside its bin, < SW_CHUNK
+#define SC_RD_SHIFT (11 + SC_RANK_BITS)                               // record delta field of the staging word
+#define SC_RD_BITS (31 - SC_RD_SHIFT)
+#define SC_RD_MASK ((1u << SC_RD_BITS) - 1u)
+static_assert(SW_CHUNK <= (1 << SC_RANK_BITS) && SW_CHUNK % (SC_THREADS * WPT) == 0 && SC_THREADS % (MFN_TILE / WPT) == 0, "scatter CTA shape");
 #define SC_TPT (SW_CHUNK / SC_THREADS / WPT)       // 8-window groups per thread per chunk
 #define SC_NW (SC_TPT * WPT)                       // windows per thread per chunk
 #define SC_SEQ_WORDS (SW_CHUNK / 32 + 2)           // staged 2-bit words of a chunk (2064 B)
@@ -40,7 +51,7 @@
 #define SW_SLICE 1024                              // entries per probe work item (one WARP)
 #define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
 #define SW_NOSPACE 0xffffffffu
-#define SW_MAX_RD 126u                             // record delta inside one chunk that fits the staging word
+#define SW_MAX_RD (SC_RD_MASK - 1u)                // record delta inside one chunk that fits the staging word (126)
 
 struct SweepParams {
   JointDev J;
@@ -71,7 +82,7 @@ struct SweepParams {
 // pass 1.  KK: mer size known at compile time (0 = read it from the table)
 // ------------------------------------------------------------------------------------------
 template <int KK, bool WIDE>
-__global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
   typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type low_t;
   extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
   unsigned long long *s_ent = (unsigned long long *)sw_smem;           // [SW_CHUNK] entries sorted by bin
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(cons
     const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
     // ---- hash this thread's windows; rank them inside their bins ---------------------------
-    // meta: bin (0..10) | rank in bin (11..23) | record delta (24..30) | counts twice (31)
+    // meta: bin (0..10) | rank in bin (11..) | record delta (SC_RD_SHIFT..30) | counts twice (31)
     low_t low[SC_NW];
     uint32_t meta[SC_NW];
 #pragma unroll
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(cons
         const uint32_t bin = (uint32_t)line >> P.lbits;
         const uint32_t rank = atomicAdd(&s_off[bin], 1u);
         low[idx] = (low_t)((((uint64_t)((uint32_t)line & lmask)) << P.tbits) | tag);
-        meta[idx] = bin | (rank << 11) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << 24) | twice;
+        meta[idx] = bin | (rank << 11) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << SC_RD_SHIFT) | twice;
       }
     }
     __syncthreads();
@@ -265,10 +276,10 @@ __global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(cons
     for (int idx = 0; idx < SC_NW; idx++) {
       const uint32_t m = meta[idx];
       if (m == 0xffffffffu) continue;
-      const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & 0x1fffu);
+      const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & ((1u << SC_RANK_BITS) - 1u));
       // staged: narrow = meta without the rank << 32 | low; wide = twice (63) | bin (52..62) | low (0..51)
       if (WIDE) s_ent[p] = ((unsigned long long)(m & 0x80000000u) << 32) | ((unsigned long long)(m & 0x7ffu) << 52) | low[idx];
-      else s_ent[p] = ((unsigned long long)(m & 0xff0007ffu) << 32) | low[idx];
+      else s_ent[p] = ((unsigned long long)(m & (0x800007ffu | (SC_RD_MASK << SC_RD_SHIFT))) << 32) | low[idx];
     }
     // where each bin's run goes: global index of the chunk's sorted position 0
 #pragma unroll
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : 2) k_sweep_scatter(cons
           const uint32_t hs = (uint32_t)(e >> 32);
           bin = hs & 0x7ffu;
           lowpart = (uint32_t)e;
-          rec = (r0 + ((hs >> 24) & 0x7fu)) | (hs & 0x80000000u);
+          rec = (r0 + ((hs >> SC_RD_SHIFT) & SC_RD_MASK)) | (hs & 0x80000000u);
           out = ((unsigned long long)rec << 32) | lowpart;
         }
         const unsigned long long dst = s_dst[bin];

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmerfin_b200.so")
+# MFN_LIB selects another build of the same library (e.g. the experimental `make exp` one) for A/B runs
+SO_PATH = os.path.abspath(os.environ["MFN_LIB"]) if os.environ.get("MFN_LIB") else os.path.join(_HERE, "libmerfin_b200.so")
 
 MFN_OK = 0
 MFN_ERR_NO_DEVICE = -1

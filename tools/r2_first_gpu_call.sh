@@ -16,3 +16,8 @@ grep "\[ingest\]" $O/bench.err | tail -3 | tee -a $O/summary.txt
 MFN_SUBSWEEPS=3 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_sub3.json 2>/dev/null; tail -1 $O/bench_sub3.json | tee -a $O/summary.txt
 # the CLI against the reference binary at BASELINE configs[1] (new -dump formatter / batching, FASTA loader, VCF reader)
 python tools/bench_cli.py --mbp 100 > $O/cli_100mbp.json 2> $O/cli.err; tail -1 $O/cli_100mbp.json | tee -a $O/summary.txt
+# the experimental scatter shape (16384-window chunks, one 1024-thread CTA per SM): correctness through the
+# sweep tests, then the headline A/B (pass_ms in the JSON line: scatter / probe)
+make -s -C merfin_b200/csrc exp -j8 > $O/make_exp.log 2>&1
+MFN_LIB=merfin_b200/libmerfin_b200_exp.so python -m pytest tests/test_gpu_parity.py -q -k "sweep or midsize or host_packing" > $O/pytest_exp.log 2>&1; echo "exp lib sweep tests rc=$?" | tee -a $O/summary.txt
+MFN_LIB=merfin_b200/libmerfin_b200_exp.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_exp.json 2>/dev/null; tail -1 $O/bench_exp.json | tee -a $O/summary.txt
