@@ -48,7 +48,9 @@ static_assert(SW_CHUNK <= (1 << SC_RANK_BITS) && SW_CHUNK % (SC_THREADS * WPT) =
 #define SC_SEQ_WORDS (SW_CHUNK / 32 + 2)           // staged 2-bit words of a chunk (2064 B)
 #define SC_OK_WORDS (SW_CHUNK / 64 + 2)            // staged validity words (1040 B)
 #define SW_MAX_BINS 2048
+#ifndef SW_SLICE
 #define SW_SLICE 1024                              // entries per probe work item (one WARP)
+#endif
 #define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
 #define SW_NOSPACE 0xffffffffu
 #define SW_MAX_RD (SC_RD_MASK - 1u)                // record delta inside one chunk that fits the staging word (126)
