@@ -202,7 +202,9 @@ struct BufferPool {
   }
   void put(std::vector<char> &&b) {
     std::lock_guard<std::mutex> g(mu);
-    if (free_.size() < 64) free_.push_back(std::move(b));
+    // keep what one call on every core can use again (two slots per worker), nothing oversized
+    const size_t keep = 2 * (size_t)std::max(1u, std::thread::hardware_concurrency());
+    if (free_.size() < keep && b.capacity() <= ((size_t)64 << 20)) free_.push_back(std::move(b));
   }
 };
 BufferPool &pool() { static BufferPool P; return P; }
