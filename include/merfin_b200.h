@@ -127,6 +127,19 @@ typedef struct {
 } mfn_joint_info_t;
 
 int  mfn_joint_info(const mfn_table *reads, mfn_joint_info_t *info);
+/* The fused table RESTRICTED to the k-mers of one shard of a resident sequence set (shard, nshards
+ * as in mfn_hist_resident / mfn_hist_host): a -hist scan only ever asks for k-mers of the sequences
+ * it scans, so this is the table the range-partitioned scan streams -- 1.5 G instead of 3.5 G entries
+ * at the 3 Gbp benchmark, 1/N of that again when N ranks each restrict to their own shard.  It plays
+ * the part of the -min/-max filter of merylExactLookup::load (kmers-exact.C:34-73): entries no
+ * lookup of this run can ask for are not loaded.  Results stay exact for ANY sequence: a window
+ * whose k-mer is not in the restricted table is looked up in the per-database tables; only the
+ * speed depends on scanning the sequences the table was built for.  Attached to `reads` next to
+ * the full fused table (which mfn_dump / mfn_score_paths keep using); needs canonical databases. */
+int  mfn_tables_restrict(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                         uint32_t shard, uint32_t nshards);
+int  mfn_tables_unrestrict(mfn_table *reads);
+int  mfn_restricted_info(const mfn_table *reads, mfn_joint_info_t *info);
 /* (value_read(kmer), value_asm(kmer)) for k-mers exactly as given, through the fused table. */
 int  mfn_joint_lookup(mfn_ctx *ctx, const mfn_table *reads, const uint64_t *kmers, uint64_t n,
                       uint32_t *v_read, uint32_t *v_asm);
@@ -179,21 +192,36 @@ typedef struct { uint32_t v_read, v_asm; uint64_t count; } mfn_pair_count;
 int  mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out);
 int  mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a);
 void mfn_accum_free(mfn_accum *a);
-/* Flat device buffer (uint64 words) holding the dense joint histogram and the
- * per-record counters: sum-all-reduce it across ranks, then fetch on any rank. */
+/* Flat device buffer (uint64 words) holding the dense joint histogram (v_read < 4096, v_asm < 64)
+ * and the per-record counters: sum-all-reduce it across ranks, then fetch / read it on any rank. */
 int  mfn_accum_device_buffer(const mfn_accum *a, void **dptr, uint64_t *nwords);
-/* Number of (v_read, v_asm) pairs that fell outside the dense tier on THIS rank
- * (they live in a rank-local side table; gather with mfn_accum_fetch per rank). */
+/* Single rank: everything the accumulator holds -- per-record counters, the dense tier and the pairs
+ * outside it, which live in a rank-local side table.  After an all-reduce of the flat buffer the
+ * header (word [1]) counts the side-table pairs of EVERY rank while this call only sees its own:
+ * it then fails with MFN_ERR_INVALID instead of dropping the others (include_dense = 0 fetches
+ * just this rank's side table). */
 int  mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int include_sparse,
                      mfn_seq_counts *per_seq /*[nseq] or NULL*/,
                      mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+/* Multi-rank recipe: all-reduce the flat buffer; mfn_accum_read it (D2H of nwords words); when its
+ * word [1] is not 0, every rank calls mfn_accum_sparse_fetch and the lists are gathered (all-gather of
+ * the counts, then of the padded lists); mfn_accum_decode_gathered sums equal pairs of different ranks
+ * and refuses a gather that does not hold exactly word [1] entries.  A real assembly (satellites, Alu:
+ * v_asm >= 64) needs this; the synthetic benchmark never leaves the dense tier. */
+int  mfn_accum_read(mfn_ctx *ctx, const mfn_accum *a, uint64_t *host_buf /*[nwords]*/);
+int  mfn_accum_sparse_fetch(mfn_ctx *ctx, const mfn_accum *a, mfn_pair_count *pairs, uint64_t pairs_cap,
+                            uint64_t *npairs /* this rank's count, also when pairs_cap is too small */);
 
 /* Layout of the flat buffer and host-side decoding of a copy of it (no GPU needed): lets a
- * caller all-reduce with any transport and decode on any rank. */
+ * caller all-reduce with any transport and decode on any rank.  mfn_accum_decode refuses a buffer
+ * whose header counts side-table pairs (MFN_ERR_INVALID): use mfn_accum_decode_gathered. */
 int  mfn_accum_layout(uint32_t nseq, uint32_t *header_words, uint32_t *dense_r, uint32_t *dense_a,
                       uint64_t *nwords);
 int  mfn_accum_decode(const uint64_t *host_buf, uint32_t nseq, mfn_seq_counts *per_seq,
                       mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
+int  mfn_accum_decode_gathered(const uint64_t *host_buf, uint32_t nseq,
+                               const mfn_pair_count *sparse, uint64_t n_sparse /* all ranks' lists, concatenated */,
+                               mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t pairs_cap, uint64_t *npairs);
 /* Global base range [g_begin, g_end) (records concatenated with one separator slot after
  * each) whose windows shard `shard` of `nshards` scans. */
 int  mfn_shard_tiles(uint64_t total_bases, uint32_t nseq, uint32_t shard, uint32_t nshards,

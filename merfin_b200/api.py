@@ -150,6 +150,20 @@ class MerylExactLookup:
     def unfuse(self):
         L.check(self._lib.mfn_tables_unfuse(self.h))
 
+    def restrict(self, asm: "MerylExactLookup", seq, shard: int = 0, nshards: int = 1):
+        """Attach the fused table restricted to the k-mers of one shard of `seq` (what a -hist scan of
+        that shard streams); lookups of other k-mers fall back to the per-database tables."""
+        L.check(self._lib.mfn_tables_restrict(self.ctx.h, self.h, asm.h, seq.h, shard, nshards))
+
+    def unrestrict(self):
+        L.check(self._lib.mfn_tables_unrestrict(self.h))
+
+    @property
+    def restricted_info(self) -> L.JointInfo:
+        i = L.JointInfo()
+        L.check(self._lib.mfn_restricted_info(self.h, C.byref(i)))
+        return i
+
     @property
     def joint_info(self) -> L.JointInfo:
         i = L.JointInfo()
@@ -264,6 +278,36 @@ class Accum:
             L.check(st)
             return per[:self.nseq], pairs[:n.value]
 
+    def read(self):
+        """The flat buffer (all-reduced or not) as a host array of uint64 words."""
+        _, n = self.device_buffer()
+        buf = np.zeros(n, dtype=np.uint64)
+        L.check(self._lib.mfn_accum_read(self.ctx.h, self.h, _ptr(buf)))
+        return buf
+
+    def sparse(self):
+        """This rank's pairs outside the dense tier."""
+        n = C.c_uint64()
+        st = self._lib.mfn_accum_sparse_fetch(self.ctx.h, self.h, None, 0, C.byref(n))
+        if st == L.MFN_OK:
+            return np.zeros(0, dtype=PAIR_DTYPE)
+        if st != L.MFN_ERR_CAPACITY:
+            L.check(st)
+        pairs = np.zeros(int(n.value), dtype=PAIR_DTYPE)
+        L.check(self._lib.mfn_accum_sparse_fetch(self.ctx.h, self.h, _ptr(pairs), len(pairs), C.byref(n)))
+        return pairs[:n.value]
+
+    def fetch_gathered(self, all_gather=None):
+        """Multi-rank fetch after the all-reduce of the flat buffer: all_gather(array) -> list of every
+        rank's array (called only when the reduced header says side-table pairs exist, and then on every
+        rank, since every rank reads the same header)."""
+        buf = self.read()
+        sparse = np.zeros(0, dtype=PAIR_DTYPE)
+        if buf[1]:
+            mine = self.sparse()
+            sparse = np.concatenate(all_gather(mine)) if all_gather else mine
+        return decode_gathered(buf, self.nseq, sparse)
+
     def close(self):
         if self.h:
             self._lib.mfn_accum_free(self.h)
@@ -278,6 +322,24 @@ class Accum:
 
 PAIR_DTYPE = np.dtype([("v_read", np.uint32), ("v_asm", np.uint32), ("count", np.uint64)])
 COUNTS_DTYPE = np.dtype([("kasm", np.uint64), ("kmissing", np.uint64)])
+
+
+def decode_gathered(buf, nseq, sparse):
+    """mfn_accum_decode_gathered: a (reduced) flat buffer + every rank's side-table pairs -> (per_seq, pairs)."""
+    lib = L.load()
+    sparse = np.ascontiguousarray(sparse, dtype=PAIR_DTYPE)
+    cap = 1 << 16
+    while True:
+        pairs = np.zeros(cap, dtype=PAIR_DTYPE)
+        per = np.zeros(max(nseq, 1), dtype=COUNTS_DTYPE)
+        n = C.c_uint64()
+        st = lib.mfn_accum_decode_gathered(_ptr(buf), nseq, _ptr(sparse) if len(sparse) else None, len(sparse),
+                                           _ptr(per), _ptr(pairs), cap, C.byref(n))
+        if st == L.MFN_ERR_CAPACITY and n.value > cap:
+            cap = int(n.value)
+            continue
+        L.check(st)
+        return per[:nseq], pairs[:n.value]
 
 
 @dataclass

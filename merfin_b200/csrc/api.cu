@@ -1,6 +1,5 @@
 // C ABI glue: context, errors, the host-buffer entry points and -completeness.
-#include "table.cuh"
-#include "table_host.h"
+#include "scan_kernel.cuh"
 
 #include <algorithm>
 #include <map>
@@ -219,7 +218,7 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
       if (pa >= pb) continue;
       const uint64_t sa = tb + (uint64_t)pa * piece_tiles, sb = std::min(te, tb + (uint64_t)pb * piece_tiles);
       mfn_sweep *w = nullptr;
-      st = mfn_sweep_begin(ctx, reads, seq, (sb - sa) * MFN_TILE, acc, zmap, zlen, zhi, &w);
+      st = mfn_sweep_begin(ctx, reads, asm_, seq, (sb - sa) * MFN_TILE, acc, zmap, zlen, zhi, &w);
       for (uint32_t p = pa; p < pb && st == MFN_OK; p++) {
         // lane G runs a few pieces ahead of the scan; the windows of a piece read k-1 bases of the next one
         st = mfn_ingest_feed(ctx, p + 3);
@@ -319,21 +318,7 @@ __global__ void __launch_bounds__(256) k_join(DevTable A, const unsigned long lo
     uint32_t va = mfn_value(A, kmers[i]);
     if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
     else {
-      // same side table as the scan kernel
-      unsigned long long key = ((unsigned long long)vr << 32) | va;
-      if (key == MFN_EMPTY64) { atomicAdd(&acc[3], 1ull); continue; }
-      uint32_t j = mfn_oa_hash(key) & sparse.mask;
-      bool done = false;
-      for (uint32_t t = 0; t <= sparse.mask && !done; t++) {
-        unsigned long long cur = sparse.keys[j];
-        if (cur == MFN_EMPTY64) {
-          cur = atomicCAS(&sparse.keys[j], MFN_EMPTY64, key);
-          if (cur == MFN_EMPTY64) { cur = key; atomicAdd(&acc[1], 1ull); }
-        }
-        if (cur == key) { atomicAdd(&sparse.counts[j], 1ull); done = true; }
-        j = (j + 1) & sparse.mask;
-      }
-      if (!done) atomicAdd(&acc[2], 1ull);
+      sparse_add(sparse, acc, vr, va, 1ull);         // same side table as the scan kernel
     }
   }
 }

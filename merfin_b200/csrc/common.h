@@ -108,6 +108,7 @@ struct mfn_joint;
 struct mfn_table {
   mfn_ctx   *ctx = nullptr;
   mfn_joint *joint = nullptr;     // fused (this, assembly) table built by mfn_tables_fuse
+  mfn_joint *hot = nullptr;       // fused table restricted to the k-mers of one sequence shard (mfn_tables_restrict)
   DevTable   dev{};
   TableStats host_stats{};
   uint32_t   min_value = 0, max_value = 0, value_offset = 0;
@@ -140,6 +141,7 @@ struct PairTable {                  // (v_read << 32 | v_asm) -> count, EMPTY = 
   unsigned long long *keys;
   unsigned long long *counts;
   uint32_t            mask;
+  unsigned long long *local_n;      // pairs inserted on THIS rank (header word [1] becomes the sum over ranks after an all-reduce)
 };
 
 struct mfn_accum {
@@ -147,6 +149,7 @@ struct mfn_accum {
   uint32_t  nseq = 0;
   uint64_t  nwords = 0;             // header + dense + 2*nseq
   unsigned long long *d_buf = nullptr;
+  unsigned long long *h_buf = nullptr;   // pinned mirror of d_buf for fetches
   PairTable sparse{};
 };
 

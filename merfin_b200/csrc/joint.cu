@@ -1,67 +1,10 @@
 // Building the joint (read, assembly) table from two per-database tables (see joint.cuh).
-#include "joint.cuh"
-#include "table_host.h"
+#include "joint_build.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <type_traits>
-
-struct JointCounts { uint32_t home, spill, stash, big; };
-
-__device__ __forceinline__ void oa2_add(const OaTable2 &t, uint64_t key, int which, uint32_t v, JointStats *st) {
-  if (key == MFN_EMPTY64) { atomicAdd(&t.special[which], v); return; }
-  uint32_t i = mfn_oa_hash(key) & t.mask;
-  for (uint32_t n = 0; n <= t.mask; n++) {
-    unsigned long long cur = t.keys[i];
-    if (cur == MFN_EMPTY64) {
-      cur = atomicCAS(&t.keys[i], MFN_EMPTY64, (unsigned long long)key);
-      if (cur == MFN_EMPTY64) cur = key;
-    }
-    if (cur == key) { atomicAdd(which ? &t.v1[i] : &t.v0[i], v); return; }
-    i = (i + 1) & t.mask;
-  }
-  atomicAdd(&st->errors, 1ull);
-}
-
-// Set field 'which' (0 = read value, 1 = assembly value) of k-mer c to v, creating the slot if needed.
-template <bool W64>
-__device__ __forceinline__ void joint_insert(const JointDev &J, uint64_t c, int which, uint32_t v, JointCounts &cnt) {
-  typedef typename std::conditional<W64, unsigned long long, unsigned int>::type slot_t;
-  constexpr int S = W64 ? 4 : 8;
-  const uint32_t vb = J.rbits + J.abits;
-  const uint32_t fmax = which ? J.amax : J.rmax;
-  const uint32_t sat = v < fmax ? v : fmax;
-  const slot_t field = which ? (slot_t)sat : ((slot_t)sat << J.abits);
-  uint64_t line, tag;
-  joint_locate(J, c, line, tag);
-  const slot_t want = (slot_t)tag << vb;
-  const uint32_t home = (uint32_t)tag & 3u;
-#pragma unroll 1
-  for (uint32_t j = 0; j < 4; j++) {
-    slot_t *slots = (slot_t *)((char *)J.lines + line * 128 + ((home + j) & 3u) * 32);
-#pragma unroll 1
-    for (int i = 0; i < S; i++) {
-      slot_t cur = *(volatile slot_t *)(slots + i);
-      if (cur == 0) {
-        slot_t old = atomicCAS(slots + i, (slot_t)0, (slot_t)(want | field));
-        if (old == 0) {
-          if (j == 0) cnt.home++; else cnt.spill++;
-          if (v > fmax) { oa2_add(J.big, c, which, v - fmax, J.stats); cnt.big++; }
-          return;
-        }
-        cur = old;
-      }
-      if ((cur >> vb) == (slot_t)tag) {            // the k-mer has a slot already: fill in our field
-        atomicOr(slots + i, field);
-        if (v > fmax) { oa2_add(J.big, c, which, v - fmax, J.stats); cnt.big++; }
-        return;
-      }
-    }
-  }
-  uint32_t a, b;
-  if (!oa2_get(J.stash, c, a, b)) cnt.stash++;
-  oa2_add(J.stash, c, which, v, J.stats);
-}
 
 template <bool W64>
 __global__ void __launch_bounds__(256) k_joint_fill(JointDev J, DevTable T, int which) {
@@ -114,27 +57,16 @@ void mfn_joint_free(mfn_joint *j) {
   delete j;
 }
 
-int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_joint **out) {
-  if (R->dev.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", R->dev.k, A->dev.k); return MFN_ERR_K_MISMATCH; }
-  if (R->dev.probe_both || A->dev.probe_both) { mfn_set_error("joint table needs canonical databases"); return MFN_ERR_UNSUPPORTED; }
-  MFN_CUDA(cudaSetDevice(ctx->device));
+// Geometry and device memory of a joint table for n k-mers (values not yet filled in).  nbig: upper
+// bound of the stored values that saturate their field, given the field maxima (sizes the excess table).
+int mfn_joint_alloc(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, uint64_t n_kmers, bool want_pow2,
+                       const std::function<uint64_t(uint32_t, uint32_t)> &count_big, mfn_joint **out) {
   const uint32_t k = R->dev.k;
-  const int grid = ctx->sm_count * 8;
-
-  unsigned long long *d_n, absent = 0;
-  MFN_CUDA(cudaMalloc(&d_n, 8));
-  MFN_CUDA(cudaMemsetAsync(d_n, 0, 8, ctx->stream));
-  k_count_absent<<<grid, 256, 0, ctx->stream>>>(A->dev, R->dev, d_n);
-  ctx->launches++;
-  MFN_CUDA(cudaMemcpyAsync(&absent, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_n);
-  const uint64_t n = std::max<uint64_t>(R->n_kmers + absent, 1024);
-
+  const uint64_t n = std::max<uint64_t>(n_kmers, 1024);
   mfn_joint *j = new mfn_joint();
-  j->reads = R; j->asm_ = A; j->n_kmers = R->n_kmers + absent;
+  j->reads = R; j->asm_ = A; j->n_kmers = n_kmers;
   JointDev &J = j->dev;
-  J.k = k; J.kmask = R->dev.kmask; J.seed = R->dev.lv[0].seed;
+  J.k = k; J.kmask = R->dev.kmask; J.seed = 0;            // the scatter pass hashes with a literal 0 seed
   const char *env = getenv("MFN_JOINT_LOAD");
   double load = env ? atof(env) : 0.70;
   if (!(load > 0.05 && load < 0.99)) load = 0.70;
@@ -146,16 +78,29 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
     unsigned __int128 space = (unsigned __int128)1 << (2 * k);
     unsigned __int128 D = space / want_lines;
     if (D >> 63) D = ((unsigned __int128)1 << 63);
-    static const uint32_t FS[4][3] = {{3, 0xAAAAAAABu, 1}, {5, 0xCCCCCCCDu, 2}, {9, 0x38E38E39u, 1}, {15, 0x88888889u, 3}};
+    static const uint32_t FS[5][3] = {{3, 0xAAAAAAABu, 1}, {5, 0xCCCCCCCDu, 2}, {9, 0x38E38E39u, 1}, {15, 0x88888889u, 3}, {1, 0, 0}};
     const uint32_t tmin = 2 * k > 32 ? 2 * k - 32 : 0;                    // h >> t must fit 32 bits
     int bf = 0; uint32_t bt = tmin;
     uint64_t best = 0;
-    for (int f = 0; f < 4; f++)
+    for (int f = 0; f < 5; f++)
       for (uint32_t t = tmin; t < 60; t++) {
         const uint64_t cand = (uint64_t)FS[f][0] << t;
         if ((unsigned __int128)cand > D) break;
         if (cand > best) { best = cand; bf = f; bt = t; }
       }
+    // A power-of-two divisor makes line, tag and the sweep's bin plain bit fields of the hash (no
+    // division in the scatter pass): take the nearest one when it keeps the load within
+    // [0.45, MFN_JOINT_LOAD_POW2 (0.75)]
+    if (want_pow2) {
+      const char *e2 = getenv("MFN_JOINT_LOAD_POW2");
+      const double hi_load = e2 ? atof(e2) : 0.75;
+      for (uint32_t t = std::max(tmin, 1u); t < 60; t++) {
+        const double lines = std::ldexp(1.0, 2 * (int)k - (int)t);
+        const double ld = (double)n / (lines * slots);
+        if (ld <= hi_load && ld >= 0.45) { best = 1ull << t; bf = 4; bt = t; break; }
+        if (ld > hi_load) break;                                              // fewer lines only get fuller
+      }
+    }
     if (best == 0) best = (uint64_t)FS[0][0] << tmin;                     // more lines wanted than the geometry allows
     J.fs_d = FS[bf][0]; J.fs_m = FS[bf][1]; J.fs_s = FS[bf][2]; J.fs_t = bt;
     J.D = best;
@@ -171,6 +116,7 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
       J.rbits = std::min(32u, avail - J.abits);
     }
     j->tag_bits = T;
+    load = std::max(load, (double)n / ((double)J.nlines * slots));       // the side tables are sized for the load actually reached
     break;
   }
   J.rmax = J.rbits >= 32 ? 0xffffffffu : ((1u << J.rbits) - 1u);
@@ -190,19 +136,7 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
   double lambda = (J.w64 ? 16 : 32) * load, pr = std::exp(-lambda), over = 0.0;
   for (int x = 1; x < 400; x++) { pr *= lambda / x; if (x > (J.w64 ? 16 : 32)) over += (x - (J.w64 ? 16 : 32)) * pr; }
   const uint64_t spill = (uint64_t)(4.0 * over / lambda * n) + 8192;
-  // saturated values: counted, so the excess table is sized exactly
-  unsigned long long nbig = 0;
-  {
-    unsigned long long *d_b;
-    MFN_CUDA(cudaMalloc(&d_b, 8));
-    MFN_CUDA(cudaMemsetAsync(d_b, 0, 8, ctx->stream));
-    k_count_above<<<grid, 256, 0, ctx->stream>>>(R->dev, J.rmax, d_b);
-    k_count_above<<<grid, 256, 0, ctx->stream>>>(A->dev, J.amax, d_b);
-    ctx->launches += 2;
-    MFN_CUDA(cudaMemcpyAsync(&nbig, d_b, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MFN_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_b);
-  }
+  const uint64_t nbig = count_big(J.rmax, J.amax);
   uint64_t caps[2] = {next_pow2(2 * spill), next_pow2(2 * nbig + 4096)};
   for (int i = 0; i < 2 && st == MFN_OK; i++) {
     oas[i]->mask = (uint32_t)(caps[i] - 1);
@@ -212,28 +146,71 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
     if (st == MFN_OK) st = dalloc((void **)&oas[i]->special, 8, 0);
   }
   if (st == MFN_OK) st = dalloc((void **)&J.stats, sizeof(JointStats), 0);
-  if (st == MFN_OK) {
-    if (J.w64) {
-      k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
-      k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
-    } else {
-      k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
-      k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
-    }
-    ctx->launches += 2;
-    if (cudaMemcpyAsync(&j->stats, J.stats, sizeof(JointStats), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-      mfn_set_error("joint table build: %s", cudaGetErrorString(cudaGetLastError()));
-      st = MFN_ERR_CUDA;
-    } else if (j->stats.errors) {
-      mfn_set_error("joint table side tables overflowed (%llu)", j->stats.errors);
-      st = MFN_ERR_CAPACITY;
-    } else if (j->stats.n_home + j->stats.n_spill + j->stats.n_stash != j->n_kmers) {
-      mfn_set_error("joint table holds %llu k-mers, expected %llu", j->stats.n_home + j->stats.n_spill + j->stats.n_stash,
-                    (unsigned long long)j->n_kmers);
-      st = MFN_ERR_CUDA;
-    }
+  if (st != MFN_OK) { mfn_joint_free(j); return st; }
+  *out = j;
+  return MFN_OK;
+}
+
+// stored values of R above rmax plus stored values of A above amax (streams both tables once)
+uint64_t mfn_joint_count_saturated(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, uint32_t rmax, uint32_t amax) {
+  unsigned long long *d_b, nbig = 0;
+  if (cudaMalloc(&d_b, 8) != cudaSuccess) return R->n_kmers / 64;
+  cudaMemsetAsync(d_b, 0, 8, ctx->stream);
+  const int grid = ctx->sm_count * 8;
+  k_count_above<<<grid, 256, 0, ctx->stream>>>(R->dev, rmax, d_b);
+  k_count_above<<<grid, 256, 0, ctx->stream>>>(A->dev, amax, d_b);
+  ctx->launches += 2;
+  cudaMemcpyAsync(&nbig, d_b, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_b);
+  return nbig;
+}
+
+// After the fill kernels: fetch the statistics and check that nothing was lost.
+int mfn_joint_finish(mfn_ctx *ctx, mfn_joint *j, bool exact_count) {
+  if (cudaMemcpyAsync(&j->stats, j->dev.stats, sizeof(JointStats), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    mfn_set_error("joint table build: %s", cudaGetErrorString(cudaGetLastError()));
+    return MFN_ERR_CUDA;
   }
+  if (j->stats.errors) { mfn_set_error("joint table side tables overflowed (%llu)", j->stats.errors); return MFN_ERR_CAPACITY; }
+  const uint64_t held = j->stats.n_home + j->stats.n_spill + j->stats.n_stash;
+  if (exact_count ? held != j->n_kmers : held > j->n_kmers) {
+    mfn_set_error("joint table holds %llu k-mers, expected %llu", (unsigned long long)held, (unsigned long long)j->n_kmers);
+    return MFN_ERR_CUDA;
+  }
+  j->n_kmers = held;
+  return MFN_OK;
+}
+
+int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_joint **out) {
+  if (R->dev.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", R->dev.k, A->dev.k); return MFN_ERR_K_MISMATCH; }
+  if (R->dev.probe_both || A->dev.probe_both) { mfn_set_error("joint table needs canonical databases"); return MFN_ERR_UNSUPPORTED; }
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8;
+
+  unsigned long long *d_n, absent = 0;
+  MFN_CUDA(cudaMalloc(&d_n, 8));
+  MFN_CUDA(cudaMemsetAsync(d_n, 0, 8, ctx->stream));
+  k_count_absent<<<grid, 256, 0, ctx->stream>>>(A->dev, R->dev, d_n);
+  ctx->launches++;
+  MFN_CUDA(cudaMemcpyAsync(&absent, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_n);
+
+  mfn_joint *j = nullptr;
+  MFN_TRY(mfn_joint_alloc(ctx, R, A, R->n_kmers + absent, false,
+                      [&](uint32_t rmax, uint32_t amax) { return mfn_joint_count_saturated(ctx, R, A, rmax, amax); }, &j));
+  const JointDev &J = j->dev;
+  if (J.w64) {
+    k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
+    k_joint_fill<true><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
+  } else {
+    k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, R->dev, 0);
+    k_joint_fill<false><<<grid, 256, 0, ctx->stream>>>(J, A->dev, 1);
+  }
+  ctx->launches += 2;
+  int st = mfn_joint_finish(ctx, j, true);
   if (st != MFN_OK) { mfn_joint_free(j); return st; }
   *out = j;
   return MFN_OK;
@@ -255,10 +232,40 @@ extern "C" int mfn_tables_unfuse(mfn_table *reads) {
   return MFN_OK;
 }
 
+extern "C" int mfn_tables_restrict(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
+                                   uint32_t shard, uint32_t nshards) {
+  if (!ctx || !reads || !asm_ || !seq || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  mfn_joint_free(reads->hot);
+  reads->hot = nullptr;
+  const uint64_t tb = seq->ntiles * shard / nshards, te = seq->ntiles * (shard + 1) / nshards;
+  mfn_table *keys = nullptr;
+  MFN_TRY(mfn_table_count_seq_range(ctx, reads->dev.k, seq, tb * MFN_TILE, te * MFN_TILE, &keys));
+  int st = mfn_joint_build_restricted(ctx, reads, asm_, keys, &reads->hot);
+  mfn_table_free(keys);
+  return st;
+}
+
+extern "C" int mfn_tables_unrestrict(mfn_table *reads) {
+  if (!reads) return MFN_ERR_INVALID;
+  mfn_joint_free(reads->hot);
+  reads->hot = nullptr;
+  return MFN_OK;
+}
+
+static int joint_info_of(const mfn_joint *j, mfn_joint_info_t *info);
+
+extern "C" int mfn_restricted_info(const mfn_table *reads, mfn_joint_info_t *info) {
+  if (!reads || !info) return MFN_ERR_INVALID;
+  return joint_info_of(reads->hot, info);
+}
+
 extern "C" int mfn_joint_info(const mfn_table *reads, mfn_joint_info_t *info) {
   if (!reads || !info) return MFN_ERR_INVALID;
+  return joint_info_of(reads->joint, info);
+}
+
+static int joint_info_of(const mfn_joint *j, mfn_joint_info_t *info) {
   memset(info, 0, sizeof *info);
-  const mfn_joint *j = reads->joint;
   if (!j) return MFN_OK;
   info->fused = 1;
   info->slot_bits = j->dev.w64 ? 64 : 32;

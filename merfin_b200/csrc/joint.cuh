@@ -30,7 +30,7 @@ struct JointStats { unsigned long long n_home, n_spill, n_stash, n_big, errors; 
 struct JointDev {
   void    *lines;
   uint64_t nlines, D, seed, kmask;
-  // D = fs_d << fs_t with fs_d in {3, 5, 9, 15}: h / D is a shift and an exact 32-bit
+  // D = fs_d << fs_t with fs_d in {1, 3, 5, 9, 15}: h / D is a shift and an exact 32-bit
   // multiply-high division by the small odd factor (fs_m, fs_s), no 64-bit divide in the probe path
   uint32_t fs_t, fs_d, fs_m, fs_s;
   uint32_t k, w64;
@@ -44,7 +44,7 @@ struct JointDev {
 __device__ __forceinline__ void joint_split(uint64_t h, uint32_t t, uint32_t d, uint32_t m, uint32_t s,
                                             uint64_t &line, uint64_t &tag) {
   const uint32_t x = (uint32_t)(h >> t);
-  const uint32_t q = __umulhi(x, m) >> s;            // x / d, exact for every 32-bit x
+  const uint32_t q = d == 1u ? x : (__umulhi(x, m) >> s);   // x / d, exact for every 32-bit x
   const uint32_t rem = x - q * d;
   line = q;
   tag = ((uint64_t)rem << t) | (h & ((1ull << t) - 1ull));

@@ -132,6 +132,14 @@ extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
 // ---------------------------------------------------------------------------
 // accumulators
 // ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sparse_clear(PairTable t) {
+  if (*t.local_n == 0) return;                 // nothing was inserted since the last clear (the usual case)
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= t.mask; i += (uint64_t)gridDim.x * blockDim.x) {
+    t.keys[i] = MFN_EMPTY64;
+    t.counts[i] = 0;
+  }
+}
+
 extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
   if (!ctx || !out) return MFN_ERR_INVALID;
   MFN_CUDA(cudaSetDevice(ctx->device));
@@ -140,9 +148,16 @@ extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
   a->nwords = MFN_ACC_HEADER + (uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2ull * nseq;
   a->sparse.mask = MFN_SPARSE_CAP - 1;
   cudaError_t e = cudaMalloc(&a->d_buf, a->nwords * 8);
+  if (e == cudaSuccess) e = cudaMallocHost(&a->h_buf, a->nwords * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&a->sparse.local_n, 8);
   if (e == cudaSuccess) e = cudaMalloc(&a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8);
   if (e == cudaSuccess) e = cudaMalloc(&a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8);
   if (e != cudaSuccess) { mfn_set_error("cudaMalloc(accumulator): %s", cudaGetErrorString(e)); mfn_accum_free(a); return MFN_ERR_NOMEM; }
+  // first clear: unconditional
+  if (e == cudaSuccess) e = cudaMemsetAsync(a->sparse.keys, 0xff, (size_t)MFN_SPARSE_CAP * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(a->sparse.counts, 0, (size_t)MFN_SPARSE_CAP * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(a->sparse.local_n, 0, 8, ctx->stream);
+  if (e != cudaSuccess) { mfn_set_error("accumulator: %s", cudaGetErrorString(e)); mfn_accum_free(a); return MFN_ERR_CUDA; }
   int st = mfn_accum_reset(ctx, a);
   if (st != MFN_OK) { mfn_accum_free(a); return st; }
   *out = a;
@@ -151,16 +166,18 @@ extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
 
 extern "C" int mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a) {
   if (!ctx || !a) return MFN_ERR_INVALID;
+  // the 64 MB side table is cleared only when something was put into it (its counter word tells, on the device)
   MFN_CUDA(cudaMemsetAsync(a->d_buf, 0, a->nwords * 8, ctx->stream));
-  MFN_CUDA(cudaMemsetAsync(a->sparse.keys, 0xff, (size_t)MFN_SPARSE_CAP * 8, ctx->stream));
-  MFN_CUDA(cudaMemsetAsync(a->sparse.counts, 0, (size_t)MFN_SPARSE_CAP * 8, ctx->stream));
+  k_sparse_clear<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(a->sparse);
+  MFN_CUDA(cudaMemsetAsync(a->sparse.local_n, 0, 8, ctx->stream));
   return MFN_OK;
 }
 
 extern "C" void mfn_accum_free(mfn_accum *a) {
   if (!a) return;
   cudaSetDevice(a->ctx->device);
-  cudaFree(a->d_buf); cudaFree(a->sparse.keys); cudaFree(a->sparse.counts);
+  cudaFree(a->d_buf); cudaFree(a->sparse.keys); cudaFree(a->sparse.counts); cudaFree(a->sparse.local_n);
+  if (a->h_buf) cudaFreeHost(a->h_buf);
   delete a;
 }
 
@@ -191,10 +208,9 @@ extern "C" int mfn_shard_tiles(uint64_t total_bases, uint32_t nseq, uint32_t sha
   return MFN_OK;
 }
 
-// Decode a (possibly all-reduced) copy of the flat accumulator buffer.
-extern "C" int mfn_accum_decode(const uint64_t *h, uint32_t nseq, mfn_seq_counts *per_seq,
-                                mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
-  if (!h || !npairs) return MFN_ERR_INVALID;
+// Dense tier and per-record counters of a copy of the flat accumulator buffer.
+static int decode_dense(const uint64_t *h, uint32_t nseq, mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t cap,
+                        uint64_t *npairs, bool *full_out) {
   if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", (unsigned long long)h[2]); return MFN_ERR_CAPACITY; }
   uint64_t n = 0;
   bool full = false;
@@ -216,36 +232,120 @@ extern "C" int mfn_accum_decode(const uint64_t *h, uint32_t nseq, mfn_seq_counts
       per_seq[i].kmissing = d[(uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2 * i + 1];
     }
   *npairs = n;
+  *full_out = full;
+  return MFN_OK;
+}
+
+// Decode a (possibly all-reduced) copy of the flat accumulator buffer.  Pairs outside the dense tier
+// are NOT in the buffer (header word [1] counts them over all ranks): a buffer that has any is refused
+// here -- gather them and use mfn_accum_decode_gathered.
+extern "C" int mfn_accum_decode(const uint64_t *h, uint32_t nseq, mfn_seq_counts *per_seq,
+                                mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!h || !npairs) return MFN_ERR_INVALID;
+  if (h[1]) {
+    mfn_set_error("%llu (v_read, v_asm) pairs outside the dense tier live in rank-local side tables that the all-reduce does not carry: "
+                  "gather them with mfn_accum_sparse_fetch on every rank and decode with mfn_accum_decode_gathered",
+                  (unsigned long long)h[1]);
+    return MFN_ERR_INVALID;
+  }
+  bool full = false;
+  MFN_TRY(decode_dense(h, nseq, per_seq, pairs, cap, npairs, &full));
   return (pairs && full) ? MFN_ERR_CAPACITY : MFN_OK;
+}
+
+extern "C" int mfn_accum_decode_gathered(const uint64_t *h, uint32_t nseq, const mfn_pair_count *sparse, uint64_t n_sparse,
+                                         mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!h || !npairs || (n_sparse && !sparse)) return MFN_ERR_INVALID;
+  if (h[1] != n_sparse) {
+    mfn_set_error("the accumulator header counts %llu side-table pairs over all ranks, %llu were supplied",
+                  (unsigned long long)h[1], (unsigned long long)n_sparse);
+    return MFN_ERR_INVALID;
+  }
+  uint64_t n = 0;
+  bool full = false;
+  MFN_TRY(decode_dense(h, nseq, per_seq, pairs, cap, &n, &full));
+  // equal pairs of different ranks are summed; ascending (v_read, v_asm), as the single-rank fetch lists them
+  std::vector<std::pair<unsigned long long, unsigned long long>> v;
+  v.reserve(n_sparse);
+  for (uint64_t i = 0; i < n_sparse; i++) v.emplace_back(((unsigned long long)sparse[i].v_read << 32) | sparse[i].v_asm, sparse[i].count);
+  std::sort(v.begin(), v.end());
+  for (size_t i = 0; i < v.size();) {
+    size_t j = i;
+    unsigned long long c = 0;
+    while (j < v.size() && v[j].first == v[i].first) c += v[j++].second;
+    if (pairs && n < cap) { pairs[n].v_read = (uint32_t)(v[i].first >> 32); pairs[n].v_asm = (uint32_t)v[i].first; pairs[n].count = c; } else full = true;
+    n++;
+    i = j;
+  }
+  *npairs = n;
+  return (pairs && full) ? MFN_ERR_CAPACITY : MFN_OK;
+}
+
+// D2H of the flat buffer into the accumulator's pinned mirror
+static int read_flat(mfn_ctx *ctx, const mfn_accum *a) {
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  MFN_CUDA(cudaMemcpyAsync(a->h_buf, a->d_buf, a->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MFN_OK;
+}
+
+extern "C" int mfn_accum_read(mfn_ctx *ctx, const mfn_accum *a, uint64_t *host_buf) {
+  if (!ctx || !a || !host_buf) return MFN_ERR_INVALID;
+  MFN_TRY(read_flat(ctx, a));
+  memcpy(host_buf, a->h_buf, a->nwords * 8);
+  return MFN_OK;
+}
+
+// this rank's side table of pairs outside the dense tier, ascending (v_read, v_asm)
+static int read_sparse(mfn_ctx *ctx, const mfn_accum *a, std::vector<std::pair<unsigned long long, unsigned long long>> &v) {
+  std::vector<unsigned long long> keys(MFN_SPARSE_CAP), counts(MFN_SPARSE_CAP);
+  MFN_CUDA(cudaMemcpyAsync(keys.data(), a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaMemcpyAsync(counts.data(), a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t i = 0; i < MFN_SPARSE_CAP; i++) if (keys[i] != MFN_EMPTY64) v.emplace_back(keys[i], counts[i]);
+  std::sort(v.begin(), v.end());
+  return MFN_OK;
+}
+
+extern "C" int mfn_accum_sparse_fetch(mfn_ctx *ctx, const mfn_accum *a, mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
+  if (!ctx || !a || !npairs) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  // the count of entries this rank inserted: one word, read before the (32 MB) table itself
+  unsigned long long any = 0;
+  MFN_CUDA(cudaMemcpyAsync(&any, a->sparse.local_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  *npairs = any;
+  if (!any) return MFN_OK;
+  if (!pairs || any > cap) return MFN_ERR_CAPACITY;
+  std::vector<std::pair<unsigned long long, unsigned long long>> v;
+  MFN_TRY(read_sparse(ctx, a, v));
+  if (v.size() != any) { mfn_set_error("side table holds %zu pairs, its counter says %llu", v.size(), any); return MFN_ERR_CUDA; }
+  for (size_t i = 0; i < v.size(); i++) { pairs[i].v_read = (uint32_t)(v[i].first >> 32); pairs[i].v_asm = (uint32_t)v[i].first; pairs[i].count = v[i].second; }
+  return MFN_OK;
 }
 
 extern "C" int mfn_accum_fetch(mfn_ctx *ctx, const mfn_accum *a, int include_dense, int include_sparse,
                                mfn_seq_counts *per_seq, mfn_pair_count *pairs, uint64_t cap, uint64_t *npairs) {
   if (!ctx || !a || !npairs) return MFN_ERR_INVALID;
-  MFN_CUDA(cudaSetDevice(ctx->device));
-  std::vector<unsigned long long> h(a->nwords);
-  MFN_CUDA(cudaMemcpyAsync(h.data(), a->d_buf, a->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  MFN_TRY(read_flat(ctx, a));
+  const unsigned long long *h = a->h_buf;
   uint64_t n = 0;
   bool full = false;
-  if (include_dense) {
-    int st = mfn_accum_decode((const uint64_t *)h.data(), a->nseq, per_seq, pairs, cap, &n);
-    if (st == MFN_ERR_CAPACITY && h[2]) return st;
-    full = (st == MFN_ERR_CAPACITY);
-  } else if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", h[2]); return MFN_ERR_CAPACITY; }
+  if (h[2]) { mfn_set_error("joint-histogram side table overflowed (%llu pairs lost)", h[2]); return MFN_ERR_CAPACITY; }
+  if (include_dense) MFN_TRY(decode_dense((const uint64_t *)h, a->nseq, per_seq, pairs, cap, &n, &full));
   auto push = [&](uint32_t vr, uint32_t va, uint64_t c) {
     if (pairs && n < cap) { pairs[n].v_read = vr; pairs[n].v_asm = va; pairs[n].count = c; } else full = true;
     n++;
   };
   if (include_sparse && h[1]) {
-    // rank-local side table of pairs outside the dense tier
-    std::vector<unsigned long long> keys(MFN_SPARSE_CAP), counts(MFN_SPARSE_CAP);
-    MFN_CUDA(cudaMemcpyAsync(keys.data(), a->sparse.keys, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MFN_CUDA(cudaMemcpyAsync(counts.data(), a->sparse.counts, (size_t)MFN_SPARSE_CAP * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MFN_CUDA(cudaStreamSynchronize(ctx->stream));
     std::vector<std::pair<unsigned long long, unsigned long long>> v;
-    for (uint32_t i = 0; i < MFN_SPARSE_CAP; i++) if (keys[i] != MFN_EMPTY64) v.emplace_back(keys[i], counts[i]);
-    std::sort(v.begin(), v.end());
+    MFN_TRY(read_sparse(ctx, a, v));
+    // a buffer that was all-reduced counts the side-table pairs of EVERY rank; this call only has its own
+    if (include_dense && v.size() != h[1]) {
+      mfn_set_error("the accumulator header counts %llu side-table pairs, this rank holds %zu: the buffer was all-reduced -- "
+                    "gather with mfn_accum_sparse_fetch and decode with mfn_accum_decode_gathered", h[1], v.size());
+      return MFN_ERR_INVALID;
+    }
     for (auto &kv : v) push((uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second);
   }
   *npairs = n;

@@ -79,7 +79,7 @@ static __device__ __noinline__ void sparse_add(const PairTable &t, unsigned long
     unsigned long long cur = t.keys[i];
     if (cur == MFN_EMPTY64) {
       cur = atomicCAS(&t.keys[i], MFN_EMPTY64, key);
-      if (cur == MFN_EMPTY64) { cur = key; atomicAdd(&acc[1], 1ull); }
+      if (cur == MFN_EMPTY64) { cur = key; atomicAdd(&acc[1], 1ull); atomicAdd(t.local_n, 1ull); }
     }
     if (cur == key) { atomicAdd(&t.counts[i], n); return; }
     i = (i + 1) & t.mask;

@@ -6,20 +6,36 @@
 // ------------------------------------------------------------------------------------------
 static uint32_t bits_of(uint64_t x) { uint32_t n = 0; while (x) { n++; x >>= 1; } return n; }
 
-// bins of 2^lbits lines: slice <= 16 MB (32 MB if that is what it takes to stay <= 2048 bins).
-// The entry's low part holds (line in bin) << tbits | tag: 32 bits when that fits (narrow entries),
-// else up to 52 bits for tables with 64-bit slots (wide entries, fewer bits left for the record).
+// The joint table a sweep of (R, A) runs against: the one restricted to the scanned sequences when
+// there is one (mfn_tables_restrict), else the full fused table.
+static const mfn_joint *sweep_table(const mfn_table *R, const mfn_table *A) {
+  const char *env = getenv("MFN_NO_RESTRICTED");
+  if (R->hot && R->hot->asm_ == A && !(env && atoi(env))) return R->hot;
+  if (R->joint && R->joint->asm_ == A) return R->joint;
+  return nullptr;
+}
+
+// Bins of 2^lbits lines: a slice of the table of at most MFN_SWEEP_SLICE_MB (default 32 MB: two of
+// them in flight fit the L2 next to the entry stream), at most SW_MAX_BINS bins.  The entry's low
+// part holds (line in bin) << tbits | tag: up to 34 bits in a narrow entry, else up to 52 bits for
+// tables with 64-bit slots (wide entries, fewer bits left for the record).  The fewer bins, the
+// cheaper the scatter pass (per-chunk zeroing, scan and one reservation per bin) and the longer its
+// runs; the bigger the slice, the lower the probe pass's L2 hit rate.
 static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, uint32_t &nbins, uint32_t &lowbits) {
   tbits = std::max(1u, bits_of(J.D - 1));
   if (J.nlines >= (1ull << 32)) return false;
+  const char *env = getenv("MFN_SWEEP_SLICE_MB");
+  uint32_t slice_mb = env ? (uint32_t)atoi(env) : 32u;
+  if (slice_mb < 1 || slice_mb > 256) slice_mb = 32;
+  const uint32_t lb_want = bits_of((uint64_t)slice_mb * (1u << 20) / 128) - 1;     // 32 MB -> 18
   for (int wide = 0; wide < 2; wide++) {
-    const uint32_t room = wide ? 52u : 32u;
+    const uint32_t room = wide ? 52u : (uint32_t)SW_MAX_LOWBITS_NARROW;
     if (wide && !J.w64) break;
     if (tbits + 1 > room) continue;
-    for (uint32_t lb : {17u, 18u}) {
-      lbits = std::min(lb, room - tbits);
+    for (uint32_t lb = std::min(lb_want, room - tbits); lb <= room - tbits && lb <= 24; lb++) {
+      lbits = lb;
       nbins = (uint32_t)ceil_div_u64(J.nlines, 1ull << lbits);
-      if (nbins <= SW_MAX_BINS) { lowbits = wide ? lbits + tbits : 32u; return true; }
+      if (nbins <= SW_MAX_BINS) { lowbits = wide ? lbits + tbits : std::max(32u, lbits + tbits); return true; }
     }
   }
   return false;
@@ -30,17 +46,18 @@ bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntile
   if (R->ctx && R->ctx->no_sweep) return false;
   const char *env = getenv("MFN_SWEEP");
   if (env && atoi(env) == 0) return false;
-  if (!R->joint || R->joint->asm_ != A) return false;
+  const mfn_joint *T = sweep_table(R, A);
+  if (!T) return false;
   uint32_t lbits, tbits, nbins, lowbits;
-  if (!sweep_geometry(R->joint->dev, lbits, tbits, nbins, lowbits)) return false;
+  if (!sweep_geometry(T->dev, lbits, tbits, nbins, lowbits)) return false;
   if ((uint64_t)nseq + 1 >= (1ull << (63 - lowbits))) return false;       // record ids must fit the entry
   if (env && atoi(env) == 1) return true;
   // wide entries have no room for a record delta: windows of a chunk that are not in the chunk's
   // first record take the side list, which is only acceptable when records are long
-  if (lowbits > 32 && ntiles * MFN_TILE < (uint64_t)nseq * 16 * SW_CHUNK) return false;
+  if (lowbits > SW_MAX_LOWBITS_NARROW && ntiles * MFN_TILE < (uint64_t)nseq * 16 * SW_CHUNK) return false;
   // worth it when the windows revisit the table lines: >= 1 window per 4 lines, and a big batch
   const uint64_t windows = ntiles * MFN_TILE;
-  return windows >= (1ull << 24) && windows * 4 >= R->joint->dev.nlines;
+  return windows >= (1ull << 24) && windows * 4 >= T->dev.nlines;
 }
 
 // A sweep over a sequence set: begin (workspace sized for `windows`), scatter any number of tile
@@ -51,13 +68,17 @@ struct mfn_sweep {
   uint32_t n_scatter = 0;
 };
 
-int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
+int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out) {
 
-  const JointDev &J = R->joint->dev;
+  const mfn_joint *T = sweep_table(R, A);
+  if (!T) { mfn_set_error("sweep: no fused table"); return MFN_ERR_INVALID; }
+  const JointDev &J = T->dev;
   mfn_sweep *w = new mfn_sweep();
   SweepParams &P = w->P;
   P.J = J;
+  P.restricted = T->restricted ? 1u : 0u;
+  if (T->restricted) { P.R = T->reads->dev; P.A = T->asm_->dev; }
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
   {
     const uint64_t gpad = (seq->ntiles + 1) * MFN_TILE + 256;            // as allocated by mfn_seq_alloc
@@ -76,7 +97,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
   }
   // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
-  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64;            // bins, side-list count, pass counters
+  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64 + 8;        // bins, side-list count, pass counters, phase cycles
   cudaError_t e = cudaMallocAsync(&P.entries, ebytes, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&w->ctl, cwords * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&P.over_lt, P.over_cap * 8, ctx->stream);
@@ -84,6 +105,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64
   if (e != cudaSuccess) { mfn_set_error("sweep workspace (%zu bytes): %s", ebytes, cudaGetErrorString(e)); delete w; return MFN_ERR_NOMEM; }
   P.bin_count = w->ctl; P.bin_valid = w->ctl + P.nbins_pad; P.over_n = w->ctl + 2 * P.nbins_pad;
   w->counters = w->ctl + 2 * P.nbins_pad + 1;
+  P.prof = w->ctl + 2 * P.nbins_pad + 4 + 64;
   MFN_CUDA(cudaMemsetAsync(w->ctl, 0, cwords * 8, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(P.bin_valid, 0xff, (size_t)P.nbins_pad * 8, ctx->stream));
   *out = w;
@@ -95,7 +117,7 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   if (w->n_scatter >= 60) { mfn_set_error("sweep: too many scatter passes"); return MFN_ERR_INVALID; }
   SweepParams P = w->P;
   P.tile_begin = tile_begin; P.tile_end = tile_end;
-  const size_t sc_smem = (size_t)SW_CHUNK * 8 + (size_t)SW_MAX_BINS * 12;
+  const size_t sc_smem = (size_t)SW_CHUNK * 8 + (size_t)P.nbins_pad * 12;
   P.counter = w->counters + 2 + w->n_scatter++;
   const uint64_t nchunks = ceil_div_u64(tile_end - tile_begin, SW_CHUNK_TILES);
   // the mer size is a compile-time constant for the common k (shifts and masks fold away)
@@ -107,16 +129,19 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
     kernel<<<grid, SC_THREADS, sc_smem, ctx->stream>>>(P);
     return MFN_OK;
   };
-  if (P.lowbits > 32) {
+  // bit-field geometry: power-of-two divisor, 34-bit low part, bin = the hash bits above it
+  const bool geo1 = P.J.fs_d == 1 && P.lowbits == 34 && P.lbits + P.tbits == 34 && P.tbits == P.J.fs_t &&
+                    2 * P.J.k >= 34 && 2 * P.J.k - 34 <= SC_BIN_BITS && P.nbins == (1u << (2 * P.J.k - 34));
+  if (P.lowbits > SW_MAX_LOWBITS_NARROW) {
     switch (P.J.k) {
-      case 31: MFN_TRY(launch(k_sweep_scatter<31, true>)); break;
-      default: MFN_TRY(launch(k_sweep_scatter<0, true>)); break;
+      case 31: MFN_TRY(launch(k_sweep_scatter<31, true, 0>)); break;
+      default: MFN_TRY(launch(k_sweep_scatter<0, true, 0>)); break;
     }
   } else {
     switch (P.J.k) {
-      case 21: MFN_TRY(launch(k_sweep_scatter<21, false>)); break;
-      case 31: MFN_TRY(launch(k_sweep_scatter<31, false>)); break;
-      default: MFN_TRY(launch(k_sweep_scatter<0, false>)); break;
+      case 21: if (geo1) MFN_TRY(launch(k_sweep_scatter<21, false, 1>)); else MFN_TRY(launch(k_sweep_scatter<21, false, 0>)); break;
+      case 31: MFN_TRY(launch(k_sweep_scatter<31, false, 0>)); break;
+      default: MFN_TRY(launch(k_sweep_scatter<0, false, 0>)); break;
     }
   }
   ctx->launches++;
@@ -133,6 +158,17 @@ int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
   mfn_sweep_launch_over(P, ctx->sm_count, ctx->stream);
   ctx->launches += 2;
   cudaError_t e = cudaGetLastError();
+#ifdef SW_PROFILE
+  {
+    unsigned long long h[8];
+    cudaMemcpyAsync(h, P.prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    unsigned long long t = 0;
+    for (int i = 0; i < 7; i++) t += h[i];
+    fprintf(stderr, "[scatter phases, %% of CTA cycles] zero+claim %.1f  hash %.1f  barrier %.1f  scan %.1f  sort %.1f  barrier %.1f  copy-out %.1f  (bins %u, lowbits %u)\n",
+            100.0 * h[0] / t, 100.0 * h[1] / t, 100.0 * h[2] / t, 100.0 * h[3] / t, 100.0 * h[4] / t, 100.0 * h[5] / t, 100.0 * h[6] / t, P.nbins, P.lowbits);
+  }
+#endif
   // a side list that overflowed is reported through the accumulator header (MFN_ERR_CAPACITY at fetch)
   cudaFreeAsync(P.entries, ctx->stream);
   cudaFreeAsync(w->ctl, ctx->stream);
@@ -146,10 +182,10 @@ int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
 int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, const mfn_kmodel *km,
                    uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc, const unsigned long long *zmap, uint32_t zlen,
                    uint32_t zhi) {
-  (void)km; (void)A;
+  (void)km;
   if (tile_begin >= tile_end) return MFN_OK;
   mfn_sweep *w = nullptr;
-  MFN_TRY(mfn_sweep_begin(ctx, R, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, zhi, &w));
+  MFN_TRY(mfn_sweep_begin(ctx, R, A, seq, (tile_end - tile_begin) * MFN_TILE, acc, zmap, zlen, zhi, &w));
   if (ctx->time_passes) mfn_ctx_mark(ctx);
   int st = mfn_sweep_scatter(ctx, w, tile_begin, tile_end);
   if (ctx->time_passes) mfn_ctx_mark(ctx);

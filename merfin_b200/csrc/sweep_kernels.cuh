@@ -29,8 +29,8 @@
 #include "scan_kernel.cuh"
 
 #define SW_THREADS 256
-// The scatter CTA's shape can be overridden at compile time for experiments (`make exp` builds
-// libmerfin_b200_exp.so with 16384-window chunks in one 1024-thread CTA per SM; MFN_LIB selects it).
+// The scatter CTA's shape can be overridden at compile time for experiments (see `make variants`
+// in the Makefile; MFN_LIB selects the library at run time).
 #ifndef SW_CHUNK_TILES
 #define SW_CHUNK_TILES 4
 #endif
@@ -38,31 +38,51 @@
 #ifndef SC_THREADS
 #define SC_THREADS 512                             // scatter CTA: two 2048-window tiles side by side, two rounds
 #endif
-#define SC_RANK_BITS (SW_CHUNK_TILES <= 4 ? 13 : 14)                 // rank of a window inside its bin, < SW_CHUNK
-#define SC_RD_SHIFT (11 + SC_RANK_BITS)                               // record delta field of the staging word
-#define SC_RD_BITS (31 - SC_RD_SHIFT)
+#ifndef SC_CTAS_PER_SM
+#define SC_CTAS_PER_SM (SC_THREADS > 512 ? 1 : (1024 / SC_THREADS))
+#endif
+// staging word of a window ("meta", 32 bits), laid out so that the sort and the copy-out need the
+// fewest ALU operations (the pass is bound by the ALU pipe):
+//   bits 0..1    bits 32..33 of the entry's low part (narrow entries wider than 32 bits)
+//   bits 2..12   bin: meta & 0x1ffc is the byte offset of the bin's 32-bit counter
+//   bits 13..    record delta against the chunk's first record
+//   next bit     the k-mer counts twice
+//   top bits     rank of the window inside its bin (< SW_CHUNK): meta >> SC_RANK_SHIFT
+#define SC_BIN_SHIFT 2
+#define SC_BIN_BITS 11
+#define SC_BIN_FIELD (((1u << SC_BIN_BITS) - 1u) << SC_BIN_SHIFT)
+#define SC_RANK_BITS (SW_CHUNK_TILES <= 1 ? 11 : SW_CHUNK_TILES <= 2 ? 12 : SW_CHUNK_TILES <= 4 ? 13 : 14)
+#define SC_RANK_SHIFT (32 - SC_RANK_BITS)
+#define SC_TWICE_BIT (SC_RANK_SHIFT - 1)
+#define SC_RD_SHIFT (SC_BIN_SHIFT + SC_BIN_BITS)
+#define SC_RD_BITS (SC_TWICE_BIT - SC_RD_SHIFT)
 #define SC_RD_MASK ((1u << SC_RD_BITS) - 1u)
+#define SC_KEEP_MASK ((1u << SC_RANK_SHIFT) - 1u)                    // everything but the rank
 static_assert(SW_CHUNK <= (1 << SC_RANK_BITS) && SW_CHUNK % (SC_THREADS * WPT) == 0 && SC_THREADS % (MFN_TILE / WPT) == 0, "scatter CTA shape");
+static_assert(SC_RD_BITS >= 3 && SC_RD_BITS <= 7, "record delta field");
 #define SC_TPT (SW_CHUNK / SC_THREADS / WPT)       // 8-window groups per thread per chunk
 #define SC_NW (SC_TPT * WPT)                       // windows per thread per chunk
 #define SC_SEQ_WORDS (SW_CHUNK / 32 + 2)           // staged 2-bit words of a chunk (2064 B)
 #define SC_OK_WORDS (SW_CHUNK / 64 + 2)            // staged validity words (1040 B)
 #define SW_MAX_BINS 2048
+#define SW_MAX_LOWBITS_NARROW 34                   // low part of a narrow entry: 32 bits in a register + 2 in the staging word
 #ifndef SW_SLICE
 #define SW_SLICE 1024                              // entries per probe work item (one WARP)
 #endif
 #define SW_QCAP 160                                // per-warp queue of slow lookups: < 32 carried + 128 per batch
 #define SW_NOSPACE 0xffffffffu
-#define SW_MAX_RD (SC_RD_MASK - 1u)                // record delta inside one chunk that fits the staging word (126)
+#define SW_MAX_RD (SC_RD_MASK - 1u)                // record delta inside one chunk that fits the staging word
 
 struct SweepParams {
   JointDev J;
+  DevTable R, A;                             // restricted joint table only: where a k-mer it does not hold is looked up
+  uint32_t restricted;
   const unsigned long long *seq2, *ok, *rec_start;
   uint64_t seq_words, ok_words;              // allocated length of seq2 / ok (TMA copies are clamped to it)
   uint32_t nseq;
   uint64_t tile_begin, tile_end;
   uint32_t lbits, tbits, nbins, nbins_pad;   // bin = line >> lbits; entry low part = (line & L-1) << tbits | tag
-  uint32_t lowbits;                          // width of the low part: 32 (narrow) or lbits + tbits (wide)
+  uint32_t lowbits;                          // width of the low part: 32..34 (narrow) or lbits + tbits (wide)
   unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b)
   uint64_t cap;
   unsigned long long *bin_count;             // [nbins_pad] reserved entries (may exceed cap)
@@ -78,18 +98,80 @@ struct SweepParams {
   uint32_t zlen;
   uint32_t zhi;                              // largest multiplicity v >= 1 with readK(v) == 0 under -prob (0: none)
   uint32_t pr_lim, pr_wmask;                 // 32-bit slots: 2^vb - 1 and the tag field mask (vb = value bits)
+  unsigned long long *prof;                  // SW_PROFILE builds: [8] cycles per phase of the scatter pass, summed over CTAs
+};
+
+// keeps the compiler from hashing all eight windows of a group before the first atomic (which needs
+// more live registers than there are): a scheduling fence every SC_FENCE_EVERY windows
+#ifndef SC_FENCE_EVERY
+#define SC_FENCE_EVERY 2
+#endif
+#ifndef SC_FENCE_KIND
+#define SC_FENCE_KIND 1
+#endif
+#if SC_FENCE_KIND == 0
+#define SC_SCHED_FENCE(u) do { } while (0)
+#elif SC_FENCE_KIND == 1
+#define SC_SCHED_FENCE(u) do { if (((u) + 1) % SC_FENCE_EVERY == 0) asm volatile("" ::: "memory"); } while (0)
+#else
+#define SC_SCHED_FENCE(u) do { if (((u) + 1) % SC_FENCE_EVERY == 0) __syncwarp(); } while (0)
+#endif
+
+// rank = live ? atomicAdd(shared counter at byte address saddr, 1) : 0, as ONE predicated instruction
+// (a C++ `if` around the atomic becomes a branch per window and splits the straight-line hash code)
+__device__ __forceinline__ uint32_t sc_rank_atomic(uint32_t saddr, uint32_t live) {
+  uint32_t rank;
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n mov.u32 %0, 0;\n @p atom.shared.add.u32 %0, [%1], 1;\n}"
+               : "=r"(rank) : "r"(saddr), "r"(live) : "memory");
+  return rank;
+}
+
+#ifdef SW_PROFILE
+#define SW_PROF_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); atomicAdd(&P.prof[i], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
+#else
+#define SW_PROF_MARK(i) do { } while (0)
+#endif
+
+// ---- the k-mer as two 32-bit halves (16 < k < 32): every 64-bit logic op or shift is two ALU
+// instructions, and half of those would work on bits that are known to be zero ---------------
+template <int K> struct Kmer2 {
+  static constexpr uint32_t HB = 2 * K - 32;                    // bits in the high half
+  static constexpr uint32_t HMASK = (1u << HB) - 1u;
+  // x ^= x >> K: the high half has fewer than K bits, so only the low half changes
+  static __device__ __forceinline__ void xorshift(uint32_t hi, uint32_t &lo) { lo ^= __funnelshift_r(lo, hi, K); }
+  // x = (x * M) mod 2^2K
+  static __device__ __forceinline__ void mul(uint32_t &hi, uint32_t &lo, uint64_t M) {
+    const uint32_t ml = (uint32_t)M, mh = (uint32_t)(M >> 32);
+    const uint64_t p = (uint64_t)lo * ml;
+    hi = ((uint32_t)(p >> 32) + lo * mh + hi * ml) & HMASK;
+    lo = (uint32_t)p;
+  }
+  // mfn_mix(c, 0, kmask, K) on halves
+  static __device__ __forceinline__ void mix(uint32_t &hi, uint32_t &lo) {
+    xorshift(hi, lo);
+    mul(hi, lo, 0xff51afd7ed558ccdull);
+    xorshift(hi, lo);
+    mul(hi, lo, 0xc4ceb9fe1a85ec53ull);
+    xorshift(hi, lo);
+  }
 };
 
 // ------------------------------------------------------------------------------------------
 // pass 1.  KK: mer size known at compile time (0 = read it from the table)
+//          WIDE: 64-bit low part (tables with 64-bit slots whose tags do not fit a narrow entry)
+//          GEO: 0 = any table divisor D = d << t, narrow low part of 32..34 bits
+//               1 = D is a power of two and the low part is exactly 34 bits: line, tag, bin and low
+//                   part are bit fields of the hash, no division and no re-assembly
 // ------------------------------------------------------------------------------------------
-template <int KK, bool WIDE>
-__global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2) k_sweep_scatter(const __grid_constant__ SweepParams P) {
+template <int KK, bool WIDE, int GEO>
+__global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : SC_CTAS_PER_SM) k_sweep_scatter(const __grid_constant__ SweepParams P) {
   typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type low_t;
-  extern __shared__ __align__(16) unsigned char sw_smem[];            // 88 KB: dynamic
+  constexpr bool HALVES = (KK > 16 && KK < 32) && !WIDE;              // hash on 32-bit halves
+  static_assert(GEO == 0 || HALVES, "the bit-field geometry is implemented for 16 < k < 32");
+  extern __shared__ __align__(16) unsigned char sw_smem[];            // dynamic: SW_CHUNK * 8 + nbins_pad * 12
   unsigned long long *s_ent = (unsigned long long *)sw_smem;           // [SW_CHUNK] entries sorted by bin
-  unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [SW_MAX_BINS] global index of the chunk's sorted position 0, per bin
-  uint32_t *s_off = (uint32_t *)(s_dst + SW_MAX_BINS);                 // [SW_MAX_BINS] counts, then exclusive offsets
+  unsigned long long *s_dst = s_ent + SW_CHUNK;                        // [nbins_pad] where the chunk's sorted position 0 would go, per bin (byte address)
+  uint32_t *s_off = (uint32_t *)(s_dst + P.nbins_pad);                 // [nbins_pad] counts, then exclusive offsets
   __shared__ uint32_t s_warp[SC_THREADS / 32];
   __shared__ unsigned long long s_chunk[2];
   __shared__ uint32_t s_total;
@@ -99,6 +181,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
   __shared__ __align__(8) unsigned long long s_bar[2];
 
   const uint32_t tid = threadIdx.x;
+  const uint32_t s_off_sa = smem_u32(s_off);
   const uint32_t grp = tid / (MFN_TILE / WPT), t8 = tid % (MFN_TILE / WPT);   // tile of the round, window group in it
   const uint32_t k = KK ? (uint32_t)KK : P.J.k;
   const uint64_t kmask = KK ? (KK == 32 ? ~0ull : ((1ull << (2 * (KK & 31))) - 1ull)) : P.J.kmask;
@@ -107,9 +190,13 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
   const uint64_t need = (1ull << (WPT + k - 1)) - 1;                   // validity bits behind a thread's 8 windows
   const bool even_k = (k & 1u) == 0;
   const uint32_t lmask = (1u << P.lbits) - 1u;
+  const uint32_t xbits = P.lowbits > 32 && !WIDE ? P.lowbits - 32 : 0; // bits of a narrow low part beyond 32
   const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, SW_CHUNK_TILES);
   const uint32_t per_thread_bins = P.nbins_pad / SC_THREADS;
   unsigned long long *const rec_acc = P.acc + MFN_ACC_HEADER + MFN_DENSE_R * MFN_DENSE_A;
+#ifdef SW_PROFILE
+  long long prof_t = clock64();
+#endif
 
   unsigned long long my_valid = 0;
   uint32_t cur_rec = 0, n_ok0 = 0;                           // record of the current chunk's first window
@@ -152,6 +239,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
     if (chunk >= nchunks) break;
     if (tid == 0) { stage(pre, buf ^ 1); pre = atomicAdd(P.counter, 1ull); }
     const uint64_t tile0 = P.tile_begin + chunk * SW_CHUNK_TILES;
+    SW_PROF_MARK(0);
 
     // record of the chunk's first window (uniform); does the chunk stay inside it?
     {
@@ -167,9 +255,9 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
     const bool one_record = (tile0 + SW_CHUNK_TILES) * MFN_TILE <= r0_end;
 
     // ---- hash this thread's windows; rank them inside their bins ---------------------------
-    // meta: bin (0..10) | rank in bin (11..) | record delta (SC_RD_SHIFT..30) | counts twice (31)
     low_t low[SC_NW];
     uint32_t meta[SC_NW];
+    uint32_t live = 0;                                                // bit idx: window idx goes to a bin
 #pragma unroll
     for (int q = 0; q < SC_TPT; q++) {
       const uint64_t tile = tile0 + q * (SC_THREADS / (MFN_TILE / WPT)) + grp;
@@ -207,41 +295,86 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
           atomicAdd(&rec_acc[2 * rec], 1ull);
           my_valid++;
           if (!WIDE && rd <= SW_MAX_RD) { rdpack |= (uint64_t)rd << (7 * u); continue; }
-          // a chunk spanning > 126 records (wide entries: any record but the chunk's first): this
-          // window goes to the side list
+          // a chunk spanning more records than the staging word can tell apart (wide entries: any
+          // record but the chunk's first): this window goes to the side list
           vmask &= ~(1u << u);
           const uint64_t x = (u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo) & kmask;
           const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
           uint64_t line, tag;
-          joint_split(mfn_mix(f < r ? f : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
+          joint_split(mfn_mix(f < r ? f : r, 0, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
           unsigned long long o = atomicAdd(P.over_n, 1ull);
           if (o < P.over_cap) { P.over_lt[o] = line * P.J.D + tag; P.over_rec[o] = rec | ((even_k && f == r) ? 0x80000000u : 0u); }
           else atomicAdd(&P.acc[2], 1ull);
         }
       }
-      // forward k-mer (first base most significant, kmers-tiny.H:82): bit-reversal for the first
-      // window, then one base shifted in per window; the stream-order slice x gives the reverse
-      // complement for free (x ^ cmask)
-      uint64_t F = mfn_rev2(lo & kmask) >> (64 - 2 * k);
+      live |= vmask << (q * WPT);
+      // Forward k-mer F (first base most significant, kmers-tiny.H:82): bit-reversal for the first
+      // window, then one base shifted in per window; the stream-order slice x (base g in the low 2
+      // bits) gives the reverse complement for free (x ^ cmask).  Straight-line code: windows that
+      // are not valid are hashed like the others and only their shared-memory atomic is predicated off.
+      if (HALVES) {
+        typedef Kmer2<KK ? KK : 21> H;
+        const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi;
+        const uint64_t F0 = mfn_rev2(lo & kmask) >> (64 - 2 * k);
+        uint32_t Fl = (uint32_t)F0, Fh = (uint32_t)(F0 >> 32);
 #pragma unroll
-      for (int u = 0; u < WPT; u++) {
-        const int idx = q * WPT + u;
-        uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
-        x &= kmask;                                             // base g in the low 2 bits
-        if (u) F = ((F << 2) | (x >> (2 * k - 2))) & kmask;
-        meta[idx] = 0xffffffffu;
-        if (!((vmask >> u) & 1u)) continue;
-        const uint64_t r = x ^ cmask;
-        const uint32_t twice = (even_k && F == r) ? 0x80000000u : 0u;
-        uint64_t line, tag;
-        joint_split(mfn_mix(F < r ? F : r, P.J.seed, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
-        const uint32_t bin = (uint32_t)line >> P.lbits;
-        const uint32_t rank = atomicAdd(&s_off[bin], 1u);
-        low[idx] = (low_t)((((uint64_t)((uint32_t)line & lmask)) << P.tbits) | tag);
-        meta[idx] = bin | (rank << 11) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << SC_RD_SHIFT) | twice;
+        for (int u = 0; u < WPT; u++) {
+          const int idx = q * WPT + u;
+          const uint32_t xl = u ? __funnelshift_r(w0, w1, 2 * u) : w0;
+          const uint32_t xf = u ? __funnelshift_r(w1, w2, 2 * u) : w1;           // high half before masking
+          if (u) {
+            const uint32_t nb = (xf >> (H::HB - 2)) & 3u;                        // the window's last base
+            Fh = __funnelshift_l(Fl, Fh, 2) & H::HMASK;
+            Fl = Fl * 4u + nb;
+          }
+          const uint32_t rl = xl ^ (uint32_t)cmask, rh = (xf & H::HMASK) ^ (uint32_t)(cmask >> 32);
+          const bool lt = Fh < rh || (Fh == rh && Fl < rl);
+          uint32_t cl = lt ? Fl : rl, ch = lt ? Fh : rh;
+          const uint32_t twice = (even_k && Fh == rh && Fl == rl) ? (1u << SC_TWICE_BIT) : 0u;
+          H::mix(ch, cl);
+          uint32_t binoff, m0;                                                   // byte offset of the bin's counter; meta without the rank
+          if (GEO == 1) {
+            // 34-bit low part = the low 34 bits of the hash; bin = the bits above: the high half IS
+            // bits 32..33 of the low part | bin << 2
+            low[idx] = (low_t)cl;
+            m0 = ch;
+            binoff = ch & ~3u;
+          } else {
+            uint64_t line, tag;
+            joint_split(((uint64_t)ch << 32) | cl, P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
+            const uint64_t lp = ((uint64_t)((uint32_t)line & lmask) << P.tbits) | tag;
+            low[idx] = (low_t)lp;
+            binoff = ((uint32_t)line >> P.lbits) << SC_BIN_SHIFT;
+            m0 = binoff | (uint32_t)(lp >> 32);
+          }
+          const uint32_t rank = sc_rank_atomic(s_off_sa + binoff, (vmask >> u) & 1u);
+          meta[idx] = m0 | (rank << SC_RANK_SHIFT) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << SC_RD_SHIFT) | twice;
+          SC_SCHED_FENCE(u);
+        }
+      } else {
+        uint64_t F = mfn_rev2(lo & kmask) >> (64 - 2 * k);
+#pragma unroll
+        for (int u = 0; u < WPT; u++) {
+          const int idx = q * WPT + u;
+          uint64_t x = u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo;
+          x &= kmask;                                             // base g in the low 2 bits
+          if (u) F = ((F << 2) | (x >> (2 * k - 2))) & kmask;
+          const uint64_t r = x ^ cmask;
+          const uint32_t twice = (even_k && F == r) ? (1u << SC_TWICE_BIT) : 0u;
+          uint64_t line, tag;
+          joint_split(mfn_mix(F < r ? F : r, 0, kmask, k), P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
+          const uint32_t bin = (uint32_t)line >> P.lbits;
+          const uint32_t rank = sc_rank_atomic(s_off_sa + bin * 4u, (vmask >> u) & 1u);
+          const uint64_t lp = (((uint64_t)((uint32_t)line & lmask)) << P.tbits) | tag;
+          low[idx] = (low_t)lp;
+          meta[idx] = (bin << SC_BIN_SHIFT) | (rank << SC_RANK_SHIFT) | (((uint32_t)(rdpack >> (7 * u)) & 0x7fu) << SC_RD_SHIFT) | twice |
+                      (WIDE ? 0u : (uint32_t)(lp >> 32));
+        }
       }
     }
+    SW_PROF_MARK(1);
     __syncthreads();
+    SW_PROF_MARK(2);
 
     // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
     constexpr uint32_t BPT = SW_MAX_BINS / SC_THREADS;
@@ -272,35 +405,51 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
       if (tid == SC_THREADS - 1) s_total = run;
     }
     __syncthreads();
+    SW_PROF_MARK(3);
 
     // ---- counting sort into shared memory (the reservations are still in flight) -----------
 #pragma unroll
     for (int idx = 0; idx < SC_NW; idx++) {
       const uint32_t m = meta[idx];
-      if (m == 0xffffffffu) continue;
-      const uint32_t p = s_off[m & 0x7ffu] + ((m >> 11) & ((1u << SC_RANK_BITS) - 1u));
+      const uint32_t p = *(const uint32_t *)((const char *)s_off + (m & SC_BIN_FIELD)) + (m >> SC_RANK_SHIFT);
       // staged: narrow = meta without the rank << 32 | low; wide = twice (63) | bin (52..62) | low (0..51)
-      if (WIDE) s_ent[p] = ((unsigned long long)(m & 0x80000000u) << 32) | ((unsigned long long)(m & 0x7ffu) << 52) | low[idx];
-      else s_ent[p] = ((unsigned long long)(m & (0x800007ffu | (SC_RD_MASK << SC_RD_SHIFT))) << 32) | low[idx];
+      if ((live >> idx) & 1u) {
+        if (WIDE) s_ent[p] = ((unsigned long long)((m >> SC_TWICE_BIT) & 1u) << 63) | ((unsigned long long)((m & SC_BIN_FIELD) >> SC_BIN_SHIFT) << 52) | low[idx];
+        else s_ent[p] = ((unsigned long long)(m & SC_KEEP_MASK) << 32) | low[idx];
+      }
     }
-    // where each bin's run goes: global index of the chunk's sorted position 0
+    // where each bin's run goes: byte address of the chunk's sorted position 0 in the bin's run
+    // (entries + (bin * cap + reservation - offset) * 8; the address of a live entry never has bit 63)
 #pragma unroll
     for (uint32_t i = 0; i < BPT; i++) {
       if (i < per_thread_bins) {
+        unsigned long long dst = (unsigned long long)(P.entries + ((unsigned long long)(b0 + i) * P.cap + got[i] - s_off[b0 + i])) & 0x7fffffffffffffffull;
         // bit 63: the run does not fit its bin (its windows go to the side list)
-        unsigned long long dst = ((unsigned long long)(b0 + i) * P.cap + got[i] - s_off[b0 + i]) & 0x7fffffffffffffffull;
         if (cnt[i] && got[i] + cnt[i] > P.cap) { atomicMin(&P.bin_valid[b0 + i], got[i]); dst |= 1ull << 63; }
         s_dst[b0 + i] = dst;
       }
     }
+    SW_PROF_MARK(4);
     __syncthreads();
+    SW_PROF_MARK(5);
 
     // ---- coalesced copy-out: consecutive threads write consecutive entries of a bin's run --
     {
       const uint32_t total = s_total;
+      const uint32_t r0s = r0 << xbits;
+      // the usual chunk (one record, k-mers cannot be their own reverse complement): the entry's high
+      // word is the chunk's record next to the staged bits 32..33 of the low part
+      const bool simple = !WIDE && one_record && !even_k;
 #pragma unroll 4
       for (uint32_t i = tid; i < total; i += SC_THREADS) {
         const unsigned long long e = s_ent[i];
+        const uint32_t hs = (uint32_t)(e >> 32);
+        const unsigned long long dst = WIDE ? s_dst[(uint32_t)(e >> 52) & 0x7ffu]
+                                            : *(const unsigned long long *)((const char *)s_dst + ((hs & SC_BIN_FIELD) << 1));
+        if (simple && (long long)dst >= 0) {
+          *(uint2 *)(dst + (unsigned long long)i * 8) = make_uint2((uint32_t)e, (hs & 3u) | r0s);
+          continue;
+        }
         uint32_t bin, rec;
         unsigned long long lowpart, out;
         if (WIDE) {
@@ -309,15 +458,14 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
           rec = r0 | ((uint32_t)(e >> 32) & 0x80000000u);
           out = lowpart | ((unsigned long long)r0 << P.lowbits) | (e & 0x8000000000000000ull);
         } else {
-          const uint32_t hs = (uint32_t)(e >> 32);
-          bin = hs & 0x7ffu;
-          lowpart = (uint32_t)e;
-          rec = (r0 + ((hs >> SC_RD_SHIFT) & SC_RD_MASK)) | (hs & 0x80000000u);
-          out = ((unsigned long long)rec << 32) | lowpart;
+          bin = (hs & SC_BIN_FIELD) >> SC_BIN_SHIFT;
+          const uint32_t tw = ((hs >> SC_TWICE_BIT) & 1u) << 31;
+          rec = (r0 + ((hs >> SC_RD_SHIFT) & SC_RD_MASK)) | tw;
+          lowpart = (unsigned long long)(uint32_t)e | ((unsigned long long)(hs & 3u) << 32);
+          out = lowpart | ((unsigned long long)(rec & 0x7fffffffu) << P.lowbits) | ((unsigned long long)tw << 32);
         }
-        const unsigned long long dst = s_dst[bin];
         if ((long long)dst >= 0) {
-          P.entries[(dst + i) & 0x7fffffffffffffffull] = out;
+          *(unsigned long long *)(dst + (unsigned long long)i * 8) = out;
         } else {
           unsigned long long o = atomicAdd(P.over_n, 1ull);
           if (o < P.over_cap) {
@@ -328,6 +476,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
         }
       }
     }
+    SW_PROF_MARK(6);
   }
   flush_rec();
   for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xffffffffu, my_valid, o);
@@ -344,7 +493,11 @@ __global__ void __launch_bounds__(SC_THREADS, (WIDE || SC_THREADS > 512) ? 1 : 2
 __device__ __forceinline__ void sweep_slow(const SweepParams &P, uint32_t *s_hist, uint32_t line, uint64_t tag,
                                            uint32_t rec_flag) {
   uint32_t vr, va;                                       // side tables are keyed by k-mer
-  joint_full(P.J, mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k), line, tag, vr, va);
+  const uint64_t c = mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k);
+  joint_full(P.J, c, line, tag, vr, va);
+  // a restricted table stores no k-mer with both values 0: (0, 0) means "not held here", and the
+  // per-database tables answer (a sequence other than the one the table was restricted to)
+  if (P.restricted && (vr | va) == 0) { vr = mfn_value(P.R, c); va = mfn_value(P.A, c); }
   if (rec_flag & 0x80000000u) { vr += vr; va += va; }    // value(f) + value(r), f == r (Q2)
   const uint32_t rec = rec_flag & 0x7fffffffu;
   bool miss = (vr == 0);
@@ -379,9 +532,10 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
   const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
   const uint32_t tbits = P.tbits;
   const uint64_t tmask64 = (1ull << tbits) - 1ull;
-  // entry fields (W64 tables may use wide entries: the low part is lowbits wide, the record above it)
-  const uint32_t lowbits = W64 ? P.lowbits : 32u;
+  // entry fields: the low part is lowbits wide (32..34 narrow, up to 52 wide), the record above it
+  const uint32_t lowbits = P.lowbits;
   const uint64_t lowmask = (1ull << lowbits) - 1ull;
+  const uint32_t himask = (uint32_t)(lowmask >> 32);               // bits of the low part in the entry's high word
   const uint32_t recmask = (uint32_t)((1ull << (63 - lowbits)) - 1ull);
   auto recflag_of = [&](unsigned long long e) { return ((uint32_t)(e >> lowbits) & recmask) | ((uint32_t)(e >> 32) & 0x80000000u); };
   const uint32_t vb = P.J.rbits + P.J.abits, abits = P.J.abits, amax = P.J.amax;
@@ -451,7 +605,8 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
         return slice + (((lp >> tbits) << 2) | (lp & 3u)) * 32;
       }
       const uint32_t lw = (uint32_t)e;
-      return slice + (uint64_t)(((lw >> tbits) << 2) | (lw & 3u)) * 32;
+      const uint32_t lib = __funnelshift_r(lw, (uint32_t)(e >> 32) & himask, tbits);   // line in bin (tbits < 32)
+      return slice + (((uint64_t)lib << 2) | (lw & 3u)) * 32;
     };
     // the few lookups the home sector cannot settle are finished 32 at a time with every lane
     // busy, instead of dragging the whole warp through the slow path once per entry

@@ -160,13 +160,13 @@ __device__ __forceinline__ bool mfn_window(const unsigned long long *seq2, const
 
 template <bool W64>
 __global__ void __launch_bounds__(256) k_count_seq(DevTable t, const unsigned long long *seq2,
-                                                   const unsigned long long *ok, uint64_t G) {
+                                                   const unsigned long long *ok, uint64_t g_begin, uint64_t G) {
   InsertCounts cnt = {0, 0, 0, 0, 0};
   // Adjacent windows of homopolymers and short tandem repeats are the same k-mer: the lanes of a
   // warp that hold equal k-mers elect one to insert their sum, so a megabase satellite costs
   // 1/32 of the increments (and of the contention on its slot).  The loop bound is warp-uniform.
   const uint32_t lane = threadIdx.x & 31;
-  for (uint64_t g0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); g0 < G; g0 += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t g0 = g_begin + blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); g0 < G; g0 += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t g = g0 + lane;
     uint64_t f = 0, r = 0;
     const bool valid = g < G && mfn_window(seq2, ok, g, t.k, t.kmask, f, r);
@@ -379,6 +379,7 @@ extern "C" void mfn_table_free(mfn_table *t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   mfn_joint_free(t->joint);
+  mfn_joint_free(t->hot);
   for (void *p : t->allocs) cudaFree(p);
   delete t;
 }
@@ -500,19 +501,28 @@ extern "C" int mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmer
 
 extern "C" int mfn_table_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, mfn_table **out) {
   if (!ctx || !seq || !out) return MFN_ERR_INVALID;
+  return mfn_table_count_seq_range(ctx, k, seq, 0, seq->G, out);
+}
+
+// The same over the windows that START in global positions [g_begin, g_end) (a shard's tile range).
+int mfn_table_count_seq_range(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, uint64_t g_begin, uint64_t g_end, mfn_table **out) {
+  if (!ctx || !seq || !out) return MFN_ERR_INVALID;
+  g_end = std::min<uint64_t>(g_end, seq->G);
+  g_begin = std::min(g_begin, g_end);
+  const uint64_t span = g_end - g_begin;
   mfn_table *t = nullptr;
   // distinct k-mers <= windows; size for that upper bound
-  MFN_TRY(mfn_table_alloc(ctx, k, seq->total_bases, &t));
+  MFN_TRY(mfn_table_alloc(ctx, k, span, &t));
   t->min_value = 1; t->max_value = 0xffffffffu; t->value_offset = 0;
   int grid = ctx->sm_count * 8;
-  if (t->dev.w64) k_count_seq<true><<<grid, 256, 0, ctx->stream>>>(t->dev, seq->d_seq2, seq->d_ok, seq->G);
-  else            k_count_seq<false><<<grid, 256, 0, ctx->stream>>>(t->dev, seq->d_seq2, seq->d_ok, seq->G);
+  if (t->dev.w64) k_count_seq<true><<<grid, 256, 0, ctx->stream>>>(t->dev, seq->d_seq2, seq->d_ok, g_begin, g_end);
+  else            k_count_seq<false><<<grid, 256, 0, ctx->stream>>>(t->dev, seq->d_seq2, seq->d_ok, g_begin, g_end);
   ctx->launches++;
   int st = (cudaGetLastError() == cudaSuccess) ? mfn_table_finalize(t, true) : MFN_ERR_CUDA;
   if (st != MFN_OK) { mfn_table_free(t); return st; }
   // The table was sized for one k-mer per base.  When far fewer are distinct (diploid or
   // repetitive assemblies), re-insert into a right-sized table: less HBM, fewer TLB misses.
-  if (t->n_kmers * 10 < seq->total_bases * 8 && seq->total_bases > (1u << 20)) {
+  if (t->n_kmers * 10 < span * 8 && span > (1u << 20)) {
     mfn_table *c = nullptr;
     st = mfn_table_alloc(ctx, k, t->n_kmers, &c);
     if (st == MFN_OK) {

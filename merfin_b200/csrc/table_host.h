@@ -72,9 +72,12 @@ struct mfn_joint {
   const mfn_table *reads = nullptr, *asm_ = nullptr;
   uint64_t n_kmers = 0, device_bytes = 0;
   uint32_t tag_bits = 0;
+  bool restricted = false;          // holds only the k-mers of one sequence shard: misses fall back to the per-database tables
   std::vector<void *> allocs;
 };
 int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_joint **out);
+int mfn_joint_build_restricted(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_table *keys, mfn_joint **out);
+int mfn_table_count_seq_range(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, uint64_t g_begin, uint64_t g_end, mfn_table **out);
 void mfn_joint_free(mfn_joint *j);
 
 // ---- range-partitioned -hist scan (sweep.cu) --------------------------------------------------
@@ -84,7 +87,7 @@ int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const m
                    uint32_t zhi);
 cudaEvent_t mfn_ctx_mark(mfn_ctx *c);
 struct mfn_sweep;
-int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
+int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out);
 int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end);
 int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w);

@@ -100,6 +100,9 @@ SIGNATURES = {
     "mfn_tables_fuse": (C.c_int, [_P, _P, _P]),
     "mfn_tables_unfuse": (C.c_int, [_P]),
     "mfn_joint_info": (C.c_int, [_P, C.POINTER(JointInfo)]),
+    "mfn_tables_restrict": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32]),
+    "mfn_tables_unrestrict": (C.c_int, [_P]),
+    "mfn_restricted_info": (C.c_int, [_P, C.POINTER(JointInfo)]),
     "mfn_joint_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "mfn_meryl_write": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, C.c_uint64]),
     "mfn_meryl_info": (C.c_int, [C.c_char_p, C.POINTER(MerylInfo)]),
@@ -112,6 +115,9 @@ SIGNATURES = {
     "mfn_accum_free": (None, [_P]),
     "mfn_accum_device_buffer": (C.c_int, [_P, _PP, C.POINTER(C.c_uint64)]),
     "mfn_accum_fetch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_accum_read": (C.c_int, [_P, _P, _P]),
+    "mfn_accum_sparse_fetch": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_accum_decode_gathered": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_accum_layout": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_uint64)]),
     "mfn_accum_decode": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),

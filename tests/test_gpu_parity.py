@@ -350,8 +350,7 @@ def test_k_mismatch_is_an_error(ctx, golden_dir):
 
 
 # ---------------------------------------------------------------------------------- sweep (range-partitioned scan)
-# (k = 32 and 11 join the list once they have passed on a GPU: tools/r2_first_gpu_call.sh runs them)
-@pytest.mark.parametrize("k", [21, 16, 6, 31] + ([32, 11] if os.environ.get("MFN_TEST_EXTRA_K") else []))
+@pytest.mark.parametrize("k", [21, 16, 6, 31, 15, 32, 11])
 def test_sweep_equals_direct_scan(ctx, monkeypatch, k):
     """The range-partitioned -hist scan gives the same joint histogram and per-record counters as
     the direct scan (forced on here; it is chosen automatically for large batches)."""
@@ -380,6 +379,27 @@ def test_sweep_equals_direct_scan(ctx, monkeypatch, k):
     got = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in s.pairs}
     assert got == exp
     assert [int(c["kasm"]) for c in s.per_seq] == [p[0] for p in per]
+    # the fused table restricted to the k-mers of the scanned sequences (what the sweep streams when it
+    # exists): same result; and restricted to HALF of them, so that the other half of the windows (and
+    # a record of k-mers neither database has) must fall back to the per-database tables
+    seq = api.SeqSet(ctx, recs)
+    R.restrict(A, seq)
+    ri = R.restricted_info
+    assert ri.fused and 0 < ri.n_kmers <= R.joint_info.n_kmers
+    r1 = api.hist(ctx, R, A, recs, km)
+    assert len(d.pairs) == len(r1.pairs) and (d.pairs == r1.pairs).all() and (d.per_seq == r1.per_seq).all()
+    R.restrict(A, seq, 0, 2)
+    # (with k = 6 either half already holds every one of the 2080 canonical 6-mers)
+    assert R.restricted_info.n_kmers < ri.n_kmers or (k <= 8 and R.restricted_info.n_kmers == ri.n_kmers)
+    extra = recs + [("novel", bytes(rng.choice(list(b"ACGT"), size=50_000).astype(np.uint8)))]
+    monkeypatch.setenv("MFN_SWEEP", "0")
+    d2 = api.hist(ctx, R, A, extra, km)
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    r2 = api.hist(ctx, R, A, extra, km)
+    assert len(d2.pairs) == len(r2.pairs) and (d2.pairs == r2.pairs).all() and (d2.per_seq == r2.per_seq).all()
+    R.unrestrict()
+    assert not R.restricted_info.fused
+    seq.close()
     R.close(); A.close()
 
 

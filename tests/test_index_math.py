@@ -12,20 +12,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _constants():
     src = open(os.path.join(ROOT, "merfin_b200", "csrc", "joint.cu")).read()
-    m = re.search(r"FS\[4\]\[3\]\s*=\s*\{(.*?)\};", src, re.S)
-    rows = re.findall(r"\{\s*(\d+)\s*,\s*(0x[0-9A-Fa-f]+)u?\s*,\s*(\d+)\s*\}", m.group(1))
-    assert len(rows) == 4
+    m = re.search(r"FS\[5\]\[3\]\s*=\s*\{(.*?)\};", src, re.S)
+    rows = re.findall(r"\{\s*(\d+)\s*,\s*(0x[0-9A-Fa-f]+|0)u?\s*,\s*(\d+)\s*\}", m.group(1))
+    assert len(rows) == 5
     return [(int(d), int(mm, 16), int(s)) for d, mm, s in rows]
+
+
+def _div(x, d, m, s):
+    """joint_split's quotient: d == 1 (power-of-two divisor) passes x through, else __umulhi(x, m) >> s."""
+    if d == 1:
+        return x
+    return ((x * np.uint64(m)) >> np.uint64(32)) >> np.uint64(s)
 
 
 def test_multiply_high_division_is_exact_for_every_32_bit_value():
     rng = np.random.default_rng(0)
     for d, m, s in _constants():
-        assert d in (3, 5, 9, 15)
+        assert d in (1, 3, 5, 9, 15)
         edge = np.array([0, 1, d - 1, d, d + 1, 2**31 - 1, 2**31, 2**32 - d - 1, 2**32 - d, 2**32 - 2, 2**32 - 1], dtype=np.uint64)
         mult = (np.arange(0, 2**32 // d, 9973, dtype=np.uint64) * np.uint64(d))            # multiples of d and their neighbours
         x = np.concatenate([edge, mult, mult[1:] - np.uint64(1), rng.integers(0, 2**32, size=4_000_000, dtype=np.uint64)])
-        q = ((x * np.uint64(m)) >> np.uint64(32)) >> np.uint64(s)                          # __umulhi(x, m) >> s; x*m < 2^64
+        q = _div(x, d, m, s)                                                               # __umulhi(x, m) >> s; x*m < 2^64
         assert (q == x // np.uint64(d)).all(), d
 
 
@@ -41,7 +48,7 @@ def test_split_reassembles_to_h():
                 h = rng.integers(0, 2**64, size=200_000, dtype=np.uint64)
             x = h >> np.uint64(t)
             assert int(x.max()) < 2**32
-            q = ((x * np.uint64(m)) >> np.uint64(32)) >> np.uint64(s)
+            q = _div(x, d, m, s)
             rem = x - q * np.uint64(d)
             tag = (rem << np.uint64(t)) | (h & np.uint64((1 << t) - 1))
             D = d << t
@@ -120,3 +127,46 @@ def test_magic_division_needs_at_most_one_correction():
             if r >= D:
                 q, r = q + 1, r - D
             assert (q, r) == divmod(h, D), (h, D)
+
+
+def test_hash_on_32_bit_halves_equals_mfn_mix(tmp_path):
+    """The scatter pass hashes 16 < k < 32 on two 32-bit halves (sweep_kernels.cuh: Kmer2) with a literal 0
+    seed; the struct is taken verbatim from the source and must equal mfn_mix(c, 0, kmask, k) for every k."""
+    import subprocess
+    tsrc = open(os.path.join(ROOT, "merfin_b200", "csrc", "table.cuh")).read()
+    m = re.search(r"__host__ __device__ __forceinline__ (uint64_t mfn_mix\(.*?\n\})", tsrc, re.S)
+    ssrc = open(os.path.join(ROOT, "merfin_b200", "csrc", "sweep_kernels.cuh")).read()
+    k2 = re.search(r"(template <int K> struct Kmer2 \{.*?\n\};)", ssrc, re.S)
+    assert m and k2
+    body = k2.group(1).replace("__device__ __forceinline__", "inline")
+    cases = "\n".join("  if (!check<%d>()) return 1;" % k for k in range(17, 32))
+    prog = r"""
+#include <cstdint>
+#include <cstdio>
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (s & 31)); }
+static inline %s
+%s
+template <int K> bool check() {
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  uint64_t s = 88172645463325252ull + K;
+  for (int i = 0; i < 300000; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    const uint64_t c = i < 4 ? (i == 0 ? 0 : i == 1 ? kmask : i == 2 ? 1 : kmask - 1) : (s & kmask);
+    uint32_t hi = (uint32_t)(c >> 32), lo = (uint32_t)c;
+    Kmer2<K>::mix(hi, lo);
+    if (((((uint64_t)hi) << 32) | lo) != mfn_mix(c, 0, kmask, K)) { printf("k=%%d differs\n", K); return false; }
+  }
+  return true;
+}
+int main() {
+%s
+  printf("ok\n");
+  return 0;
+}
+""" % (m.group(1), body, cases)
+    cpp = tmp_path / "halves.cpp"
+    cpp.write_text(prog)
+    exe = str(tmp_path / "halves")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, str(cpp)])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", p.stdout

@@ -79,6 +79,74 @@ def test_two_rank_shard_allreduce_decode(golden_dir, tmp_path):
     assert 0 < int(mine) < int(total)              # both ranks contributed
 
 
+def _worker_sparse(rank, world, port, out):
+    """Pairs outside the dense tier (v_asm >= 64 or v_read >= 4096) are not in the flat buffer: each rank keeps
+    its own list, the reduced header counts them over all ranks, and the decode wants exactly that many."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from merfin_b200 import api, lib as L
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = L.load()
+    nseq = 3
+    hw, dr, da, nw = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+    lib.mfn_accum_layout(nseq, C.byref(hw), C.byref(dr), C.byref(da), C.byref(nw))
+    buf = np.zeros(nw.value, dtype=np.int64)
+    rng = np.random.default_rng(100 + rank)
+    # dense pairs
+    for _ in range(1000):
+        vr, va = int(rng.integers(0, dr.value)), int(rng.integers(0, da.value))
+        buf[hw.value + va * dr.value + vr] += 1
+    # side-table pairs: some shared between the ranks (must be summed), some private
+    mine = {(5000, 3): 10 + rank, (17, 64): 2, (4096 + rank, 100 + rank): 7}
+    sparse = np.array([(vr, va, c) for (vr, va), c in sorted(mine.items())], dtype=api.PAIR_DTYPE)
+    buf[1] = len(sparse)
+    expect_dense = torch.from_numpy(buf.copy())
+    t = torch.from_numpy(buf)
+    dist.all_reduce(t)
+    dist.all_reduce(expect_dense)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sparse)
+    ok = True
+    if rank == 0:
+        ubuf = buf.view(np.uint64)
+        per = np.zeros(nseq, dtype=api.COUNTS_DTYPE)
+        pairs = np.zeros(1 << 16, dtype=api.PAIR_DTYPE)
+        n = C.c_uint64()
+        # the plain decode must refuse a buffer whose header counts side-table pairs ...
+        st = lib.mfn_accum_decode(ubuf.ctypes.data_as(C.c_void_p), nseq, per.ctypes.data_as(C.c_void_p),
+                                  pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(n))
+        ok = ok and st == L.MFN_ERR_INVALID
+        # ... and so must a gather that misses a rank
+        try:
+            api.decode_gathered(ubuf, nseq, gathered[0])
+            ok = False
+        except L.MfnError as e:
+            ok = ok and e.status == L.MFN_ERR_INVALID
+        per, got = api.decode_gathered(ubuf, nseq, np.concatenate(gathered))
+        want = {}
+        for r in range(world):
+            for (vr, va), c in {(5000, 3): 10 + r, (17, 64): 2, (4096 + r, 100 + r): 7}.items():
+                want[(vr, va)] = want.get((vr, va), 0) + c
+        d = expect_dense.numpy()
+        for va in range(da.value):
+            for vr in np.nonzero(d[hw.value + va * dr.value: hw.value + (va + 1) * dr.value])[0]:
+                want[(int(vr), va)] = int(d[hw.value + va * dr.value + vr])
+        have = {(int(p["v_read"]), int(p["v_asm"])): int(p["count"]) for p in got}
+        ok = ok and have == want and len(got) == len(want)
+        open(out, "w").write(str(int(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_side_table_pairs_are_gathered(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_worker_sparse, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "1"
+
+
 def test_shard_ranges_partition_the_windows():
     from merfin_b200 import lib as L
     lib = L.load()
