@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sample-mbp", type=float, default=24.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shards", type=int, default=0,
+                    help="development aid, 1 GPU: time shard 0 of N exactly as rank 0 of an N-GPU run would (no collective); "
+                         "the line is marked emulated and is not a bench value")
+    ap.add_argument("--no-direct-check", action="store_true", help="skip the untimed direct-scan pass that re-derives the result")
     return ap.parse_args()
 
 
@@ -276,6 +280,10 @@ def main():
     # the host packing lane of mfn_hist_host uses the host cores: split them between the ranks of this box
     if "MFN_HOST_PACK_THREADS" not in os.environ and world > 1:
         os.environ["MFN_HOST_PACK_THREADS"] = str(max(1, ((os.cpu_count() or 2) - 2) // world))
+    srank, sworld = rank, world                  # shard of the assembly this process scans
+    if args.emulate_shards > 1 and world == 1:
+        srank, sworld = 0, args.emulate_shards
+        config["emulated"] = f"shard 0 of {sworld} on one GPU, no collective: development figure, not a bench value"
     ctx = api.Context(local)
     # a non-default torch stream: our kernels, torch's events and NCCL are all ordered on it
     stream = torch.cuda.Stream(device=dev)
@@ -284,7 +292,7 @@ def main():
     lib = api.L.load()
     config = {"workload": f"{total / 1e9:.2f} Gbp synthetic diploid assembly (24 records, 0.1% SNVs, 1% N) + "
                           f"synthetic {2 * COV_PER_COPY:.0f}x read table, k={K}, -hist",
-              "k": K, "records": len(lens), "parallelism": f"tiles sharded over {world} GPU(s), tables replicated",
+              "k": K, "records": len(lens), "parallelism": f"tiles sharded over {world} GPU(s); read/assembly/fused tables replicated, the streamed table restricted to each rank's shard",
               "l2_policy": "inputs larger than L2 (24 GB of window entries and a 25 GB table stream through the 126 MB L2 every step)"}
 
     if args.impl == "reference":
@@ -292,6 +300,14 @@ def main():
         times = cb["hist_seconds"][args.warmup:]
         v = stotal * len(times) / sum(times)
         cb["value"] = v
+        # say what this arm ran: a bounded sample of the workload with its own (smaller) databases
+        config = dict(config)
+        config["full_workload"] = config["workload"]
+        config["workload"] = (f"SAMPLE of the {total / 1e9:.2f} Gbp workload: {stotal / 1e6:.1f} Mbp (first {stotal // len(lens)} bases of each of the "
+                              f"{len(lens)} records) + own k={K} read/assembly meryl DBs of the sample, -hist, reference merfin on {cb['cores']} host threads; "
+                              f"each step = one reference run over the sample, hist phase only")
+        config["parallelism"] = f"{cb['cores']} host threads (reference -threads), no GPU"
+        config["l2_policy"] = "n/a (CPU)"
         print(json.dumps({"impl": "reference", "metric": "bases/sec (-hist k=21)", "value": v, "unit": "bases/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
@@ -317,7 +333,7 @@ def main():
     restricted = not os.environ.get("MFN_NO_JOINT") and os.environ.get("MFN_BENCH_RESTRICT", "1") != "0"
     if restricted:
         # the table the range-partitioned scan streams: only the k-mers of this rank's shard of the assembly
-        R.restrict(A, seq, rank, world)
+        R.restrict(A, seq, srank, sworld)
     ctx.sync()
     setup_s = time.time() - t0
     ai, ri = A.info, R.info
@@ -330,7 +346,7 @@ def main():
         hi = R.restricted_info
         config["restricted_table"] = {"kmers": int(hi.n_kmers), "GB": round(hi.device_bytes / 1e9, 2), "lines": int(hi.lines),
                                       "tag_bits": int(hi.tag_bits), "spill_frac": round(hi.n_spill / max(1, hi.n_kmers), 4),
-                                      "stash": int(hi.n_stash), "scope": f"k-mers of shard {rank} of {world} (each rank its own)"}
+                                      "stash": int(hi.n_stash), "scope": f"k-mers of shard {srank} of {sworld} (each rank its own)"}
     config["tables"] = {"asm_kmers": int(ai.n_kmers), "read_kmers": int(ri.n_kmers),
                         "asm_GB": round(ai.device_bytes / 1e9, 2), "read_GB": round(ri.device_bytes / 1e9, 2),
                         "read_level2_frac": round(ri.n_level2 / max(1, ri.n_kmers), 4),
@@ -343,14 +359,14 @@ def main():
 
     def step_resident():
         acc.reset()
-        api.hist_resident(ctx, R, A, seq, None, acc, rank, world)
+        api.hist_resident(ctx, R, A, seq, None, acc, srank, sworld)
         if world > 1:
             dist.all_reduce(acc_t)
 
     def step_e2e():
         acc.reset()
         api.L.check(lib.mfn_hist_host(ctx.h, R.h, A.h, bases_ptr, off.ctypes.data_as(C.c_void_p), len(lens),
-                                      None, rank, world, acc.h))
+                                      None, srank, sworld, acc.h))
         if world > 1:
             dist.all_reduce(acc_t)
         per, pairs = acc.fetch()                 # D2H of the reduced histogram + counters
@@ -398,7 +414,7 @@ def main():
         for _ in range(n):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            api.hist_resident(ctx, R, A, seq, None, acc, rank, world)
+            api.hist_resident(ctx, R, A, seq, None, acc, srank, sworld)
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
@@ -444,11 +460,34 @@ def main():
 
     # result checks: resident and host-buffer paths agree; counters consistent
     acc.reset()
-    api.hist_resident(ctx, R, A, seq, None, acc, rank, world)
+    api.hist_resident(ctx, R, A, seq, None, acc, srank, sworld)
     if world > 1:
         dist.all_reduce(acc_t)
     per2, pairs2 = acc.fetch()
     same = (len(pairs2) == len(res.pairs) and bool((pairs2 == res.pairs).all()) and bool((per2 == res.per_seq).all()))
+    # Full-size parity, untimed: the same shard once more with the DIRECT scan (k_scan: one complete lookup per
+    # window in the full fused table, no range partitioning, no restricted table, no side lists) -- a different
+    # kernel, a different table and a different accumulation order must give the same integers.
+    direct_same, direct_ms = None, None
+    if not args.no_direct_check:
+        prev = os.environ.get("MFN_SWEEP")
+        os.environ["MFN_SWEEP"] = "0"
+        try:
+            acc.reset()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            api.hist_resident(ctx, R, A, seq, None, acc, srank, sworld)
+            b.record()
+            if world > 1:
+                dist.all_reduce(acc_t)
+            per3, pairs3 = acc.fetch()
+            direct_ms = a.elapsed_time(b)
+            direct_same = (len(pairs3) == len(pairs2) and bool((pairs3 == pairs2).all()) and bool((per3 == per2).all()))
+        finally:
+            if prev is None:
+                del os.environ["MFN_SWEEP"]
+            else:
+                os.environ["MFN_SWEEP"] = prev
     summary, _, _ = res.report()
 
     if rank == 0:
@@ -457,16 +496,23 @@ def main():
             peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        bases_rank = total / world
+        bases_rank = total / sworld
         achieved = bases_rank * BYTES_PER_BASE / (k_ms / 1e3) / 1e9
-        traffic, traffic_src = None, None
+        swept = scatter_ms is not None
+        # DRAM bytes one launch of the pair has to move by construction (per rank): every window's 8-byte entry
+        # written by pass 1 and read by pass 2, the table the probe pass streams once, the packed sequence.
+        # The table does NOT shrink with N unless it is restricted to the rank's shard.
+        table_bytes = (int(R.restricted_info.lines) if restricted else int(ji.lines) if ji.fused else 0) * 128
+        windows_rank = int(res.report()[0].kasm) / sworld if sworld > 1 else int(res.report()[0].kasm)
+        model = windows_rank * 16 + table_bytes + bases_rank * 0.375 if swept else None
+        traffic, traffic_src = model, "model: windows x 16 B (entry written + read) + table lines x 128 B + 0.375 B/base of packed sequence"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and sworld == 1:
             tj = json.load(open(tp))
-            if tj.get("dram_bytes_per_base"):
+            # the ncu figure only stands for the configuration it was captured on
+            if tj.get("dram_bytes_per_base") and bool(tj.get("restricted_table")) == bool(restricted):
                 traffic = tj["dram_bytes_per_base"] * bases_rank
                 traffic_src = tj.get("source")
-        swept = scatter_ms is not None
         kernel_name = ("k_sweep_scatter<21,false> + k_sweep_probe<false> (range-partitioned scan of the joint table)" if swept
                        else "k_scan<2> (joint table)" if ji.fused else "k_scan<0> (two tables)")
         out = {"metric": "bases/sec (-hist k=21)", "value": value, "unit": "bases/s", "n_gpus": world,
@@ -481,13 +527,18 @@ def main():
                             "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                             "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": k_ms,
                             "pass_ms": {"scatter": scatter_ms, "probe": probe_ms} if swept else None,
-                            "bases_per_launch": bases_rank, "algorithmic_bytes_per_base": BYTES_PER_BASE},
+                            "bases_per_launch": bases_rank, "algorithmic_bytes_per_base": BYTES_PER_BASE,
+                            "traffic_model": model,
+                            # how close the pair runs to the time its OWN DRAM traffic needs at the copy peak (the contract
+                            # `frac` above counts 64.25 algorithmic bytes per base, which the sweep does not move)
+                            "frac_of_own_traffic": (traffic / 1e9 / peak_gbs) / (k_ms / 1e3) if traffic else None},
                "clocks": clocks, "weak_scaling": weak,
                "result": {"kasm": int(summary.kasm), "kmissing": int(summary.kmissing),
-                          "qv_star": summary.qv_star, "resident_equals_e2e": bool(same)}}
+                          "qv_star": summary.qv_star, "resident_equals_e2e": bool(same),
+                          "sweep_equals_direct": direct_same, "direct_scan_ms": direct_ms}}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb, _ = cpu_baseline(ctx, asm_np, lens, args.sample_mbp)
+                cb, _ = cpu_baseline(ctx, asm_np, lens, args.sample_mbp, repeats=2)
             except Exception as e:                      # the headline line must come out whatever the CPU leg does
                 cb = {"value": None, "unit": "bases/s", "cores": os.cpu_count() or 1, "kind": "reference",
                       "sample": "failed: %s" % (str(e)[:200],)}

@@ -89,15 +89,15 @@ int mfn_joint_alloc(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, uint64
         if (cand > best) { best = cand; bf = f; bt = t; }
       }
     // A power-of-two divisor makes line, tag and the sweep's bin plain bit fields of the hash (no
-    // division in the scatter pass): take the nearest one when it keeps the load within
-    // [0.45, MFN_JOINT_LOAD_POW2 (0.75)]
+    // division in the scatter pass): the one whose load falls in (hi / 2, hi], hi = MFN_JOINT_LOAD_POW2 (0.75)
     if (want_pow2) {
       const char *e2 = getenv("MFN_JOINT_LOAD_POW2");
-      const double hi_load = e2 ? atof(e2) : 0.75;
+      double hi_load = e2 ? atof(e2) : 0.75;
+      if (!(hi_load > 0.1 && hi_load < 0.99)) hi_load = 0.75;
       for (uint32_t t = std::max(tmin, 1u); t < 60; t++) {
         const double lines = std::ldexp(1.0, 2 * (int)k - (int)t);
         const double ld = (double)n / (lines * slots);
-        if (ld <= hi_load && ld >= 0.45) { best = 1ull << t; bf = 4; bt = t; break; }
+        if (ld <= hi_load && ld > hi_load / 2) { best = 1ull << t; bf = 4; bt = t; break; }
         if (ld > hi_load) break;                                              // fewer lines only get fuller
       }
     }

@@ -1,5 +1,5 @@
 // Range-partitioned -hist scan: host side and the two main passes (see sweep_kernels.cuh).
-#include "sweep_kernels.cuh"
+#include "sweep_scatter3.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host
@@ -97,7 +97,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const 
   }
   // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
-  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 64 + 8;        // bins, side-list count, pass counters, phase cycles
+  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 4096 + 8;      // bins, side-list count, pass counters (one per scatter pass), phase cycles
   cudaError_t e = cudaMallocAsync(&P.entries, ebytes, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&w->ctl, cwords * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&P.over_lt, P.over_cap * 8, ctx->stream);
@@ -105,7 +105,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const 
   if (e != cudaSuccess) { mfn_set_error("sweep workspace (%zu bytes): %s", ebytes, cudaGetErrorString(e)); delete w; return MFN_ERR_NOMEM; }
   P.bin_count = w->ctl; P.bin_valid = w->ctl + P.nbins_pad; P.over_n = w->ctl + 2 * P.nbins_pad;
   w->counters = w->ctl + 2 * P.nbins_pad + 1;
-  P.prof = w->ctl + 2 * P.nbins_pad + 4 + 64;
+  P.prof = w->ctl + 2 * P.nbins_pad + 4 + 4096;
   MFN_CUDA(cudaMemsetAsync(w->ctl, 0, cwords * 8, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(P.bin_valid, 0xff, (size_t)P.nbins_pad * 8, ctx->stream));
   *out = w;
@@ -114,7 +114,7 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const 
 
 int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end) {
   if (tile_begin >= tile_end) return MFN_OK;
-  if (w->n_scatter >= 60) { mfn_set_error("sweep: too many scatter passes"); return MFN_ERR_INVALID; }
+  if (w->n_scatter >= 4000) { mfn_set_error("sweep: too many scatter passes"); return MFN_ERR_INVALID; }
   SweepParams P = w->P;
   P.tile_begin = tile_begin; P.tile_end = tile_end;
   const size_t sc_smem = (size_t)SW_CHUNK * 8 + (size_t)P.nbins_pad * 12;
@@ -132,7 +132,24 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   // bit-field geometry: power-of-two divisor, 34-bit low part, bin = the hash bits above it
   const bool geo1 = P.J.fs_d == 1 && P.lowbits == 34 && P.lbits + P.tbits == 34 && P.tbits == P.J.fs_t &&
                     2 * P.J.k >= 34 && 2 * P.J.k - 34 <= SC_BIN_BITS && P.nbins == (1u << (2 * P.J.k - 34));
-  if (P.lowbits > SW_MAX_LOWBITS_NARROW) {
+  // scatter3 (sweep_scatter3.cuh): k = 21, narrow entries, few bins, entry indices below 2^32
+  const char *env3 = getenv("MFN_SCATTER");
+  const bool s3 = !(env3 && atoi(env3) == 2) && P.J.k == 21 && P.lowbits <= SW_MAX_LOWBITS_NARROW && P.nbins <= S3_MAX_BINS &&
+                  (uint64_t)P.nbins * P.cap + S3_CHUNK < (1ull << 32);
+  if (s3) {
+    P.nbins_pad = (P.nbins + S3_THREADS - 1) / S3_THREADS * S3_THREADS;
+    const size_t smem3 = s3_smem_bytes(P.nbins_pad);
+    const uint64_t nchunks3 = ceil_div_u64(tile_end - tile_begin, S3_TILES);
+    auto launch3 = [&](auto kernel) -> int {
+      int per_sm = 0;
+      MFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, S3_THREADS, smem3);
+      const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks3);
+      kernel<<<grid, S3_THREADS, smem3, ctx->stream>>>(P);
+      return MFN_OK;
+    };
+    if (geo1) MFN_TRY(launch3(k_sweep_scatter3<21, 1>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0>));
+  } else if (P.lowbits > SW_MAX_LOWBITS_NARROW) {
     switch (P.J.k) {
       case 31: MFN_TRY(launch(k_sweep_scatter<31, true, 0>)); break;
       default: MFN_TRY(launch(k_sweep_scatter<0, true, 0>)); break;
