@@ -283,7 +283,6 @@ def main():
     srank, sworld = rank, world                  # shard of the assembly this process scans
     if args.emulate_shards > 1 and world == 1:
         srank, sworld = 0, args.emulate_shards
-        config["emulated"] = f"shard 0 of {sworld} on one GPU, no collective: development figure, not a bench value"
     ctx = api.Context(local)
     # a non-default torch stream: our kernels, torch's events and NCCL are all ordered on it
     stream = torch.cuda.Stream(device=dev)
@@ -294,6 +293,8 @@ def main():
                           f"synthetic {2 * COV_PER_COPY:.0f}x read table, k={K}, -hist",
               "k": K, "records": len(lens), "parallelism": f"tiles sharded over {world} GPU(s); read/assembly/fused tables replicated, the streamed table restricted to each rank's shard",
               "l2_policy": "inputs larger than L2 (24 GB of window entries and a 25 GB table stream through the 126 MB L2 every step)"}
+    if sworld != world:
+        config["emulated"] = f"shard 0 of {sworld} on one GPU, no collective: development figure, not a bench value"
 
     if args.impl == "reference":
         cb, stotal = cpu_baseline(ctx, asm_np, lens, args.sample_mbp, repeats=args.warmup + args.steps)

@@ -89,11 +89,11 @@ int mfn_joint_alloc(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, uint64
         if (cand > best) { best = cand; bf = f; bt = t; }
       }
     // A power-of-two divisor makes line, tag and the sweep's bin plain bit fields of the hash (no
-    // division in the scatter pass): the one whose load falls in (hi / 2, hi], hi = MFN_JOINT_LOAD_POW2 (0.75)
+    // division in the scatter pass): the one whose load falls in (hi / 2, hi], hi = MFN_JOINT_LOAD_POW2 (0.62: at most 2.5 % of the k-mers spill out of their home sector)
     if (want_pow2) {
       const char *e2 = getenv("MFN_JOINT_LOAD_POW2");
-      double hi_load = e2 ? atof(e2) : 0.75;
-      if (!(hi_load > 0.1 && hi_load < 0.99)) hi_load = 0.75;
+      double hi_load = e2 ? atof(e2) : 0.62;
+      if (!(hi_load > 0.1 && hi_load < 0.99)) hi_load = 0.62;
       for (uint32_t t = std::max(tmin, 1u); t < 60; t++) {
         const double lines = std::ldexp(1.0, 2 * (int)k - (int)t);
         const double ld = (double)n / (lines * slots);

@@ -148,7 +148,12 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
       kernel<<<grid, S3_THREADS, smem3, ctx->stream>>>(P);
       return MFN_OK;
     };
-    if (geo1) MFN_TRY(launch3(k_sweep_scatter3<21, 1>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0>));
+    // the same with a 33-bit low part (twice the bins of half the size)
+    const bool geo2 = P.J.fs_d == 1 && P.lowbits == 33 && P.lbits + P.tbits == 33 && P.tbits == P.J.fs_t &&
+                      2 * P.J.k - 33 <= SC_BIN_BITS && P.nbins == (1u << (2 * P.J.k - 33));
+    if (geo1) MFN_TRY(launch3(k_sweep_scatter3<21, 1>));
+    else if (geo2) MFN_TRY(launch3(k_sweep_scatter3<21, 2>));
+    else MFN_TRY(launch3(k_sweep_scatter3<21, 0>));
   } else if (P.lowbits > SW_MAX_LOWBITS_NARROW) {
     switch (P.J.k) {
       case 31: MFN_TRY(launch(k_sweep_scatter<31, true, 0>)); break;

@@ -23,8 +23,7 @@
 #define S3_THREADS 256
 #define S3_TILES 2
 #define S3_CHUNK (S3_TILES * MFN_TILE)            // 4096 windows per CTA round
-#define S3_NW (S3_CHUNK / S3_THREADS)              // 16 windows per thread: two groups of 8
-#define S3_GROUPS (S3_NW / WPT)
+#define S3_NW (S3_CHUNK / S3_THREADS)              // 16 consecutive windows per thread
 #define S3_MAX_BINS 512
 #define S3_SEQ_WORDS (S3_CHUNK / 32 + 2)
 #define S3_OK_WORDS (S3_CHUNK / 64 + 2)
@@ -54,9 +53,11 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   __shared__ __align__(16) uint32_t s_warp[S3_THREADS / 32];
   __shared__ unsigned long long s_chunk[2];
   __shared__ uint32_t s_total, s_over;
-  __shared__ __align__(16) unsigned long long s_seq[2][S3_SEQ_WORDS];
-  __shared__ __align__(16) unsigned long long s_ok[2][S3_OK_WORDS];
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  // the chunk's 2-bit words and validity bits (incl. a 64-base halo), staged by TMA.  ONE buffer: the
+  // next chunk's copy is issued after barrier (1), when every thread has sliced its windows out of it
+  __shared__ __align__(16) unsigned long long s_seq[S3_SEQ_WORDS];
+  __shared__ __align__(16) unsigned long long s_ok[S3_OK_WORDS];
+  __shared__ __align__(8) unsigned long long s_bar;
 
   const uint32_t tid = threadIdx.x;
   const uint32_t s_cnt_sa = smem_u32(s_cnt);
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   constexpr uint64_t kmask = (1ull << (2 * KK)) - 1ull;
   constexpr uint64_t kbits = (1ull << KK) - 1;
   constexpr uint64_t cmask = 0xaaaaaaaaaaaaaaaaull & kmask;
-  constexpr uint64_t need = (1ull << (WPT + KK - 1)) - 1;                 // validity bits behind a thread's 8 windows
+  constexpr uint64_t need = (1ull << (S3_NW + KK - 1)) - 1;               // validity bits behind a thread's 16 windows
   const uint32_t lmask = (1u << P.lbits) - 1u;
   const uint32_t xbits = P.lowbits - 32;
   const uint64_t nchunks = ceil_div_u64(P.tile_end - P.tile_begin, S3_TILES);
@@ -91,9 +92,9 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
     const uint64_t w2 = t0 * (MFN_TILE / 32), wo = t0 * (MFN_TILE / 64);
     const uint32_t n2 = (uint32_t)min((uint64_t)S3_SEQ_WORDS, P.seq_words - w2) & ~1u;
     const uint32_t no = (uint32_t)min((uint64_t)S3_OK_WORDS, P.ok_words - wo) & ~1u;
-    mbar_expect_tx(&s_bar[buf], (n2 + no) * 8);
-    tma_load_1d(s_seq[buf], P.seq2 + w2, n2 * 8, &s_bar[buf]);
-    tma_load_1d(s_ok[buf], P.ok + wo, no * 8, &s_bar[buf]);
+    mbar_expect_tx(&s_bar, (n2 + no) * 8);
+    tma_load_1d(s_seq, P.seq2 + w2, n2 * 8, &s_bar);
+    tma_load_1d(s_ok, P.ok + wo, no * 8, &s_bar);
   };
   // side list: a window that cannot go to its bin (h = line * D + tag)
   auto to_side_list = [&](uint64_t h, uint32_t rec_flag) {
@@ -105,8 +106,7 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   unsigned long long pre = 0;
   for (uint32_t i = tid; i < P.nbins_pad; i += S3_THREADS) s_cnt[i] = 0;
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage(atomicAdd(P.counter, 1ull), 0);
     pre = atomicAdd(P.counter, 1ull);
@@ -128,30 +128,29 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
     const uint32_t r0 = cur_rec;
     const uint64_t r0_end = cur_end;
     const bool one_record = (tile0 + S3_TILES) * MFN_TILE <= r0_end;
-    mbar_wait(&s_bar[buf], (it >> 1) & 1);
+    mbar_wait(&s_bar, it & 1);
     SW_PROF_MARK(0);
 
-    // ---- hash this thread's windows; rank them inside their bins ---------------------------
+    // ---- hash this thread's 16 consecutive windows; rank them inside their bins ------------
     uint32_t meta[S3_NW];
     uint32_t live = 0;
-#pragma unroll
-    for (int q = 0; q < S3_GROUPS; q++) {
-      const uint64_t tile = tile0 + q;
-      const uint32_t j0 = q * MFN_TILE + tid * WPT;                       // position in the staged chunk
+    {
+      const uint32_t j0 = tid * S3_NW;                                    // position in the staged chunk
+      const uint64_t tile = tile0 + (j0 >> 11);
       uint64_t lo = 0, hi = 0, okb = 0;
       if (tile < P.tile_end) {
-        const uint32_t w = j0 >> 5, sh = (j0 & 31) * 2;
-        const uint64_t a = s_seq[buf][w], b = s_seq[buf][w + 1];
-        lo = sh ? ((a >> sh) | (b << (64 - sh))) : a;
-        hi = b >> sh;
+        const uint32_t w = j0 >> 5;
+        const uint64_t a = s_seq[w], b = s_seq[w + 1];
+        lo = (j0 & 16) ? ((a >> 32) | (b << 32)) : a;                     // j0 is a multiple of 16: the shift is 0 or 32 bits
+        hi = (j0 & 16) ? (b >> 32) : b;
         const uint32_t wo = j0 >> 6, so = j0 & 63;
-        const uint64_t c = s_ok[buf][wo], d = s_ok[buf][wo + 1];
+        const uint64_t c = s_ok[wo], d = s_ok[wo + 1];
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
       const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi;
       const uint64_t F0 = mfn_rev2(lo & kmask) >> (64 - 2 * k);
       uint32_t Fl = (uint32_t)F0, Fh = (uint32_t)(F0 >> 32);
-      uint32_t lows[WPT];
+      uint32_t lows[S3_NW];
       // canonical k-mer of window u, hashed: (ch, cl); rolls the forward k-mer F by one base
       auto hash_window = [&](int u, uint32_t &ch, uint32_t &cl) {
         const uint32_t xl = u ? __funnelshift_r(w0, w1, 2 * u) : w0;
@@ -162,14 +161,16 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
           Fl = Fl * 4u + nb;
         }
         const uint32_t rl = xl ^ (uint32_t)cmask, rh = (xf & H::HMASK) ^ (uint32_t)(cmask >> 32);
-        const bool lt = Fh < rh || (Fh == rh && Fl < rl);
+        const bool lt = (((uint64_t)Fh << 32) | Fl) < (((uint64_t)rh << 32) | rl);
         cl = lt ? Fl : rl; ch = lt ? Fh : rh;
         H::mix(ch, cl);
       };
-      // (ch, cl) -> low word, staging word without the rank, byte offset of the bin's counter
+      // (ch, cl) -> low word, staging word without the rank (bin << 2 | low part bits 32..33)
       auto place = [&](uint32_t ch, uint32_t cl, uint32_t &low, uint32_t &m0) {
         if (GEO == 1) {
-          low = cl; m0 = ch;                                             // bin << 2 | low part bits 32..33 IS the high half
+          low = cl; m0 = ch;                                             // 34-bit low part: the high half IS bin << 2 | bits 32..33
+        } else if (GEO == 2) {
+          low = cl; m0 = 2u * ch - (ch & 1u);                            // 33-bit low part: (ch >> 1) << 2 | (ch & 1)
         } else {
           uint64_t line, tag;
           joint_split(((uint64_t)ch << 32) | cl, P.J.fs_t, P.J.fs_d, P.J.fs_m, P.J.fs_s, line, tag);
@@ -179,30 +180,30 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
         }
       };
       if (one_record && (okb & need) == need) {
-        // the usual group: 8 valid windows of the chunk's record
-        n_ok0 += WPT;
-        live |= 0xffu << (q * WPT);
+        // the usual case: 16 valid windows of the chunk's record
+        n_ok0 += S3_NW;
+        live = 0xffffu;
 #pragma unroll
-        for (int u = 0; u < WPT; u++) {
+        for (int u = 0; u < S3_NW; u++) {
           uint32_t ch, cl, m0;
           hash_window(u, ch, cl);
           place(ch, cl, lows[u], m0);
           const uint32_t rank = atomicAdd((uint32_t *)((char *)s_cnt + (m0 & S3_BIN_FIELD)), 1u);
-          meta[q * WPT + u] = m0 | (rank << S3_RANK_SHIFT);
+          meta[u] = m0 | (rank << S3_RANK_SHIFT);
           SC_SCHED_FENCE(u);
         }
       } else {
         uint32_t vmask = 0;
 #pragma unroll
-        for (int u = 0; u < WPT; u++) if (((okb >> u) & kbits) == kbits) vmask |= 1u << u;
-        // record of each window
-        uint64_t rdpack = 0;                                       // 6 bits per window
+        for (int u = 0; u < S3_NW; u++) if (((okb >> u) & kbits) == kbits) vmask |= 1u << u;
+        // record of each window: 4 bits of delta per window here, bigger deltas take the side list
+        uint64_t rdpack = 0;
         if (one_record || vmask == 0) n_ok0 += __popc(vmask);
         else {
-          const uint64_t g0 = tile * MFN_TILE + tid * WPT;
+          const uint64_t g0 = tile0 * MFN_TILE + j0;
           uint32_t rec = r0;
           uint64_t next_start = r0_end;
-          for (int u = 0; u < WPT; u++) {
+          for (int u = 0; u < S3_NW; u++) {
             if (!((vmask >> u) & 1u)) continue;
             const uint64_t g = g0 + u;
             while (g >= next_start) { rec++; next_start = (rec < P.nseq) ? P.rec_start[rec + 1] : ~0ull; }
@@ -210,26 +211,26 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
             if (rd == 0) { n_ok0++; continue; }
             atomicAdd(&rec_acc[2 * rec], 1ull);
             my_valid++;
-            if (rd <= S3_MAX_RD) { rdpack |= (uint64_t)rd << (6 * u); continue; }
-            // more records in this chunk than the staging word can tell apart: side list
+            if (rd <= 15u) { rdpack |= (uint64_t)rd << (4 * u); continue; }
+            // more records in this chunk than the staging word tells apart: side list
             vmask &= ~(1u << u);
             const uint64_t x = (u ? ((lo >> (2 * u)) | (hi << (64 - 2 * u))) : lo) & kmask;
             const uint64_t r = x ^ cmask, f = mfn_rev2(x) >> (64 - 2 * k);
             to_side_list(mfn_mix(f < r ? f : r, 0, kmask, k), rec);
           }
         }
-        live |= vmask << (q * WPT);
+        live = vmask;
 #pragma unroll
-        for (int u = 0; u < WPT; u++) {
+        for (int u = 0; u < S3_NW; u++) {
           uint32_t ch, cl, m0;
           hash_window(u, ch, cl);
           place(ch, cl, lows[u], m0);
           const uint32_t rank = sc_rank_atomic(s_cnt_sa + (m0 & S3_BIN_FIELD), (vmask >> u) & 1u);
-          meta[q * WPT + u] = m0 | (rank << S3_RANK_SHIFT) | (((uint32_t)(rdpack >> (6 * u)) & S3_RD_MASK) << S3_RD_SHIFT);
+          meta[u] = m0 | (rank << S3_RANK_SHIFT) | (((uint32_t)(rdpack >> (4 * u)) & 15u) << S3_RD_SHIFT);
         }
       }
-      s_low4[(2 * q) * S3_THREADS + tid] = make_uint4(lows[0], lows[1], lows[2], lows[3]);
-      s_low4[(2 * q + 1) * S3_THREADS + tid] = make_uint4(lows[4], lows[5], lows[6], lows[7]);
+#pragma unroll
+      for (int j = 0; j < S3_NW / 4; j++) s_low4[j * S3_THREADS + tid] = make_uint4(lows[4 * j], lows[4 * j + 1], lows[4 * j + 2], lows[4 * j + 3]);
     }
     SW_PROF_MARK(1);
     __syncthreads();                                                      // (1) the counts are complete
@@ -275,19 +276,23 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
         const uint4 v = s_low4[j * S3_THREADS + tid];
         lows[4 * j] = v.x; lows[4 * j + 1] = v.y; lows[4 * j + 2] = v.z; lows[4 * j + 3] = v.w;
       }
-      if (live == 0xffffu) {
+      // all offset loads of a half before its stores: the compiler cannot tell that s_ent and s_off do
+      // not overlap, and would otherwise wait for every LDS before the next STS
 #pragma unroll
-        for (int idx = 0; idx < S3_NW; idx++) {
-          const uint32_t m = meta[idx];
-          const uint32_t p = *(const uint32_t *)((const char *)s_off + (m & S3_BIN_FIELD)) + (m >> S3_RANK_SHIFT);
-          s_ent[p] = ((unsigned long long)(m & S3_KEEP_MASK) << 32) | lows[idx];
+      for (int h = 0; h < S3_NW; h += 8) {
+        uint32_t pos[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const uint32_t m = meta[h + i];
+          pos[i] = *(const uint32_t *)((const char *)s_off + (m & S3_BIN_FIELD)) + (m >> S3_RANK_SHIFT);
         }
-      } else {
+        if (live == 0xffffu) {
 #pragma unroll
-        for (int idx = 0; idx < S3_NW; idx++) {
-          const uint32_t m = meta[idx];
-          const uint32_t p = *(const uint32_t *)((const char *)s_off + (m & S3_BIN_FIELD)) + (m >> S3_RANK_SHIFT);
-          if ((live >> idx) & 1u) s_ent[p] = ((unsigned long long)(m & S3_KEEP_MASK) << 32) | lows[idx];
+          for (int i = 0; i < 8; i++) s_ent[pos[i]] = ((unsigned long long)(meta[h + i] & S3_KEEP_MASK) << 32) | lows[h + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if ((live >> (h + i)) & 1u) s_ent[pos[i]] = ((unsigned long long)(meta[h + i] & S3_KEEP_MASK) << 32) | lows[h + i];
         }
       }
     }
