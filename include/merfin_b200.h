@@ -261,10 +261,41 @@ int  mfn_dump(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
               uint32_t *v_read /*[total bases]*/, uint32_t *v_asm, uint8_t *valid);
 
 /* Variant path scoring (varMer.C:66-90 probes): same as mfn_dump over a batch of
- * short path strings. */
+ * short path strings.  mfn_dump and mfn_score_paths may be called from several host threads on
+ * one ctx (the device part of a call holds the ctx's lock); output buffers in pinned memory
+ * (mfn_host_alloc) are filled at full PCIe speed. */
 int  mfn_score_paths(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_,
                      const char *paths, const uint64_t *path_off, uint64_t npaths,
                      uint32_t *v_read, uint32_t *v_asm, uint8_t *valid);
+
+/* ---- -filter / -polish / -better / -strict / -loose (merfin-variants.C:131-310) --------------
+ * The reference's unit of work is processVariants(G, T, S) for one sequence record S: cluster the
+ * record's variants, enumerate the allele combinations of every cluster, score every path with
+ * varMer::score and let the mode's selector write VCF records.  The same here: mfn_vcf_load =
+ * vcfFile::load (vcf.C:93-151), mfn_vcf_cluster = mergeChrPosGT (vcf.C:156-246),
+ * mfn_variants_process = processVariants for one record (its probes are batched through
+ * mfn_score_paths).  Records are independent: call mfn_variants_process from as many host threads
+ * as there are cores.  shard / nshards split the clusters of the record into consecutive ranges
+ * (rank r of N scores range r of every record, no collective; the texts of ranks 0..N-1 concatenate
+ * to the unsharded result -- the job-array grain of scripts/parallel1/_submit_merfin.sh, made finer
+ * than one contig). */
+typedef struct mfn_vcf mfn_vcf;
+typedef struct { uint64_t headers, records, contigs, contig_ids, excluded, clusters; } mfn_vcf_info_t;
+enum { MFN_MODE_FILTER = 4, MFN_MODE_POLISH = 5, MFN_MODE_BETTER = 6, MFN_MODE_STRICT = 7, MFN_MODE_LOOSE = 8 };  /* merfin-globals.H:32-40 */
+int  mfn_vcf_load(const char *path, mfn_vcf **out);
+int  mfn_vcf_cluster(mfn_vcf *v, uint32_t k, uint32_t comb, int nosplit);      /* prints the reference's per-contig summary to stderr */
+int  mfn_vcf_info(const mfn_vcf *v, mfn_vcf_info_t *info);
+/* header lines, each followed by '\n'; *need = bytes wanted (call with buf = NULL to size) */
+int  mfn_vcf_header(const mfn_vcf *v, char *buf, uint64_t cap, uint64_t *need);
+uint64_t mfn_vcf_clusters_of(const mfn_vcf *v, const char *ident);
+void mfn_vcf_free(mfn_vcf *v);
+/* *result (and *debug when debug != NULL: the -debug records, var_mer_id = running id) are
+ * malloc'ed texts the caller releases with mfn_text_free. */
+int  mfn_variants_process(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, mfn_vcf *v,
+                          const char *ident, const char *seq, uint64_t seq_len, int mode, uint32_t comb,
+                          const mfn_kmodel *km, uint32_t shard, uint32_t nshards,
+                          char **result, uint64_t *result_len, char **debug, uint64_t *debug_len, uint64_t *var_mer_id);
+void mfn_text_free(char *p);
 
 /* -completeness (merfin-completeness.C:48-144): every k-mer of the read DB as
  * stored (one strand, raw values, no -min/-max, Q4) joined with the raw

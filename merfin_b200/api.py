@@ -8,6 +8,7 @@ reference.  All compute happens in libmerfin_b200.so on the GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -474,6 +475,64 @@ def score_paths(ctx: Context, reads, asm, paths):
     L.check(L.load().mfn_score_paths(ctx.h, reads.h, asm.h, _ptr(bases), _ptr(off), len(off) - 1,
                                      _ptr(vr), _ptr(va), _ptr(ok)))
     return off, vr[:n], va[:n], ok[:n]
+
+
+class Vcf:
+    """A loaded VCF (vcfFile::load, vcf.C:93-151) whose variants can be clustered (mergeChrPosGT,
+    vcf.C:156-246) and scored record by record (processVariants, merfin-variants.C:131-310)."""
+
+    def __init__(self, path: str):
+        self.h = C.c_void_p()
+        L.check(L.load().mfn_vcf_load(os.fsencode(path), C.byref(self.h)))
+
+    def cluster(self, k: int, comb: int = 15, nosplit: bool = False):
+        L.check(L.load().mfn_vcf_cluster(self.h, k, comb, int(nosplit)))
+
+    @property
+    def info(self) -> L.VcfInfo:
+        i = L.VcfInfo()
+        L.check(L.load().mfn_vcf_info(self.h, C.byref(i)))
+        return i
+
+    def header(self) -> bytes:
+        lib = L.load()
+        need = C.c_uint64()
+        L.check(lib.mfn_vcf_header(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 1)
+        L.check(lib.mfn_vcf_header(self.h, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value]
+
+    def clusters_of(self, ident: str) -> int:
+        return int(L.load().mfn_vcf_clusters_of(self.h, ident.encode()))
+
+    def close(self):
+        if self.h:
+            L.load().mfn_vcf_free(self.h)
+            self.h = C.c_void_p()
+
+
+def variants_process(ctx: Context, reads, asm, vcf: Vcf, ident: str, seq, mode: str, kmodel: KModel, comb: int = 15,
+                     shard: int = 0, nshards: int = 1, debug: bool = False, seq_len: int | None = None):
+    """processVariants for one sequence record -> the VCF text merfin appends for it (bytes), and the
+    -debug records when asked.  `seq`: bytes, or an integer address of seq_len bytes."""
+    lib = L.load()
+    res, dbg = C.c_void_p(), C.c_void_p()
+    rlen, dlen, vid = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    if isinstance(seq, (bytes, bytearray)):
+        keep = bytes(seq)
+        ptr, n = C.cast(C.c_char_p(keep), C.c_void_p), len(keep)
+    else:
+        ptr, n = C.c_void_p(int(seq)), int(seq_len)
+    L.check(lib.mfn_variants_process(ctx.h, reads.h, asm.h, vcf.h, ident.encode(), ptr, n, L.MFN_MODE[mode], comb,
+                                     C.byref(kmodel.c), shard, nshards, C.byref(res), C.byref(rlen),
+                                     C.byref(dbg) if debug else None, C.byref(dlen) if debug else None, C.byref(vid)))
+    out = C.string_at(res, rlen.value) if res else b""
+    lib.mfn_text_free(res)
+    d = None
+    if debug:
+        d = C.string_at(dbg, dlen.value) if dbg else b""
+        lib.mfn_text_free(dbg)
+    return (out, d) if debug else out
 
 
 def completeness(ctx: Context, reads_dir: str, asm_dir: str, kmodel: KModel):

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 
 
 // ---------------------------------------------------------------------------
@@ -270,18 +271,26 @@ extern "C" int mfn_hist(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *a
   return st;
 }
 
+// mfn_dump / mfn_score_paths: pack the records, one direct scan that writes the pair per position, D2H.
+// Several host threads may call this on one ctx: the device part holds ctx->dump_mu (the scratch
+// streams and staging buffers of the ctx are shared), the callers' own work overlaps with it.
+// Output arrays come from the stream-ordered pool (no cudaMalloc / cudaFree per call).
 static int dump_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const char *bases,
                      const uint64_t *off, uint64_t nrec, uint32_t *v_read, uint32_t *v_asm, uint8_t *valid) {
   if (!ctx || !reads || !asm_ || !off) return MFN_ERR_INVALID;
   if (nrec > 0xfffffff0ull) return MFN_ERR_INVALID;
   if (nrec == 0 || off[nrec] == off[0]) return MFN_OK;
+  std::lock_guard<std::mutex> lk(ctx->dump_mu);
+  MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_seq *seq = nullptr;
   MFN_TRY(mfn_seq_create(ctx, bases, off, (uint32_t)nrec, &seq));
   uint64_t n = seq->total_bases;
   uint32_t *dr = nullptr, *da = nullptr; uint8_t *dv = nullptr;
   int st = MFN_OK;
-  if (cudaMalloc(&dr, n * 4) != cudaSuccess || cudaMalloc(&da, n * 4) != cudaSuccess || cudaMalloc(&dv, n) != cudaSuccess) {
-    mfn_set_error("cudaMalloc(dump output, %llu positions)", (unsigned long long)n);
+  if (cudaMallocAsync(&dr, n * 4, ctx->stream) != cudaSuccess || cudaMallocAsync(&da, n * 4, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(&dv, n, ctx->stream) != cudaSuccess) {
+    mfn_set_error("device memory for the dump output (%llu positions)", (unsigned long long)n);
+    cudaGetLastError();
     st = MFN_ERR_NOMEM;
   }
   if (st == MFN_OK) st = mfn_dump_resident(ctx, reads, asm_, seq, dr, da, dv);
@@ -289,10 +298,12 @@ static int dump_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_
     cudaMemcpyAsync(v_read, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(v_asm, da, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(valid, dv, n, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { mfn_set_error("dump: %s", cudaGetErrorString(e)); st = MFN_ERR_CUDA; }
   }
-  cudaFree(dr); cudaFree(da); cudaFree(dv);
+  if (dr) cudaFreeAsync(dr, ctx->stream);
+  if (da) cudaFreeAsync(da, ctx->stream);
+  if (dv) cudaFreeAsync(dv, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (st == MFN_OK && e != cudaSuccess) { mfn_set_error("dump: %s", cudaGetErrorString(e)); st = MFN_ERR_CUDA; }
   mfn_seq_free(seq);
   return st;
 }

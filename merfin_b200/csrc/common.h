@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -99,6 +100,7 @@ struct mfn_ctx {
   std::vector<cudaEvent_t> pass_ev;      // triples: before scatter, between, after probe
   size_t pass_ev_used = 0;
   struct mfn_ingest *ingest = nullptr;   // host packing lane of the host-buffer -hist path (ingest.cu)
+  std::mutex dump_mu;                    // mfn_dump / mfn_score_paths: one device section at a time per ctx
   struct mfn_seq   *scratch_seq = nullptr;
   struct mfn_accum *scratch_acc = nullptr;
 };

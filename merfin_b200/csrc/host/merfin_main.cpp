@@ -18,7 +18,6 @@
 #include "../../../include/merfin_b200.h"
 #include "dump_driver.h"
 #include "fasta.h"
-#include "variants.h"
 
 enum { OP_NONE = 0, OP_HIST, OP_COMPL, OP_DUMP, OP_FILTER, OP_POLISH, OP_BETTER, OP_STRICT, OP_LOOSE };
 
@@ -29,10 +28,18 @@ struct Globals {
   uint32_t comb = 15;
   uint32_t threads = 0;          // host threads for the -dump formatter (0 = all cores)
   int report = OP_NONE, device = 0;
+  uint32_t shard = 0, nshards = 1;   // -shard i/n: variant modes score cluster range i of n of every record
   bool nosplit = false, skipMissing = false, debug = false, nofuse = false;
   std::vector<uint32_t> probK;
   std::vector<double> probP;
 };
+
+// 'path' for /bin/sh: single quotes, with every embedded single quote written as '\''
+static std::string shell_quote(const std::string &p) {
+  std::string q = "'";
+  for (char c : p) { if (c == '\'') q += "'\\''"; else q += c; }
+  return q + "'";
+}
 
 static void die(const char *what) {
   fprintf(stderr, "%s: %s\n", what, mfn_last_error());
@@ -51,6 +58,7 @@ static void usage(const char *argv0, const std::vector<std::string> &err) {
   fprintf(stderr, "  Options:      -seqmers <seq.meryl>  -min m  -max m  -comb N  -nosplit  -debug\n");
   fprintf(stderr, "                -threads t  (host threads of the -dump formatter)   -memory m   (accepted for compatibility)\n");
   fprintf(stderr, "                -device d   CUDA device to use (default 0)\n");
+  fprintf(stderr, "                -shard i/n  variant modes: score cluster range i of n of every record (records only in the output when i > 0)\n");
   fprintf(stderr, "  This is the B200 build of merfin's k-mer evaluation; flags and outputs follow merfin.\n\n");
   for (const std::string &e : err) fputs(e.c_str(), stderr);
   exit(1);
@@ -118,6 +126,10 @@ int main(int argc, char **argv) {
     else if (is("-memory")) next();
     else if (is("-device")) G.device = atoi(next());
     else if (is("-nofuse")) G.nofuse = true;
+    else if (is("-shard")) {
+      const char *v = next();
+      if (sscanf(v, "%u/%u", &G.shard, &G.nshards) != 2 || G.nshards == 0 || G.shard >= G.nshards) err.push_back(std::string("Bad -shard '") + v + "' (want i/n with i < n).\n");
+    }
     else if (is("-nosplit")) G.nosplit = true;
     else if (is("-filter")) G.report = OP_FILTER;
     else if (is("-better")) G.report = OP_BETTER;
@@ -285,41 +297,29 @@ int main(int argc, char **argv) {
   // ---- variants (merfin-variants.C) --------------------------------------------------------------
   if (variants) {
     fprintf(stderr, "-- Opening vcf file '%s'.\n", G.vcfName);
-    mfnv::VcfFile vcf;
-    if (!vcf.load(G.vcfName, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
-    fprintf(stderr, "   Collected %lu header lines.\n", (unsigned long)vcf.headers.size());
-    fprintf(stderr, "   Loaded %lu records:\n", (unsigned long)vcf.records.size());
-    fprintf(stderr, "      %-8lu unique contig%s\n", (unsigned long)vcf.byChr.size(), vcf.byChr.size() == 1 ? "" : "s");
-    fprintf(stderr, "      %-8u contig IDs\n", vcf.numChr);
-    fprintf(stderr, "   Excluded %lu invalid records\n\n", (unsigned long)vcf.excluded);
+    mfn_vcf *vcf = nullptr;
+    if (mfn_vcf_load(G.vcfName, &vcf) != MFN_OK) { fprintf(stderr, "ERROR: %s\n", mfn_last_error()); return 1; }
+    mfn_vcf_info_t vi;
+    mfn_vcf_info(vcf, &vi);
+    fprintf(stderr, "   Collected %lu header lines.\n", (unsigned long)vi.headers);
+    fprintf(stderr, "   Loaded %lu records:\n", (unsigned long)vi.records);
+    fprintf(stderr, "      %-8lu unique contig%s\n", (unsigned long)vi.contigs, vi.contigs == 1 ? "" : "s");
+    fprintf(stderr, "      %-8u contig IDs\n", (unsigned)vi.contig_ids);
+    fprintf(stderr, "   Excluded %lu invalid records\n\n", (unsigned long)vi.excluded);
     fprintf(stderr, "Merge variants within %u-mer bases, splitting combinations greater than %u.\n", K, G.comb);
-    vcf.mergeChrPosGT(K, G.comb, G.nosplit);
+    if (mfn_vcf_cluster(vcf, K, G.comb, G.nosplit) != MFN_OK) die("-vcf");
     fprintf(stderr, "-- Generate variant mers and score them.\n");
 
-    mfnv::Options opt;
-    opt.k = K; opt.comb = G.comb; opt.km = km; opt.debug = G.debug;
-    opt.mode = G.report == OP_POLISH ? mfnv::POLISH : G.report == OP_BETTER ? mfnv::BETTER : G.report == OP_STRICT ? mfnv::STRICT
-             : G.report == OP_LOOSE ? mfnv::LOOSE : mfnv::FILTER;
-    mfnv::PathScorer scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, std::vector<uint32_t> &vr,
-                                  std::vector<uint32_t> &va, std::vector<uint8_t> &ok) -> int {
-      vr.assign(paths.size() + 1, 0); va.assign(paths.size() + 1, 0); ok.assign(paths.size() + 1, 0);
-      int st = mfn_score_paths(ctx, R, A, paths.data(), off.data(), off.size() - 1, vr.data(), va.data(), ok.data());
-      if (st != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
-      return st;
-    };
+    const int mode = G.report == OP_POLISH ? MFN_MODE_POLISH : G.report == OP_BETTER ? MFN_MODE_BETTER : G.report == OP_STRICT ? MFN_MODE_STRICT
+                   : G.report == OP_LOOSE ? MFN_MODE_LOOSE : MFN_MODE_FILTER;
     std::string outPath = std::string(G.outName) + (G.report == OP_POLISH ? ".polish.vcf" : ".filter.vcf");   // merfin-variants.C:324-327 (Q7)
     FILE *O = nullptr, *D = nullptr;
-    // Records are independent: path enumeration and selection run on host threads (one record
-    // per task, like the reference's sweatShop workers), the device call is one at a time, and
-    // the results are written in record order, so the output does not depend on the thread count.
-    std::mutex gpu_mu;
-    mfnv::PathScorer locked_scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, std::vector<uint32_t> &vr,
-                                         std::vector<uint32_t> &va, std::vector<uint8_t> &ok) -> int {
-      std::lock_guard<std::mutex> lk(gpu_mu);
-      return scorer(paths, off, vr, va, ok);
-    };
+    // Records are independent: path enumeration and selection run on host threads (one record per
+    // task, like the reference's sweatShop workers; mfn_variants_process batches the record's probes
+    // through the device), and the results are written in record order, so the output does not
+    // depend on the thread count.
     const size_t nrec = S.nseq();
-    std::vector<std::string> results(nrec), dbgs(nrec);
+    std::vector<char *> results(nrec, nullptr), dbgs(nrec, nullptr);
     std::vector<int> status(nrec, 0);
     unsigned nthreads = G.threads ? G.threads : std::max(1u, std::thread::hardware_concurrency());
     if (G.debug) nthreads = 1;                                   // debug records carry a running id
@@ -334,11 +334,11 @@ int main(int argc, char **argv) {
       auto worker = [&]() {
         for (size_t j; (j = next++) < nrec;) {
           const size_t i = order[j];
-          auto it = vcf.byChr.find(S.ident[i]);
-          if (it == vcf.byChr.end()) continue;
+          if (mfn_vcf_clusters_of(vcf, S.ident[i].c_str()) == 0) continue;
           uint64_t localId = 0;
-          status[i] = mfnv::process_sequence(S.ident[i], S.seq(i), S.length(i), it->second, opt, locked_scorer, results[i],
-                                             G.debug ? &dbgs[i] : nullptr, nthreads == 1 ? varMerId : localId);
+          status[i] = mfn_variants_process(ctx, R, A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb, &km, G.shard, G.nshards,
+                                           &results[i], nullptr, G.debug ? &dbgs[i] : nullptr, nullptr, nthreads == 1 ? &varMerId : &localId);
+          if (status[i] != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
         }
       };
       std::vector<std::thread> th;
@@ -348,19 +348,27 @@ int main(int argc, char **argv) {
     }
     for (size_t i = 0; i < nrec; i++) {
       if (status[i] != 0) return 1;
+      if (!results[i]) continue;
       if (!O) {                                                  // outputVariants: header once, then every record's result
         O = fopen(outPath.c_str(), "w");
         if (!O) { fprintf(stderr, "cannot write '%s'\n", outPath.c_str()); return 1; }
-        for (const std::string &h : vcf.headers) fprintf(O, "%s\n", h.c_str());
+        uint64_t need = 0;
+        mfn_vcf_header(vcf, nullptr, 0, &need);
+        std::vector<char> hdr(need + 1);
+        mfn_vcf_header(vcf, hdr.data(), need, &need);
+        if (G.shard == 0) fwrite(hdr.data(), 1, need, O);        // shards > 0 write records only: `cat` of the shard files is the whole output
       }
-      fputs(results[i].c_str(), O);
-      if (G.debug && !dbgs[i].empty()) {
-        if (!D) { std::string cmd = "gzip -1c > '" + std::string(G.outName) + ".00.debug.gz'"; D = popen(cmd.c_str(), "w"); }
-        if (D) fputs(dbgs[i].c_str(), D);
+      fputs(results[i], O);
+      mfn_text_free(results[i]);
+      if (G.debug && dbgs[i] && dbgs[i][0]) {
+        if (!D) { std::string cmd = "gzip -1c > " + shell_quote(std::string(G.outName) + ".00.debug.gz"); D = popen(cmd.c_str(), "w"); }
+        if (D) fputs(dbgs[i], D);
       }
+      mfn_text_free(dbgs[i]);
     }
     if (O) fclose(O);
     if (D) pclose(D);
+    mfn_vcf_free(vcf);
   }
 
   mfn_table_free(R);

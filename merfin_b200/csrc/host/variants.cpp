@@ -443,75 +443,94 @@ static std::string best_filter(const VarMer &vm, uint32_t k) {                  
 // ---------------------------------------------------------------------------------------------
 int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen, std::vector<PosGT *> &clusters,
                      const Options &opt, const PathScorer &scorer, std::string &result, std::string *debug,
-                     uint64_t &varMerId) {
-  fprintf(stderr, "Processing sequence %s for variants\n", ident.c_str());
-  struct Work { VarMer vm; uint32_t rStart, rEnd; size_t first_path; };
+                     uint64_t &varMerId, size_t cluster_begin, size_t cluster_end, size_t batch_clusters) {
+  if (!getenv("MFN_QUIET")) fprintf(stderr, "Processing sequence %s for variants\n", ident.c_str());
+  cluster_end = std::min(cluster_end, clusters.size());
+  if (cluster_begin >= cluster_end) return 0;
+  if (batch_clusters == 0) batch_clusters = cluster_end - cluster_begin;
+  // `prob` is carried from window to window (and cluster to cluster) like the reference's local: it
+  // is left uninitialised there until the first valid window (Q5).  A range that does not start at
+  // the record's first cluster scores a few clusters before it first (results dropped) to enter
+  // with the value a whole-record run would carry in.
+  double prob = 1.0;
+  const size_t PREROLL = 4;
+  const size_t first = cluster_begin > PREROLL ? cluster_begin - PREROLL : 0;
+
+  struct Work { VarMer vm; uint32_t rStart, rEnd; size_t first_path; bool keep; };
   std::vector<Work> work;
-  work.reserve(clusters.size());
   std::string paths;
-  std::vector<uint64_t> off(1, 0);
-
-  for (PosGT *pg : clusters) {
-    uint32_t rStart = pg->rStart, rEnd = pg->rEnd;
-    const uint32_t K_PADD = opt.k - 1;
-    if (rStart > K_PADD) rStart -= K_PADD; else rStart = 0;
-    if (rEnd < seqLen - K_PADD) rEnd += K_PADD; else rEnd = (uint32_t)seqLen;        // (unsigned, as the reference)
-    std::vector<uint32_t> idxList, lenList;
-    std::vector<std::vector<std::string>> haps;
-    for (GtAllele *g : pg->gts) { idxList.push_back(g->pos - rStart); lenList.push_back(g->refLen); haps.push_back(g->alleles); }
-    if (rEnd < rStart || seqLen < rEnd) {                                            // dnaSeq::copy fails (sequence.C:521)
-      fprintf(stderr, "PANIC : Invalid region specified: %s : %u - %u\n", ident.c_str(), rStart, rEnd);
-      continue;
+  std::vector<uint64_t> off;
+  ScoreOut sc;
+  for (size_t b0 = first; b0 < cluster_end;) {
+    // the pre-roll clusters ride along with the first batch
+    const size_t b1 = std::min(cluster_end, (b0 < cluster_begin ? cluster_begin : b0) + batch_clusters);
+    work.clear();
+    work.reserve(b1 - b0);
+    paths.clear();
+    off.assign(1, 0);
+    for (size_t ci = b0; ci < b1; ci++) {
+      PosGT *pg = clusters[ci];
+      uint32_t rStart = pg->rStart, rEnd = pg->rEnd;
+      const uint32_t K_PADD = opt.k - 1;
+      if (rStart > K_PADD) rStart -= K_PADD; else rStart = 0;
+      if (rEnd < seqLen - K_PADD) rEnd += K_PADD; else rEnd = (uint32_t)seqLen;        // (unsigned, as the reference)
+      std::vector<uint32_t> idxList, lenList;
+      std::vector<std::vector<std::string>> haps;
+      for (GtAllele *g : pg->gts) { idxList.push_back(g->pos - rStart); lenList.push_back(g->refLen); haps.push_back(g->alleles); }
+      const bool keep = ci >= cluster_begin;
+      if (rEnd < rStart || seqLen < rEnd) {                                            // dnaSeq::copy fails (sequence.C:521)
+        if (keep) fprintf(stderr, "PANIC : Invalid region specified: %s : %u - %u\n", ident.c_str(), rStart, rEnd);
+        continue;
+      }
+      if (idxList.size() > opt.comb) {
+        if (keep) fprintf(stderr, "PANIC : Combination %s:%u-%u has too many variants ( found %lu > %u ) to evaluate. Consider filtering the vcf upfront. Skipping...\n",
+                          ident.c_str(), rStart, rEnd, (unsigned long)pg->gts.size(), opt.comb);
+        continue;
+      }
+      work.emplace_back();
+      Work &w = work.back();
+      w.vm.posGt = pg; w.rStart = rStart; w.rEnd = rEnd; w.first_path = off.size() - 1; w.keep = keep;
+      std::vector<int> path;
+      traverse(0, idxList, lenList, haps, std::string(seq + rStart, rEnd - rStart), path, w.vm);
+      for (const std::string &s : w.vm.seqs) { paths += s; off.push_back(paths.size()); }
     }
-    if (idxList.size() > opt.comb) {
-      fprintf(stderr, "PANIC : Combination %s:%u-%u has too many variants ( found %lu > %u ) to evaluate. Consider filtering the vcf upfront. Skipping...\n",
-              ident.c_str(), rStart, rEnd, (unsigned long)pg->gts.size(), opt.comb);
-      continue;
+
+    if (!paths.empty() || off.size() > 1) {
+      int st = scorer(paths, off, sc);
+      if (st != 0) return st;
     }
-    work.emplace_back();
-    Work &w = work.back();
-    w.vm.posGt = pg; w.rStart = rStart; w.rEnd = rEnd; w.first_path = off.size() - 1;
-    std::vector<int> path;
-    traverse(0, idxList, lenList, haps, std::string(seq + rStart, rEnd - rStart), path, w.vm);
-    for (const std::string &s : w.vm.seqs) { paths += s; off.push_back(paths.size()); }
-  }
 
-  std::vector<uint32_t> vr, va;
-  std::vector<uint8_t> ok;
-  if (!paths.empty() || off.size() > 1) {
-    int st = scorer(paths, off, vr, va, ok);
-    if (st != 0) return st;
-  }
-
-  double prob = 1.0;        // the reference leaves it uninitialised until the first valid window (Q5)
-  for (Work &w : work) {
-    VarMer &vm = w.vm;
-    score(vm, opt, vr.data(), va.data(), ok.data(), off, w.first_path, prob);
-    if (debug) {
-      char buf[512];
-      for (size_t idx = 0; idx < vm.seqs.size(); idx++) {
-        snprintf(buf, sizeof buf, "%lu\t%s:%u-%u\t", (unsigned long)varMerId++, ident.c_str(), w.rStart, w.rEnd);
-        *debug += buf; *debug += vm.seqs[idx];
-        snprintf(buf, sizeof buf, "\t%u\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\t", vm.numMs[idx], vm.minAbsK((int)idx), vm.maxAbsK((int)idx),
-                 vm.medAbsK((int)idx), vm.avgAbsK((int)idx), vm.totdK((int)idx));
-        *debug += buf;
-        for (size_t i = 0; i < vm.gtPaths[idx].size(); i++) {
-          int alt = vm.gtPaths[idx][i];
-          if (alt > 0) {
-            const GtAllele *g = vm.posGt->gts[i];
-            *debug += ident + " " + std::to_string(g->pos + 1) + " . " + g->alleles[0] + " " + g->alleles[alt] + " . PASS . GT 1/1  ";
+    for (Work &w : work) {
+      VarMer &vm = w.vm;
+      score(vm, opt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
+      if (!w.keep) continue;
+      if (debug) {
+        char buf[512];
+        for (size_t idx = 0; idx < vm.seqs.size(); idx++) {
+          snprintf(buf, sizeof buf, "%lu\t%s:%u-%u\t", (unsigned long)varMerId++, ident.c_str(), w.rStart, w.rEnd);
+          *debug += buf; *debug += vm.seqs[idx];
+          snprintf(buf, sizeof buf, "\t%u\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\t", vm.numMs[idx], vm.minAbsK((int)idx), vm.maxAbsK((int)idx),
+                   vm.medAbsK((int)idx), vm.avgAbsK((int)idx), vm.totdK((int)idx));
+          *debug += buf;
+          for (size_t i = 0; i < vm.gtPaths[idx].size(); i++) {
+            int alt = vm.gtPaths[idx][i];
+            if (alt > 0) {
+              const GtAllele *g = vm.posGt->gts[i];
+              *debug += ident + " " + std::to_string(g->pos + 1) + " . " + g->alleles[0] + " " + g->alleles[alt] + " . PASS . GT 1/1  ";
+            }
           }
+          *debug += "\n";
         }
-        *debug += "\n";
+      }
+      switch (opt.mode) {
+        case POLISH: result += best_variant(vm, opt.k); break;
+        case BETTER: result += better_or_strict(vm); break;
+        case STRICT: result += better_or_strict(vm); break;
+        case LOOSE:  result += loose(vm); break;
+        default:     result += best_filter(vm, opt.k); break;
       }
     }
-    switch (opt.mode) {
-      case POLISH: result += best_variant(vm, opt.k); break;
-      case BETTER: result += better_or_strict(vm); break;
-      case STRICT: result += better_or_strict(vm); break;
-      case LOOSE:  result += loose(vm); break;
-      default:     result += best_filter(vm, opt.k); break;
-    }
+    b0 = b1;
   }
   return 0;
 }

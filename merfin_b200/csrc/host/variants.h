@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -54,11 +55,17 @@ struct VcfFile {
   void mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit);   // vcf.C:156-246
 };
 
-// paths: concatenated path strings + offsets (as mfn_score_paths takes them); the scorer fills one
-// (v_read, v_asm, valid) per base position (window start) of every path.
-typedef std::function<int(const std::string &paths, const std::vector<uint64_t> &off,
-                          std::vector<uint32_t> &v_read, std::vector<uint32_t> &v_asm,
-                          std::vector<uint8_t> &valid)> PathScorer;
+// paths: concatenated path strings + offsets (as mfn_score_paths takes them); the scorer leaves one
+// (v_read, v_asm, valid) per base position (window start) of every path in `out`: either in out's own
+// vectors or in memory it owns itself (pinned buffers of the GPU scorer), kept alive through out.hold.
+struct ScoreOut {
+  const uint32_t *v_read = nullptr, *v_asm = nullptr;
+  const uint8_t *valid = nullptr;
+  std::vector<uint32_t> vr_store, va_store;
+  std::vector<uint8_t> ok_store;
+  std::shared_ptr<void> hold;
+};
+typedef std::function<int(const std::string &paths, const std::vector<uint64_t> &off, ScoreOut &out)> PathScorer;
 
 struct Options {
   uint32_t k = 0, comb = 15;
@@ -70,8 +77,10 @@ struct Options {
 // All clusters of one sequence record: returns the VCF text merfin appends to its output for this
 // record (processVariants' s->result) and, if opt.debug, the debug lines.  `varMerId` numbers
 // the debug lines across records.
+// Clusters [cluster_begin, cluster_end) only (a shard of the record; the outputs of consecutive ranges
+// concatenate to the whole record's), scored in batches of batch_clusters (0: all at once).
 int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen, std::vector<PosGT *> &clusters,
                      const Options &opt, const PathScorer &scorer, std::string &result, std::string *debug,
-                     uint64_t &varMerId);
+                     uint64_t &varMerId, size_t cluster_begin = 0, size_t cluster_end = (size_t)-1, size_t batch_clusters = 0);
 
 }  // namespace mfnv

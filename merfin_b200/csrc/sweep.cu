@@ -97,15 +97,21 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const 
   }
   // workspace from the stream-ordered pool: reused across steps without cudaMalloc cost
   const size_t ebytes = (size_t)P.nbins * P.cap * 8;
-  const size_t cwords = 2 * (size_t)P.nbins_pad + 4 + 4096 + 8;      // bins, side-list count, pass counters (one per scatter pass), phase cycles
+  {
+    const char *es = getenv("MFN_BIN_STRIDE");
+    P.cstride = es ? (uint32_t)atoi(es) : 1u;
+    if (P.cstride < 1 || P.cstride > 64) P.cstride = 1;
+  }
+  const size_t cbins = (size_t)P.nbins_pad * P.cstride;               // counters, then bin_valid
+  const size_t cwords = cbins + (size_t)P.nbins_pad + 4 + 4096 + 8;      // bins, side-list count, pass counters (one per scatter pass), phase cycles
   cudaError_t e = cudaMallocAsync(&P.entries, ebytes, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&w->ctl, cwords * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&P.over_lt, P.over_cap * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&P.over_rec, P.over_cap * 4, ctx->stream);
   if (e != cudaSuccess) { mfn_set_error("sweep workspace (%zu bytes): %s", ebytes, cudaGetErrorString(e)); delete w; return MFN_ERR_NOMEM; }
-  P.bin_count = w->ctl; P.bin_valid = w->ctl + P.nbins_pad; P.over_n = w->ctl + 2 * P.nbins_pad;
-  w->counters = w->ctl + 2 * P.nbins_pad + 1;
-  P.prof = w->ctl + 2 * P.nbins_pad + 4 + 4096;
+  P.bin_count = w->ctl; P.bin_valid = w->ctl + cbins; P.over_n = w->ctl + cbins + P.nbins_pad;
+  w->counters = w->ctl + cbins + P.nbins_pad + 1;
+  P.prof = w->ctl + cbins + P.nbins_pad + 4 + 4096;
   MFN_CUDA(cudaMemsetAsync(w->ctl, 0, cwords * 8, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(P.bin_valid, 0xff, (size_t)P.nbins_pad * 8, ctx->stream));
   *out = w;

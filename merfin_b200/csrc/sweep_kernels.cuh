@@ -85,7 +85,8 @@ struct SweepParams {
   uint32_t lowbits;                          // width of the low part: 32..34 (narrow) or lbits + tbits (wide)
   unsigned long long *entries;               // bin b: entries[b * cap .. b * cap + n_b)
   uint64_t cap;
-  unsigned long long *bin_count;             // [nbins_pad] reserved entries (may exceed cap)
+  unsigned long long *bin_count;             // [nbins_pad * cstride] reserved entries of bin b at [b * cstride] (may exceed cap)
+  uint32_t cstride;                          // words between two bins' counters (spreads the reservation atomics over L2 lines)
   unsigned long long *bin_valid;             // [nbins_pad] first reservation that did not fit (~0: none)
   unsigned long long *over_lt;               // windows that found no room in their bin: h = line * D + tag ...
   uint32_t *over_rec;                        //   ... and record id (bit 31: counts twice)
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(SC_THREADS, WIDE ? 1 : SC_CTAS_PER_SM) k_sweep
 #pragma unroll
       for (uint32_t i = 0; i < BPT; i++) {
         got[i] = 0;
-        if (cnt[i]) got[i] = atomicAdd(&P.bin_count[b0 + i], (unsigned long long)cnt[i]);
+        if (cnt[i]) got[i] = atomicAdd(&P.bin_count[(size_t)(b0 + i) * P.cstride], (unsigned long long)cnt[i]);
       }
       uint32_t incl = sum;
       for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) break;
     const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
-    const uint64_t cnt = min(min(P.bin_count[bin], P.bin_valid[bin]), (unsigned long long)P.cap);
+    const uint64_t cnt = min(min(P.bin_count[bin * P.cstride], P.bin_valid[bin]), (unsigned long long)P.cap);
     if (s * SW_SLICE >= cnt) continue;
     const unsigned long long *src = P.entries + bin * P.cap + s * SW_SLICE;
     const uint32_t n = (uint32_t)min((uint64_t)SW_SLICE, cnt - s * SW_SLICE);

@@ -53,11 +53,11 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   __shared__ __align__(16) uint32_t s_warp[S3_THREADS / 32];
   __shared__ unsigned long long s_chunk[2];
   __shared__ uint32_t s_total, s_over;
-  // the chunk's 2-bit words and validity bits (incl. a 64-base halo), staged by TMA.  ONE buffer: the
-  // next chunk's copy is issued after barrier (1), when every thread has sliced its windows out of it
-  __shared__ __align__(16) unsigned long long s_seq[S3_SEQ_WORDS];
-  __shared__ __align__(16) unsigned long long s_ok[S3_OK_WORDS];
-  __shared__ __align__(8) unsigned long long s_bar;
+  // the chunk's 2-bit words and validity bits (incl. a 64-base halo), staged by TMA one chunk ahead
+  // (with a single buffer the copy could only start after barrier (1) and its latency showed: +4 %)
+  __shared__ __align__(16) unsigned long long s_seq[2][S3_SEQ_WORDS];
+  __shared__ __align__(16) unsigned long long s_ok[2][S3_OK_WORDS];
+  __shared__ __align__(8) unsigned long long s_bar[2];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t s_cnt_sa = smem_u32(s_cnt);
@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
     const uint64_t w2 = t0 * (MFN_TILE / 32), wo = t0 * (MFN_TILE / 64);
     const uint32_t n2 = (uint32_t)min((uint64_t)S3_SEQ_WORDS, P.seq_words - w2) & ~1u;
     const uint32_t no = (uint32_t)min((uint64_t)S3_OK_WORDS, P.ok_words - wo) & ~1u;
-    mbar_expect_tx(&s_bar, (n2 + no) * 8);
-    tma_load_1d(s_seq, P.seq2 + w2, n2 * 8, &s_bar);
-    tma_load_1d(s_ok, P.ok + wo, no * 8, &s_bar);
+    mbar_expect_tx(&s_bar[buf], (n2 + no) * 8);
+    tma_load_1d(s_seq[buf], P.seq2 + w2, n2 * 8, &s_bar[buf]);
+    tma_load_1d(s_ok[buf], P.ok + wo, no * 8, &s_bar[buf]);
   };
   // side list: a window that cannot go to its bin (h = line * D + tag)
   auto to_side_list = [&](uint64_t h, uint32_t rec_flag) {
@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   unsigned long long pre = 0;
   for (uint32_t i = tid; i < P.nbins_pad; i += S3_THREADS) s_cnt[i] = 0;
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage(atomicAdd(P.counter, 1ull), 0);
     pre = atomicAdd(P.counter, 1ull);
@@ -128,7 +129,9 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
     const uint32_t r0 = cur_rec;
     const uint64_t r0_end = cur_end;
     const bool one_record = (tile0 + S3_TILES) * MFN_TILE <= r0_end;
-    mbar_wait(&s_bar, it & 1);
+    // the other staging buffer was last read before barrier (1) of the previous round
+    if (tid == 0) { stage(pre, buf ^ 1); pre = atomicAdd(P.counter, 1ull); }
+    mbar_wait(&s_bar[buf], (it >> 1) & 1);
     SW_PROF_MARK(0);
 
     // ---- hash this thread's 16 consecutive windows; rank them inside their bins ------------
@@ -140,11 +143,11 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
       uint64_t lo = 0, hi = 0, okb = 0;
       if (tile < P.tile_end) {
         const uint32_t w = j0 >> 5;
-        const uint64_t a = s_seq[w], b = s_seq[w + 1];
+        const uint64_t a = s_seq[buf][w], b = s_seq[buf][w + 1];
         lo = (j0 & 16) ? ((a >> 32) | (b << 32)) : a;                     // j0 is a multiple of 16: the shift is 0 or 32 bits
         hi = (j0 & 16) ? (b >> 32) : b;
         const uint32_t wo = j0 >> 6, so = j0 & 63;
-        const uint64_t c = s_ok[wo], d = s_ok[wo + 1];
+        const uint64_t c = s_ok[buf][wo], d = s_ok[buf][wo + 1];
         okb = so ? ((c >> so) | (d << (64 - so))) : c;
       }
       const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi;
@@ -235,7 +238,6 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
     SW_PROF_MARK(1);
     __syncthreads();                                                      // (1) the counts are complete
     SW_PROF_MARK(2);
-    if (tid == 0) { stage(pre, buf ^ 1); pre = atomicAdd(P.counter, 1ull); }
 
     // ---- exclusive scan of the bin counts; reserve space in the global bins ----------------
     const uint32_t b0 = tid * bpt;
@@ -246,8 +248,8 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
       s_cnt[b0] = 0;
       if (bpt > 1) { cnt1 = s_cnt[b0 + 1]; s_cnt[b0 + 1] = 0; }
       // the reservations are in flight until the end of the sort
-      if (cnt0) got0 = atomicAdd(&P.bin_count[b0], (unsigned long long)cnt0);
-      if (cnt1) got1 = atomicAdd(&P.bin_count[b0 + 1], (unsigned long long)cnt1);
+      if (cnt0) got0 = atomicAdd(&P.bin_count[(size_t)b0 * P.cstride], (unsigned long long)cnt0);
+      if (cnt1) got1 = atomicAdd(&P.bin_count[(size_t)(b0 + 1) * P.cstride], (unsigned long long)cnt1);
       const uint32_t sum = cnt0 + cnt1;
       uint32_t incl = sum;
 #pragma unroll

@@ -74,6 +74,13 @@ class HistSummary(C.Structure):
                 ("n_undr", C.c_uint32), ("n_over", C.c_uint32)]
 
 
+class VcfInfo(C.Structure):
+    _fields_ = [("headers", C.c_uint64), ("records", C.c_uint64), ("contigs", C.c_uint64), ("contig_ids", C.c_uint64),
+                ("excluded", C.c_uint64), ("clusters", C.c_uint64)]
+
+
+MFN_MODE = {"filter": 4, "polish": 5, "better": 6, "strict": 7, "loose": 8}
+
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
 
@@ -130,6 +137,16 @@ SIGNATURES = {
     "mfn_dump_resident": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mfn_dump": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
     "mfn_score_paths": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "mfn_vcf_load": (C.c_int, [C.c_char_p, _PP]),
+    "mfn_vcf_cluster": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int]),
+    "mfn_vcf_info": (C.c_int, [_P, C.POINTER(VcfInfo)]),
+    "mfn_vcf_header": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_vcf_clusters_of": (C.c_uint64, [_P, C.c_char_p]),
+    "mfn_vcf_free": (None, [_P]),
+    "mfn_variants_process": (C.c_int, [_P, _P, _P, _P, C.c_char_p, _P, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(KModel),
+                                       C.c_uint32, C.c_uint32, _PP, C.POINTER(C.c_uint64), _PP, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64)]),
+    "mfn_text_free": (None, [_P]),
     "mfn_completeness": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_completeness_shard": (C.c_int, [_P, C.c_char_p, _P, C.c_uint32, C.c_uint32, _P]),
     "mfn_hist_report": (C.c_int, [_P, C.c_uint64, C.POINTER(KModel), C.c_uint32, _P, _P, C.c_uint32,

@@ -78,6 +78,59 @@ def test_cli_variant_modes(golden_dir, tmp_path, mode):
         assert gzip.open(tmp_path / "out.00.debug.gz", "rt").read() == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
 
 
+def test_cli_variant_shards_concatenate(golden_dir, tmp_path):
+    """-shard i/n scores cluster range i of n of every record (the multi-GPU sharding of -polish / -filter):
+    the shard files, concatenated per record, hold exactly the lines of the unsharded output."""
+    d = os.path.join(golden_dir, "g1_k21")
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", "8", "-vcf", os.path.join(d, "calls.vcf")]
+    for mode, produced in (("polish", "polish"), ("filter", "filter")):
+        want = open(os.path.join(d, f"ref.{mode}.vcf")).read().splitlines()
+        got = []
+        for i in range(3):
+            _run(base + ["-" + mode, "-output", f"s{i}", "-shard", f"{i}/3"], str(tmp_path))
+            got += open(tmp_path / f"s{i}.{produced}.vcf").read().splitlines()
+        hdr = [l for l in want if l.startswith("#")]
+        assert [l for l in got if l.startswith("#")] == hdr                  # the header comes from shard 0 only
+        # records of a contig are written shard by shard: same multiset, and the same order inside every contig
+        body_w, body_g = [l for l in want if not l.startswith("#")], [l for l in got if not l.startswith("#")]
+        assert sorted(body_w) == sorted(body_g)
+        for c in {l.split("\t")[0] for l in body_w}:
+            assert [l for l in body_w if l.split("\t")[0] == c] == [l for l in body_g if l.split("\t")[0] == c]
+
+
+def test_variants_abi_shards_and_threads(golden_dir):
+    """mfn_variants_process through the ctypes stub: every record in 1 piece and in 4 shards, called from
+    several host threads at once (the device part of mfn_score_paths is serialised inside the library)."""
+    import threading
+    import oracle_lib as O
+    from merfin_b200 import api
+    d = os.path.join(golden_dir, "g1_k21")
+    recs = O.read_fasta(os.path.join(d, "asm.fa"))
+    ctx = api.Context(0)
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    R.fuse(A)
+    km = api.KModel(8.0)
+    vcf = api.Vcf(os.path.join(d, "calls.vcf"))
+    vcf.cluster(21)
+    assert vcf.info.records > 0 and vcf.info.clusters > 0
+    want = open(os.path.join(d, "ref.polish.vcf"), "rb").read()
+    whole = vcf.header() + b"".join(api.variants_process(ctx, R, A, vcf, n, b, "polish", km) for n, b in recs)
+    assert whole == want
+    out = {}
+
+    def work(i, n, b):
+        out[i] = b"".join(api.variants_process(ctx, R, A, vcf, n, b, "polish", km, shard=s, nshards=4) for s in range(4))
+    th = [threading.Thread(target=work, args=(i, n, b)) for i, (n, b) in enumerate(recs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert vcf.header() + b"".join(out[i] for i in range(len(recs))) == want
+    vcf.close(); R.close(); A.close(); ctx.close()
+
+
 def test_cli_usage_errors(tmp_path):
     p = subprocess.run([MERFIN, "-hist"], capture_output=True, text=True)
     assert p.returncode == 1

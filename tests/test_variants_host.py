@@ -52,6 +52,18 @@ def test_polish_debug_log_matches_reference(harness, golden_dir, tmp_path):
     assert got == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
 
 
+@pytest.mark.parametrize("extra", [("--shards", "3"), ("--batch", "2"), ("--shards", "4", "--batch", "1")])
+def test_cluster_ranges_and_batches_concatenate(harness, golden_dir, tmp_path, extra):
+    """A record processed as consecutive cluster ranges (the multi-GPU sharding of -polish) and in small
+    scorer batches gives the same VCF and the same per-path debug records as in one piece."""
+    d = os.path.join(golden_dir, "g1_k21")
+    for mode in ("polish", "filter", "loose"):
+        assert _run(harness, d, mode, 8, *extra) == open(os.path.join(d, f"ref.{mode}.vcf")).read()
+    assert _run(harness, d, "polish", 8, os.path.join(d, "prob.csv"), *extra) == open(os.path.join(d, "ref.probpolish.vcf")).read()
+    _run(harness, d, "polish", 8, "--debug", *extra, cwd=str(tmp_path))
+    assert open(tmp_path / "harness.debug").read() == gzip.open(os.path.join(d, "ref.polish.debug.gz"), "rt").read()
+
+
 def test_threaded_vcf_parse_keeps_file_order(harness, golden_dir, monkeypatch):
     """The VCF is parsed on several host threads; clustering starts from the file order (the
     reference's sort is not stable), so the output must not depend on the thread count."""

@@ -2,7 +2,7 @@
 // the CPU oracle as the path scorer, so the host-side control logic (VCF parsing, clustering,
 // path enumeration, selectors) can be checked against the reference's golden VCFs without a GPU.
 // Test infrastructure only.
-//   variant_harness <asm.fa> <reads.meryl> <asm.meryl> <calls.vcf> <mode> <peak> [prob.csv] [--debug] [--comb N] [--nosplit]
+//   variant_harness <asm.fa> <reads.meryl> <asm.meryl> <calls.vcf> <mode> <peak> [prob.csv] [--debug] [--comb N] [--nosplit] [--shards N] [--batch B]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,10 +27,13 @@ int main(int argc, char **argv) {
   std::vector<uint32_t> pk; std::vector<double> pp;
   bool debug = false, nosplit = false;
   uint32_t comb = 15;
+  size_t shards = 1, batch = 0;      // --shards N: every record in N consecutive cluster ranges; --batch B: B clusters per scorer call
   for (int a = 7; a < argc; a++) {
     if (!strcmp(argv[a], "--debug")) { debug = true; continue; }
     if (!strcmp(argv[a], "--nosplit")) { nosplit = true; continue; }
     if (!strcmp(argv[a], "--comb") && a + 1 < argc) { comb = (uint32_t)atoi(argv[++a]); continue; }
+    if (!strcmp(argv[a], "--shards") && a + 1 < argc) { shards = (size_t)atoi(argv[++a]); continue; }
+    if (!strcmp(argv[a], "--batch") && a + 1 < argc) { batch = (size_t)atoi(argv[++a]); continue; }
     FILE *F = fopen(argv[a], "r"); char line[256];
     while (F && fgets(line, sizeof line, F)) {
       unsigned k; double p; char extra;
@@ -43,11 +46,11 @@ int main(int argc, char **argv) {
   opt.km = mfn_kmodel{atof(argv[6]), (uint32_t)pk.size(), pk.data(), pp.data()};
   opt.mode = mode == "polish" ? mfnv::POLISH : mode == "better" ? mfnv::BETTER : mode == "strict" ? mfnv::STRICT : mode == "loose" ? mfnv::LOOSE : mfnv::FILTER;
   vcf.mergeChrPosGT(opt.k, opt.comb, nosplit);
-  mfnv::PathScorer scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, std::vector<uint32_t> &vr,
-                                std::vector<uint32_t> &va, std::vector<uint8_t> &ok) -> int {
-    vr.assign(paths.size() + 1, 0); va.assign(paths.size() + 1, 0); ok.assign(paths.size() + 1, 0);
+  mfnv::PathScorer scorer = [&](const std::string &paths, const std::vector<uint64_t> &off, mfnv::ScoreOut &out) -> int {
+    out.vr_store.assign(paths.size() + 1, 0); out.va_store.assign(paths.size() + 1, 0); out.ok_store.assign(paths.size() + 1, 0);
     for (size_t i = 0; i + 1 < off.size(); i++)
-      o_pairs(R, A, paths.data() + off[i], off[i + 1] - off[i], vr.data() + off[i], va.data() + off[i], ok.data() + off[i]);
+      o_pairs(R, A, paths.data() + off[i], off[i + 1] - off[i], out.vr_store.data() + off[i], out.va_store.data() + off[i], out.ok_store.data() + off[i]);
+    out.v_read = out.vr_store.data(); out.v_asm = out.va_store.data(); out.valid = out.ok_store.data();
     return 0;
   };
   for (const std::string &h : vcf.headers) printf("%s\n", h.c_str());
@@ -57,7 +60,10 @@ int main(int argc, char **argv) {
     auto it = vcf.byChr.find(S.ident[i]);
     if (it == vcf.byChr.end()) continue;
     std::string result, dbg;
-    if (mfnv::process_sequence(S.ident[i], S.seq(i), S.length(i), it->second, opt, scorer, result, debug ? &dbg : nullptr, id)) return 1;
+    const size_t nc = it->second.size();
+    for (size_t sh = 0; sh < shards; sh++)
+      if (mfnv::process_sequence(S.ident[i], S.seq(i), S.length(i), it->second, opt, scorer, result, debug ? &dbg : nullptr, id,
+                                 nc * sh / shards, nc * (sh + 1) / shards, batch)) return 1;
     fputs(result.c_str(), stdout);
     dbg_all += dbg;
   }
