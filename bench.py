@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sample-mbp", type=float, default=24.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="hist", choices=["hist", "polish"],
+                    help="hist: the headline (BASELINE configs[2]); polish: variants/s of -polish over a synthetic VCF (configs[3], bench_modes.py)")
+    ap.add_argument("--variants", type=int, default=0, help="--mode polish: VCF records (default 5 000 000 per 3 Gbp)")
     ap.add_argument("--emulate-shards", type=int, default=0,
                     help="development aid, 1 GPU: time shard 0 of N exactly as rank 0 of an N-GPU run would (no collective); "
                          "the line is marked emulated and is not a bench value")
@@ -296,6 +299,25 @@ def main():
     if sworld != world:
         config["emulated"] = f"shard 0 of {sworld} on one GPU, no collective: development figure, not a bench value"
 
+    if args.impl == "reference" and args.mode == "polish":
+        import bench_modes
+        names = [f"rec{i + 1}" for i in range(len(lens))]
+        nvar = int(args.variants if args.variants else round(5_000_000 * total / 3.0e9))
+        cb = bench_modes.polish_cpu_baseline(args, sys.modules[__name__], ctx, api, asm_np, lens, names, nvar, total,
+                                             repeats=args.warmup + args.steps)
+        times = cb["polish_seconds"][args.warmup:]
+        nsample = cb["value"] * min(cb["polish_seconds"])
+        v = nsample * len(times) / sum(times)
+        cb["value"] = v
+        config = dict(config, full_workload=config["workload"].replace("-hist", "-polish"),
+                      workload=f"SAMPLE of the -polish workload: {cb['sample']}; each step = one reference run over the sample",
+                      parallelism=f"{cb['cores']} host threads (reference -threads), no GPU", l2_policy="n/a (CPU)")
+        print(json.dumps({"impl": "reference", "metric": "variants/sec (-polish k=21)", "value": v, "unit": "variants/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
     if args.impl == "reference":
         cb, stotal = cpu_baseline(ctx, asm_np, lens, args.sample_mbp, repeats=args.warmup + args.steps)
         times = cb["hist_seconds"][args.warmup:]
@@ -331,7 +353,7 @@ def main():
     R = api.MerylExactLookup.synth_reads(ctx, A, COV_PER_COPY, int(total * 0.67), 7)
     if not os.environ.get("MFN_NO_JOINT"):
         R.fuse(A)                                # one 128-byte line per window instead of two
-    restricted = not os.environ.get("MFN_NO_JOINT") and os.environ.get("MFN_BENCH_RESTRICT", "1") != "0"
+    restricted = not os.environ.get("MFN_NO_JOINT") and os.environ.get("MFN_BENCH_RESTRICT", "1") != "0" and args.mode == "hist"
     if restricted:
         # the table the range-partitioned scan streams: only the k-mers of this rank's shard of the assembly
         R.restrict(A, seq, srank, sworld)
@@ -352,6 +374,15 @@ def main():
                         "asm_GB": round(ai.device_bytes / 1e9, 2), "read_GB": round(ri.device_bytes / 1e9, 2),
                         "read_level2_frac": round(ri.n_level2 / max(1, ri.n_kmers), 4),
                         "slot_bits": int(ri.slot_bits), "setup_s": round(setup_s, 1)}
+
+    if args.mode == "polish":
+        import bench_modes
+        rc = bench_modes.polish(args, sys.modules[__name__], ctx, api, lib, torch, dist, rank, world, local, dev, asm_np, lens, off,
+                                R, A, config, setup_s)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return rc
 
     acc = api.Accum(ctx, len(lens))
     ptr, nwords = acc.device_buffer()

@@ -293,12 +293,16 @@ static int dump_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_
     cudaGetLastError();
     st = MFN_ERR_NOMEM;
   }
+  // (mfn_ctx_time_passes: "scatter" = the scan kernel incl. its output memsets, "probe" = the D2H of the result)
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   if (st == MFN_OK) st = mfn_dump_resident(ctx, reads, asm_, seq, dr, da, dv);
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   if (st == MFN_OK) {
     cudaMemcpyAsync(v_read, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(v_asm, da, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(valid, dv, n, cudaMemcpyDeviceToHost, ctx->stream);
   }
+  if (ctx->time_passes) mfn_ctx_mark(ctx);
   if (dr) cudaFreeAsync(dr, ctx->stream);
   if (da) cudaFreeAsync(da, ctx->stream);
   if (dv) cudaFreeAsync(dv, ctx->stream);

@@ -181,11 +181,13 @@ void VcfFile::mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit) {
       merged++;
       dead.push_back(in[ii]);
     }
-    fprintf(stderr, "%s : Reduced %lu variants down to %lu combinations for evaluation:\n", kv.first.c_str(),
-            (unsigned long)in.size(), (unsigned long)out.size());
-    if (removed > 0) fprintf(stderr, "%s :   Removed %u empty alleles.\n", kv.first.c_str(), removed);
-    if (nsplit > 0) fprintf(stderr, "%s :   Split   %u complicated combinations.\n", kv.first.c_str(), nsplit);
-    if (merged > 0) fprintf(stderr, "%s :   Merged  %u variants into combinations.\n", kv.first.c_str(), merged);
+    if (!getenv("MFN_QUIET")) {
+      fprintf(stderr, "%s : Reduced %lu variants down to %lu combinations for evaluation:\n", kv.first.c_str(),
+              (unsigned long)in.size(), (unsigned long)out.size());
+      if (removed > 0) fprintf(stderr, "%s :   Removed %u empty alleles.\n", kv.first.c_str(), removed);
+      if (nsplit > 0) fprintf(stderr, "%s :   Split   %u complicated combinations.\n", kv.first.c_str(), nsplit);
+      if (merged > 0) fprintf(stderr, "%s :   Merged  %u variants into combinations.\n", kv.first.c_str(), merged);
+    }
     for (auto *d : dead) delete d;
     in.swap(out);
   }

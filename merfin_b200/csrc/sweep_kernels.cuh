@@ -509,6 +509,19 @@ __device__ __forceinline__ void sweep_slow(const SweepParams &P, uint32_t *s_his
   else sparse_add(P.sparse, P.acc, vr, va, 1ull);
 }
 
+// a 32-byte sector of the table slice the grid is working on.  SW_TABLE_EVICT_LAST (experiment): ask the
+// L2 to keep these lines over the entry stream (which is already loaded evict_first)
+__device__ __forceinline__ void sweep_load_sector(const char *p, Bucket &b) {
+#ifdef SW_TABLE_EVICT_LAST
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+               : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]),
+                 "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+               : "l"(p));
+}
+
 // 32-byte home sector -> slot payload (both value fields), or ~0 when the tag is not in it.
 // A stored slot is  tag << vb | values  with values != 0, so  slot - (tag << vb) - 1 < 2^vb - 1
 // exactly for the matching slot; the minimum over the 8 slots finds it (VIADDMNMX / VIMNMX3).
@@ -630,9 +643,9 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
             const char *linep = slice + (uint64_t)lib * 128;
             const uint32_t home = lw & 3u;
             Bucket b1, b2, b3;
-            mfn_load_bucket(linep, (home + 1) & 3u, b1);
-            mfn_load_bucket(linep, (home + 2) & 3u, b2);
-            mfn_load_bucket(linep, (home + 3) & 3u, b3);
+            sweep_load_sector(linep + ((home + 1) & 3u) * 32, b1);
+            sweep_load_sector(linep + ((home + 2) & 3u) * 32, b2);
+            sweep_load_sector(linep + ((home + 3) & 3u) * 32, b3);
             const uint32_t nwant = ~((lw << vb) & P.pr_wmask);
             const uint32_t pay = min(sweep_match32(b1, nwant, P.pr_lim), min(sweep_match32(b2, nwant, P.pr_lim), sweep_match32(b3, nwant, P.pr_lim)));
             const uint32_t vr = pay >> abits, va = pay & amax;
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
       if (bt + 1 < nfull) load_entries(bt + 1, enext);         // in flight while this batch probes
       Bucket b[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) mfn_load_bucket(sector_of(e[u]), 0, b[u]);
+      for (int u = 0; u < 4; u++) sweep_load_sector(sector_of(e[u]), b[u]);
 #pragma unroll
       for (int u = 0; u < 4; u++) settle(e[u], b[u]);
       drain(32u);
@@ -665,7 +678,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe(const __grid_cons
     for (uint32_t i = (nfull << 7) + lane; i < n; i += 32) {
       const unsigned long long e = src[i];
       Bucket b;
-      mfn_load_bucket(sector_of(e), 0, b);
+      sweep_load_sector(sector_of(e), b);
       settle(e, b);
     }
     drain(1u);                                                 // the queue is emptied before the bin changes

@@ -127,3 +127,41 @@ def test_adversarial_vcf_against_reference(harness, tmp_path, seed, k, flags):
     res = fuzz_variants.run(seed, k=k, flags=flags, nvar=60, L=4000, work=str(tmp_path))
     assert all(v.startswith("ok ") for v in res.values()), res
     assert sum(int(v.split()[1]) for v in res.values()) > 200
+
+
+@pytest.mark.skipif(not (os.path.exists(MERFIN) and os.path.exists(MERYL)), reason="oracle/_ref not built (reference sources absent)")
+def test_bench_vcf_generator_against_reference(harness, tmp_path):
+    """The synthetic VCF of `bench.py --mode polish` (bench_modes.synth_vcf: SNVs, 1-4 bp insertions and deletions,
+    1/2 genotypes, neighbours within 15 bp) through the reference and through the product's front-end: same
+    .polish.vcf / .filter.vcf, in one piece and as 3 cluster ranges per record."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench_modes
+    from merfin_b200 import synth
+    d = str(tmp_path)
+    k = 21
+    truth = synth.make_assembly(120000, 3, 99, n_run=15, lower_run=0, dup_len=1500)
+    asm, _ = synth.plant_errors(truth, 60, 5, false_per_rec=0)
+    synth.write_fasta(os.path.join(d, "asm.fa"), asm, width=80)
+    names = [n for n, _ in asm]
+    lens = [len(b) for _, b in asm]
+    asm_np = np.concatenate([np.asarray(b, dtype=np.uint8) for _, b in asm])
+    n = bench_modes.synth_vcf(os.path.join(d, "calls.vcf"), asm_np, lens, names, 1500, seed=3)
+    assert n > 1000
+    reads = synth.simulate_reads(truth, 12, 120, 0.005, 17)
+    synth.write_fasta(os.path.join(d, "reads.fa"), reads, prefix="r")
+    for fa, db in (("reads.fa", "reads.meryl"), ("asm.fa", "asm.meryl")):
+        p = subprocess.run([MERYL, "threads=1", "count", f"k={k}", "memory=1", fa, "output", db], cwd=d, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+    total = 0
+    for mode in ("polish", "filter"):
+        p = subprocess.run([MERFIN, "-" + mode, "-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl",
+                            "-vcf", "calls.vcf", "-peak", "10", "-threads", "1", "-memory", "4", "-output", "ref." + mode],
+                           cwd=d, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        want = open(os.path.join(d, "ref.%s.%s.vcf" % (mode, mode))).read()
+        assert _run(harness, d, mode, 10) == want, mode
+        assert _run(harness, d, mode, 10, "--shards", "3", "--batch", "50") == want, mode
+        total += sum(1 for l in want.splitlines() if not l.startswith("#"))
+    assert total > 10                          # (random edits are mostly rejected by the selectors)
