@@ -212,6 +212,12 @@ int  mfn_accum_read(mfn_ctx *ctx, const mfn_accum *a, uint64_t *host_buf /*[nwor
 int  mfn_accum_sparse_fetch(mfn_ctx *ctx, const mfn_accum *a, mfn_pair_count *pairs, uint64_t pairs_cap,
                             uint64_t *npairs /* this rank's count, also when pairs_cap is too small */);
 
+/* One process driving several devices: dst += src over the flat buffer, copied device to device
+ * (NVLink between peers) and added by a kernel on dst's device, on dst's stream; src's ctx must be
+ * idle (mfn_ctx_sync).  The single-process counterpart of the all-reduce above; pairs outside the
+ * dense tier are gathered as described there (mfn_accum_sparse_fetch per device). */
+int  mfn_accum_add_from(mfn_ctx *dst_ctx, mfn_accum *dst, const mfn_accum *src);
+
 /* Layout of the flat buffer and host-side decoding of a copy of it (no GPU needed): lets a
  * caller all-reduce with any transport and decode on any rank.  mfn_accum_decode refuses a buffer
  * whose header counts side-table pairs (MFN_ERR_INVALID): use mfn_accum_decode_gathered. */
@@ -350,6 +356,20 @@ int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const
 void mfn_pack_host_range(const char *bases, const uint64_t *rec_start, uint32_t nseq, uint64_t g_begin,
                          uint64_t g_end, uint64_t *seq2_out, uint64_t *ok_out);
 const char *mfn_pack_host_isa(void);       /* "avx2" or "scalar" */
+
+/* ---- choice of the -hist scan ------------------------------------------------------------
+ * -hist over a big batch runs as the range-partitioned scan whenever a fused or
+ * restricted table exists; its bins are sized for k-mers that spread over the table (15 % slack
+ * and a side list of 1/16 of the windows).  A batch dominated by a handful of k-mers can overflow
+ * that: the loss is recorded in the accumulator and mfn_accum_fetch / mfn_accum_decode then fail
+ * with MFN_ERR_CAPACITY instead of returning a short count.  mfn_hist retries by itself; callers of
+ * mfn_hist_host / mfn_hist_resident (which return before the device is done) recover with
+ *     mfn_ctx_set_sweep(ctx, 0); mfn_accum_reset(ctx, acc); <the same call again>; mfn_ctx_set_sweep(ctx, -1);
+ * mode: -1 automatic (default), 0 never (always the direct scan), 1 whenever a table allows it.
+ * The MFN_SWEEP environment variable, when set, overrides the automatic choice the same way.
+ * The ctx is NOT thread-safe (one host thread drives a ctx at a time) except where a function says
+ * otherwise (mfn_dump, mfn_score_paths, mfn_variants_process). */
+int  mfn_ctx_set_sweep(mfn_ctx *ctx, int mode);
 
 /* ---- timing hooks for benchmarks -------------------------------------------- */
 /* Number of kernels this library launched on the ctx since creation. */

@@ -42,6 +42,10 @@ class Context:
     def h2d_bytes(self) -> int:
         return int(self._lib.mfn_ctx_h2d_bytes(self.h))
 
+    def set_sweep(self, mode: int):
+        """-1 automatic, 0 never, 1 whenever possible: which -hist scan runs (mfn_ctx_set_sweep)."""
+        L.check(self._lib.mfn_ctx_set_sweep(self.h, mode))
+
     def time_passes(self, enable: bool = True):
         """Bracket the passes of every range-partitioned -hist scan with CUDA events."""
         L.check(self._lib.mfn_ctx_time_passes(self.h, 1 if enable else 0))

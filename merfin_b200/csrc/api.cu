@@ -102,6 +102,12 @@ extern "C" int mfn_ctx_sync(mfn_ctx *c) {
   return MFN_OK;
 }
 
+extern "C" int mfn_ctx_set_sweep(mfn_ctx *c, int mode) {
+  if (!c || mode < -1 || mode > 1) return MFN_ERR_INVALID;
+  c->sweep_mode = mode;
+  return MFN_OK;
+}
+
 extern "C" uint64_t mfn_ctx_launch_count(const mfn_ctx *c) { return c ? c->launches.load() : 0; }
 
 extern "C" uint64_t mfn_ctx_h2d_bytes(const mfn_ctx *c) { return c ? c->h2d_bytes.load() : 0; }
@@ -257,11 +263,12 @@ extern "C" int mfn_hist(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *a
   unsigned long long lost = 0;
   MFN_CUDA(cudaMemcpyAsync(&lost, acc->d_buf + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFN_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (lost && !ctx->no_sweep) {
-    ctx->no_sweep = true;
+  if (lost && ctx->sweep_mode != 0) {
+    const int keep_mode = ctx->sweep_mode;
+    ctx->sweep_mode = 0;
     int st2 = mfn_accum_reset(ctx, acc);
     if (st2 == MFN_OK) st2 = mfn_hist_host(ctx, reads, asm_, bases, seq_off, nseq, km, 0, 1, acc);
-    ctx->no_sweep = false;
+    ctx->sweep_mode = keep_mode;
     if (st2 != MFN_OK) return st2;
   }
   uint32_t keep = acc->nseq;
@@ -326,15 +333,46 @@ extern "C" int mfn_score_paths(mfn_ctx *ctx, const mfn_table *reads, const mfn_t
 // ---------------------------------------------------------------------------
 // -completeness: stream the read DB, probe the (raw) assembly table
 // ---------------------------------------------------------------------------
+// The read database holds ~2 error k-mers per genomic one, and they all land in the cells (1, 0) and
+// (2, 0): with one global atomic per k-mer the pass ran at the speed of the L2's atomic unit on two
+// addresses.  So: equal pairs of a warp are combined first (match_any), the pairs go to a per-CTA
+// shared-memory tier [v_asm < 16][v_read < 512] that is flushed once, and each thread has four
+// independent lookups in flight.
 __global__ void __launch_bounds__(256) k_join(DevTable A, const unsigned long long *kmers, const uint32_t *values,
                                               uint64_t n, unsigned long long *acc, PairTable sparse) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t vr = values[i];
-    uint32_t va = mfn_value(A, kmers[i]);
-    if (vr < MFN_DENSE_R && va < MFN_DENSE_A) atomicAdd(&acc[MFN_ACC_HEADER + va * MFN_DENSE_R + vr], 1ull);
-    else {
-      sparse_add(sparse, acc, vr, va, 1ull);         // same side table as the scan kernel
+  __shared__ uint32_t s_hist[SH_R * SH_A];
+  for (uint32_t i = threadIdx.x; i < SH_R * SH_A; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  // whole warps stay in the loop together (match_any needs the full mask): the bound is rounded up per warp
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; (i0 - lane) < n; i0 += 4 * stride) {
+    uint32_t vr[4], va[4];
+    bool live[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint64_t i = i0 + u * stride;
+      live[u] = i < n;
+      vr[u] = live[u] ? values[i] : 0u;
+      va[u] = live[u] ? mfn_value(A, kmers[i]) : 0u;
     }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const bool small = live[u] && vr[u] < SH_R && va[u] < SH_A;
+      const uint32_t key = small ? va[u] * SH_R + vr[u] : 0xffffffffu - lane;     // others: unique keys, no grouping
+      const uint32_t m = __match_any_sync(0xffffffffu, key);
+      if (small) {
+        if (lane == (uint32_t)__ffs(m) - 1u) atomicAdd(&s_hist[key], (uint32_t)__popc(m));
+      } else if (live[u]) {
+        if (vr[u] < MFN_DENSE_R && va[u] < MFN_DENSE_A) atomicAdd(&acc[MFN_ACC_HEADER + va[u] * MFN_DENSE_R + vr[u]], 1ull);
+        else sparse_add(sparse, acc, vr[u], va[u], 1ull);         // same side table as the scan kernel
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < SH_R * SH_A; i += blockDim.x) {
+    const uint32_t c = s_hist[i];
+    if (c) atomicAdd(&acc[MFN_ACC_HEADER + (i / SH_R) * MFN_DENSE_R + (i % SH_R)], (unsigned long long)c);
   }
 }
 

@@ -95,7 +95,7 @@ struct mfn_ctx {
   void  *h_pinned = nullptr;
   size_t pinned_cap = 0;
   // optional per-pass timing of the sweep (mfn_ctx_time_passes)
-  bool no_sweep = false;                 // retry path of mfn_hist after a sweep ran out of side-list room
+  int  sweep_mode = -1;                  // mfn_ctx_set_sweep: -1 automatic, 0 never, 1 whenever possible
   bool time_passes = false;
   std::vector<cudaEvent_t> pass_ev;      // triples: before scatter, between, after probe
   size_t pass_ev_used = 0;

@@ -29,6 +29,7 @@ struct Globals {
   uint32_t threads = 0;          // host threads for the -dump formatter (0 = all cores)
   int report = OP_NONE, device = 0;
   uint32_t shard = 0, nshards = 1;   // -shard i/n: variant modes score cluster range i of n of every record
+  std::vector<int> devices;          // -devices a,b,...: -hist / -completeness / variant modes shard their work over these GPUs
   bool nosplit = false, skipMissing = false, debug = false, nofuse = false;
   std::vector<uint32_t> probK;
   std::vector<double> probP;
@@ -40,6 +41,8 @@ static std::string shell_quote(const std::string &p) {
   for (char c : p) { if (c == '\'') q += "'\\''"; else q += c; }
   return q + "'";
 }
+
+#define MFN_TRY_MAIN(call) do { int s_ = (call); if (s_ != MFN_OK) return s_; } while (0)
 
 static void die(const char *what) {
   fprintf(stderr, "%s: %s\n", what, mfn_last_error());
@@ -58,6 +61,7 @@ static void usage(const char *argv0, const std::vector<std::string> &err) {
   fprintf(stderr, "  Options:      -seqmers <seq.meryl>  -min m  -max m  -comb N  -nosplit  -debug\n");
   fprintf(stderr, "                -threads t  (host threads of the -dump formatter)   -memory m   (accepted for compatibility)\n");
   fprintf(stderr, "                -device d   CUDA device to use (default 0)\n");
+  fprintf(stderr, "                -devices a,b,..  shard -hist / -completeness / the variant modes over several GPUs of this box (same output)\n");
   fprintf(stderr, "                -shard i/n  variant modes: score cluster range i of n of every record (records only in the output when i > 0)\n");
   fprintf(stderr, "  This is the B200 build of merfin's k-mer evaluation; flags and outputs follow merfin.\n\n");
   for (const std::string &e : err) fputs(e.c_str(), stderr);
@@ -107,6 +111,64 @@ static double histoQV(double kval, double ktot, uint32_t k) {          // merfin
   return -10.0 * log10(1.0 - pow(1.0 - kval / ktot, 1.0 / k));
 }
 
+// One GPU of a -devices run: its own ctx and its own replica of the tables.
+struct Dev {
+  int id = 0;
+  mfn_ctx *ctx = nullptr;
+  mfn_table *R = nullptr, *A = nullptr;
+  mfn_accum *acc = nullptr;
+  int status = MFN_OK;
+  std::string error;
+};
+
+// run fn(d) for every device on its own host thread
+template <class F> static void on_devices(std::vector<Dev> &devs, F fn) {
+  std::vector<std::thread> th;
+  for (size_t d = 1; d < devs.size(); d++) th.emplace_back([&, d]() { fn(devs[d], d); });
+  fn(devs[0], 0);
+  for (auto &t : th) t.join();
+}
+
+static bool devices_ok(std::vector<Dev> &devs, const char *what) {
+  for (Dev &d : devs)
+    if (d.status != MFN_OK) { fprintf(stderr, "%s (device %d): %s\n", what, d.id, d.error.c_str()); return false; }
+  return true;
+}
+
+// Sum the accumulators of all devices into device 0's (device-to-device copies, NVLink between peers)
+// and decode: per-record counters and the (v_read, v_asm) pairs, incl. the pairs outside the dense
+// tier, which are gathered from every device's side table.
+static int reduce_and_fetch(std::vector<Dev> &devs, uint32_t nseq, std::vector<mfn_seq_counts> *per, std::vector<mfn_pair_count> &pairs, uint64_t &np) {
+  for (size_t d = 1; d < devs.size(); d++) {
+    MFN_TRY_MAIN(mfn_ctx_sync(devs[d].ctx));
+    MFN_TRY_MAIN(mfn_accum_add_from(devs[0].ctx, devs[0].acc, devs[d].acc));
+  }
+  uint64_t nwords = 0;
+  uint32_t hw = 0, dr = 0, da = 0;
+  MFN_TRY_MAIN(mfn_accum_layout(nseq, &hw, &dr, &da, &nwords));
+  std::vector<uint64_t> buf(nwords);
+  MFN_TRY_MAIN(mfn_accum_read(devs[0].ctx, devs[0].acc, buf.data()));
+  std::vector<mfn_pair_count> sparse;
+  if (buf[1]) {
+    for (Dev &d : devs) {
+      uint64_t n = 0;
+      int st = mfn_accum_sparse_fetch(d.ctx, d.acc, nullptr, 0, &n);
+      if (st != MFN_OK && st != MFN_ERR_CAPACITY) return st;
+      if (!n) continue;
+      const size_t at = sparse.size();
+      sparse.resize(at + n);
+      MFN_TRY_MAIN(mfn_accum_sparse_fetch(d.ctx, d.acc, sparse.data() + at, n, &n));
+    }
+  }
+  if (per) per->assign(nseq + 1, mfn_seq_counts{0, 0});
+  int st = mfn_accum_decode_gathered(buf.data(), nseq, sparse.data(), sparse.size(), per ? per->data() : nullptr, pairs.data(), pairs.size(), &np);
+  if (st == MFN_ERR_CAPACITY && np > pairs.size()) {
+    pairs.resize(np);
+    st = mfn_accum_decode_gathered(buf.data(), nseq, sparse.data(), sparse.size(), per ? per->data() : nullptr, pairs.data(), pairs.size(), &np);
+  }
+  return st;
+}
+
 int main(int argc, char **argv) {
   Globals G;
   std::vector<std::string> err;
@@ -125,6 +187,17 @@ int main(int argc, char **argv) {
     else if (is("-threads")) G.threads = (uint32_t)strtoul(next(), nullptr, 10);
     else if (is("-memory")) next();
     else if (is("-device")) G.device = atoi(next());
+    else if (is("-devices")) {
+      const char *v = next();
+      for (const char *p = v; *p;) {
+        char *e2 = nullptr;
+        long d = strtol(p, &e2, 10);
+        if (e2 == p || d < 0) { err.push_back(std::string("Bad -devices '") + v + "' (want a comma-separated list of device numbers).\n"); break; }
+        G.devices.push_back((int)d);
+        p = (*e2 == ',') ? e2 + 1 : e2;
+        if (*e2 && *e2 != ',') { err.push_back(std::string("Bad -devices '") + v + "'.\n"); break; }
+      }
+    }
     else if (is("-nofuse")) G.nofuse = true;
     else if (is("-shard")) {
       const char *v = next();
@@ -160,8 +233,13 @@ int main(int argc, char **argv) {
   load_Kmetric(G);
   mfn_kmodel km = {G.peak, (uint32_t)G.probK.size(), G.probK.data(), G.probP.data()};
 
-  mfn_ctx *ctx = nullptr;
-  if (mfn_ctx_create(&ctx, G.device) != MFN_OK) die("cannot use the GPU");
+  if (G.devices.empty()) G.devices.push_back(G.device);
+  std::vector<Dev> devs(G.devices.size());
+  for (size_t d = 0; d < devs.size(); d++) devs[d].id = G.devices[d];
+  on_devices(devs, [&](Dev &D, size_t) { D.status = mfn_ctx_create(&D.ctx, D.id); if (D.status != MFN_OK) D.error = mfn_last_error(); });
+  if (!devices_ok(devs, "cannot use the GPU")) return 1;
+  mfn_ctx *ctx = devs[0].ctx;
+  const uint32_t ND = (uint32_t)devs.size();
 
   // ---- -completeness streams both databases (merfin-completeness.C:48-144) ----------------------
   if (G.report == OP_COMPL) {
@@ -169,30 +247,40 @@ int main(int argc, char **argv) {
     std::vector<mfn_pair_count> pairs(1 << 20);
     uint64_t np = 0;
     int st;
-    if (G.seqDBname) {
+    if (G.seqDBname && ND == 1) {
       st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np);
       if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_completeness(ctx, G.readDBname, G.seqDBname, pairs.data(), pairs.size(), &np); }
     } else {
-      // the reference builds <sequence>.meryl with "meryl count" first (merfin-globals.C:168-189) and
-      // streams that; here the assembly k-mers are counted on the GPU and joined in place
+      // Every device joins its share of the read database's data files (files [64 d / N, 64 (d + 1) / N):
+      // the grain of the reference's OpenMP loop, merfin-completeness.C:65) with its own replica of the raw
+      // assembly table; the joint histograms are summed on device 0.  Without -seqmers the reference builds
+      // <sequence>.meryl with "meryl count" first (merfin-globals.C:168-189); here the assembly k-mers are
+      // counted on the GPU and joined in place.
       mfn_meryl_info_t mi;
       if (mfn_meryl_info(G.readDBname, &mi) != MFN_OK) die("-readmers");
-      fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", mi.k, G.seqName);
       SeqSet S;
-      std::string e;
-      if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
-      mfn_seq *seq = nullptr;
-      mfn_table *A = nullptr;
-      mfn_accum *acc = nullptr;
-      if (mfn_seq_create(ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq) != MFN_OK) die("-sequence");
-      if (mfn_table_count_seq(ctx, mi.k, seq, &A) != MFN_OK) die("counting -sequence");
-      mfn_seq_free(seq);
-      st = mfn_accum_create(ctx, 0, &acc);
-      if (st == MFN_OK) st = mfn_completeness_shard(ctx, G.readDBname, A, 0, 1, acc);
-      if (st == MFN_OK) st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs.data(), pairs.size(), &np);
-      if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_accum_fetch(ctx, acc, 1, 1, nullptr, pairs.data(), pairs.size(), &np); }
-      mfn_accum_free(acc);
-      mfn_table_free(A);
+      if (!G.seqDBname) {
+        fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", mi.k, G.seqName);
+        std::string e;
+        if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
+      }
+      on_devices(devs, [&](Dev &D, size_t d) {
+        int st2;
+        if (G.seqDBname) st2 = mfn_table_load(D.ctx, G.seqDBname, 0, 0xffffffffu, &D.A);      // raw values: offset 0
+        else {
+          mfn_seq *seq = nullptr;
+          st2 = mfn_seq_create(D.ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq);
+          if (st2 == MFN_OK) st2 = mfn_table_count_seq(D.ctx, mi.k, seq, &D.A);
+          mfn_seq_free(seq);
+        }
+        if (st2 == MFN_OK) st2 = mfn_accum_create(D.ctx, 0, &D.acc);
+        if (st2 == MFN_OK) st2 = mfn_completeness_shard(D.ctx, G.readDBname, D.A, (uint32_t)d, ND, D.acc);
+        D.status = st2;
+        if (st2 != MFN_OK) D.error = mfn_last_error();
+      });
+      if (!devices_ok(devs, "completeness")) return 1;
+      st = reduce_and_fetch(devs, 0, nullptr, pairs, np);
+      for (Dev &D : devs) { mfn_accum_free(D.acc); mfn_table_free(D.A); D.acc = nullptr; D.A = nullptr; }
     }
     if (st != MFN_OK) die("completeness");
     double total = 0, undr = 0;
@@ -201,7 +289,7 @@ int main(int argc, char **argv) {
     fprintf(stderr, "TOTAL readK:   %15.2f\n", total);
     fprintf(stderr, "TOTAL undrcpy:    %15.5f\n", undr);
     fprintf(stderr, "COMPLETENESS:             %0.5f\n", 1.0 - undr / total);
-    mfn_ctx_destroy(ctx);
+    for (Dev &D : devs) mfn_ctx_destroy(D.ctx);
     fprintf(stderr, "Bye!\n");
     return 0;
   }
@@ -212,28 +300,38 @@ int main(int argc, char **argv) {
   std::string e;
   if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
 
-  mfn_table *R = nullptr, *A = nullptr;
+  // every device loads its own replica of the tables (the databases are decoded on the device)
   fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.readDBname);
-  if (mfn_table_load(ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, &R) != MFN_OK) die("-readmers");
-  mfn_table_info_t ri;
+  if (G.seqDBname) fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.seqDBname);
+  else fprintf(stderr, "-- No -seqmer given. Counting the k-mers of '%s' on the GPU.\n", G.seqName);
+  on_devices(devs, [&](Dev &D, size_t) {
+    int st = mfn_table_load(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, &D.R);
+    mfn_table_info_t ri;
+    if (st == MFN_OK) st = mfn_table_info(D.R, &ri);
+    if (st == MFN_OK) {
+      if (G.seqDBname) st = mfn_table_load(D.ctx, G.seqDBname, 0, 0xffffffffu, &D.A);
+      else {
+        // the reference shells out to "meryl count" here (merfin-globals.C:168-189); we count on the GPU
+        mfn_seq *seq = nullptr;
+        st = mfn_seq_create(D.ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq);
+        if (st == MFN_OK) st = mfn_table_count_seq(D.ctx, ri.k, seq, &D.A);
+        mfn_seq_free(seq);
+      }
+    }
+    D.status = st;
+    if (st != MFN_OK) D.error = mfn_last_error();
+  });
+  if (!devices_ok(devs, "loading the databases")) return 1;
+  mfn_table *R = devs[0].R, *A = devs[0].A;
+  mfn_table_info_t ri, ai;
   mfn_table_info(R, &ri);
-  const uint32_t K = ri.k;
-  if (G.seqDBname) {
-    fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.seqDBname);
-    if (mfn_table_load(ctx, G.seqDBname, 0, 0xffffffffu, &A) != MFN_OK) die("-seqmers");
-  } else {
-    // the reference shells out to "meryl count" here (merfin-globals.C:168-189); we count on the GPU
-    fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", K, G.seqName);
-    mfn_seq *seq = nullptr;
-    if (mfn_seq_create(ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq) != MFN_OK) die("-sequence");
-    if (mfn_table_count_seq(ctx, K, seq, &A) != MFN_OK) die("counting -sequence");
-    mfn_seq_free(seq);
-  }
-  mfn_table_info_t ai;
   mfn_table_info(A, &ai);
+  const uint32_t K = ri.k;
   if (ai.k != K) { fprintf(stderr, "mer size mismatch, can't process this set of files.\n"); return 1; }
-  if (!G.nofuse && ri.canonical && ai.canonical && mfn_tables_fuse(ctx, R, A) != MFN_OK)
-    fprintf(stderr, "-- (fused table not built: %s)\n", mfn_last_error());
+  if (!G.nofuse && ri.canonical && ai.canonical) {
+    on_devices(devs, [&](Dev &D, size_t) { D.status = mfn_tables_fuse(D.ctx, D.R, D.A); if (D.status != MFN_OK) D.error = mfn_last_error(); });
+    for (Dev &D : devs) if (D.status != MFN_OK) { fprintf(stderr, "-- (fused table not built on device %d: %s)\n", D.id, D.error.c_str()); D.status = MFN_OK; }
+  }
 
   // ---- -hist (merfin-histogram.C) ----------------------------------------------------------------
   if (G.report == OP_HIST) {
@@ -241,8 +339,33 @@ int main(int argc, char **argv) {
     std::vector<mfn_seq_counts> per(S.nseq() + 1);
     std::vector<mfn_pair_count> pairs(1 << 20);
     uint64_t np = 0;
-    int st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np);
-    if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np); }
+    int st;
+    if (ND == 1) {
+      st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np);
+      if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np); }
+    } else {
+      // device d scans tiles [T d / N, T (d + 1) / N) of the whole sequence set (uploading only those bases)
+      // into its own accumulator; one reduction at the end
+      on_devices(devs, [&](Dev &D, size_t d) {
+        int st2 = mfn_accum_create(D.ctx, (uint32_t)S.nseq(), &D.acc);
+        for (int attempt = 0; st2 == MFN_OK && attempt < 2; attempt++) {
+          st2 = mfn_hist_host(D.ctx, D.R, D.A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, (uint32_t)d, ND, D.acc);
+          if (st2 != MFN_OK) break;
+          // the range-partitioned scan reports a shard it could not hold through the accumulator: redo it with the direct scan
+          uint64_t np2 = 0;
+          int sf = mfn_accum_fetch(D.ctx, D.acc, 0, 0, nullptr, nullptr, 0, &np2);
+          if (sf != MFN_ERR_CAPACITY || attempt == 1) { st2 = sf; break; }
+          mfn_ctx_set_sweep(D.ctx, 0);
+          st2 = mfn_accum_reset(D.ctx, D.acc);
+        }
+        mfn_ctx_set_sweep(D.ctx, -1);
+        D.status = st2;
+        if (st2 != MFN_OK) D.error = mfn_last_error();
+      });
+      if (!devices_ok(devs, "-hist")) return 1;
+      st = reduce_and_fetch(devs, (uint32_t)S.nseq(), &per, pairs, np);
+      for (Dev &D : devs) { mfn_accum_free(D.acc); D.acc = nullptr; }
+    }
     if (st != MFN_OK) die("-hist");
     uint64_t cum = 0;
     for (size_t i = 0; i < S.nseq(); i++) {                        // the per-sequence lines of outputHistogram
@@ -323,6 +446,7 @@ int main(int argc, char **argv) {
     std::vector<int> status(nrec, 0);
     unsigned nthreads = G.threads ? G.threads : std::max(1u, std::thread::hardware_concurrency());
     if (G.debug) nthreads = 1;                                   // debug records carry a running id
+    if (G.debug && ND > 1) { fprintf(stderr, "-debug runs on one device.\n"); return 1; }
     nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, nrec));
     uint64_t varMerId = 0;
     {
@@ -336,8 +460,20 @@ int main(int argc, char **argv) {
           const size_t i = order[j];
           if (mfn_vcf_clusters_of(vcf, S.ident[i].c_str()) == 0) continue;
           uint64_t localId = 0;
-          status[i] = mfn_variants_process(ctx, R, A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb, &km, G.shard, G.nshards,
-                                           &results[i], nullptr, G.debug ? &dbgs[i] : nullptr, nullptr, nthreads == 1 ? &varMerId : &localId);
+          if (ND == 1) {
+            status[i] = mfn_variants_process(ctx, R, A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb, &km, G.shard, G.nshards,
+                                             &results[i], nullptr, G.debug ? &dbgs[i] : nullptr, nullptr, nthreads == 1 ? &varMerId : &localId);
+          } else {
+            // -devices: cluster range d of N of this record goes to device d; the texts concatenate to the record's result
+            std::string all;
+            for (uint32_t d = 0; d < ND && status[i] == MFN_OK; d++) {
+              char *part = nullptr;
+              status[i] = mfn_variants_process(devs[d].ctx, devs[d].R, devs[d].A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb,
+                                               &km, d, ND, &part, nullptr, nullptr, nullptr, &localId);
+              if (part) { all += part; mfn_text_free(part); }
+            }
+            if (status[i] == MFN_OK) { results[i] = (char *)malloc(all.size() + 1); memcpy(results[i], all.c_str(), all.size() + 1); }
+          }
           if (status[i] != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
         }
       };
@@ -371,9 +507,11 @@ int main(int argc, char **argv) {
     mfn_vcf_free(vcf);
   }
 
-  mfn_table_free(R);
-  mfn_table_free(A);
-  mfn_ctx_destroy(ctx);
+  for (Dev &D : devs) {
+    mfn_table_free(D.R);
+    mfn_table_free(D.A);
+    mfn_ctx_destroy(D.ctx);
+  }
   fprintf(stderr, "Bye!\n");
   return 0;
 }

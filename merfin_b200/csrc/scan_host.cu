@@ -164,6 +164,31 @@ extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
   return MFN_OK;
 }
 
+// dst[i] += src[i] over the flat accumulator buffer (src: a staging copy on dst's device)
+__global__ void __launch_bounds__(256) k_accum_add(unsigned long long *dst, const unsigned long long *src, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = src[i];
+    if (v) dst[i] += v;
+  }
+}
+
+// One process driving several devices (the CLI's -devices): add the flat buffer of `src` (another
+// device's accumulator) into `dst`.  The copy goes device to device (NVLink when the devices are
+// peers); the caller has synchronised src's ctx.  Equivalent to one step of the all-reduce that
+// one-process-per-GPU callers run with NCCL.
+extern "C" int mfn_accum_add_from(mfn_ctx *ctx, mfn_accum *dst, const mfn_accum *src) {
+  if (!ctx || !dst || !src || dst->nwords != src->nwords) return MFN_ERR_INVALID;
+  MFN_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long *tmp = nullptr;
+  MFN_CUDA(cudaMallocAsync(&tmp, dst->nwords * 8, ctx->stream));
+  MFN_CUDA(cudaMemcpyPeerAsync(tmp, ctx->device, src->d_buf, src->ctx->device, dst->nwords * 8, ctx->stream));
+  k_accum_add<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(dst->d_buf, tmp, dst->nwords);
+  ctx->launches++;
+  MFN_CUDA(cudaGetLastError());
+  MFN_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  return MFN_OK;
+}
+
 extern "C" int mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a) {
   if (!ctx || !a) return MFN_ERR_INVALID;
   // the 64 MB side table is cleared only when something was put into it (its counter word tells, on the device)

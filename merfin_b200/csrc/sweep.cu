@@ -46,7 +46,8 @@ static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, 
 
 // Can (and should) this scan use the sweep?
 bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, uint32_t nseq) {
-  if (R->ctx && R->ctx->no_sweep) return false;
+  const int mode = R->ctx ? R->ctx->sweep_mode : -1;
+  if (mode == 0) return false;
   const char *env = getenv("MFN_SWEEP");
   if (env && atoi(env) == 0) return false;
   const mfn_joint *T = sweep_table(R, A);
@@ -54,7 +55,7 @@ bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntile
   uint32_t lbits, tbits, nbins, lowbits;
   if (!sweep_geometry(T->dev, lbits, tbits, nbins, lowbits)) return false;
   if ((uint64_t)nseq + 1 >= (1ull << (63 - lowbits))) return false;       // record ids must fit the entry
-  if (env && atoi(env) == 1) return true;
+  if (mode == 1 || (env && atoi(env) == 1)) return true;
   // wide entries have no room for a record delta: windows of a chunk that are not in the chunk's
   // first record take the side list, which is only acceptable when records are long
   if (lowbits > SW_MAX_LOWBITS_NARROW && ntiles * MFN_TILE < (uint64_t)nseq * 16 * SW_CHUNK) return false;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "mfn_ctx_device": (C.c_int, [_P]),
     "mfn_ctx_set_stream": (C.c_int, [_P, _P]),
     "mfn_ctx_sync": (C.c_int, [_P]),
+    "mfn_ctx_set_sweep": (C.c_int, [_P, C.c_int]),
     "mfn_host_alloc": (C.c_int, [_PP, C.c_size_t]),
     "mfn_host_free": (None, [_P]),
     "mfn_table_load": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.c_uint32, _PP]),
@@ -125,6 +126,7 @@ SIGNATURES = {
     "mfn_accum_read": (C.c_int, [_P, _P, _P]),
     "mfn_accum_sparse_fetch": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_accum_decode_gathered": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_accum_add_from": (C.c_int, [_P, _P, _P]),
     "mfn_accum_layout": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_uint64)]),
     "mfn_accum_decode": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),

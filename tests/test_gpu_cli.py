@@ -47,6 +47,48 @@ def test_cli_hist_dump_completeness(golden_dir, tmp_path, name, peak):
         assert l in err
 
 
+def _device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    lists = ["0,0", "0,0,0"]                      # several contexts on one GPU: the whole multi-device path of the CLI
+    if n >= 2:
+        lists.append(",".join(str(i) for i in range(min(n, 8))))
+    return lists
+
+
+@pytest.mark.parametrize("name,peak", [("g1_k21", 8), ("g2_k6", 3), ("g3_k31", 6)])
+def test_cli_devices_same_output(golden_dir, tmp_path, name, peak):
+    """-devices a,b,...: -hist / -completeness shard their work over several contexts (tiles resp. data files of
+    the read database), the accumulators are summed device to device, and the output is byte for byte the
+    single-device one (= the reference's).  Runs with one context per listed device, so '0,0' exercises the
+    path on a one-GPU box; with >= 2 GPUs the real device list is used as well."""
+    d = os.path.join(golden_dir, name)
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", str(peak)]
+    tail = [l for l in open(os.path.join(d, "ref.completeness")).read().splitlines() if not l.startswith("thread")]
+    for devs in _device_lists():
+        err = _run(base + ["-hist", "-output", "out.hist", "-devices", devs], str(tmp_path))
+        assert open(tmp_path / "out.hist", "rb").read() == open(os.path.join(d, "ref.hist"), "rb").read(), devs
+        assert _summary(err) == open(os.path.join(d, "ref.hist.summary")).read(), devs
+        assert open(os.path.join(d, "ref.hist.perseq")).read() in err
+        err = _run(base + ["-completeness", "-devices", devs], str(tmp_path))
+        for l in tail:
+            assert l in err, devs
+        err = _run(base[:2] + base[4:] + ["-completeness", "-devices", devs], str(tmp_path))
+        for l in tail:
+            assert l in err, devs
+
+
+def test_cli_devices_variants(golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "g1_k21")
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", "8", "-vcf", os.path.join(d, "calls.vcf")]
+    for devs in _device_lists():
+        for mode, produced in (("polish", "polish"), ("filter", "filter"), ("loose", "filter")):
+            _run(base + ["-" + mode, "-output", "o", "-devices", devs], str(tmp_path))
+            assert open(tmp_path / f"o.{produced}.vcf").read() == open(os.path.join(d, f"ref.{mode}.vcf")).read(), (devs, mode)
+
+
 def test_cli_min_max_prob_skipmissing(golden_dir, tmp_path):
     d = os.path.join(golden_dir, "g1_k21")
     base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),

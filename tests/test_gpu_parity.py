@@ -584,6 +584,20 @@ def test_sweep_overflow_falls_back_to_the_direct_scan(ctx, monkeypatch):
     s = api.hist(ctx, R, A, recs, km)
     assert len(d.pairs) == len(s.pairs) and (d.pairs == s.pairs).all() and (d.per_seq == s.per_seq).all()
     assert int(s.per_seq["kasm"][0]) == 5_000_000 - 20
+    # the entry points that return before the device is done (mfn_hist_resident / mfn_hist_host) report the
+    # loss at fetch; the caller recovers with mfn_ctx_set_sweep(ctx, 0) and the same call again
+    from merfin_b200 import lib as L
+    acc = api.Accum(ctx, len(recs))
+    api.hist_resident(ctx, R, A, seq, km, acc)
+    with pytest.raises(L.MfnError) as e:
+        acc.fetch()
+    assert e.value.status == L.MFN_ERR_CAPACITY
+    ctx.set_sweep(0)
+    acc.reset()
+    api.hist_resident(ctx, R, A, seq, km, acc)
+    ctx.set_sweep(-1)
+    per, pairs = acc.fetch()
+    assert len(pairs) == len(d.pairs) and (pairs == d.pairs).all() and (per == d.per_seq).all()
     seq.close(); R.close(); A.close()
 
 
