@@ -140,6 +140,30 @@ int  mfn_tables_restrict(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_, 
                          uint32_t shard, uint32_t nshards);
 int  mfn_tables_unrestrict(mfn_table *reads);
 int  mfn_restricted_info(const mfn_table *reads, mfn_joint_info_t *info);
+/* The same table built from a read database that is STREAMED through the device and never resident
+ * (a database of twice the HBM, BASELINE configs[4]; kmers-exact.C:95-146 gives up when the table does
+ * not fit -memory): its blocks are decoded chunk by chunk and semi-joined on the device against the
+ * k-mers of the sequence shard; read-only k-mers (two thirds of a 30x database) are dropped on the
+ * spot, so the table never holds more than one entry per distinct k-mer of the shard.  *reads_out is
+ * a read-table handle WITHOUT a per-database table behind it: it serves -hist (mfn_hist_resident /
+ * mfn_hist_host, always as the range-partitioned scan) of the sequences it was restricted to; windows of
+ * other sequences would read as absent from the reads, and mfn_dump / mfn_score_paths refuse it.
+ * min_value / max_value as in mfn_table_load.  mfn_tables_restrict_synth is the benchmark's stand-in
+ * for a database of any size: the synthetic read database of mfn_table_synth_reads (same draws),
+ * its n_error error k-mers generated in chunks of chunk_kmers and pushed through the same semi-join. */
+typedef struct {
+  uint64_t db_kmers;       /* k-mers the database holds (streamed) */
+  uint64_t kept_kmers;     /* of those, k-mers of the shard that went into the table */
+  uint64_t shard_kmers;    /* distinct k-mers of the sequence shard */
+  uint64_t table_bytes;    /* device memory of the restricted table */
+  double   seconds;        /* wall clock of the call */
+} mfn_stream_stats;
+int  mfn_tables_restrict_stream(mfn_ctx *ctx, const char *reads_dir, uint32_t min_value, uint32_t max_value,
+                                const mfn_table *asm_, const mfn_seq *seq, uint32_t shard, uint32_t nshards,
+                                mfn_table **reads_out, mfn_stream_stats *stats /* or NULL */);
+int  mfn_tables_restrict_synth(mfn_ctx *ctx, const mfn_table *asm_, const mfn_seq *seq, uint32_t shard, uint32_t nshards,
+                               double cov_per_copy, uint64_t n_error, uint64_t seed, uint64_t chunk_kmers,
+                               mfn_table **reads_out, mfn_stream_stats *stats /* or NULL */);
 /* (value_read(kmer), value_asm(kmer)) for k-mers exactly as given, through the fused table. */
 int  mfn_joint_lookup(mfn_ctx *ctx, const mfn_table *reads, const uint64_t *kmers, uint64_t n,
                       uint32_t *v_read, uint32_t *v_asm);

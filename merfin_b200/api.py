@@ -130,6 +130,27 @@ class MerylExactLookup:
         L.check(L.load().mfn_table_synth_reads(ctx.h, None, asm.h, cov_per_copy, n_error, seed, C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def restrict_stream(cls, ctx: Context, meryl_dir: str, asm: "MerylExactLookup", seq, shard: int = 0, nshards: int = 1,
+                        minV: int = 0, maxV: int = 0xFFFFFFFF):
+        """A read-table handle whose database was streamed through the device into the restricted fused
+        table of one shard of `seq` (mfn_tables_restrict_stream): serves -hist of that shard only.
+        Returns (handle, StreamStats)."""
+        h, st = C.c_void_p(), L.StreamStats()
+        L.check(L.load().mfn_tables_restrict_stream(ctx.h, meryl_dir.encode(), minV, maxV, asm.h, seq.h, shard, nshards,
+                                                    C.byref(h), C.byref(st)))
+        return cls(ctx, h), st
+
+    @classmethod
+    def restrict_synth(cls, ctx: Context, asm: "MerylExactLookup", seq, cov_per_copy: float, n_error: int, seed: int,
+                       chunk_kmers: int = 0, shard: int = 0, nshards: int = 1):
+        """The synthetic read database of synth_reads (same draws), streamed: its n_error error k-mers are
+        generated in chunks and semi-joined against the shard's k-mers (mfn_tables_restrict_synth)."""
+        h, st = C.c_void_p(), L.StreamStats()
+        L.check(L.load().mfn_tables_restrict_synth(ctx.h, asm.h, seq.h, shard, nshards, cov_per_copy, n_error, seed, chunk_kmers,
+                                                   C.byref(h), C.byref(st)))
+        return cls(ctx, h), st
+
     @property
     def info(self) -> L.TableInfo:
         i = L.TableInfo()

@@ -197,6 +197,10 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
   const uint64_t tb = seq->ntiles * shard / nshards, te = seq->ntiles * (shard + 1) / nshards;
   const uint64_t pieces = std::max<uint64_t>(1, std::min<uint64_t>(16, (te - tb) / 8192));
   if (reads->dev.k != asm_->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", reads->dev.k, asm_->dev.k); return MFN_ERR_K_MISMATCH; }
+  if (reads->streamed && !mfn_sweep_applicable(reads, asm_, te - tb, seq->nseq)) {
+    mfn_set_error("this read table was streamed (mfn_tables_restrict_stream): it serves -hist of the sequences it was restricted to only");
+    return MFN_ERR_UNSUPPORTED;
+  }
   if (mfn_sweep_applicable(reads, asm_, te - tb, seq->nseq)) {
     // Range-partitioned scan.  The shard is cut into sub-sweeps of ~1.5e9 windows: each scatters its
     // pieces as soon as they are packed and then probes its bins, so the probe pass of one

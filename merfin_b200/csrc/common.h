@@ -111,6 +111,7 @@ struct mfn_table {
   mfn_ctx   *ctx = nullptr;
   mfn_joint *joint = nullptr;     // fused (this, assembly) table built by mfn_tables_fuse
   mfn_joint *hot = nullptr;       // fused table restricted to the k-mers of one sequence shard (mfn_tables_restrict)
+  bool       streamed = false;    // no per-database table behind this handle: the database was streamed into `hot` (joint_stream.cu)
   DevTable   dev{};
   TableStats host_stats{};
   uint32_t   min_value = 0, max_value = 0, value_offset = 0;

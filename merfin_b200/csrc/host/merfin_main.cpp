@@ -301,20 +301,26 @@ int main(int argc, char **argv) {
   if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
 
   // every device loads its own replica of the tables (the databases are decoded on the device)
+  mfn_meryl_info_t rmi;
+  if (mfn_meryl_info(G.readDBname, &rmi) != MFN_OK) die("-readmers");
+  const uint32_t K = rmi.k;
+  // -hist does not need the read database resident: it is streamed through the device into the table
+  // restricted to the k-mers of each device's share of the sequences (mfn_tables_restrict_stream);
+  // the resident tables are loaded only if that is not possible (non-canonical database, odd batch)
+  bool stream_reads = G.report == OP_HIST && !G.nofuse && !getenv("MFN_NO_STREAM") && S.nseq() > 0;
   fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.readDBname);
   if (G.seqDBname) fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.seqDBname);
-  else fprintf(stderr, "-- No -seqmer given. Counting the k-mers of '%s' on the GPU.\n", G.seqName);
+  else fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", K, G.seqName);
+  auto load_reads = [&](Dev &D) -> int { return mfn_table_load(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, &D.R); };
   on_devices(devs, [&](Dev &D, size_t) {
-    int st = mfn_table_load(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, &D.R);
-    mfn_table_info_t ri;
-    if (st == MFN_OK) st = mfn_table_info(D.R, &ri);
+    int st = stream_reads ? MFN_OK : load_reads(D);
     if (st == MFN_OK) {
       if (G.seqDBname) st = mfn_table_load(D.ctx, G.seqDBname, 0, 0xffffffffu, &D.A);
       else {
         // the reference shells out to "meryl count" here (merfin-globals.C:168-189); we count on the GPU
         mfn_seq *seq = nullptr;
         st = mfn_seq_create(D.ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq);
-        if (st == MFN_OK) st = mfn_table_count_seq(D.ctx, ri.k, seq, &D.A);
+        if (st == MFN_OK) st = mfn_table_count_seq(D.ctx, K, seq, &D.A);
         mfn_seq_free(seq);
       }
     }
@@ -322,16 +328,19 @@ int main(int argc, char **argv) {
     if (st != MFN_OK) D.error = mfn_last_error();
   });
   if (!devices_ok(devs, "loading the databases")) return 1;
-  mfn_table *R = devs[0].R, *A = devs[0].A;
   mfn_table_info_t ri, ai;
-  mfn_table_info(R, &ri);
-  mfn_table_info(A, &ai);
-  const uint32_t K = ri.k;
+  mfn_table_info(devs[0].A, &ai);
   if (ai.k != K) { fprintf(stderr, "mer size mismatch, can't process this set of files.\n"); return 1; }
-  if (!G.nofuse && ri.canonical && ai.canonical) {
-    on_devices(devs, [&](Dev &D, size_t) { D.status = mfn_tables_fuse(D.ctx, D.R, D.A); if (D.status != MFN_OK) D.error = mfn_last_error(); });
-    for (Dev &D : devs) if (D.status != MFN_OK) { fprintf(stderr, "-- (fused table not built on device %d: %s)\n", D.id, D.error.c_str()); D.status = MFN_OK; }
-  }
+  // the fused table of the resident pair (one probe per window instead of two)
+  auto fuse_all = [&]() {
+    mfn_table_info(devs[0].R, &ri);
+    if (!G.nofuse && ri.canonical && ai.canonical) {
+      on_devices(devs, [&](Dev &D, size_t) { D.status = mfn_tables_fuse(D.ctx, D.R, D.A); if (D.status != MFN_OK) D.error = mfn_last_error(); });
+      for (Dev &D : devs) if (D.status != MFN_OK) { fprintf(stderr, "-- (fused table not built on device %d: %s)\n", D.id, D.error.c_str()); D.status = MFN_OK; }
+    }
+  };
+  if (!stream_reads) fuse_all();
+  mfn_table *R = devs[0].R, *A = devs[0].A;
 
   // ---- -hist (merfin-histogram.C) ----------------------------------------------------------------
   if (G.report == OP_HIST) {
@@ -339,11 +348,46 @@ int main(int argc, char **argv) {
     std::vector<mfn_seq_counts> per(S.nseq() + 1);
     std::vector<mfn_pair_count> pairs(1 << 20);
     uint64_t np = 0;
-    int st;
-    if (ND == 1) {
+    int st = MFN_OK;
+    bool done = false;
+    if (stream_reads) {
+      // device d: pack the sequences, stream the read database into the table of tiles [T d / N, T (d + 1) / N),
+      // scan those tiles
+      on_devices(devs, [&](Dev &D, size_t d) {
+        mfn_seq *seq = nullptr;
+        mfn_table *T = nullptr;
+        int st2 = mfn_seq_create(D.ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq);
+        if (st2 == MFN_OK) st2 = mfn_tables_restrict_stream(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, D.A, seq, (uint32_t)d, ND, &T, nullptr);
+        if (st2 == MFN_OK) st2 = mfn_accum_create(D.ctx, (uint32_t)S.nseq(), &D.acc);
+        if (st2 == MFN_OK) st2 = mfn_hist_resident(D.ctx, T, D.A, seq, &km, (uint32_t)d, ND, D.acc);
+        uint64_t np2 = 0;
+        if (st2 == MFN_OK) st2 = mfn_accum_fetch(D.ctx, D.acc, 0, 0, nullptr, nullptr, 0, &np2);     // a bin or the side list overflowed?
+        D.status = st2;
+        if (st2 != MFN_OK) D.error = mfn_last_error();
+        mfn_table_free(T);
+        mfn_seq_free(seq);
+      });
+      bool retry = false;
+      for (Dev &D : devs) if (D.status == MFN_ERR_UNSUPPORTED || D.status == MFN_ERR_CAPACITY) retry = true;
+      if (!retry) {
+        if (!devices_ok(devs, "-hist")) return 1;
+        st = reduce_and_fetch(devs, (uint32_t)S.nseq(), &per, pairs, np);
+        done = true;
+      } else {
+        for (Dev &D : devs) if (D.status != MFN_OK) { fprintf(stderr, "-- (read database loaded instead of streamed: %s)\n", D.error.c_str()); break; }
+      }
+      for (Dev &D : devs) { mfn_accum_free(D.acc); D.acc = nullptr; D.status = MFN_OK; }
+      if (!done) {
+        on_devices(devs, [&](Dev &D, size_t) { D.status = load_reads(D); if (D.status != MFN_OK) D.error = mfn_last_error(); });
+        if (!devices_ok(devs, "-readmers")) return 1;
+        fuse_all();
+        R = devs[0].R;
+      }
+    }
+    if (!done && ND == 1) {
       st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np);
       if (st == MFN_ERR_CAPACITY && np > pairs.size()) { pairs.resize(np); st = mfn_hist(ctx, R, A, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &km, per.data(), pairs.data(), pairs.size(), &np); }
-    } else {
+    } else if (!done) {
       // device d scans tiles [T d / N, T (d + 1) / N) of the whole sequence set (uploading only those bases)
       // into its own accumulator; one reduction at the end
       on_devices(devs, [&](Dev &D, size_t d) {

@@ -5,8 +5,9 @@
 // host side
 // ---------------------------------------------------------------------------
 
-static int check_tables(const mfn_table *R, const mfn_table *A) {
+static int check_tables(const mfn_table *R, const mfn_table *A, bool per_position = false) {
   if (!R || !A) return MFN_ERR_INVALID;
+  if (per_position && R->streamed) { mfn_set_error("this read table was streamed (mfn_tables_restrict_stream): -dump and path scoring need the database resident (mfn_table_load)"); return MFN_ERR_UNSUPPORTED; }
   if (R->dev.k != A->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", R->dev.k, A->dev.k); return MFN_ERR_K_MISMATCH; }
   return MFN_OK;
 }
@@ -97,7 +98,14 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   MFN_TRY(mfn_build_zmap(ctx, km, &zmap, &P.zlen, &zhi));
   P.zmap = zmap;
   int st;
-  if (mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0, seq->nseq))
+  const bool sweep = mfn_sweep_applicable(reads, asm_, P.tile_end > P.tile_begin ? P.tile_end - P.tile_begin : 0, seq->nseq);
+  if (reads->streamed && !sweep) {
+    if (zmap) cudaFreeAsync(zmap, ctx->stream);
+    mfn_set_error("this read table was streamed (mfn_tables_restrict_stream): it serves -hist of the sequences it was restricted to, "
+                  "with this assembly table, through the range-partitioned scan only");
+    return MFN_ERR_UNSUPPORTED;
+  }
+  if (sweep)
     st = mfn_sweep_hist(ctx, reads, asm_, seq, km, P.tile_begin, P.tile_end, acc, zmap, P.zlen, zhi);
   else
     st = launch_scan(ctx, P, false, use_joint(reads, asm_, P));
@@ -116,7 +124,7 @@ extern "C" int mfn_hist_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
 extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
                                  uint32_t *d_v_read, uint32_t *d_v_asm, uint8_t *d_valid) {
   if (!ctx || !seq || !d_v_read || !d_v_asm || !d_valid) return MFN_ERR_INVALID;
-  MFN_TRY(check_tables(reads, asm_));
+  MFN_TRY(check_tables(reads, asm_, true));
   MFN_CUDA(cudaSetDevice(ctx->device));
   MFN_CUDA(cudaMemsetAsync(d_v_read, 0, seq->total_bases * 4, ctx->stream));
   MFN_CUDA(cudaMemsetAsync(d_v_asm, 0, seq->total_bases * 4, ctx->stream));

@@ -46,6 +46,12 @@ static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, 
 
 // Can (and should) this scan use the sweep?
 bool mfn_sweep_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, uint32_t nseq) {
+  if (R->streamed) {
+    // no per-database table to fall back on: the range-partitioned scan of the restricted table or nothing
+    const mfn_joint *T = R->hot && R->hot->asm_ == A ? R->hot : nullptr;
+    uint32_t lbits, tbits, nbins, lowbits;
+    return T && sweep_geometry(T->dev, lbits, tbits, nbins, lowbits) && (uint64_t)nseq + 1 < (1ull << (63 - lowbits));
+  }
   const int mode = R->ctx ? R->ctx->sweep_mode : -1;
   if (mode == 0) return false;
   const char *env = getenv("MFN_SWEEP");

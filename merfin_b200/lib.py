@@ -74,6 +74,11 @@ class HistSummary(C.Structure):
                 ("n_undr", C.c_uint32), ("n_over", C.c_uint32)]
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("db_kmers", C.c_uint64), ("kept_kmers", C.c_uint64), ("shard_kmers", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("seconds", C.c_double)]
+
+
 class VcfInfo(C.Structure):
     _fields_ = [("headers", C.c_uint64), ("records", C.c_uint64), ("contigs", C.c_uint64), ("contig_ids", C.c_uint64),
                 ("excluded", C.c_uint64), ("clusters", C.c_uint64)]
@@ -111,6 +116,9 @@ SIGNATURES = {
     "mfn_tables_restrict": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32]),
     "mfn_tables_unrestrict": (C.c_int, [_P]),
     "mfn_restricted_info": (C.c_int, [_P, C.POINTER(JointInfo)]),
+    "mfn_tables_restrict_stream": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32, C.c_uint32, _PP, C.POINTER(StreamStats)]),
+    "mfn_tables_restrict_synth": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _PP,
+                                            C.POINTER(StreamStats)]),
     "mfn_joint_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "mfn_meryl_write": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, C.c_uint64]),
     "mfn_meryl_info": (C.c_int, [C.c_char_p, C.POINTER(MerylInfo)]),

@@ -173,6 +173,26 @@ def test_variants_abi_shards_and_threads(golden_dir):
     vcf.close(); R.close(); A.close(); ctx.close()
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "merfin")), reason="oracle/_ref not built (reference sources absent)")
+def test_cli_100mbp_against_reference():
+    """BASELINE configs[1] at full size: 100 Mbp FASTA + on-disk meryl databases through the CLI and through the
+    unmodified reference binary (tools/bench_cli.py): -hist file and summary block, the 2.8 GB -dump file,
+    -polish / -filter VCFs identical."""
+    import json
+    import sys
+    mbp = os.environ.get("MFN_TEST_CLI_MBP", "100")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_cli.py"), "--mbp", mbp, "--variants", "40000"],
+                       capture_output=True, text=True, timeout=1500)
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    if os.environ.get("MFN_TEST_OUT"):                       # keep the timings of the run (profiles/)
+        open(os.environ["MFN_TEST_OUT"], "w").write(json.dumps(r) + "\n")
+    assert r["hist_file_identical"] and r["hist_summary_identical"], r
+    assert r["dump_file_identical"] and r["dump_bytes"] > 20 * float(mbp) * 1e6, r
+    assert r["polish_vcf_same_lines"] and r["filter_vcf_same_lines"] and r["polish_vcf_records"] > 1000, r
+    print(json.dumps(r))
+
+
 def test_cli_usage_errors(tmp_path):
     p = subprocess.run([MERFIN, "-hist"], capture_output=True, text=True)
     assert p.returncode == 1

@@ -565,6 +565,63 @@ def test_completeness_shards_sum_to_the_whole(ctx, golden_dir):
     acc.close(); A.close()
 
 
+@pytest.mark.parametrize("name", ["g1_k21", "g3_k31"])
+def test_streamed_read_database(ctx, golden_dir, name):
+    """A read database streamed through the device into the restricted table (never resident: the answer to a
+    database bigger than the HBM) gives the -hist result of the resident tables, whole and in two shards,
+    also with -min/-max; -dump and path scoring refuse the handle."""
+    from merfin_b200 import api, lib as L
+    d = os.path.join(golden_dir, name)
+    recs = O.read_fasta(os.path.join(d, "asm.fa"))
+    km = api.KModel(8.0)
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    seq = api.SeqSet(ctx, recs)
+    for minV, maxV in ((0, 0xFFFFFFFF), (2, 12)):
+        R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"), minV, maxV)
+        want = api.hist(ctx, R, A, recs, km)
+        S, st = api.MerylExactLookup.restrict_stream(ctx, os.path.join(d, "reads.meryl"), A, seq, minV=minV, maxV=maxV)
+        assert st.db_kmers == api.meryl_info(os.path.join(d, "reads.meryl"))["n_distinct"] and 0 < st.kept_kmers <= st.shard_kmers
+        acc = api.Accum(ctx, len(recs))
+        api.hist_resident(ctx, S, A, seq, km, acc)
+        per, pairs = acc.fetch()
+        assert len(pairs) == len(want.pairs) and (pairs == want.pairs).all() and (per == want.per_seq).all()
+        # two shards, each with the table of its own half of the windows
+        acc.reset()
+        for sh in range(2):
+            S2, _ = api.MerylExactLookup.restrict_stream(ctx, os.path.join(d, "reads.meryl"), A, seq, sh, 2, minV=minV, maxV=maxV)
+            api.hist_resident(ctx, S2, A, seq, km, acc, sh, 2)
+            ctx.sync()
+            S2.close()
+        per, pairs = acc.fetch()
+        assert len(pairs) == len(want.pairs) and (pairs == want.pairs).all() and (per == want.per_seq).all()
+        with pytest.raises(L.MfnError) as e:
+            api.dump(ctx, S, A, recs)
+        assert e.value.status == L.MFN_ERR_UNSUPPORTED
+        acc.close(); S.close(); R.close()
+    seq.close(); A.close()
+
+
+def test_streamed_synthetic_database_equals_resident(ctx):
+    """mfn_tables_restrict_synth (the benchmark's database of any size, error k-mers generated in chunks and pushed
+    through the semi-join) against the same synthetic database built as a resident table: same -hist result."""
+    from merfin_b200 import api
+    rng = np.random.default_rng(8)
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1_500_000)
+    recs = [("a", base[:800_000].tobytes()), ("b", base[700_000:].tobytes()), ("n", b"ACGTN" * 2000)]
+    seq = api.SeqSet(ctx, recs)
+    A = api.MerylExactLookup.count_sequence(ctx, 21, seq)
+    R = api.MerylExactLookup.synth_reads(ctx, A, 12.0, 3_000_000, 5)
+    km = api.KModel(12.0)
+    want = api.hist(ctx, R, A, recs, km)
+    S, st = api.MerylExactLookup.restrict_synth(ctx, A, seq, 12.0, 3_000_000, 5, chunk_kmers=400_000)
+    assert st.db_kmers == 3_000_000 + A.nKmers() and st.shard_kmers == A.nKmers()
+    acc = api.Accum(ctx, len(recs))
+    api.hist_resident(ctx, S, A, seq, km, acc)
+    per, pairs = acc.fetch()
+    assert len(pairs) == len(want.pairs) and (pairs == want.pairs).all() and (per == want.per_seq).all()
+    acc.close(); S.close(); R.close(); A.close(); seq.close()
+
+
 def test_sweep_overflow_falls_back_to_the_direct_scan(ctx, monkeypatch):
     """A batch dominated by one k-mer (5 Mbp of poly-A) sends nearly every window to a single
     bin; the range-partitioned scan runs out of room there and mfn_hist redoes the batch with the

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--modes", default="hist,dump,score,completeness")
     ap.add_argument("--ks", default="15,21,31")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--db-fracs", default="0.25,1.0,2.0", help="dbsweep: read-database sizes as fractions of one GPU's HBM")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -76,7 +77,7 @@ def main():
         d.update({"gbp": total / 1e9, "data": "synthetic", "device": torch.cuda.get_device_name(0)})
         print(json.dumps(d), flush=True)
 
-    for k in [int(x) for x in args.ks.split(",")]:
+    for k in ([int(x) for x in args.ks.split(",")] if set(modes) - {"dbsweep"} else []):
         A = api.MerylExactLookup.count_sequence(ctx, k, seq)
         R = api.MerylExactLookup.synth_reads(ctx, A, B.COV_PER_COPY, int(total * 0.67), 7)
         R.fuse(A)
@@ -160,6 +161,51 @@ def main():
             finally:
                 shutil.rmtree(d, ignore_errors=True)
         R.close(); A.close()
+
+    if "dbsweep" in modes:
+        # BASELINE configs[4]: read-database size sweep, k = 21, incl. a database of twice the HBM.  The database is the
+        # synthetic one of bench.py with more error k-mers; it is STREAMED through the semi-join (mfn_tables_restrict_synth)
+        # and never resident, so the table the scan probes stays the size of the assembly's k-mer set.
+        k = 21
+        hbm = torch.cuda.get_device_properties(0).total_memory
+        A = api.MerylExactLookup.count_sequence(ctx, k, seq)
+        per_kmer = 7.3                                   # bytes per k-mer of a resident read table (25.7 GB / 3.53 G k-mers at the benchmark)
+        base_err = int(total * 0.67)
+        ref = None
+        for frac in [float(x) for x in args.db_fracs.split(",")]:
+            n_kmers = int(frac * hbm / per_kmer)
+            n_error = max(base_err, n_kmers - A.nKmers())
+            t0 = time.time()
+            S, st = api.MerylExactLookup.restrict_synth(ctx, A, seq, B.COV_PER_COPY, n_error, 7, chunk_kmers=1 << 28)
+            ctx.sync()
+            build_s = time.time() - t0
+            acc = api.Accum(ctx, len(lens))
+            ctx.time_passes(True)
+            ms = ev_ms(lambda: (acc.reset(), api.hist_resident(ctx, S, A, seq, None, acc, 0, 1)), args.steps)
+            sc, pr, ns = ctx.pass_times()
+            ctx.time_passes(False)
+            per, pairs = acc.fetch()
+            row = {"mode": "-hist, read database streamed through the semi-join (never resident)", "k": k,
+                   "db_fraction_of_hbm": frac, "db_kmers": int(st.db_kmers), "db_resident_table_GB_if_loaded": round(st.db_kmers * per_kmer / 1e9, 1),
+                   "hbm_GB": round(hbm / 1e9, 1), "kept_error_kmers": int(st.kept_kmers), "shard_kmers": int(st.shard_kmers),
+                   "restricted_table_GB": round(st.table_bytes / 1e9, 2), "stream_build_s": round(build_s, 2),
+                   "stream_kmers_per_s": st.db_kmers / build_s, "ms": ms, "bases_per_s": total / ms * 1e3,
+                   "roofline_frac": total * 64.25 / (ms / 1e3) / 1e9 / peak_gbs,
+                   "pass_ms": {"scatter": sc / ns, "probe": pr / ns} if ns else None,
+                   "kasm": int(per["kasm"].sum()), "kmissing": int(per["kmissing"].sum())}
+            if frac <= 0.3:
+                # small enough to load as well: the resident table of the same database gives the same integers
+                R = api.MerylExactLookup.synth_reads(ctx, A, B.COV_PER_COPY, n_error, 7)
+                R.fuse(A)
+                acc.reset()
+                api.hist_resident(ctx, R, A, seq, None, acc, 0, 1)
+                per2, pairs2 = acc.fetch()
+                row["equals_resident_table"] = bool(len(pairs2) == len(pairs) and (pairs2 == pairs).all() and (per2 == per).all())
+                row["resident_read_table_GB"] = round(R.info.device_bytes / 1e9, 2)
+                R.close()
+            emit(row)
+            acc.close(); S.close()
+        A.close()
     return 0
 
 
