@@ -10,6 +10,7 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -40,6 +41,13 @@ static std::string shell_quote(const std::string &p) {
   std::string q = "'";
   for (char c : p) { if (c == '\'') q += "'\\''"; else q += c; }
   return q + "'";
+}
+
+// MFN_TIMELINE=1: seconds since the start of main at every phase, to stderr
+static std::chrono::steady_clock::time_point g_t0;
+static void mark(const char *what) {
+  static const bool on = getenv("MFN_TIMELINE") != nullptr;
+  if (on) fprintf(stderr, "[timeline] %8.3f s  %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(), what);
 }
 
 #define MFN_TRY_MAIN(call) do { int s_ = (call); if (s_ != MFN_OK) return s_; } while (0)
@@ -170,6 +178,7 @@ static int reduce_and_fetch(std::vector<Dev> &devs, uint32_t nseq, std::vector<m
 }
 
 int main(int argc, char **argv) {
+  g_t0 = std::chrono::steady_clock::now();
   Globals G;
   std::vector<std::string> err;
   for (int a = 1; a < argc; a++) {
@@ -238,6 +247,7 @@ int main(int argc, char **argv) {
   for (size_t d = 0; d < devs.size(); d++) devs[d].id = G.devices[d];
   on_devices(devs, [&](Dev &D, size_t) { D.status = mfn_ctx_create(&D.ctx, D.id); if (D.status != MFN_OK) D.error = mfn_last_error(); });
   if (!devices_ok(devs, "cannot use the GPU")) return 1;
+  mark("CUDA contexts created");
   mfn_ctx *ctx = devs[0].ctx;
   const uint32_t ND = (uint32_t)devs.size();
 
@@ -300,6 +310,7 @@ int main(int argc, char **argv) {
   std::string e;
   if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
 
+  mark("sequences loaded");
   // every device loads its own replica of the tables (the databases are decoded on the device)
   mfn_meryl_info_t rmi;
   if (mfn_meryl_info(G.readDBname, &rmi) != MFN_OK) die("-readmers");
@@ -328,6 +339,7 @@ int main(int argc, char **argv) {
     if (st != MFN_OK) D.error = mfn_last_error();
   });
   if (!devices_ok(devs, "loading the databases")) return 1;
+  mark("tables loaded");
   mfn_table_info_t ri, ai;
   mfn_table_info(devs[0].A, &ai);
   if (ai.k != K) { fprintf(stderr, "mer size mismatch, can't process this set of files.\n"); return 1; }
@@ -357,11 +369,14 @@ int main(int argc, char **argv) {
         mfn_seq *seq = nullptr;
         mfn_table *T = nullptr;
         int st2 = mfn_seq_create(D.ctx, S.bases.data(), S.off.data(), (uint32_t)S.nseq(), &seq);
+        if (d == 0) mark("sequences packed on the device");
         if (st2 == MFN_OK) st2 = mfn_tables_restrict_stream(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, D.A, seq, (uint32_t)d, ND, &T, nullptr);
+        if (d == 0) mark("read database streamed into the restricted table");
         if (st2 == MFN_OK) st2 = mfn_accum_create(D.ctx, (uint32_t)S.nseq(), &D.acc);
         if (st2 == MFN_OK) st2 = mfn_hist_resident(D.ctx, T, D.A, seq, &km, (uint32_t)d, ND, D.acc);
         uint64_t np2 = 0;
         if (st2 == MFN_OK) st2 = mfn_accum_fetch(D.ctx, D.acc, 0, 0, nullptr, nullptr, 0, &np2);     // a bin or the side list overflowed?
+        if (d == 0) mark("scanned");
         D.status = st2;
         if (st2 != MFN_OK) D.error = mfn_last_error();
         mfn_table_free(T);
@@ -551,11 +566,13 @@ int main(int argc, char **argv) {
     mfn_vcf_free(vcf);
   }
 
+  mark("report written");
   for (Dev &D : devs) {
     mfn_table_free(D.R);
     mfn_table_free(D.A);
     mfn_ctx_destroy(D.ctx);
   }
+  mark("device memory released");
   fprintf(stderr, "Bye!\n");
   return 0;
 }

@@ -266,20 +266,22 @@ std::string VarMer::hetRecord(int idx1, int idx2) const {                       
 // merfin-variants.C:22-126.  idxList is shared down the recursion (shifted by the length change of
 // every ALT taken so far and restored afterwards); lenList is private to each level.
 static void traverse(uint32_t idx, std::vector<uint32_t> &idxList, std::vector<uint32_t> lenList,
-                     const std::vector<std::vector<std::string>> &haps, const std::string &candidate,
+                     const std::vector<const std::vector<std::string> *> &haps, const std::string &candidate,
                      std::vector<int> &path, VarMer &vm) {
-  const std::vector<std::string> &alts = haps[idx];
+  const std::vector<std::string> &alts = *haps[idx];
   const uint32_t refLen = lenList[idx];
   const uint32_t last = (uint32_t)idxList.size() - 1;
   for (size_t j = 0; j < alts.size(); j++) {
     path.push_back((int)j);
-    std::string replaced = candidate;
+    std::string changed;                                          // the candidate with this ALT put in (the REF allele keeps `candidate`)
+    const std::string &replaced = j > 0 ? changed : candidate;
     int skipped = 0, delta = 0;
     bool overlaps = false, done = false;
     if (j > 0) {
       lenList[idx] = refLen;
       const std::string &hap = alts[j];
-      replaced.replace(idxList[idx], lenList[idx], hap);          // throws like std::string::replace if out of range
+      changed = candidate;
+      changed.replace(idxList[idx], lenList[idx], hap);           // throws like std::string::replace if out of range
       delta = (int)hap.size() - (int)lenList[idx];
       const uint32_t affected = idxList[idx] + lenList[idx];
       lenList[idx] = (uint32_t)hap.size();
@@ -304,8 +306,23 @@ static void traverse(uint32_t idx, std::vector<uint32_t> &idxList, std::vector<u
   }
 }
 
+// merfinGlobal::getK (merfin-globals.C:66-98) per read multiplicity, tabulated once per call of
+// process_sequence: the replay below asks for it once per window of every path
+struct KTable {
+  static constexpr uint32_t N = 4096;
+  std::vector<double> rk, pr;
+  const mfn_kmodel *km;
+  explicit KTable(const mfn_kmodel *m) : rk(N), pr(N), km(m) {
+    for (uint32_t v = 0; v < N; v++) { double a; mfn_getK(m, v, 0, &rk[v], &a, &pr[v]); }
+  }
+  inline void get(uint32_t vr, double &readK, double &prob) const {
+    if (vr < N) { readK = rk[vr]; prob = pr[vr]; }
+    else { double a; mfn_getK(km, vr, 0, &readK, &a, &prob); }
+  }
+};
+
 // varMer.C:48-145 from the integer pairs of every window of every path
-static void score(VarMer &vm, const Options &opt, const uint32_t *vr, const uint32_t *va, const uint8_t *ok,
+static void score(VarMer &vm, const Options &opt, const KTable &kt, const uint32_t *vr, const uint32_t *va, const uint8_t *ok,
                   const std::vector<uint64_t> &off, size_t first_path, double &prob) {
   const uint32_t k = opt.k;
   for (size_t ii = 0; ii < vm.seqs.size(); ii++) {
@@ -315,16 +332,19 @@ static void score(VarMer &vm, const Options &opt, const uint32_t *vr, const uint
     std::vector<double> ks, dks;
     const size_t nwin = L >= k ? L - k + 1 : 0;
     if (opt.mode != FILTER) { ks.reserve(nwin); dks.reserve(nwin); }
+    const size_t nvar = vm.idxPaths[ii].size();
+    const uint32_t *ipath = vm.idxPaths[ii].data(), *lpath = vm.lenPaths[ii].data();
+    const int *gpath = vm.gtPaths[ii].data();
     for (size_t w = 0; w < nwin; w++) {
       double readK = 0, asmK = 0;
-      if (ok[base + w]) mfn_getK(&opt.km, vr[base + w], va[base + w], &readK, &asmK, &prob);
+      if (ok[base + w]) { kt.get(vr[base + w], readK, prob); asmK = (double)va[base + w]; }
       if (readK == 0) numM++;
       if (opt.mode == FILTER) { idx++; continue; }
       const double oD = fabs(readK - asmK) * prob;
-      for (size_t jj = 0; jj < vm.idxPaths[ii].size(); jj++) {
-        const uint32_t ip = vm.idxPaths[ii][jj], lp = vm.lenPaths[ii][jj];
+      for (size_t jj = 0; jj < nvar; jj++) {
+        const uint32_t ip = ipath[jj], lp = lpath[jj];
         // unsigned arithmetic as in the reference: ip + 1 - k wraps when ip < k - 1 (Q5)
-        if (vm.gtPaths[ii][jj] > 0 && (uint32_t)(ip + 1 - k) <= idx && idx < (uint32_t)(ip + lp + k)) { asmK++; break; }
+        if (gpath[jj] > 0 && (uint32_t)(ip + 1 - k) <= idx && idx < (uint32_t)(ip + lp + k)) { asmK++; break; }
       }
       double kMetric;
       if (readK == 0) kMetric = -1;
@@ -463,6 +483,7 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
   std::string paths;
   std::vector<uint64_t> off;
   ScoreOut sc;
+  const KTable kt(&opt.km);
   for (size_t b0 = first; b0 < cluster_end;) {
     // the pre-roll clusters ride along with the first batch
     const size_t b1 = std::min(cluster_end, (b0 < cluster_begin ? cluster_begin : b0) + batch_clusters);
@@ -477,8 +498,8 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
       if (rStart > K_PADD) rStart -= K_PADD; else rStart = 0;
       if (rEnd < seqLen - K_PADD) rEnd += K_PADD; else rEnd = (uint32_t)seqLen;        // (unsigned, as the reference)
       std::vector<uint32_t> idxList, lenList;
-      std::vector<std::vector<std::string>> haps;
-      for (GtAllele *g : pg->gts) { idxList.push_back(g->pos - rStart); lenList.push_back(g->refLen); haps.push_back(g->alleles); }
+      std::vector<const std::vector<std::string> *> haps;
+      for (GtAllele *g : pg->gts) { idxList.push_back(g->pos - rStart); lenList.push_back(g->refLen); haps.push_back(&g->alleles); }
       const bool keep = ci >= cluster_begin;
       if (rEnd < rStart || seqLen < rEnd) {                                            // dnaSeq::copy fails (sequence.C:521)
         if (keep) fprintf(stderr, "PANIC : Invalid region specified: %s : %u - %u\n", ident.c_str(), rStart, rEnd);
@@ -504,7 +525,7 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
 
     for (Work &w : work) {
       VarMer &vm = w.vm;
-      score(vm, opt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
+      score(vm, opt, kt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
       if (!w.keep) continue;
       if (debug) {
         char buf[512];

@@ -107,8 +107,10 @@ def main():
         ref = os.path.join(ROOT, "oracle", "_ref", "merfin")
         common = ["-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl", "-peak", str(B.PEAK)]
         res = {}
+        os.environ["MFN_TIMELINE"] = "1"
         t, err = run([ours, "-hist"] + common + ["-output", "ours.hist"], d, repeat=2)
         res["ours_hist_s"] = round(t, 2); ours_sum = summary(err)
+        res["ours_hist_timeline"] = [l.replace("[timeline]", "").strip() for l in err.splitlines() if l.startswith("[timeline]")]
         if not args.no_dump:
             t, err = run([ours, "-dump"] + common + ["-output", "ours.dump"], d)
             res["ours_dump_s"] = round(t, 2)
@@ -128,6 +130,7 @@ def main():
                 for mode, produced in (("-polish", "%s.polish.vcf"), ("-filter", "%s.filter.vcf")):
                     t, err = run([ours, mode] + common + ["-vcf", "calls.vcf", "-output", "ours"], d, repeat=2)
                     res["ours_%s_s" % mode[1:]] = round(t, 2)
+                    res["ours_%s_timeline" % mode[1:]] = [l.replace("[timeline]", "").strip() for l in err.splitlines() if l.startswith("[timeline]")]
                     t, err = run([ref, mode] + common + ["-vcf", "calls.vcf", "-threads", th, "-memory", "64", "-output", "ref"], d, repeat=2)
                     res["ref_%s_s" % mode[1:]] = round(t, 2)
                     a, b = open(os.path.join(d, produced % "ours"), "rb").read(), open(os.path.join(d, produced % "ref"), "rb").read()
