@@ -191,9 +191,18 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
             return v
 
         def process(v):
-            """All records, this rank's cluster range of each, on `threads` host threads; returns the texts in record order."""
-            order = sorted(range(len(lens)), key=lambda i: -lens[i])
-            out = [b""] * len(lens)
+            """All records, this rank's cluster range of each, on `threads` host threads; returns the texts in record order.
+            A record's range is cut further into pieces of ~50 000 clusters (shard = rank * S + s of world * S): records
+            are long and few, and one record per task leaves the threads waiting for the biggest one."""
+            tasks = []
+            for i in range(len(lens)):
+                nc = v.clusters_of(names[i])
+                if nc == 0:
+                    continue
+                S = max(1, -(-nc // (world * 50000)))
+                tasks += [(nc // (world * S), i, s, S) for s in range(S)]
+            tasks.sort(reverse=True)
+            parts = {}
             nxt = [0]
             lock = threading.Lock()
             err = []
@@ -203,22 +212,25 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
                     with lock:
                         j = nxt[0]
                         nxt[0] += 1
-                    if j >= len(order):
+                    if j >= len(tasks):
                         return
-                    i = order[j]
+                    _, i, s_, S = tasks[j]
                     try:
-                        out[i] = api.variants_process(ctx, R, A, v, names[i], base + int(off[i]), "polish", km,
-                                                      shard=rank, nshards=world, seq_len=int(lens[i]))
+                        parts[(i, s_)] = api.variants_process(ctx, R, A, v, names[i], base + int(off[i]), "polish", km,
+                                                              shard=rank * S + s_, nshards=world * S, seq_len=int(lens[i]))
                     except Exception as e:                       # noqa: BLE001
                         err.append(e)
                         return
-            th = [threading.Thread(target=worker) for _ in range(min(threads, len(order)))]
+            th = [threading.Thread(target=worker) for _ in range(min(threads, max(1, len(tasks))))]
             for t in th:
                 t.start()
             for t in th:
                 t.join()
             if err:
                 raise err[0]
+            out = [b""] * len(lens)
+            for (i, s_) in sorted(parts):
+                out[i] += parts[(i, s_)]
             return out
 
         def barrier():

@@ -506,40 +506,63 @@ int main(int argc, char **argv) {
     unsigned nthreads = G.threads ? G.threads : std::max(1u, std::thread::hardware_concurrency());
     if (G.debug) nthreads = 1;                                   // debug records carry a running id
     if (G.debug && ND > 1) { fprintf(stderr, "-debug runs on one device.\n"); return 1; }
-    nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, nrec));
     uint64_t varMerId = 0;
     {
-      // biggest records first (they bound the makespan)
-      std::vector<size_t> order(nrec);
-      for (size_t i = 0; i < nrec; i++) order[i] = i;
-      if (nthreads > 1) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return S.length(a) > S.length(b); });
-      std::atomic<size_t> next{0};
-      auto worker = [&]() {
-        for (size_t j; (j = next++) < nrec;) {
-          const size_t i = order[j];
-          if (mfn_vcf_clusters_of(vcf, S.ident[i].c_str()) == 0) continue;
-          uint64_t localId = 0;
-          if (ND == 1) {
-            status[i] = mfn_variants_process(ctx, R, A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb, &km, G.shard, G.nshards,
-                                             &results[i], nullptr, G.debug ? &dbgs[i] : nullptr, nullptr, nthreads == 1 ? &varMerId : &localId);
-          } else {
-            // -devices: cluster range d of N of this record goes to device d; the texts concatenate to the record's result
-            std::string all;
-            for (uint32_t d = 0; d < ND && status[i] == MFN_OK; d++) {
-              char *part = nullptr;
-              status[i] = mfn_variants_process(devs[d].ctx, devs[d].R, devs[d].A, vcf, S.ident[i].c_str(), S.seq(i), S.length(i), mode, G.comb,
-                                               &km, d, ND, &part, nullptr, nullptr, nullptr, &localId);
-              if (part) { all += part; mfn_text_free(part); }
-            }
-            if (status[i] == MFN_OK) { results[i] = (char *)malloc(all.size() + 1); memcpy(results[i], all.c_str(), all.size() + 1); }
+      // A task = one piece of one record's clusters: the pieces of a record are consecutive cluster ranges
+      // (mfn_variants_process shard / nshards) whose texts concatenate to the record's result.  With -devices the
+      // pieces of a record are dealt to the devices in turn; with -shard i/n only the pieces of range i are run.
+      // Records are long and few (24 at the benchmark): one record per task would leave the threads waiting
+      // for the biggest one.
+      struct Task { size_t rec; uint32_t piece, npieces, shard, nshards, dev; uint64_t weight; char *text = nullptr; };
+      std::vector<Task> tasks;
+      for (size_t i = 0; i < nrec; i++) {
+        const uint64_t nc = mfn_vcf_clusters_of(vcf, S.ident[i].c_str());
+        if (nc == 0) continue;
+        const uint32_t outer = ND > 1 ? ND : G.nshards;               // ranges that exist before the split into pieces
+        const char *pe = getenv("MFN_VARIANT_PIECE");                 // clusters per piece (tests make it small)
+        const uint64_t piece = pe && atoll(pe) > 0 ? (uint64_t)atoll(pe) : 50000;
+        uint32_t per = G.debug ? 1u : (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, (nc / outer + piece - 1) / piece));
+        for (uint32_t o = 0; o < outer; o++) {
+          if (ND == 1 && o != G.shard) continue;
+          for (uint32_t p = 0; p < per; p++) {
+            Task t;
+            t.rec = i; t.piece = o * per + p; t.npieces = outer * per; t.shard = o * per + p; t.nshards = outer * per;
+            t.dev = ND > 1 ? o : 0; t.weight = nc / (outer * per);
+            tasks.push_back(t);
           }
-          if (status[i] != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
+        }
+      }
+      std::vector<size_t> order(tasks.size());
+      for (size_t i = 0; i < order.size(); i++) order[i] = i;
+      nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, tasks.size()));
+      if (nthreads > 1) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tasks[a].weight > tasks[b].weight; });
+      std::atomic<size_t> next{0};
+      std::vector<int> tstatus(tasks.size(), MFN_OK);
+      auto worker = [&]() {
+        for (size_t j; (j = next++) < order.size();) {
+          Task &t = tasks[order[j]];
+          uint64_t localId = 0;
+          Dev &D = devs[t.dev];
+          tstatus[order[j]] = mfn_variants_process(D.ctx, D.R, D.A, vcf, S.ident[t.rec].c_str(), S.seq(t.rec), S.length(t.rec), mode, G.comb, &km,
+                                                   t.shard, t.nshards, &t.text, nullptr, G.debug ? &dbgs[t.rec] : nullptr, nullptr,
+                                                   nthreads == 1 ? &varMerId : &localId);
+          if (tstatus[order[j]] != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
         }
       };
       std::vector<std::thread> th;
       for (unsigned t = 1; t < nthreads; t++) th.emplace_back(worker);
       worker();
       for (auto &t : th) t.join();
+      // the pieces of a record, in order, are its result
+      std::vector<std::string> joined(nrec);
+      std::vector<char> has(nrec, 0);
+      for (size_t j = 0; j < tasks.size(); j++) {                 // tasks were created in (record, piece) order
+        Task &t = tasks[j];
+        if (tstatus[j] != MFN_OK) status[t.rec] = tstatus[j];
+        if (t.text) { joined[t.rec] += t.text; has[t.rec] = 1; mfn_text_free(t.text); }
+      }
+      for (size_t i = 0; i < nrec; i++)
+        if (has[i]) { results[i] = (char *)malloc(joined[i].size() + 1); memcpy(results[i], joined[i].c_str(), joined[i].size() + 1); }
     }
     for (size_t i = 0; i < nrec; i++) {
       if (status[i] != 0) return 1;

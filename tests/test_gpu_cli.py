@@ -79,11 +79,14 @@ def test_cli_devices_same_output(golden_dir, tmp_path, name, peak):
             assert l in err, devs
 
 
-def test_cli_devices_variants(golden_dir, tmp_path):
+def test_cli_devices_variants(golden_dir, tmp_path, monkeypatch):
+    """Variant modes over several contexts, and with every record cut into pieces of 7 clusters that are scored as
+    separate tasks (the CLI does that with 50 000 clusters per piece to keep its host threads busy)."""
     d = os.path.join(golden_dir, "g1_k21")
+    monkeypatch.setenv("MFN_VARIANT_PIECE", "7")
     base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
             "-readmers", os.path.join(d, "reads.meryl"), "-peak", "8", "-vcf", os.path.join(d, "calls.vcf")]
-    for devs in _device_lists():
+    for devs in ["0"] + _device_lists():
         for mode, produced in (("polish", "polish"), ("filter", "filter"), ("loose", "filter")):
             _run(base + ["-" + mode, "-output", "o", "-devices", devs], str(tmp_path))
             assert open(tmp_path / f"o.{produced}.vcf").read() == open(os.path.join(d, f"ref.{mode}.vcf")).read(), (devs, mode)
