@@ -109,6 +109,7 @@ struct mfn_joint;
 
 struct mfn_table {
   mfn_ctx   *ctx = nullptr;
+  int        device = 0;          // (kept apart from ctx: the object may be freed after its ctx)
   mfn_joint *joint = nullptr;     // fused (this, assembly) table built by mfn_tables_fuse
   mfn_joint *hot = nullptr;       // fused table restricted to the k-mers of one sequence shard (mfn_tables_restrict)
   bool       streamed = false;    // no per-database table behind this handle: the database was streamed into `hot` (joint_stream.cu)
@@ -123,6 +124,7 @@ struct mfn_table {
 
 struct mfn_seq {
   mfn_ctx  *ctx = nullptr;
+  int       device = 0;
   uint32_t  nseq = 0;
   uint64_t  total_bases = 0;      // caller's concatenated length
   uint64_t  G = 0;                // global coordinates incl. one separator per record
@@ -149,6 +151,7 @@ struct PairTable {                  // (v_read << 32 | v_asm) -> count, EMPTY = 
 
 struct mfn_accum {
   mfn_ctx  *ctx = nullptr;
+  int       device = 0;
   uint32_t  nseq = 0;
   uint64_t  nwords = 0;             // header + dense + 2*nseq
   unsigned long long *d_buf = nullptr;

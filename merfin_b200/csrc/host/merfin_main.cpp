@@ -351,7 +351,10 @@ int main(int argc, char **argv) {
       for (Dev &D : devs) if (D.status != MFN_OK) { fprintf(stderr, "-- (fused table not built on device %d: %s)\n", D.id, D.error.c_str()); D.status = MFN_OK; }
     }
   };
-  if (!stream_reads) fuse_all();
+  // The fused table costs one random insert per k-mer of both databases; a scan of a whole assembly earns that
+  // back many times over, a few hundred thousand variant paths do not (decided below, once the VCF is read).
+  const bool fuse_later = variants;
+  if (!stream_reads && !fuse_later) fuse_all();
   mfn_table *R = devs[0].R, *A = devs[0].A;
 
   // ---- -hist (merfin-histogram.C) ----------------------------------------------------------------
@@ -490,6 +493,14 @@ int main(int argc, char **argv) {
     fprintf(stderr, "   Excluded %lu invalid records\n\n", (unsigned long)vi.excluded);
     fprintf(stderr, "Merge variants within %u-mer bases, splitting combinations greater than %u.\n", K, G.comb);
     if (mfn_vcf_cluster(vcf, K, G.comb, G.nosplit) != MFN_OK) die("-vcf");
+    {
+      // ~100 path bases (windows) per VCF record against one insert per k-mer of the two tables
+      mfn_table_info_t tr, ta;
+      mfn_table_info(devs[0].R, &tr);
+      mfn_table_info(devs[0].A, &ta);
+      if (vi.records * 100 > (tr.n_kmers + ta.n_kmers) / 2) fuse_all();
+      mark("VCF loaded and clustered");
+    }
     fprintf(stderr, "-- Generate variant mers and score them.\n");
 
     const int mode = G.report == OP_POLISH ? MFN_MODE_POLISH : G.report == OP_BETTER ? MFN_MODE_BETTER : G.report == OP_STRICT ? MFN_MODE_STRICT

@@ -217,7 +217,7 @@ int meryl_stream_to_device_gpu(mfn_ctx *ctx, const MerylIndex &idx,
   std::vector<size_t> fwords(nfiles, 0);
   for (uint32_t f = file_begin; f < nfiles; f++)
     if (!file_words(meryl_file_name(idx, f, false), fwords[f])) { mfn_set_error("cannot read '%s'", meryl_file_name(idx, f, false).c_str()); return MFN_ERR_IO; }
-  const size_t GROUP_WORDS = (size_t)1 << 25;               // 256 MiB of file image per group
+  const size_t GROUP_WORDS = (size_t)1 << 23;               // 64 MiB of file image per group (two pinned buffers of the group size: pinning costs ~0.4 s per GB, which a small database would not earn back)
   std::vector<Group> groups;
   for (uint32_t f = file_begin; f < nfiles;) {
     Group g; g.f0 = f;

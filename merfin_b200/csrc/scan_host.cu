@@ -152,7 +152,7 @@ extern "C" int mfn_accum_create(mfn_ctx *ctx, uint32_t nseq, mfn_accum **out) {
   if (!ctx || !out) return MFN_ERR_INVALID;
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_accum *a = new mfn_accum();
-  a->ctx = ctx; a->nseq = nseq;
+  a->ctx = ctx; a->device = ctx->device; a->nseq = nseq;
   a->nwords = MFN_ACC_HEADER + (uint64_t)MFN_DENSE_R * MFN_DENSE_A + 2ull * nseq;
   a->sparse.mask = MFN_SPARSE_CAP - 1;
   cudaError_t e = cudaMalloc(&a->d_buf, a->nwords * 8);
@@ -208,7 +208,7 @@ extern "C" int mfn_accum_reset(mfn_ctx *ctx, mfn_accum *a) {
 
 extern "C" void mfn_accum_free(mfn_accum *a) {
   if (!a) return;
-  cudaSetDevice(a->ctx->device);
+  cudaSetDevice(a->device);
   cudaFree(a->d_buf); cudaFree(a->sparse.keys); cudaFree(a->sparse.counts); cudaFree(a->sparse.local_n);
   if (a->h_buf) cudaFreeHost(a->h_buf);
   delete a;

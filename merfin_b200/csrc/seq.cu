@@ -56,6 +56,7 @@ int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq 
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_seq *s = new mfn_seq();
   s->ctx = ctx;
+  s->device = ctx->device;
   s->nseq = nseq;
   s->total_bases = nseq ? seq_off[nseq] - seq_off[0] : 0;
   s->rec_start.resize((size_t)nseq + 1);
@@ -163,7 +164,7 @@ extern "C" int mfn_seq_info(const mfn_seq *s, uint64_t *total_bases, uint32_t *n
 
 extern "C" void mfn_seq_free(mfn_seq *s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
+  cudaSetDevice(s->device);
   cudaFree(s->d_seq2); cudaFree(s->d_ok); cudaFree(s->d_rec_start);
   delete s;
 }

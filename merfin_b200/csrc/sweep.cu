@@ -151,25 +151,31 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   // scatter3 (sweep_scatter3.cuh): k = 21, narrow entries, few bins, entry indices below 2^32
   const char *env3 = getenv("MFN_SCATTER");
   const bool s3 = !(env3 && atoi(env3) == 2) && P.J.k == 21 && P.lowbits <= SW_MAX_LOWBITS_NARROW && P.nbins <= S3_MAX_BINS &&
-                  (uint64_t)P.nbins * P.cap + S3_CHUNK < (1ull << 32);
+                  (uint64_t)P.nbins * P.cap + 8192 < (1ull << 32);
   if (s3) {
-    P.nbins_pad = (P.nbins + S3_THREADS - 1) / S3_THREADS * S3_THREADS;
-    const size_t smem3 = s3_smem_bytes(P.nbins_pad);
-    const uint64_t nchunks3 = ceil_div_u64(tile_end - tile_begin, S3_TILES);
+    const char *envt = getenv("MFN_S3_TILES");
+    const int tiles = envt && (atoi(envt) == 2 || atoi(envt) == 4) ? atoi(envt) : (P.nbins <= 256 ? 2 : 4);
+    const uint32_t threads3 = (uint32_t)tiles * 128;
+    P.nbins_pad = (P.nbins + threads3 - 1) / threads3 * threads3;
+    const size_t smem3 = s3_smem_bytes(P.nbins_pad, tiles);
+    const uint64_t nchunks3 = ceil_div_u64(tile_end - tile_begin, (uint64_t)tiles);
     auto launch3 = [&](auto kernel) -> int {
       int per_sm = 0;
       MFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, S3_THREADS, smem3);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads3, smem3);
       const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks3);
-      kernel<<<grid, S3_THREADS, smem3, ctx->stream>>>(P);
+      kernel<<<grid, threads3, smem3, ctx->stream>>>(P);
       return MFN_OK;
     };
     // the same with a 33-bit low part (twice the bins of half the size)
     const bool geo2 = P.J.fs_d == 1 && P.lowbits == 33 && P.lbits + P.tbits == 33 && P.tbits == P.J.fs_t &&
                       2 * P.J.k - 33 <= SC_BIN_BITS && P.nbins == (1u << (2 * P.J.k - 33));
-    if (geo1) MFN_TRY(launch3(k_sweep_scatter3<21, 1>));
-    else if (geo2) MFN_TRY(launch3(k_sweep_scatter3<21, 2>));
-    else MFN_TRY(launch3(k_sweep_scatter3<21, 0>));
+    const int geo = geo1 ? 1 : geo2 ? 2 : 0;
+    if (tiles == 2) {
+      if (geo == 1) MFN_TRY(launch3(k_sweep_scatter3<21, 1, 2>)); else if (geo == 2) MFN_TRY(launch3(k_sweep_scatter3<21, 2, 2>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0, 2>));
+    } else {
+      if (geo == 1) MFN_TRY(launch3(k_sweep_scatter3<21, 1, 4>)); else if (geo == 2) MFN_TRY(launch3(k_sweep_scatter3<21, 2, 4>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0, 4>));
+    }
   } else if (P.lowbits > SW_MAX_LOWBITS_NARROW) {
     switch (P.J.k) {
       case 31: MFN_TRY(launch(k_sweep_scatter<31, true, 0>)); break;

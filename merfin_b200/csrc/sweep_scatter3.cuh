@@ -20,29 +20,27 @@
 #pragma once
 #include "sweep_kernels.cuh"
 
-#define S3_THREADS 256
-#define S3_TILES 2
-#define S3_CHUNK (S3_TILES * MFN_TILE)            // 4096 windows per CTA round
-#define S3_NW (S3_CHUNK / S3_THREADS)              // 16 consecutive windows per thread
 #define S3_MAX_BINS 512
-#define S3_SEQ_WORDS (S3_CHUNK / 32 + 2)
-#define S3_OK_WORDS (S3_CHUNK / 64 + 2)
-// staging word: bits 0..1 low part bits 32..33 | bits 2..12 bin | bits 13..18 record delta | bit 19 counts twice | bits 20..31 rank
+// staging word: bits 0..1 low part bits 32..33 | bits 2..12 bin | bits 13..18 record delta | rank above (12 bits for
+// 4096-window chunks, 13 for 8192)
 #define S3_BIN_FIELD 0x1ffcu
 #define S3_RD_SHIFT 13
 #define S3_RD_MASK 0x3fu
-#define S3_TWICE_BIT 19
-#define S3_RANK_SHIFT 20
-#define S3_KEEP_MASK ((1u << S3_RANK_SHIFT) - 1u)
-#define S3_MAX_RD (S3_RD_MASK - 1u)
-static_assert(S3_CHUNK <= (1 << (32 - S3_RANK_SHIFT)), "rank field");
-static_assert((S3_SEQ_WORDS * 8) % 16 == 0 && (S3_OK_WORDS * 8) % 16 == 0, "TMA sizes are multiples of 16 B");
 
-static inline size_t s3_smem_bytes(uint32_t nbins_pad) { return (size_t)S3_CHUNK * 8 + (size_t)S3_CHUNK * 4 + (size_t)nbins_pad * 12; }
+// shape: TILES = 2 -> 256 threads, 4096-window chunks, 4 CTAs per SM (up to 256 bins);
+//        TILES = 4 -> 512 threads, 8192-window chunks, 2 CTAs per SM: with 512 bins the runs of a 4096-window chunk
+//        are 8 entries (64 B) long and the pass takes 14.7 ms instead of 10.6 at 3 Gbp; twice the chunk, same runs
+static inline size_t s3_smem_bytes(uint32_t nbins_pad, int tiles) { return (size_t)tiles * MFN_TILE * 12 + (size_t)nbins_pad * 12; }
 
-template <int KK, int GEO>
-__global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_constant__ SweepParams P) {
+template <int KK, int GEO, int TILES>
+__global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatter3(const __grid_constant__ SweepParams P) {
   static_assert(KK > 16 && KK < 32 && (KK & 1), "scatter3: odd 16 < k < 32");
+  static_assert(TILES == 2 || TILES == 4, "scatter3 shapes");
+  constexpr uint32_t S3_THREADS = TILES * 128, S3_TILES = TILES, S3_CHUNK = TILES * MFN_TILE, S3_NW = 16;
+  constexpr uint32_t S3_SEQ_WORDS = S3_CHUNK / 32 + 2, S3_OK_WORDS = S3_CHUNK / 64 + 2, S3_NWARPS = S3_THREADS / 32;
+  constexpr uint32_t S3_RANK_SHIFT = TILES == 2 ? 20 : 19, S3_KEEP_MASK = (1u << S3_RANK_SHIFT) - 1u;
+  static_assert(S3_CHUNK <= (1u << (32 - S3_RANK_SHIFT)), "rank field");
+  static_assert((S3_SEQ_WORDS * 8) % 16 == 0 && (S3_OK_WORDS * 8) % 16 == 0, "TMA sizes are multiples of 16 B");
   typedef Kmer2<KK> H;
   extern __shared__ __align__(16) unsigned char sw_smem[];
   unsigned long long *s_ent = (unsigned long long *)sw_smem;            // [S3_CHUNK] entries sorted by bin
@@ -50,7 +48,7 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
   uint32_t *s_cnt = (uint32_t *)(s_low4 + 4 * S3_THREADS);                // [nbins_pad] counts (zero between chunks)
   uint32_t *s_off = s_cnt + P.nbins_pad;                                  // [nbins_pad] exclusive offsets
   uint32_t *s_dst = s_off + P.nbins_pad;                                  // [nbins_pad] entry index of sorted position 0 in the bin's run
-  __shared__ __align__(16) uint32_t s_warp[S3_THREADS / 32];
+  __shared__ __align__(16) uint32_t s_warp[S3_NWARPS];
   __shared__ unsigned long long s_chunk[2];
   __shared__ uint32_t s_total, s_over;
   // the chunk's 2-bit words and validity bits (incl. a 64-base halo), staged by TMA one chunk ahead
@@ -257,11 +255,13 @@ __global__ void __launch_bounds__(S3_THREADS, 4) k_sweep_scatter3(const __grid_c
       if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
       if (tid == 0) s_over = 0;
       __syncthreads();                                                    // (2)
-      const uint4 wa = *(const uint4 *)&s_warp[0], wb = *(const uint4 *)&s_warp[4];
       const uint32_t w = tid >> 5;
       uint32_t wbase = 0;
-      wbase += w > 0 ? wa.x : 0u; wbase += w > 1 ? wa.y : 0u; wbase += w > 2 ? wa.z : 0u; wbase += w > 3 ? wa.w : 0u;
-      wbase += w > 4 ? wb.x : 0u; wbase += w > 5 ? wb.y : 0u; wbase += w > 6 ? wb.z : 0u;
+#pragma unroll
+      for (uint32_t x = 0; x < S3_NWARPS; x += 4) {
+        const uint4 t4 = *(const uint4 *)&s_warp[x];
+        wbase += w > x ? t4.x : 0u; wbase += w > x + 1 ? t4.y : 0u; wbase += w > x + 2 ? t4.z : 0u; wbase += w > x + 3 ? t4.w : 0u;
+      }
       const uint32_t run = wbase + incl - sum;
       s_off[b0] = run;
       if (bpt > 1) s_off[b0 + 1] = run + cnt0;

@@ -249,6 +249,8 @@ int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **o
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_table *t = new mfn_table();
   t->ctx = ctx;
+  t->device = ctx->device;
+  t->device = ctx->device;
   DevTable &d = t->dev;
   d.k = k;
   d.kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
@@ -354,7 +356,7 @@ int mfn_table_finalize(mfn_table *t, bool counted) {
 
 extern "C" void mfn_table_free(mfn_table *t) {
   if (!t) return;
-  cudaSetDevice(t->ctx->device);
+  cudaSetDevice(t->device);
   mfn_joint_free(t->joint);
   mfn_joint_free(t->hot);
   for (void *p : t->allocs) cudaFree(p);

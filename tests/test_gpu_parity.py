@@ -657,7 +657,7 @@ def test_sweep_overflow_falls_back_to_the_direct_scan(ctx, monkeypatch):
     ctx.set_sweep(-1)
     per, pairs = acc.fetch()
     assert len(pairs) == len(d.pairs) and (pairs == d.pairs).all() and (per == d.per_seq).all()
-    seq.close(); R.close(); A.close()
+    acc.close(); seq.close(); R.close(); A.close()
 
 
 def test_cli_dump_in_batches(golden_dir, tmp_path):
