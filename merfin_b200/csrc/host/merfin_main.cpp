@@ -52,6 +52,21 @@ static void mark(const char *what) {
 
 #define MFN_TRY_MAIN(call) do { int s_ = (call); if (s_ != MFN_OK) return s_; } while (0)
 
+// Output files as the reference's compressedFileWriter opens them (files-compressed.C:95-141): a name ending in
+// .gz / .bz2 / .xz is written through the matching compressor, anything else as it is.
+struct OutFile {
+  FILE *f = nullptr;
+  bool piped = false;
+  bool open(const std::string &path) {
+    auto ends = [&](const char *e) { const size_t n = strlen(e); return path.size() > n && path.compare(path.size() - n, n, e) == 0; };
+    const char *tool = ends(".gz") ? "gzip -1c" : ends(".bz2") ? "bzip2 -9c" : ends(".xz") ? "xz -1c" : nullptr;
+    if (tool) { f = popen((std::string(tool) + " > " + shell_quote(path)).c_str(), "w"); piped = true; }
+    else f = fopen(path.c_str(), "w");
+    return f != nullptr;
+  }
+  void close() { if (f) { if (piped) pclose(f); else fclose(f); f = nullptr; } }
+};
+
 static void die(const char *what) {
   fprintf(stderr, "%s: %s\n", what, mfn_last_error());
   exit(1);
@@ -448,10 +463,10 @@ int main(int argc, char **argv) {
       mfn_hist_format(undr.data(), sum.n_undr, over.data(), sum.n_over, nullptr, 0, &need);
       std::vector<char> text(need + 1);
       mfn_hist_format(undr.data(), sum.n_undr, over.data(), sum.n_over, text.data(), need + 1, &need);
-      FILE *F = fopen(G.outName, "w");
-      if (!F) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; }
-      fwrite(text.data(), 1, need, F);
-      fclose(F);
+      OutFile F;
+      if (!F.open(G.outName)) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; }
+      fwrite(text.data(), 1, need, F.f);
+      F.close();
       fprintf(stderr, "\n");
       fprintf(stderr, "K-mers not found in reads (missing) : %lu\n", (unsigned long)sum.kmissing);
       fprintf(stderr, "K-mers overly represented in assembly: %.2f\n", sum.koverCpy);
@@ -469,14 +484,15 @@ int main(int argc, char **argv) {
     fprintf(stderr, "-- Dump per-base k* metric to '%s'.\n", G.outName);
     // records go through the GPU in batches while the previous batch is formatted on the host threads
     // and written in position order (host/dump_driver.cpp)
-    FILE *F = nullptr;
-    if (!G.skipMissing && S.nseq() > 0) { F = fopen(G.outName, "w"); if (!F) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; } }
+    OutFile OF;
+    if (!G.skipMissing && S.nseq() > 0 && !OF.open(G.outName)) { fprintf(stderr, "cannot write '%s'\n", G.outName); return 1; }
+    FILE *F = OF.f;
     DumpBatchFn pairs = [&](const char *bases, const uint64_t *off, uint32_t nrec, uint32_t *vr, uint32_t *va, uint8_t *ok) {
       return mfn_dump(ctx, R, A, bases, off, nrec, vr, va, ok);
     };
     std::string derr;
     if (dump_records(S, &km, F ? fileno(F) : -1, (int)G.threads, 0, pairs, stderr, &derr) != MFN_OK) { fprintf(stderr, "-dump: %s\n", derr.c_str()); return 1; }
-    if (F) fclose(F);
+    OF.close();
   }
 
   // ---- variants (merfin-variants.C) --------------------------------------------------------------
@@ -506,6 +522,7 @@ int main(int argc, char **argv) {
     const int mode = G.report == OP_POLISH ? MFN_MODE_POLISH : G.report == OP_BETTER ? MFN_MODE_BETTER : G.report == OP_STRICT ? MFN_MODE_STRICT
                    : G.report == OP_LOOSE ? MFN_MODE_LOOSE : MFN_MODE_FILTER;
     std::string outPath = std::string(G.outName) + (G.report == OP_POLISH ? ".polish.vcf" : ".filter.vcf");   // merfin-variants.C:324-327 (Q7)
+    OutFile OO;
     FILE *O = nullptr, *D = nullptr;
     // Records are independent: path enumeration and selection run on host threads (one record per
     // task, like the reference's sweatShop workers; mfn_variants_process batches the record's probes
@@ -579,7 +596,7 @@ int main(int argc, char **argv) {
       if (status[i] != 0) return 1;
       if (!results[i]) continue;
       if (!O) {                                                  // outputVariants: header once, then every record's result
-        O = fopen(outPath.c_str(), "w");
+        if (OO.open(outPath)) O = OO.f;
         if (!O) { fprintf(stderr, "cannot write '%s'\n", outPath.c_str()); return 1; }
         uint64_t need = 0;
         mfn_vcf_header(vcf, nullptr, 0, &need);
@@ -595,7 +612,7 @@ int main(int argc, char **argv) {
       }
       mfn_text_free(dbgs[i]);
     }
-    if (O) fclose(O);
+    OO.close();
     if (D) pclose(D);
     mfn_vcf_free(vcf);
   }

@@ -196,6 +196,22 @@ def test_cli_100mbp_against_reference():
     print(json.dumps(r))
 
 
+def test_cli_compressed_outputs(golden_dir, tmp_path):
+    """-output names ending in .gz / .bz2 / .xz are written through the compressor, as the reference's
+    compressedFileWriter does; a path with a single quote in it is quoted for the shell."""
+    import bz2
+    import lzma
+    d = os.path.join(golden_dir, "g1_k21")
+    base = ["-sequence", os.path.join(d, "asm.fa"), "-seqmers", os.path.join(d, "asm.meryl"),
+            "-readmers", os.path.join(d, "reads.meryl"), "-peak", "8"]
+    want = open(os.path.join(d, "ref.hist"), "rb").read()
+    for name, opener in (("o.hist.gz", gzip.open), ("o.hist.bz2", bz2.open), ("o.hist.xz", lzma.open), ("it's.hist.gz", gzip.open)):
+        _run(base + ["-hist", "-output", name], str(tmp_path))
+        assert opener(tmp_path / name, "rb").read() == want, name
+    _run(base + ["-dump", "-output", "o.dump.gz"], str(tmp_path))
+    assert gzip.open(tmp_path / "o.dump.gz", "rb").read() == gzip.open(os.path.join(d, "ref.dump.gz"), "rb").read()
+
+
 def test_cli_usage_errors(tmp_path):
     p = subprocess.run([MERFIN, "-hist"], capture_output=True, text=True)
     assert p.returncode == 1
