@@ -15,22 +15,21 @@ static const mfn_joint *sweep_table(const mfn_table *R, const mfn_table *A) {
   return nullptr;
 }
 
-// Bins of 2^lbits lines: a slice of the table of at most MFN_SWEEP_SLICE_MB, at most SW_MAX_BINS bins.
-// Default 64 MB: measured at the 3 Gbp benchmark (restricted table of 2^27 lines, profiles/r02_call6_summary.txt),
-// 256 bins of 64 MB cost the probe pass 14.8 ms instead of 12.0 ms with 512 bins of 32 MB (two slices in
-// flight no longer fit the L2), but the scatter pass 10.6 ms instead of 16.5 (14.8 with the counters
-// spread): half the runs, twice as long.  The entry's low
-// part holds (line in bin) << tbits | tag: up to 34 bits in a narrow entry, else up to 52 bits for
-// tables with 64-bit slots (wide entries, fewer bits left for the record).  The fewer bins, the
-// cheaper the scatter pass (per-chunk zeroing, scan and one reservation per bin) and the longer its
-// runs; the bigger the slice, the lower the probe pass's L2 hit rate.
+// Bins of 2^lbits lines: a slice of the table of at most MFN_SWEEP_SLICE_MB (default 32 MB: two of them in
+// flight fit the L2 next to the entry stream), at most SW_MAX_BINS bins.  The entry's low part holds
+// (line in bin) << tbits | tag: up to 34 bits in a narrow entry, else up to 52 bits for tables with 64-bit
+// slots (wide entries, fewer bits left for the record).  Measured at the 3 Gbp benchmark (restricted table of
+// 2^27 lines; profiles/r02_call12_summary.txt): 512 bins of 32 MB = scatter 12.8 ms (8192-window chunks) +
+// probe 12.3 ms; 256 bins of 64 MB = scatter 10.65 ms (4096-window chunks, 4 CTAs per SM) + probe 14.5 ms
+// (two slices in flight no longer fit the L2: the table is read 2.3 x).  Same sum, but the host-buffer path
+// exposes the last probe pass, so the shorter probe wins end to end (39.2 against 42.3 ms).
 static bool sweep_geometry(const JointDev &J, uint32_t &lbits, uint32_t &tbits, uint32_t &nbins, uint32_t &lowbits) {
   tbits = std::max(1u, bits_of(J.D - 1));
   if (J.nlines >= (1ull << 32)) return false;
   const char *env = getenv("MFN_SWEEP_SLICE_MB");
-  uint32_t slice_mb = env ? (uint32_t)atoi(env) : 64u;
-  if (slice_mb < 1 || slice_mb > 256) slice_mb = 64;
-  const uint32_t lb_want = bits_of((uint64_t)slice_mb * (1u << 20) / 128) - 1;     // 64 MB -> 19
+  uint32_t slice_mb = env ? (uint32_t)atoi(env) : 32u;
+  if (slice_mb < 1 || slice_mb > 256) slice_mb = 32;
+  const uint32_t lb_want = bits_of((uint64_t)slice_mb * (1u << 20) / 128) - 1;     // 32 MB -> 18
   for (int wide = 0; wide < 2; wide++) {
     const uint32_t room = wide ? 52u : (uint32_t)SW_MAX_LOWBITS_NARROW;
     if (wide && !J.w64) break;
