@@ -132,7 +132,10 @@ extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
   ScanParams P{};
   P.R = reads->dev; P.A = asm_->dev;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
-  P.tile_begin = 0; P.tile_end = seq->ntiles;
+  // big batches over a fused table: the range-partitioned path (sweep_dump.cu); the direct scan does the rest
+  uint64_t done_tiles = 0;
+  MFN_TRY(mfn_sweep_dump(ctx, reads, asm_, seq, d_v_read, d_v_asm, d_valid, &done_tiles));
+  P.tile_begin = done_tiles; P.tile_end = seq->ntiles;
   P.out_vr = d_v_read; P.out_va = d_v_asm; P.out_valid = d_valid;
   return launch_scan(ctx, P, true, use_joint(reads, asm_, P));
 }

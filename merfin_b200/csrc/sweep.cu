@@ -236,3 +236,105 @@ int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const m
   if (ctx->time_passes) mfn_ctx_mark(ctx);
   return st != MFN_OK ? st : st2;
 }
+
+// ------------------------------------------------------------------------------------------
+// -dump / path scoring through the range-partitioned scan (sweep_dump.cu)
+// ------------------------------------------------------------------------------------------
+void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_t stream);
+void mfn_sweep_dump_launch_gather(const uint32_t *where, const unsigned long long *entries, const unsigned long long *rec_start, uint32_t nseq,
+                                  uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream);
+
+// k = 21 (scatter3), canonical 32-bit-slot table, narrow entries, at most 512 bins
+bool mfn_sweep_dump_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, bool force) {
+  if (R->streamed) return false;
+  const mfn_joint *T = sweep_table(R, A);
+  if (!T || T->dev.k != 21 || T->dev.w64) return false;
+  uint32_t lbits, tbits, nbins, lowbits;
+  if (!sweep_geometry(T->dev, lbits, tbits, nbins, lowbits)) return false;
+  if (lowbits > SW_MAX_LOWBITS_NARROW || nbins > S3_MAX_BINS) return false;
+  const uint64_t windows = ntiles * MFN_TILE;
+  return force || windows * 4 >= T->dev.nlines;               // worth it when the windows revisit the table lines
+}
+
+int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t tile_begin, uint64_t tile_end,
+                         uint32_t *d_vr, uint32_t *d_va, uint8_t *d_valid, int *ok) {
+  *ok = 0;
+  const mfn_joint *T = sweep_table(R, A);
+  const JointDev &J = T->dev;
+  SweepParams P{};
+  P.J = J;
+  P.restricted = T->restricted ? 1u : 0u;
+  if (T->restricted) { P.R = T->reads->dev; P.A = T->asm_->dev; }
+  P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
+  {
+    const uint64_t gpad = (seq->ntiles + 1) * MFN_TILE + 256;
+    P.seq_words = gpad / 32 + 8; P.ok_words = gpad / 64 + 8;
+  }
+  if (!sweep_geometry(J, P.lbits, P.tbits, P.nbins, P.lowbits)) return MFN_OK;
+  const uint64_t windows = (tile_end - tile_begin) * MFN_TILE;
+  P.cap = ((uint64_t)((double)windows / P.nbins * 1.15) + 2048 + 31) & ~31ull;
+  if ((uint64_t)P.nbins * P.cap + 8192 >= (1ull << 32)) return MFN_OK;
+  P.cstride = 1;
+  P.tile_begin = tile_begin; P.tile_end = tile_end;
+  {
+    const uint32_t vb = (J.rbits + J.abits) & 31u;
+    P.pr_lim = (1u << vb) - 1u;
+    P.pr_wmask = ((1u << P.tbits) - 1u) << vb;
+  }
+  const int tiles = P.nbins <= 256 ? 2 : 4;
+  const uint32_t threads3 = (uint32_t)tiles * 128;
+  P.nbins_pad = (P.nbins + threads3 - 1) / threads3 * threads3;
+  const uint64_t nchunks = ceil_div_u64(tile_end - tile_begin, (uint64_t)tiles);
+  const size_t nwhere = (size_t)nchunks * tiles * MFN_TILE;
+  unsigned long long *ctl = nullptr;
+  const size_t cwords = (size_t)P.nbins_pad + 8;                       // bin counts, overflow count, two work counters
+  cudaError_t e = cudaMallocAsync(&P.entries, (size_t)P.nbins * P.cap * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&P.where, nwhere * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&ctl, cwords * 8, ctx->stream);
+  if (e != cudaSuccess) {
+    // no room for the workspace: not an error, the direct scan needs none
+    cudaGetLastError();
+    if (P.entries) cudaFreeAsync(P.entries, ctx->stream);
+    if (P.where) cudaFreeAsync(P.where, ctx->stream);
+    return MFN_OK;
+  }
+  MFN_CUDA(cudaMemsetAsync(ctl, 0, cwords * 8, ctx->stream));
+  P.bin_count = ctl; P.over_n = ctl + P.nbins_pad; P.counter = ctl + P.nbins_pad + 1;
+  P.over_cap = 0;
+  const bool geo1 = J.fs_d == 1 && P.lowbits == 34 && P.lbits + P.tbits == 34 && P.tbits == J.fs_t && P.nbins == (1u << (2 * J.k - 34));
+  const bool geo2 = J.fs_d == 1 && P.lowbits == 33 && P.lbits + P.tbits == 33 && P.tbits == J.fs_t && P.nbins == (1u << (2 * J.k - 33));
+  const size_t smem3 = s3_smem_bytes(P.nbins_pad, tiles);
+  auto launch3 = [&](auto kernel) -> int {
+    int per_sm = 0;
+    MFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads3, smem3);
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), nchunks);
+    kernel<<<grid, threads3, smem3, ctx->stream>>>(P);
+    return MFN_OK;
+  };
+  const int geo = geo1 ? 1 : geo2 ? 2 : 0;
+  if (tiles == 2) {
+    if (geo == 1) MFN_TRY(launch3(k_sweep_scatter3<21, 1, 2, true>)); else if (geo == 2) MFN_TRY(launch3(k_sweep_scatter3<21, 2, 2, true>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0, 2, true>));
+  } else {
+    if (geo == 1) MFN_TRY(launch3(k_sweep_scatter3<21, 1, 4, true>)); else if (geo == 2) MFN_TRY(launch3(k_sweep_scatter3<21, 2, 4, true>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0, 4, true>));
+  }
+  ctx->launches++;
+  // did every run fit its bin?  (the outputs are only written by the last pass)
+  unsigned long long over = 0;
+  MFN_CUDA(cudaMemcpyAsync(&over, P.over_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFN_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (over == 0) {
+    P.counter = ctl + P.nbins_pad + 2;
+    mfn_sweep_dump_launch_probe(P, ctx->sm_count, ctx->stream);
+    mfn_sweep_dump_launch_gather(P.where, P.entries, seq->d_rec_start, seq->nseq, tile_begin * MFN_TILE, tile_end * MFN_TILE,
+                                 d_vr, d_va, d_valid, ctx->stream);
+    ctx->launches += 2;
+    *ok = 1;
+  }
+  cudaError_t e2 = cudaGetLastError();
+  cudaFreeAsync(P.entries, ctx->stream);
+  cudaFreeAsync(P.where, ctx->stream);
+  cudaFreeAsync(ctl, ctx->stream);
+  if (e2 != cudaSuccess) { mfn_set_error("dump sweep: %s", cudaGetErrorString(e2)); return MFN_ERR_CUDA; }
+  return MFN_OK;
+}

@@ -1,0 +1,145 @@
+// -dump / path scoring through the range-partitioned scan (see sweep_kernels.cuh, sweep_scatter3.cuh).
+//
+// The direct scan (k_scan<DUMP>) pays one random 128-byte HBM line per window: 34 Gbases/s, 0.38 of the
+// 72.25 B/base roofline.  -dump needs its answers in window order, which the two-pass scan does not give --
+// but it can put them back:
+//   pass 1  k_sweep_scatter3<.., DUMP>  as for -hist, and where[window] = index of the window's entry
+//   pass 2  k_sweep_probe_dump          bins in order; every entry is OVERWRITTEN by its (v_read, v_asm) pair
+//   pass 3  k_sweep_gather              windows in order: out[position] = entries[where[window]]
+// Pass 3's 8-byte gathers are DRAM-friendly: the 8192 windows of a chunk left their entries in one run of
+// ~128 bytes per bin, and the CTA that gathers the chunk reads all of them.  DRAM traffic per window:
+// 8 + 4 written, 8 + table/windows read, 8 written, 4 + 8 read, 9 written -- about 55 bytes instead of 128+.
+// (own translation unit: the probe kernel calls the out-of-line complete lookup; ptxas 12.9 crashes when two
+// entries of a module share it)
+#include "sweep_scatter3.cuh"
+
+// (v_read, v_asm) of one entry whose home sector does not settle it: the other sectors of the line, then the
+// complete lookup; a table restricted to other sequences falls back to the per-database tables
+static __device__ __forceinline__ void dump_slow(const SweepParams &P, uint32_t line, uint64_t tag, uint32_t &vr, uint32_t &va) {
+  const uint64_t c = mfn_unmix((uint64_t)line * P.J.D + tag, P.J.seed, P.J.kmask, P.J.k);
+  joint_full(P.J, c, line, tag, vr, va);
+  if (P.restricted && (vr | va) == 0) { vr = mfn_value(P.R, c); va = mfn_value(P.A, c); }
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid_constant__ SweepParams P) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
+  const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
+  const uint32_t tbits = P.tbits;
+  const uint64_t tmask64 = (1ull << tbits) - 1ull;
+  const uint64_t lowmask = (1ull << P.lowbits) - 1ull;
+  const uint32_t himask = (uint32_t)(lowmask >> 32);
+  const uint32_t vb = P.J.rbits + P.J.abits, abits = P.J.abits, amax = P.J.amax, rmax = P.J.rmax;
+
+  while (true) {
+    uint64_t item = 0;
+    if (lane == 0) item = atomicAdd(P.counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    const uint64_t bin = item / slices_per_bin, s = item % slices_per_bin;
+    const uint64_t cnt = min(P.bin_count[bin * P.cstride], (unsigned long long)P.cap);
+    if (s * SW_SLICE >= cnt) continue;
+    unsigned long long *src = P.entries + bin * P.cap + s * SW_SLICE;
+    const uint32_t n = (uint32_t)min((uint64_t)SW_SLICE, cnt - s * SW_SLICE);
+    const uint32_t line0 = (uint32_t)bin << P.lbits;
+    const char *slice = (const char *)P.J.lines + (uint64_t)line0 * 128;
+
+    auto line_in_bin = [&](unsigned long long e) { return __funnelshift_r((uint32_t)e, (uint32_t)(e >> 32) & himask, tbits); };
+    auto sector_of = [&](unsigned long long e) { return slice + (((uint64_t)line_in_bin(e) << 2) | ((uint32_t)e & 3u)) * 32; };
+    // entry + its home sector -> the pair, packed as v_asm << 32 | v_read
+    auto resolve = [&](unsigned long long e, const Bucket &b) -> unsigned long long {
+      const uint32_t lw = (uint32_t)e;
+      const uint32_t pay = sweep_match32(b, ~((lw << vb) & P.pr_wmask), P.pr_lim);
+      uint32_t vr = pay >> abits, va = pay & amax;
+      if (pay == 0xffffffffu || vr >= rmax || va >= amax) {
+        const uint64_t lp = e & lowmask;
+        dump_slow(P, line0 + (uint32_t)(lp >> tbits), lp & tmask64, vr, va);
+      }
+      return ((unsigned long long)va << 32) | vr;
+    };
+    const uint32_t nfull = n >> 7;
+#pragma unroll 1
+    for (uint32_t bt = 0; bt < nfull; bt++) {
+      unsigned long long e[4];
+      unsigned long long *p = src + bt * 128u + lane * 4u;
+      asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(p));
+      Bucket b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) sweep_load_sector(sector_of(e[u]), b[u]);
+      unsigned long long r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) r[u] = resolve(e[u], b[u]);
+      asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]) : "memory");
+    }
+    for (uint32_t i = (nfull << 7) + lane; i < n; i += 32) {
+      const unsigned long long e = src[i];
+      Bucket b;
+      sweep_load_sector(sector_of(e), b);
+      src[i] = resolve(e, b);
+    }
+  }
+}
+
+// pass 3: windows in order.  A thread takes 8 consecutive windows; positions are reported in the caller's
+// coordinates (one separator slot per earlier record, as k_scan<DUMP> does).
+__global__ void __launch_bounds__(256) k_sweep_gather(const uint32_t *__restrict__ where, const unsigned long long *__restrict__ entries,
+                                                      const unsigned long long *__restrict__ rec_start, uint32_t nseq, uint64_t g_begin,
+                                                      uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid) {
+  const uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 8;
+  const uint64_t g0 = g_begin + t;
+  if (g0 >= g_end) return;
+  const uint4 w0 = *(const uint4 *)(where + t), w1 = *(const uint4 *)(where + t + 4);
+  const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  unsigned long long r[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
+  // record of the first window (binary search), then walk
+  uint32_t rec;
+  {
+    uint32_t a = 0, b = nseq;
+    while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= g0) a = m; else b = m - 1; }
+    rec = a;
+  }
+  uint64_t next_start = rec < nseq ? rec_start[rec + 1] : ~0ull;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const uint64_t g = g0 + u;
+    if (g >= g_end) break;
+    while (g >= next_start) { rec++; next_start = rec < nseq ? rec_start[rec + 1] : ~0ull; }
+    if (w[u] == 0xffffffffu || rec >= nseq) continue;          // outputs were zeroed: valid = 0
+    const uint64_t sidx = g - rec;
+    out_vr[sidx] = (uint32_t)r[u]; out_va[sidx] = (uint32_t)(r[u] >> 32); out_valid[sidx] = 1;
+  }
+}
+
+// Host side.  *done_tiles = how many leading tiles of the sequence set got their outputs from the
+// range-partitioned path (0: it does not apply); the caller runs the direct scan over the rest.
+int mfn_sweep_dump(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint32_t *d_vr, uint32_t *d_va,
+                   uint8_t *d_valid, uint64_t *done_tiles) {
+  *done_tiles = 0;
+  const char *env = getenv("MFN_DUMP_SWEEP");
+  if (env && atoi(env) == 0) return MFN_OK;
+  const bool force = env && atoi(env) == 1;
+  if (!force && seq->ntiles * MFN_TILE < (1ull << 24)) return MFN_OK;
+  if (!mfn_sweep_dump_applicable(R, A, seq->ntiles, force)) return MFN_OK;
+  // pieces of at most ~1.5e9 windows: entry indices stay below 2^32
+  const uint64_t piece_tiles = 720000;
+  for (uint64_t tb = 0; tb < seq->ntiles; tb += piece_tiles) {
+    const uint64_t te = std::min(seq->ntiles, tb + piece_tiles);
+    int ok = 0;
+    MFN_TRY(mfn_sweep_dump_piece(ctx, R, A, seq, tb, te, d_vr, d_va, d_valid, &ok));
+    if (!ok) break;                                          // a bin overflowed: the direct scan takes it from here
+    *done_tiles = te;
+  }
+  return MFN_OK;
+}
+
+void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_t stream) {
+  k_sweep_probe_dump<<<sm_count * 3, SW_THREADS, 0, stream>>>(P);
+}
+
+void mfn_sweep_dump_launch_gather(const uint32_t *where, const unsigned long long *entries, const unsigned long long *rec_start, uint32_t nseq,
+                                  uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream) {
+  const uint64_t threads = ceil_div_u64(g_end - g_begin, 8);
+  k_sweep_gather<<<(unsigned)ceil_div_u64(threads, 256), 256, 0, stream>>>(where, entries, rec_start, nseq, g_begin, g_end, out_vr, out_va, out_valid);
+}

@@ -32,7 +32,10 @@
 //        are 8 entries (64 B) long and the pass takes 14.7 ms instead of 10.6 at 3 Gbp; twice the chunk, same runs
 static inline size_t s3_smem_bytes(uint32_t nbins_pad, int tiles) { return (size_t)tiles * MFN_TILE * 12 + (size_t)nbins_pad * 12; }
 
-template <int KK, int GEO, int TILES>
+// DUMP: the -dump / path-scoring flavour (sweep_dump.cu): no records and no counters; every valid window's
+// entry index is written to P.where[window] (0xffffffff: no window), so that the pair the probe pass leaves in
+// the entry can be gathered back in position order afterwards.
+template <int KK, int GEO, int TILES, bool DUMP = false>
 __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatter3(const __grid_constant__ SweepParams P) {
   static_assert(KK > 16 && KK < 32 && (KK & 1), "scatter3: odd 16 < k < 32");
   static_assert(TILES == 2 || TILES == 4, "scatter3 shapes");
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
     const uint64_t chunk = s_chunk[buf];              // written before the previous round's barriers (or the one above)
     if (chunk >= nchunks) break;
     const uint64_t tile0 = P.tile_begin + chunk * S3_TILES;
-    {
+    if (!DUMP) {
       const uint64_t gt = tile0 * MFN_TILE;
       if (gt >= cur_end) {
         flush_rec();
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
     }
     const uint32_t r0 = cur_rec;
     const uint64_t r0_end = cur_end;
-    const bool one_record = (tile0 + S3_TILES) * MFN_TILE <= r0_end;
+    const bool one_record = DUMP || (tile0 + S3_TILES) * MFN_TILE <= r0_end;
+    uint32_t *const where = DUMP ? P.where + (tile0 - P.tile_begin) * MFN_TILE : nullptr;    // this chunk's slice
     // the other staging buffer was last read before barrier (1) of the previous round
     if (tid == 0) { stage(pre, buf ^ 1); pre = atomicAdd(P.counter, 1ull); }
     mbar_wait(&s_bar[buf], (it >> 1) & 1);
@@ -199,7 +203,10 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
         for (int u = 0; u < S3_NW; u++) if (((okb >> u) & kbits) == kbits) vmask |= 1u << u;
         // record of each window: 4 bits of delta per window here, bigger deltas take the side list
         uint64_t rdpack = 0;
-        if (one_record || vmask == 0) n_ok0 += __popc(vmask);
+        if (DUMP) {
+#pragma unroll
+          for (int u = 0; u < S3_NW; u++) if (!((vmask >> u) & 1u)) where[j0 + u] = 0xffffffffu;
+        } else if (one_record || vmask == 0) n_ok0 += __popc(vmask);
         else {
           const uint64_t g0 = tile0 * MFN_TILE + j0;
           uint32_t rec = r0;
@@ -288,13 +295,19 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
           const uint32_t m = meta[h + i];
           pos[i] = *(const uint32_t *)((const char *)s_off + (m & S3_BIN_FIELD)) + (m >> S3_RANK_SHIFT);
         }
+        // staged high word: bin << 2 | low-part bits 32..33, and above them the record delta -- or, DUMP, the
+        // window's index in the chunk
+        auto staged = [&](int idx) -> unsigned long long {
+          const uint32_t hw = DUMP ? ((meta[idx] & 0x1fffu) | ((tid * S3_NW + (uint32_t)idx) << 13)) : (meta[idx] & S3_KEEP_MASK);
+          return ((unsigned long long)hw << 32) | lows[idx];
+        };
         if (live == 0xffffu) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) s_ent[pos[i]] = ((unsigned long long)(meta[h + i] & S3_KEEP_MASK) << 32) | lows[h + i];
+          for (int i = 0; i < 8; i++) s_ent[pos[i]] = staged(h + i);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            if ((live >> (h + i)) & 1u) s_ent[pos[i]] = ((unsigned long long)(meta[h + i] & S3_KEEP_MASK) << 32) | lows[h + i];
+            if ((live >> (h + i)) & 1u) s_ent[pos[i]] = staged(h + i);
         }
       }
     }
@@ -315,7 +328,23 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
       const uint32_t total = s_total;
       const uint32_t r0s = r0 << xbits;
       unsigned long long *const ent = P.entries;
-      if (one_record && !s_over) {
+      if (DUMP) {
+        // entry = low part only; where[window] = the entry's index.  A run that does not fit its bin makes the whole
+        // call fall back to the direct scan (over_n != 0 is checked by the host before the probe pass).
+        for (uint32_t i = tid; i < total; i += S3_THREADS) {
+          const unsigned long long e = s_ent[i];
+          const uint32_t hs = (uint32_t)(e >> 32);
+          const uint32_t bin = (hs & S3_BIN_FIELD) >> 2;
+          const uint32_t d = *(const uint32_t *)((const char *)s_dst + (hs & S3_BIN_FIELD)) + i;
+          if ((unsigned long long)d < (unsigned long long)(bin + 1) * P.cap) {
+            *(uint2 *)(ent + d) = make_uint2((uint32_t)e, hs & 3u);
+            where[hs >> 13] = d;
+          } else {
+            where[hs >> 13] = 0xffffffffu;
+            atomicAdd(P.over_n, 1ull);
+          }
+        }
+      } else if (one_record && !s_over) {
         // the entry's high word: the chunk's record next to the staged bits 32..33 of the low part
         if (total == S3_CHUNK) {
 #pragma unroll
@@ -354,6 +383,7 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
     }
     SW_PROF_MARK(6);
   }
+  if (DUMP) return;
   flush_rec();
   for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xffffffffu, my_valid, o);
   if ((tid & 31) == 0 && my_valid) atomicAdd(&P.acc[0], my_valid);

@@ -91,4 +91,10 @@ int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const 
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out);
 int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end);
 int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w);
+// -dump through the range-partitioned scan (sweep_dump.cu / sweep.cu)
+bool mfn_sweep_dump_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, bool force);
+int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t tile_begin, uint64_t tile_end,
+                         uint32_t *d_vr, uint32_t *d_va, uint8_t *d_valid, int *ok);
+int mfn_sweep_dump(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint32_t *d_vr, uint32_t *d_va,
+                   uint8_t *d_valid, uint64_t *done_tiles);
 int mfn_build_zmap(mfn_ctx *ctx, const mfn_kmodel *km, unsigned long long **d_zmap, uint32_t *zlen, uint32_t *zhi);
