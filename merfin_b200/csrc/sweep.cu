@@ -319,6 +319,10 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
     if (geo == 1) MFN_TRY(launch3(k_sweep_scatter3<21, 1, 4, true>)); else if (geo == 2) MFN_TRY(launch3(k_sweep_scatter3<21, 2, 4, true>)); else MFN_TRY(launch3(k_sweep_scatter3<21, 0, 4, true>));
   }
   ctx->launches++;
+  // MFN_DUMP_DEBUG=1: milliseconds of the three passes to stderr
+  const bool dbg = getenv("MFN_DUMP_DEBUG") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (dbg) { for (auto &x : ev) cudaEventCreate(&x); cudaEventRecord(ev[1], ctx->stream); }
   // did every run fit its bin?  (the outputs are only written by the last pass)
   unsigned long long over = 0;
   MFN_CUDA(cudaMemcpyAsync(&over, P.over_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -326,11 +330,21 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
   if (over == 0) {
     P.counter = ctl + P.nbins_pad + 2;
     mfn_sweep_dump_launch_probe(P, ctx->sm_count, ctx->stream);
+    if (dbg) cudaEventRecord(ev[2], ctx->stream);
     mfn_sweep_dump_launch_gather(P.where, P.entries, seq->d_rec_start, seq->nseq, tile_begin * MFN_TILE, tile_end * MFN_TILE,
                                  d_vr, d_va, d_valid, ctx->stream);
     ctx->launches += 2;
     *ok = 1;
+    if (dbg) {
+      cudaEventRecord(ev[3], ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      float b = 0, c = 0;
+      cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
+      fprintf(stderr, "[dump sweep] %llu windows, %u bins, lowbits %u, %d-tile chunks: probe %.2f ms, gather %.2f ms (scatter = the rest of the call)\n",
+              (unsigned long long)windows, P.nbins, P.lowbits, tiles, b, c);
+    }
   }
+  if (dbg) for (auto &x : ev) if (x) cudaEventDestroy(x);
   cudaError_t e2 = cudaGetLastError();
   cudaFreeAsync(P.entries, ctx->stream);
   cudaFreeAsync(P.where, ctx->stream);

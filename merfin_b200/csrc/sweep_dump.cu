@@ -22,7 +22,16 @@ static __device__ __forceinline__ void dump_slow(const SweepParams &P, uint32_t 
 }
 
 __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid_constant__ SweepParams P) {
-  const uint32_t lane = threadIdx.x & 31;
+  // per-warp queue of the entries the home sector does not settle (index in the work item): finished 32 at a
+  // time with every lane busy, as in k_sweep_probe -- inline, every batch of 128 entries would wait for the
+  // two or three dependent loads of its 2-4 % spilled k-mers
+  __shared__ uint16_t s_q[SW_THREADS / 32][SW_QCAP];
+  __shared__ uint32_t s_qn[SW_THREADS / 32];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_qn[wid] = 0;
+  __syncwarp();
+  uint16_t *const q = s_q[wid];
+  uint32_t *const qn_p = &s_qn[wid];
   const uint64_t slices_per_bin = ceil_div_u64(P.cap, SW_SLICE);
   const uint64_t nitems = (uint64_t)P.nbins * slices_per_bin;
   const uint32_t tbits = P.tbits;
@@ -46,37 +55,54 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
 
     auto line_in_bin = [&](unsigned long long e) { return __funnelshift_r((uint32_t)e, (uint32_t)(e >> 32) & himask, tbits); };
     auto sector_of = [&](unsigned long long e) { return slice + (((uint64_t)line_in_bin(e) << 2) | ((uint32_t)e & 3u)) * 32; };
-    // entry + its home sector -> the pair, packed as v_asm << 32 | v_read
-    auto resolve = [&](unsigned long long e, const Bucket &b) -> unsigned long long {
+    // entry i of the item + its home sector: the pair (v_asm << 32 | v_read) is stored over the entry, or the
+    // entry is queued
+    auto settle = [&](uint32_t i, unsigned long long e, const Bucket &b) {
       const uint32_t lw = (uint32_t)e;
       const uint32_t pay = sweep_match32(b, ~((lw << vb) & P.pr_wmask), P.pr_lim);
-      uint32_t vr = pay >> abits, va = pay & amax;
-      if (pay == 0xffffffffu || vr >= rmax || va >= amax) {
-        const uint64_t lp = e & lowmask;
-        dump_slow(P, line0 + (uint32_t)(lp >> tbits), lp & tmask64, vr, va);
+      const uint32_t vr = pay >> abits, va = pay & amax;
+      if (pay != 0xffffffffu && vr < rmax && va < amax) src[i] = ((unsigned long long)va << 32) | vr;
+      else q[atomicAdd(qn_p, 1u)] = (uint16_t)i;
+    };
+    auto drain = [&](uint32_t thr) {
+      __syncwarp();
+      uint32_t qn = *(volatile uint32_t *)qn_p;
+      while (qn >= thr) {
+        const uint32_t take = min(qn, 32u);
+        if (lane < take) {
+          const uint32_t i = q[qn - take + lane];
+          const unsigned long long e = src[i];
+          const uint64_t lp = e & lowmask;
+          uint32_t vr, va;
+          dump_slow(P, line0 + (uint32_t)(lp >> tbits), lp & tmask64, vr, va);
+          src[i] = ((unsigned long long)va << 32) | vr;
+        }
+        qn -= take;
+        __syncwarp();
+        if (lane == 0) *qn_p = qn;
+        __syncwarp();
       }
-      return ((unsigned long long)va << 32) | vr;
     };
     const uint32_t nfull = n >> 7;
 #pragma unroll 1
     for (uint32_t bt = 0; bt < nfull; bt++) {
       unsigned long long e[4];
-      unsigned long long *p = src + bt * 128u + lane * 4u;
-      asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(p));
+      const uint32_t i0 = bt * 128u + lane * 4u;
+      asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(src + i0));
       Bucket b[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) sweep_load_sector(sector_of(e[u]), b[u]);
-      unsigned long long r[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) r[u] = resolve(e[u], b[u]);
-      asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]) : "memory");
+      for (int u = 0; u < 4; u++) settle(i0 + u, e[u], b[u]);
+      drain(32u);
     }
     for (uint32_t i = (nfull << 7) + lane; i < n; i += 32) {
       const unsigned long long e = src[i];
       Bucket b;
       sweep_load_sector(sector_of(e), b);
-      src[i] = resolve(e, b);
+      settle(i, e, b);
     }
+    drain(1u);                                                 // the queue is emptied before the item changes
   }
 }
 
