@@ -106,35 +106,53 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
   }
 }
 
-// pass 3: windows in order.  A thread takes 8 consecutive windows; positions are reported in the caller's
-// coordinates (one separator slot per earlier record, as k_scan<DUMP> does).
+// pass 3: windows in order.  A CTA takes 2048 consecutive windows; a thread gathers the pairs of 8 of them (where[]
+// read as two 16-byte words, eight independent 8-byte gathers in flight), the CTA transposes through shared memory
+// and writes the outputs with consecutive lanes on consecutive positions (4-byte stores at a 32-byte stride cost
+// ten times the L2 write requests).  Positions are reported in the caller's coordinates (one separator slot per
+// earlier record, as k_scan<DUMP> does).
+#define GATHER_WINDOWS 2048
 __global__ void __launch_bounds__(256) k_sweep_gather(const uint32_t *__restrict__ where, const unsigned long long *__restrict__ entries,
                                                       const unsigned long long *__restrict__ rec_start, uint32_t nseq, uint64_t g_begin,
                                                       uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid) {
-  const uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 8;
-  const uint64_t g0 = g_begin + t;
-  if (g0 >= g_end) return;
-  const uint4 w0 = *(const uint4 *)(where + t), w1 = *(const uint4 *)(where + t + 4);
-  const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-  unsigned long long r[8];
+  __shared__ unsigned long long s_pair[GATHER_WINDOWS];
+  __shared__ uint8_t s_ok[GATHER_WINDOWS];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t t0 = (uint64_t)blockIdx.x * GATHER_WINDOWS;            // first window of the CTA, relative to g_begin
+  const uint64_t gc = g_begin + t0;
+  {
+    const uint64_t t = t0 + tid * 8;
+    uint32_t w[8];
+    if (g_begin + t < g_end) {
+      const uint4 w0 = *(const uint4 *)(where + t), w1 = *(const uint4 *)(where + t + 4);
+      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+    } else {
 #pragma unroll
-  for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
-  // record of the first window (binary search), then walk
-  uint32_t rec;
+      for (int u = 0; u < 8; u++) w[u] = 0xffffffffu;
+    }
+    unsigned long long r[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 8; u++) { s_pair[tid * 8 + u] = r[u]; s_ok[tid * 8 + u] = w[u] != 0xffffffffu; }
+  }
+  __syncthreads();
+  // record of the CTA's first window (uniform binary search), then every element walks from there (records are long)
+  uint32_t rec0;
   {
     uint32_t a = 0, b = nseq;
-    while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= g0) a = m; else b = m - 1; }
-    rec = a;
+    while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= gc) a = m; else b = m - 1; }
+    rec0 = a;
   }
-  uint64_t next_start = rec < nseq ? rec_start[rec + 1] : ~0ull;
-#pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const uint64_t g = g0 + u;
-    if (g >= g_end) break;
-    while (g >= next_start) { rec++; next_start = rec < nseq ? rec_start[rec + 1] : ~0ull; }
-    if (w[u] == 0xffffffffu || rec >= nseq) continue;          // outputs were zeroed: valid = 0
+  for (uint32_t i = tid; i < GATHER_WINDOWS; i += 256) {
+    if (!s_ok[i]) continue;                                             // outputs were zeroed: valid = 0
+    const uint64_t g = gc + i;
+    uint32_t rec = rec0;
+    while (rec < nseq && g >= rec_start[rec + 1]) rec++;
+    if (rec >= nseq) continue;
     const uint64_t sidx = g - rec;
-    out_vr[sidx] = (uint32_t)r[u]; out_va[sidx] = (uint32_t)(r[u] >> 32); out_valid[sidx] = 1;
+    const unsigned long long r = s_pair[i];
+    out_vr[sidx] = (uint32_t)r; out_va[sidx] = (uint32_t)(r >> 32); out_valid[sidx] = 1;
   }
 }
 
@@ -166,6 +184,5 @@ void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_
 
 void mfn_sweep_dump_launch_gather(const uint32_t *where, const unsigned long long *entries, const unsigned long long *rec_start, uint32_t nseq,
                                   uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream) {
-  const uint64_t threads = ceil_div_u64(g_end - g_begin, 8);
-  k_sweep_gather<<<(unsigned)ceil_div_u64(threads, 256), 256, 0, stream>>>(where, entries, rec_start, nseq, g_begin, g_end, out_vr, out_va, out_valid);
+  k_sweep_gather<<<(unsigned)ceil_div_u64(g_end - g_begin, GATHER_WINDOWS), 256, 0, stream>>>(where, entries, rec_start, nseq, g_begin, g_end, out_vr, out_va, out_valid);
 }

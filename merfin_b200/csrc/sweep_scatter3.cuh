@@ -204,8 +204,6 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
         // record of each window: 4 bits of delta per window here, bigger deltas take the side list
         uint64_t rdpack = 0;
         if (DUMP) {
-#pragma unroll
-          for (int u = 0; u < S3_NW; u++) if (!((vmask >> u) & 1u)) where[j0 + u] = 0xffffffffu;
         } else if (one_record || vmask == 0) n_ok0 += __popc(vmask);
         else {
           const uint64_t g0 = tile0 * MFN_TILE + j0;
@@ -329,8 +327,15 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
       const uint32_t r0s = r0 << xbits;
       unsigned long long *const ent = P.entries;
       if (DUMP) {
-        // entry = low part only; where[window] = the entry's index.  A run that does not fit its bin makes the whole
-        // call fall back to the direct scan (over_n != 0 is checked by the host before the probe pass).
+        // entry = low part only; where[window] = the entry's index, staged in the low-word area (dead since the
+        // sort) so that it reaches global memory as 16-byte stores instead of one 4-byte store per window.  A run
+        // that does not fit its bin makes the whole call fall back to the direct scan (over_n != 0 is checked by
+        // the host before the probe pass).
+        uint32_t *const s_where = (uint32_t *)s_low4;
+        if (live != 0xffffu) {
+#pragma unroll
+          for (int u = 0; u < (int)S3_NW; u++) if (!((live >> u) & 1u)) s_where[tid * S3_NW + u] = 0xffffffffu;
+        }
         for (uint32_t i = tid; i < total; i += S3_THREADS) {
           const unsigned long long e = s_ent[i];
           const uint32_t hs = (uint32_t)(e >> 32);
@@ -338,12 +343,16 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
           const uint32_t d = *(const uint32_t *)((const char *)s_dst + (hs & S3_BIN_FIELD)) + i;
           if ((unsigned long long)d < (unsigned long long)(bin + 1) * P.cap) {
             *(uint2 *)(ent + d) = make_uint2((uint32_t)e, hs & 3u);
-            where[hs >> 13] = d;
+            s_where[hs >> 13] = d;
           } else {
-            where[hs >> 13] = 0xffffffffu;
+            s_where[hs >> 13] = 0xffffffffu;
             atomicAdd(P.over_n, 1ull);
           }
         }
+        __syncthreads();                                                  // (5, DUMP only)
+#pragma unroll
+        for (uint32_t i = tid; i < S3_CHUNK / 4; i += S3_THREADS) ((uint4 *)where)[i] = ((const uint4 *)s_where)[i];
+        __syncthreads();                                                  // (6, DUMP only) the next round's low words may be written
       } else if (one_record && !s_over) {
         // the entry's high word: the chunk's record next to the staged bits 32..33 of the low part
         if (total == S3_CHUNK) {

@@ -97,6 +97,9 @@ def main():
                   "kasm": int(per["kasm"].sum()), "kmissing": int(per["kmissing"].sum())})
             acc.close()
         if "dump" in modes and k == 21:
+            # (the table restricted to the scanned sequences, as bench.py uses it: the range-partitioned -dump takes it)
+            if not os.environ.get("MFN_MODES_NO_RESTRICT"):
+                R.restrict(A, seq)
             n = total
             vr = torch.empty(n, dtype=torch.int32, device=dev)
             va = torch.empty(n, dtype=torch.int32, device=dev)
@@ -106,6 +109,7 @@ def main():
             emit({"mode": "-dump resident (pairs per position left on the device)", **tinfo, "ms": ms, "bases_per_s": total / ms * 1e3,
                   "roofline_frac": total * 72.25 / (ms / 1e3) / 1e9 / peak_gbs, "valid": int(ok.sum().item())})
             del vr, va, ok
+            R.unrestrict()
         if "score" in modes and k == 21:
             # BASELINE configs[3]: variant-path scoring; paths = 2(k-1)+1 windows around an SNV, 2 paths per variant
             npaths, plen = 4_000_000, 2 * (k - 1) + 1 + k - 1
