@@ -57,11 +57,17 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
     auto sector_of = [&](unsigned long long e) { return slice + (((uint64_t)line_in_bin(e) << 2) | ((uint32_t)e & 3u)) * 32; };
     // entry i of the item + its home sector: the pair (v_asm << 32 | v_read) is stored over the entry, or the
     // entry is queued
-    auto settle = [&](uint32_t i, unsigned long long e, const Bucket &b) {
+    // -> true and the pair, or false (the entry has to take the queue)
+    auto lookup = [&](unsigned long long e, const Bucket &b, unsigned long long &pair) -> bool {
       const uint32_t lw = (uint32_t)e;
       const uint32_t pay = sweep_match32(b, ~((lw << vb) & P.pr_wmask), P.pr_lim);
       const uint32_t vr = pay >> abits, va = pay & amax;
-      if (pay != 0xffffffffu && vr < rmax && va < amax) src[i] = ((unsigned long long)va << 32) | vr;
+      pair = ((unsigned long long)va << 32) | vr;
+      return pay != 0xffffffffu && vr < rmax && va < amax;
+    };
+    auto settle = [&](uint32_t i, unsigned long long e, const Bucket &b) {
+      unsigned long long pair;
+      if (lookup(e, b, pair)) src[i] = pair;
       else q[atomicAdd(qn_p, 1u)] = (uint16_t)i;
     };
     auto drain = [&](uint32_t thr) {
@@ -92,8 +98,20 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
       Bucket b[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) sweep_load_sector(sector_of(e[u]), b[u]);
+      // the usual lane has all four settled: one 32-byte store (an L2 request per entry costs as much as the probe itself)
+      unsigned long long r[4];
+      bool okk[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) settle(i0 + u, e[u], b[u]);
+      for (int u = 0; u < 4; u++) okk[u] = lookup(e[u], b[u], r[u]);
+      if (okk[0] && okk[1] && okk[2] && okk[3]) {
+        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(src + i0), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]) : "memory");
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (okk[u]) src[i0 + u] = r[u];
+          else q[atomicAdd(qn_p, 1u)] = (uint16_t)(i0 + u);
+        }
+      }
       drain(32u);
     }
     for (uint32_t i = (nfull << 7) + lane; i < n; i += 32) {
@@ -106,53 +124,43 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
   }
 }
 
-// pass 3: windows in order.  A CTA takes 2048 consecutive windows; a thread gathers the pairs of 8 of them (where[]
-// read as two 16-byte words, eight independent 8-byte gathers in flight), the CTA transposes through shared memory
-// and writes the outputs with consecutive lanes on consecutive positions (4-byte stores at a 32-byte stride cost
-// ten times the L2 write requests).  Positions are reported in the caller's coordinates (one separator slot per
-// earlier record, as k_scan<DUMP> does).
+// pass 3: windows in order.  A CTA takes 2048 consecutive windows, a thread the 8 of them at stride 256, so that
+// every load of where[], every output store and every record walk has consecutive lanes on consecutive windows
+// (a first version gave each thread 8 adjacent windows and transposed through shared memory: 16-way bank
+// conflicts, MIO throttle, 13.7 ms per Gbp).  Eight independent 8-byte gathers are in flight per thread; the
+// ~16 windows that share a 128-byte run of entries sit in the same one or two CTAs.  Positions are reported in the
+// caller's coordinates (one separator slot per earlier record, as k_scan<DUMP> does).
 #define GATHER_WINDOWS 2048
 __global__ void __launch_bounds__(256) k_sweep_gather(const uint32_t *__restrict__ where, const unsigned long long *__restrict__ entries,
                                                       const unsigned long long *__restrict__ rec_start, uint32_t nseq, uint64_t g_begin,
                                                       uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid) {
-  __shared__ unsigned long long s_pair[GATHER_WINDOWS];
-  __shared__ uint8_t s_ok[GATHER_WINDOWS];
   const uint32_t tid = threadIdx.x;
   const uint64_t t0 = (uint64_t)blockIdx.x * GATHER_WINDOWS;            // first window of the CTA, relative to g_begin
   const uint64_t gc = g_begin + t0;
-  {
-    const uint64_t t = t0 + tid * 8;
-    uint32_t w[8];
-    if (g_begin + t < g_end) {
-      const uint4 w0 = *(const uint4 *)(where + t), w1 = *(const uint4 *)(where + t + 4);
-      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
-    } else {
+  uint32_t w[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) w[u] = 0xffffffffu;
-    }
-    unsigned long long r[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
-#pragma unroll
-    for (int u = 0; u < 8; u++) { s_pair[tid * 8 + u] = r[u]; s_ok[tid * 8 + u] = w[u] != 0xffffffffu; }
+  for (int u = 0; u < 8; u++) {
+    const uint64_t t = t0 + tid + 256u * u;
+    w[u] = g_begin + t < g_end ? __ldg(where + t) : 0xffffffffu;
   }
-  __syncthreads();
-  // record of the CTA's first window (uniform binary search), then every element walks from there (records are long)
-  uint32_t rec0;
+  unsigned long long r[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
+  // record of the CTA's first window (uniform binary search), then every window walks from there (records are long)
+  uint32_t rec;
   {
     uint32_t a = 0, b = nseq;
     while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= gc) a = m; else b = m - 1; }
-    rec0 = a;
+    rec = a;
   }
-  for (uint32_t i = tid; i < GATHER_WINDOWS; i += 256) {
-    if (!s_ok[i]) continue;                                             // outputs were zeroed: valid = 0
-    const uint64_t g = gc + i;
-    uint32_t rec = rec0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    if (w[u] == 0xffffffffu) continue;                                  // outputs were zeroed: valid = 0
+    const uint64_t g = gc + tid + 256u * u;
     while (rec < nseq && g >= rec_start[rec + 1]) rec++;
-    if (rec >= nseq) continue;
+    if (rec >= nseq) break;
     const uint64_t sidx = g - rec;
-    const unsigned long long r = s_pair[i];
-    out_vr[sidx] = (uint32_t)r; out_va[sidx] = (uint32_t)(r >> 32); out_valid[sidx] = 1;
+    out_vr[sidx] = (uint32_t)r[u]; out_va[sidx] = (uint32_t)(r[u] >> 32); out_valid[sidx] = 1;
   }
 }
 
