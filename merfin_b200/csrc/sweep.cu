@@ -241,8 +241,8 @@ int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const m
 // -dump / path scoring through the range-partitioned scan (sweep_dump.cu)
 // ------------------------------------------------------------------------------------------
 void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_t stream);
-void mfn_sweep_dump_launch_gather(const uint32_t *where, const unsigned long long *entries, const unsigned long long *rec_start, uint32_t nseq,
-                                  uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream);
+void mfn_sweep_dump_launch_gather(const SweepParams &P, int tiles, uint64_t nchunks, uint64_t g_begin, uint64_t g_end,
+                                  uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream);
 
 // k = 21 (scatter3), canonical 32-bit-slot table, narrow entries, at most 512 bins
 bool mfn_sweep_dump_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, bool force) {
@@ -290,12 +290,14 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
   const size_t cwords = (size_t)P.nbins_pad + 8;                       // bin counts, overflow count, two work counters
   cudaError_t e = cudaMallocAsync(&P.entries, (size_t)P.nbins * P.cap * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&P.where, nwhere * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&P.runs, (size_t)nchunks * P.nbins_pad * sizeof(uint2), ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&ctl, cwords * 8, ctx->stream);
   if (e != cudaSuccess) {
     // no room for the workspace: not an error, the direct scan needs none
     cudaGetLastError();
     if (P.entries) cudaFreeAsync(P.entries, ctx->stream);
     if (P.where) cudaFreeAsync(P.where, ctx->stream);
+    if (P.runs) cudaFreeAsync(P.runs, ctx->stream);
     return MFN_OK;
   }
   MFN_CUDA(cudaMemsetAsync(ctl, 0, cwords * 8, ctx->stream));
@@ -331,8 +333,7 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
     P.counter = ctl + P.nbins_pad + 2;
     mfn_sweep_dump_launch_probe(P, ctx->sm_count, ctx->stream);
     if (dbg) cudaEventRecord(ev[2], ctx->stream);
-    mfn_sweep_dump_launch_gather(P.where, P.entries, seq->d_rec_start, seq->nseq, tile_begin * MFN_TILE, tile_end * MFN_TILE,
-                                 d_vr, d_va, d_valid, ctx->stream);
+    mfn_sweep_dump_launch_gather(P, tiles, nchunks, tile_begin * MFN_TILE, tile_end * MFN_TILE, d_vr, d_va, d_valid, ctx->stream);
     ctx->launches += 2;
     *ok = 1;
     if (dbg) {
@@ -348,6 +349,7 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
   cudaError_t e2 = cudaGetLastError();
   cudaFreeAsync(P.entries, ctx->stream);
   cudaFreeAsync(P.where, ctx->stream);
+  cudaFreeAsync(P.runs, ctx->stream);
   cudaFreeAsync(ctl, ctx->stream);
   if (e2 != cudaSuccess) { mfn_set_error("dump sweep: %s", cudaGetErrorString(e2)); return MFN_ERR_CUDA; }
   return MFN_OK;

@@ -124,43 +124,69 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep_probe_dump(const __grid
   }
 }
 
-// pass 3: windows in order.  A CTA takes 2048 consecutive windows, a thread the 8 of them at stride 256, so that
-// every load of where[], every output store and every record walk has consecutive lanes on consecutive windows
-// (a first version gave each thread 8 adjacent windows and transposed through shared memory: 16-way bank
-// conflicts, MIO throttle, 13.7 ms per Gbp).  Eight independent 8-byte gathers are in flight per thread; the
-// ~16 windows that share a 128-byte run of entries sit in the same one or two CTAs.  Positions are reported in the
-// caller's coordinates (one separator slot per earlier record, as k_scan<DUMP> does).
-#define GATHER_WINDOWS 2048
-__global__ void __launch_bounds__(256) k_sweep_gather(const uint32_t *__restrict__ where, const unsigned long long *__restrict__ entries,
-                                                      const unsigned long long *__restrict__ rec_start, uint32_t nseq, uint64_t g_begin,
-                                                      uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid) {
-  const uint32_t tid = threadIdx.x;
-  const uint64_t t0 = (uint64_t)blockIdx.x * GATHER_WINDOWS;            // first window of the CTA, relative to g_begin
-  const uint64_t gc = g_begin + t0;
-  uint32_t w[8];
+// pass 3: windows in order, one CTA per chunk of the scatter pass.  The chunk's pairs sit in one run of ~16 entries
+// per bin; the CTA copies whole runs into shared memory (a warp per run: consecutive lanes on consecutive entries,
+// i.e. DRAM reads of whole sectors and lines -- a first version gathered 8 bytes per window straight from global
+// memory and ran at the random-sector rate of the DRAM, 10.3 ms per Gbp), then every window picks its pair by
+// (bin, rank).  Positions are reported in the caller's coordinates (one separator slot per earlier record, as
+// k_scan<DUMP> does).
+template <int TILES>
+__global__ void __launch_bounds__(TILES * 128) k_sweep_gather(const uint32_t *__restrict__ where, const uint2 *__restrict__ runs,
+                                                              const unsigned long long *__restrict__ entries, uint32_t nbins_pad,
+                                                              const unsigned long long *__restrict__ rec_start, uint32_t nseq,
+                                                              uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid) {
+  constexpr uint32_t THREADS = TILES * 128, CHUNK = TILES * MFN_TILE, NW = CHUNK / THREADS;
+  extern __shared__ __align__(16) unsigned char gsm[];
+  unsigned long long *s_ent = (unsigned long long *)gsm;                // [CHUNK] the chunk's pairs, bin by bin
+  uint32_t *s_off = (uint32_t *)(s_ent + CHUNK);                        // [nbins_pad] where each bin's run starts in s_ent
+  __shared__ uint32_t s_warp[THREADS / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint64_t chunk = blockIdx.x;
+  const uint2 *const run = runs + chunk * nbins_pad;
+  // exclusive scan of the run lengths (nbins_pad is a multiple of THREADS: 1 or 2 bins per thread)
+  const uint32_t bpt = nbins_pad / THREADS, b0 = tid * bpt;
+  const uint32_t c0 = run[b0].y, c1 = bpt > 1 ? run[b0 + 1].y : 0u;
+  {
+    const uint32_t sum = c0 + c1;
+    uint32_t incl = sum;
 #pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const uint64_t t = t0 + tid + 256u * u;
-    w[u] = g_begin + t < g_end ? __ldg(where + t) : 0xffffffffu;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t x = 0; x < wid; x++) wbase += s_warp[x];
+    const uint32_t at = wbase + incl - sum;
+    s_off[b0] = at;
+    if (bpt > 1) s_off[b0 + 1] = at + c0;
   }
-  unsigned long long r[8];
-#pragma unroll
-  for (int u = 0; u < 8; u++) r[u] = w[u] != 0xffffffffu ? __ldg(entries + w[u]) : 0ull;
-  // record of the CTA's first window (uniform binary search), then every window walks from there (records are long)
+  __syncthreads();
+  // a warp per run
+  for (uint32_t b = wid; b < nbins_pad; b += THREADS / 32) {
+    const uint2 r = run[b];
+    const uint32_t at = s_off[b];
+    for (uint32_t i = lane; i < r.y; i += 32) s_ent[at + i] = __ldg(entries + r.x + i);
+  }
+  __syncthreads();
+  const uint64_t t0 = chunk * CHUNK;                                    // first window of the chunk, relative to g_begin
+  const uint64_t gc = g_begin + t0;
   uint32_t rec;
   {
     uint32_t a = 0, b = nseq;
     while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= gc) a = m; else b = m - 1; }
     rec = a;
   }
-#pragma unroll
-  for (int u = 0; u < 8; u++) {
-    if (w[u] == 0xffffffffu) continue;                                  // outputs were zeroed: valid = 0
-    const uint64_t g = gc + tid + 256u * u;
+#pragma unroll 4
+  for (uint32_t u = 0; u < NW; u++) {
+    const uint32_t i = tid + THREADS * u;
+    const uint64_t g = gc + i;
+    if (g >= g_end) break;
+    const uint32_t w = __ldg(where + t0 + i);
+    if (w == 0xffffffffu) continue;                                     // outputs were zeroed: valid = 0
     while (rec < nseq && g >= rec_start[rec + 1]) rec++;
     if (rec >= nseq) break;
+    const unsigned long long r = s_ent[s_off[w >> 13] + (w & 0x1fffu)];
     const uint64_t sidx = g - rec;
-    out_vr[sidx] = (uint32_t)r[u]; out_va[sidx] = (uint32_t)(r[u] >> 32); out_valid[sidx] = 1;
+    out_vr[sidx] = (uint32_t)r; out_va[sidx] = (uint32_t)(r >> 32); out_valid[sidx] = 1;
   }
 }
 
@@ -190,7 +216,14 @@ void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_
   k_sweep_probe_dump<<<sm_count * 3, SW_THREADS, 0, stream>>>(P);
 }
 
-void mfn_sweep_dump_launch_gather(const uint32_t *where, const unsigned long long *entries, const unsigned long long *rec_start, uint32_t nseq,
-                                  uint64_t g_begin, uint64_t g_end, uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream) {
-  k_sweep_gather<<<(unsigned)ceil_div_u64(g_end - g_begin, GATHER_WINDOWS), 256, 0, stream>>>(where, entries, rec_start, nseq, g_begin, g_end, out_vr, out_va, out_valid);
+void mfn_sweep_dump_launch_gather(const SweepParams &P, int tiles, uint64_t nchunks, uint64_t g_begin, uint64_t g_end,
+                                  uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream) {
+  const size_t smem = (size_t)tiles * MFN_TILE * 8 + (size_t)P.nbins_pad * 4;
+  if (tiles == 2) {
+    cudaFuncSetAttribute(k_sweep_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sweep_gather<2><<<(unsigned)nchunks, 256, smem, stream>>>(P.where, P.runs, P.entries, P.nbins_pad, P.rec_start, P.nseq, g_begin, g_end, out_vr, out_va, out_valid);
+  } else {
+    cudaFuncSetAttribute(k_sweep_gather<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sweep_gather<4><<<(unsigned)nchunks, 512, smem, stream>>>(P.where, P.runs, P.entries, P.nbins_pad, P.rec_start, P.nseq, g_begin, g_end, out_vr, out_va, out_valid);
+  }
 }

@@ -99,7 +99,8 @@ struct SweepParams {
   uint32_t zlen;
   uint32_t zhi;                              // largest multiplicity v >= 1 with readK(v) == 0 under -prob (0: none)
   uint32_t pr_lim, pr_wmask;                 // 32-bit slots: 2^vb - 1 and the tag field mask (vb = value bits)
-  uint32_t *where;                           // -dump flavour: entry index of every window of the range (0xffffffff: none)
+  uint32_t *where;                           // -dump flavour: bin << 13 | rank in the bin's run of the chunk, per window (0xffffffff: none)
+  uint2 *runs;                               // -dump flavour: [chunk][nbins_pad] (entry index of the run's start, length)
   unsigned long long *prof;                  // SW_PROFILE builds: [8] cycles per phase of the scatter pass, summed over CTAs
 };
 

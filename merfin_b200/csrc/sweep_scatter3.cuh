@@ -316,6 +316,12 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
       s_dst[b0] = b0 * cap + (uint32_t)got0 - s_off[b0];
       if (bpt > 1) s_dst[b0 + 1] = (b0 + 1) * cap + (uint32_t)got1 - s_off[b0 + 1];
       if ((cnt0 && got0 + cnt0 > P.cap) || (cnt1 && got1 + cnt1 > P.cap)) s_over = 1;       // a run crosses the end of its bin
+      if (DUMP) {
+        // where every bin's run of this chunk starts and how long it is: the gather pass reads whole runs
+        uint2 *const runs = P.runs + chunk * P.nbins_pad;
+        runs[b0] = make_uint2(b0 * cap + (uint32_t)got0, cnt0);
+        if (bpt > 1) runs[b0 + 1] = make_uint2((b0 + 1) * cap + (uint32_t)got1, cnt1);
+      }
     }
     SW_PROF_MARK(4);
     __syncthreads();                                                      // (4) sorted entries and destinations are ready
@@ -327,8 +333,8 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
       const uint32_t r0s = r0 << xbits;
       unsigned long long *const ent = P.entries;
       if (DUMP) {
-        // entry = low part only; where[window] = the entry's index, staged in the low-word area (dead since the
-        // sort) so that it reaches global memory as 16-byte stores instead of one 4-byte store per window.  A run
+        // entry = low part only; where[window] = bin << 13 | rank of the window in the bin's run of this chunk, staged
+        // in the low-word area (dead since the sort) so that it reaches global memory as 16-byte stores.  A run
         // that does not fit its bin makes the whole call fall back to the direct scan (over_n != 0 is checked by
         // the host before the probe pass).
         uint32_t *const s_where = (uint32_t *)s_low4;
@@ -341,13 +347,10 @@ __global__ void __launch_bounds__(TILES * 128, TILES == 2 ? 4 : 2) k_sweep_scatt
           const uint32_t hs = (uint32_t)(e >> 32);
           const uint32_t bin = (hs & S3_BIN_FIELD) >> 2;
           const uint32_t d = *(const uint32_t *)((const char *)s_dst + (hs & S3_BIN_FIELD)) + i;
-          if ((unsigned long long)d < (unsigned long long)(bin + 1) * P.cap) {
-            *(uint2 *)(ent + d) = make_uint2((uint32_t)e, hs & 3u);
-            s_where[hs >> 13] = d;
-          } else {
-            s_where[hs >> 13] = 0xffffffffu;
-            atomicAdd(P.over_n, 1ull);
-          }
+          const uint32_t rank = i - *(const uint32_t *)((const char *)s_off + (hs & S3_BIN_FIELD));
+          if ((unsigned long long)d < (unsigned long long)(bin + 1) * P.cap) *(uint2 *)(ent + d) = make_uint2((uint32_t)e, hs & 3u);
+          else atomicAdd(P.over_n, 1ull);
+          s_where[hs >> 13] = (bin << 13) | rank;
         }
         __syncthreads();                                                  // (5, DUMP only)
 #pragma unroll
