@@ -139,13 +139,17 @@ __global__ void __launch_bounds__(TILES * 128) k_sweep_gather(const uint32_t *__
   extern __shared__ __align__(16) unsigned char gsm[];
   unsigned long long *s_ent = (unsigned long long *)gsm;                // [CHUNK] the chunk's pairs, bin by bin
   uint32_t *s_off = (uint32_t *)(s_ent + CHUNK);                        // [nbins_pad] where each bin's run starts in s_ent
+  uint32_t *s_start = s_off + nbins_pad;                                // [nbins_pad] ... and in P.entries
   __shared__ uint32_t s_warp[THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint64_t chunk = blockIdx.x;
   const uint2 *const run = runs + chunk * nbins_pad;
   // exclusive scan of the run lengths (nbins_pad is a multiple of THREADS: 1 or 2 bins per thread)
   const uint32_t bpt = nbins_pad / THREADS, b0 = tid * bpt;
-  const uint32_t c0 = run[b0].y, c1 = bpt > 1 ? run[b0 + 1].y : 0u;
+  const uint2 r0 = run[b0], r1 = bpt > 1 ? run[b0 + 1] : make_uint2(0u, 0u);
+  const uint32_t c0 = r0.y, c1 = r1.y;
+  s_start[b0] = r0.x;
+  if (bpt > 1) s_start[b0 + 1] = r1.x;
   {
     const uint32_t sum = c0 + c1;
     uint32_t incl = sum;
@@ -160,11 +164,26 @@ __global__ void __launch_bounds__(TILES * 128) k_sweep_gather(const uint32_t *__
     if (bpt > 1) s_off[b0 + 1] = at + c0;
   }
   __syncthreads();
-  // a warp per run
-  for (uint32_t b = wid; b < nbins_pad; b += THREADS / 32) {
-    const uint2 r = run[b];
-    const uint32_t at = s_off[b];
-    for (uint32_t i = lane; i < r.y; i += 32) s_ent[at + i] = __ldg(entries + r.x + i);
+  // the chunk's entries, bin by bin: thread j copies sorted positions j, j + THREADS, ... (consecutive lanes on
+  // consecutive entries of a run; all of a thread's loads in flight together -- a warp per run with its
+  // data-dependent inner loop waited for one DRAM access per run, 32 in a row: 37 us per CTA)
+  {
+    const uint32_t total = s_off[nbins_pad - 1] + run[nbins_pad - 1].y;
+    unsigned long long v[NW];
+    uint32_t nbits = 0;
+    while ((1u << nbits) < nbins_pad) nbits++;
+#pragma unroll
+    for (uint32_t u = 0; u < NW; u++) {
+      const uint32_t p = tid + THREADS * u;
+      v[u] = 0;
+      if (p < total) {
+        uint32_t b = 0;                                                   // largest b with s_off[b] <= p
+        for (uint32_t step = 1u << (nbits - 1); step; step >>= 1) if (b + step < nbins_pad && s_off[b + step] <= p) b += step;
+        v[u] = __ldg(entries + s_start[b] + (p - s_off[b]));
+      }
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < NW; u++) { const uint32_t p = tid + THREADS * u; if (p < total) s_ent[p] = v[u]; }
   }
   __syncthreads();
   const uint64_t t0 = chunk * CHUNK;                                    // first window of the chunk, relative to g_begin
@@ -218,7 +237,7 @@ void mfn_sweep_dump_launch_probe(const SweepParams &P, int sm_count, cudaStream_
 
 void mfn_sweep_dump_launch_gather(const SweepParams &P, int tiles, uint64_t nchunks, uint64_t g_begin, uint64_t g_end,
                                   uint32_t *out_vr, uint32_t *out_va, uint8_t *out_valid, cudaStream_t stream) {
-  const size_t smem = (size_t)tiles * MFN_TILE * 8 + (size_t)P.nbins_pad * 4;
+  const size_t smem = (size_t)tiles * MFN_TILE * 8 + (size_t)P.nbins_pad * 8;
   if (tiles == 2) {
     cudaFuncSetAttribute(k_sweep_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_sweep_gather<2><<<(unsigned)nchunks, 256, smem, stream>>>(P.where, P.runs, P.entries, P.nbins_pad, P.rec_start, P.nseq, g_begin, g_end, out_vr, out_va, out_valid);

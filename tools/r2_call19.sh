@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round 2, GPU call 18: -dump through the range-partitioned scan, second try (queued slow path): parity + per-pass times
+# Round 2, GPU call 19: -dump through the range-partitioned scan, second try (queued slow path): parity + per-pass times
 cd "$(dirname "$0")/.." || exit 1
-O=gpurun_out/r2_call18
+O=gpurun_out/r2_call19
 mkdir -p $O
 timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "dump_through" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt
 tail -8 $O/pytest_sel.log | cut -c1-300 | tee -a $O/summary.txt
