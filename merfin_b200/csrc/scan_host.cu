@@ -1,6 +1,8 @@
 // Host side of the scan kernels: launches, accumulators, fetch.
 #include "scan_kernel.cuh"
 
+#include <algorithm>
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -126,15 +128,25 @@ extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
   if (!ctx || !seq || !d_v_read || !d_v_asm || !d_valid) return MFN_ERR_INVALID;
   MFN_TRY(check_tables(reads, asm_, true));
   MFN_CUDA(cudaSetDevice(ctx->device));
-  MFN_CUDA(cudaMemsetAsync(d_v_read, 0, seq->total_bases * 4, ctx->stream));
-  MFN_CUDA(cudaMemsetAsync(d_v_asm, 0, seq->total_bases * 4, ctx->stream));
-  MFN_CUDA(cudaMemsetAsync(d_valid, 0, seq->total_bases, ctx->stream));
   ScanParams P{};
   P.R = reads->dev; P.A = asm_->dev;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
   // big batches over a fused table: the range-partitioned path (sweep_dump.cu); the direct scan does the rest
   uint64_t done_tiles = 0;
   MFN_TRY(mfn_sweep_dump(ctx, reads, asm_, seq, d_v_read, d_v_asm, d_valid, &done_tiles));
+  // the range-partitioned path writes every position of its tiles; the direct scan relies on zeroed outputs
+  {
+    const uint64_t g = std::min(done_tiles * MFN_TILE, seq->G);
+    const uint64_t rec = (uint64_t)(std::upper_bound(seq->rec_start.begin(), seq->rec_start.end(), g) - seq->rec_start.begin()) - 1;
+    // first caller position not written yet: g - rec, or the next record's first base when g is a separator slot or beyond
+    uint64_t s0 = rec >= seq->nseq ? seq->total_bases : std::min<uint64_t>(g - rec, seq->rec_start[rec + 1] - 1 - rec);
+    if (done_tiles == 0) s0 = 0;
+    if (s0 < seq->total_bases) {
+      MFN_CUDA(cudaMemsetAsync(d_v_read + s0, 0, (seq->total_bases - s0) * 4, ctx->stream));
+      MFN_CUDA(cudaMemsetAsync(d_v_asm + s0, 0, (seq->total_bases - s0) * 4, ctx->stream));
+      MFN_CUDA(cudaMemsetAsync(d_valid + s0, 0, seq->total_bases - s0, ctx->stream));
+    }
+  }
   P.tile_begin = done_tiles; P.tile_end = seq->ntiles;
   P.out_vr = d_v_read; P.out_va = d_v_asm; P.out_valid = d_valid;
   return launch_scan(ctx, P, true, use_joint(reads, asm_, P));

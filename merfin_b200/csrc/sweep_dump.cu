@@ -144,6 +144,12 @@ __global__ void __launch_bounds__(TILES * 128) k_sweep_gather(const uint32_t *__
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint64_t chunk = blockIdx.x;
   const uint2 *const run = runs + chunk * nbins_pad;
+  const uint64_t t0 = chunk * CHUNK;                                    // first window of the chunk, relative to g_begin
+  const uint64_t gc = g_begin + t0;
+  // this thread's windows (tid, tid + THREADS, ...): their (bin, rank) words are on their way while the runs are copied
+  uint32_t wv[NW];
+#pragma unroll
+  for (uint32_t u = 0; u < NW; u++) wv[u] = gc + tid + THREADS * u < g_end ? __ldg(where + t0 + tid + THREADS * u) : 0xfffffffeu;
   // exclusive scan of the run lengths (nbins_pad is a multiple of THREADS: 1 or 2 bins per thread)
   const uint32_t bpt = nbins_pad / THREADS, b0 = tid * bpt;
   const uint2 r0 = run[b0], r1 = bpt > 1 ? run[b0 + 1] : make_uint2(0u, 0u);
@@ -186,26 +192,25 @@ __global__ void __launch_bounds__(TILES * 128) k_sweep_gather(const uint32_t *__
     for (uint32_t u = 0; u < NW; u++) { const uint32_t p = tid + THREADS * u; if (p < total) s_ent[p] = v[u]; }
   }
   __syncthreads();
-  const uint64_t t0 = chunk * CHUNK;                                    // first window of the chunk, relative to g_begin
-  const uint64_t gc = g_begin + t0;
   uint32_t rec;
   {
     uint32_t a = 0, b = nseq;
     while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (rec_start[m] <= gc) a = m; else b = m - 1; }
     rec = a;
   }
-#pragma unroll 4
+  uint64_t next_start = rec < nseq ? rec_start[rec + 1] : ~0ull;
+#pragma unroll
   for (uint32_t u = 0; u < NW; u++) {
-    const uint32_t i = tid + THREADS * u;
-    const uint64_t g = gc + i;
-    if (g >= g_end) break;
-    const uint32_t w = __ldg(where + t0 + i);
-    if (w == 0xffffffffu) continue;                                     // outputs were zeroed: valid = 0
-    while (rec < nseq && g >= rec_start[rec + 1]) rec++;
+    const uint32_t w = wv[u];
+    if (w == 0xfffffffeu) break;                                        // past the end of the range
+    const uint64_t g = gc + tid + THREADS * u;
+    while (g >= next_start) { rec++; next_start = rec < nseq ? rec_start[rec + 1] : ~0ull; }
     if (rec >= nseq) break;
-    const unsigned long long r = s_ent[s_off[w >> 13] + (w & 0x1fffu)];
-    const uint64_t sidx = g - rec;
-    out_vr[sidx] = (uint32_t)r; out_va[sidx] = (uint32_t)(r >> 32); out_valid[sidx] = 1;
+    if (g + 1 == next_start) continue;                                  // the separator slot: no position of the caller's
+    const bool ok = w != 0xffffffffu;
+    const unsigned long long r = ok ? s_ent[s_off[w >> 13] + (w & 0x1fffu)] : 0ull;
+    const uint64_t sidx = g - rec;                                      // every position of the range is written: no memset needed
+    out_vr[sidx] = (uint32_t)r; out_va[sidx] = (uint32_t)(r >> 32); out_valid[sidx] = ok ? 1 : 0;
   }
 }
 
