@@ -113,15 +113,55 @@ def offsets_of(lens):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML from a thread every 2 ms (a timed region of
+    a few milliseconds at N = 8 is over before nvidia-smi -lms prints its first line), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.rows, self.p = index, [], None
+        self.sm, self.mx, self.bits, self.stop_flag, self.thread, self.nvml = [], None, 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: go through the UUID of the torch device
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+                    break
+            self.nvml, self.h = pynvml, h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:                                       # noqa: BLE001
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:                                   # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml:
+            try:
+                self.mx = int(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            except Exception:                                   # noqa: BLE001
+                self.mx = None
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -135,6 +175,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join()
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(v for k, v in self.REASONS.items() if self.bits & k), "samples": len(sm), "source": "nvml, 2 ms"}
         if self.p:
             self.p.terminate()
         sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
@@ -142,7 +188,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def device_tensor_view(ptr, nwords):
