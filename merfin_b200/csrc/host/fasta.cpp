@@ -20,9 +20,13 @@ bool slurp_file(const std::string &path, std::vector<char> &data, std::string &e
   FILE *F = nullptr;
   bool piped = false;
   std::string cmd;
-  if (ends_with(path, ".gz")) cmd = "gzip -dc '" + path + "'";
-  else if (ends_with(path, ".bz2")) cmd = "bzip2 -dc '" + path + "'";
-  else if (ends_with(path, ".xz")) cmd = "xz -dc '" + path + "'";
+  // the path goes through /bin/sh: single quotes, every embedded single quote written as '\''
+  std::string q = "'";
+  for (char c : path) { if (c == '\'') q += "'\\''"; else q += c; }
+  q += "'";
+  if (ends_with(path, ".gz")) cmd = "gzip -dc " + q;
+  else if (ends_with(path, ".bz2")) cmd = "bzip2 -dc " + q;
+  else if (ends_with(path, ".xz")) cmd = "xz -dc " + q;
   if (!cmd.empty()) {
     FILE *probe = fopen(path.c_str(), "rb");
     if (!probe) { err = "cannot open '" + path + "'"; return false; }

@@ -202,14 +202,15 @@ struct VarMer {
   std::vector<std::vector<int>> gtPaths;
   std::vector<std::vector<uint32_t>> idxPaths, lenPaths;
   std::vector<uint32_t> numMs;
-  std::vector<std::vector<double>> kstrs, dkstrs;
+  std::vector<std::vector<double>> kstrs, dkstrs;   // per window; kept only for the -debug statistics
+  std::vector<double> totdKs;                        // sum of a path's dkstrs, added up in window order
 
   void addSeqPath(const std::string &seq, const std::vector<int> &path, const std::vector<uint32_t> &idx,
                   const std::vector<uint32_t> &len) {                                // varMer.C:37-45
     if (std::find(seqs.begin(), seqs.end(), seq) != seqs.end()) return;
     seqs.push_back(seq); gtPaths.push_back(path); idxPaths.push_back(idx); lenPaths.push_back(len);
   }
-  double totdK(int i) const { double s = 0; for (double d : dkstrs[i]) s += d; return s; }           // :646-659
+  double totdK(int i) const { return totdKs[i]; }                                                    // :646-659 (same additions, same order)
   double minAbsK(int i) const {                                                                      // :553-569
     double m = DBL_MAX;
     for (double a : kstrs[i]) { if (a < 0) continue; if (a < m) m = a; }
@@ -330,8 +331,10 @@ static void score(VarMer &vm, const Options &opt, const KTable &kt, const uint32
     const uint64_t base = off[first_path + ii];
     uint32_t numM = 0, idx = 0;
     std::vector<double> ks, dks;
+    double totd = 0;
     const size_t nwin = L >= k ? L - k + 1 : 0;
-    if (opt.mode != FILTER) { ks.reserve(nwin); dks.reserve(nwin); }
+    const bool keep = opt.debug;                     // the per-window values are only read by the -debug statistics
+    if (opt.mode != FILTER && keep) { ks.reserve(nwin); dks.reserve(nwin); }
     const size_t nvar = vm.idxPaths[ii].size();
     const uint32_t *ipath = vm.idxPaths[ii].data(), *lpath = vm.lenPaths[ii].data();
     const int *gpath = vm.gtPaths[ii].data();
@@ -351,11 +354,12 @@ static void score(VarMer &vm, const Options &opt, const KTable &kt, const uint32
       else if (readK > asmK) kMetric = readK / asmK - 1;
       else kMetric = asmK / readK - 1;
       const double nD = fabs(readK - asmK) * prob;
-      ks.push_back(kMetric);
-      dks.push_back(oD - nD);
+      totd += oD - nD;
+      if (keep) { ks.push_back(kMetric); dks.push_back(oD - nD); }
       idx++;
     }
-    vm.numMs.push_back(numM); vm.kstrs.push_back(std::move(ks)); vm.dkstrs.push_back(std::move(dks));
+    vm.numMs.push_back(numM); vm.totdKs.push_back(totd);
+    if (keep) { vm.kstrs.push_back(std::move(ks)); vm.dkstrs.push_back(std::move(dks)); }
   }
 }
 
@@ -483,6 +487,8 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
   std::string paths;
   std::vector<uint64_t> off;
   ScoreOut sc;
+  Options sopt = opt;
+  sopt.debug = debug != nullptr;                     // the per-window values are kept exactly when the debug records are written
   const KTable kt(&opt.km);
   for (size_t b0 = first; b0 < cluster_end;) {
     // the pre-roll clusters ride along with the first batch
@@ -525,7 +531,7 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
 
     for (Work &w : work) {
       VarMer &vm = w.vm;
-      score(vm, opt, kt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
+      score(vm, sopt, kt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
       if (!w.keep) continue;
       if (debug) {
         char buf[512];
