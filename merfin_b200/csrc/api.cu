@@ -224,8 +224,16 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
       waited[i] = 1;
       return mfn_ingest_wait(ctx, i);
     };
+    // Only the LAST sub-sweep's probe pass is exposed (nothing is left to ingest under it), so with two
+    // sub-sweeps the first one takes the bigger share of the pieces (MFN_SUBSWEEP_FIRST, default 0.5 = even)
+    double first_share = 0.5;
+    if (const char *ef = getenv("MFN_SUBSWEEP_FIRST")) { first_share = atof(ef); if (!(first_share > 0.05 && first_share < 0.95)) first_share = 0.5; }
+    auto bound = [&](uint64_t sw) -> uint32_t {
+      if (nsw == 2 && sw == 1) return (uint32_t)std::min<uint64_t>(np, std::max<uint64_t>(1, (uint64_t)(np * first_share + 0.5)));
+      return (uint32_t)(np * sw / nsw);
+    };
     for (uint64_t sw = 0; sw < nsw && st == MFN_OK; sw++) {
-      const uint32_t pa = (uint32_t)(np * sw / nsw), pb = (uint32_t)(np * (sw + 1) / nsw);
+      const uint32_t pa = bound(sw), pb = sw + 1 == nsw ? np : bound(sw + 1);
       if (pa >= pb) continue;
       const uint64_t sa = tb + (uint64_t)pa * piece_tiles, sb = std::min(te, tb + (uint64_t)pb * piece_tiles);
       mfn_sweep *w = nullptr;
