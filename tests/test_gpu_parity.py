@@ -624,21 +624,64 @@ def test_streamed_synthetic_database_equals_resident(ctx, k):
     acc.close(); S.close(); R.close(); A.close(); seq.close()
 
 
-@pytest.mark.parametrize("restricted", [False, True])
-def test_dump_through_the_range_partitioned_scan(ctx, monkeypatch, restricted):
-    """-dump's pairs per position through scatter -> probe (entries overwritten by their pairs) -> gather equal the
-    direct scan's, for records with N runs, lower case, short and empty records; with the full fused table
-    (division geometry) and with the restricted one (bit-field geometry)."""
-    from merfin_b200 import api
-    # (big enough for 32-bit table slots: 20-bit tags need >= 2^22 table lines)
-    rng = np.random.default_rng(21)
+def _big_records(rng):
+    """110 Mbp in records that exercise every path of the k = 21 scatter kernel at a size where the tables have
+    32-bit slots (>= 2^22 lines): N runs, lower case, empty / short / all-N records, and a crowd of tiny records
+    inside one chunk (more records than the staging word tells apart: side list)."""
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     a = rng.choice(acgt, size=80_000_000)
     a[500_000:500_700] = ord("N")
     a[900_000:900_050] += 32                               # lower case
     b = rng.choice(acgt, size=30_000_000)
     b[100:130] = ord("N")
-    recs = [("a", a.tobytes()), ("empty", b""), ("short", b"ACGTACGTAC"), ("b", b.tobytes()), ("dup", a[:300_000].tobytes()), ("n", b"N" * 5000)]
+    tiny = [("t%d" % i, rng.choice(acgt, size=int(rng.integers(25, 90))).tobytes()) for i in range(60)]
+    return ([("a", a.tobytes()), ("empty", b""), ("short", b"ACGTACGTAC")] + tiny +
+            [("b", b.tobytes()), ("dup", a[:300_000].tobytes()), ("n", b"N" * 5000)])
+
+
+@pytest.mark.parametrize("restricted", [False, True])
+def test_scatter3_hist_equals_direct_scan(ctx, monkeypatch, restricted):
+    """-hist through k_sweep_scatter3 (k = 21, narrow entries: needs tables with 32-bit slots, i.e. >= 70 M k-mers)
+    against the direct scan: joint histogram and per-record counters, full fused table (division geometry) and
+    restricted table (bit-field geometry); also in two shards and through the host-buffer path."""
+    from merfin_b200 import api
+    recs = _big_records(np.random.default_rng(22))
+    seq = api.SeqSet(ctx, recs)
+    A = api.MerylExactLookup.count_sequence(ctx, 21, seq)
+    R = api.MerylExactLookup.synth_reads(ctx, A, 10.0, 2_000_000, 9)
+    R.fuse(A)
+    assert R.joint_info.slot_bits == 32
+    if restricted:
+        R.restrict(A, seq)
+    km = api.KModel(10.0)
+    acc = api.Accum(ctx, len(recs))
+    monkeypatch.setenv("MFN_SWEEP", "0")
+    api.hist_resident(ctx, R, A, seq, km, acc)
+    per0, pairs0 = acc.fetch()
+    monkeypatch.setenv("MFN_SWEEP", "1")
+    acc.reset()
+    l0 = ctx.launches
+    api.hist_resident(ctx, R, A, seq, km, acc)
+    assert ctx.launches - l0 >= 3                            # scatter, probe, side list
+    per1, pairs1 = acc.fetch()
+    assert len(pairs0) == len(pairs1) and (pairs0 == pairs1).all() and (per0 == per1).all()
+    acc.reset()
+    for sh in range(2):
+        api.hist_resident(ctx, R, A, seq, km, acc, sh, 2)
+    per2, pairs2 = acc.fetch()
+    assert len(pairs0) == len(pairs2) and (pairs0 == pairs2).all() and (per0 == per2).all()
+    h = api.hist(ctx, R, A, recs, km)                        # host buffers: both ingest lanes, sub-sweeps
+    assert len(pairs0) == len(h.pairs) and (pairs0 == h.pairs).all() and (per0 == h.per_seq).all()
+    acc.close(); seq.close(); R.close(); A.close()
+
+
+@pytest.mark.parametrize("restricted", [False, True])
+def test_dump_through_the_range_partitioned_scan(ctx, monkeypatch, restricted):
+    """-dump's pairs per position through scatter -> probe (entries overwritten by their pairs) -> gather equal the
+    direct scan's, for records with N runs, lower case, short and empty records; with the full fused table
+    (division geometry) and with the restricted one (bit-field geometry)."""
+    from merfin_b200 import api
+    recs = _big_records(np.random.default_rng(21))
     seq = api.SeqSet(ctx, recs)
     A = api.MerylExactLookup.count_sequence(ctx, 21, seq)
     R = api.MerylExactLookup.synth_reads(ctx, A, 10.0, 2_000_000, 9)
