@@ -184,7 +184,7 @@ def test_cli_100mbp_against_reference():
     import json
     import sys
     mbp = os.environ.get("MFN_TEST_CLI_MBP", "100")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_cli.py"), "--mbp", mbp, "--variants", "40000"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_cli.py"), "--mbp", mbp, "--variants", "40000", "--repeat", "1"],
                        capture_output=True, text=True, timeout=1500)
     assert p.returncode == 0, p.stderr[-3000:]
     r = json.loads(p.stdout.strip().splitlines()[-1])

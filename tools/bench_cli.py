@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--no-dump", action="store_true")
     ap.add_argument("--variants", type=int, default=200000, help="records of the synthetic VCF for -polish / -filter (0 = skip)")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--repeat", type=int, default=2, help="runs per timed command (best is reported)")
     args = ap.parse_args()
     import torch
     from merfin_b200 import api
@@ -108,7 +109,7 @@ def main():
         common = ["-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl", "-peak", str(B.PEAK)]
         res = {}
         os.environ["MFN_TIMELINE"] = "1"
-        t, err = run([ours, "-hist"] + common + ["-output", "ours.hist"], d, repeat=2)
+        t, err = run([ours, "-hist"] + common + ["-output", "ours.hist"], d, repeat=args.repeat)
         res["ours_hist_s"] = round(t, 2); ours_sum = summary(err)
         res["ours_hist_timeline"] = [l.replace("[timeline]", "").strip() for l in err.splitlines() if l.startswith("[timeline]")]
         if not args.no_dump:
@@ -116,7 +117,7 @@ def main():
             res["ours_dump_s"] = round(t, 2)
         if os.path.exists(ref):
             th = str(min(os.cpu_count() or 1, len(lens)))
-            t, err = run([ref, "-hist"] + common + ["-threads", th, "-memory", "64", "-output", "ref.hist"], d, repeat=2)
+            t, err = run([ref, "-hist"] + common + ["-threads", th, "-memory", "64", "-output", "ref.hist"], d, repeat=args.repeat)
             res["ref_hist_s"] = round(t, 2); ref_sum = summary(err)
             res["hist_file_identical"] = open(os.path.join(d, "ours.hist"), "rb").read() == open(os.path.join(d, "ref.hist"), "rb").read()
             res["hist_summary_identical"] = ours_sum == ref_sum
@@ -128,10 +129,10 @@ def main():
                 res["dump_file_identical"] = md5(os.path.join(d, "ours.dump")) == md5(os.path.join(d, "ref.dump"))
             if args.variants:
                 for mode, produced in (("-polish", "%s.polish.vcf"), ("-filter", "%s.filter.vcf")):
-                    t, err = run([ours, mode] + common + ["-vcf", "calls.vcf", "-output", "ours"], d, repeat=2)
+                    t, err = run([ours, mode] + common + ["-vcf", "calls.vcf", "-output", "ours"], d, repeat=args.repeat)
                     res["ours_%s_s" % mode[1:]] = round(t, 2)
                     res["ours_%s_timeline" % mode[1:]] = [l.replace("[timeline]", "").strip() for l in err.splitlines() if l.startswith("[timeline]")]
-                    t, err = run([ref, mode] + common + ["-vcf", "calls.vcf", "-threads", th, "-memory", "64", "-output", "ref"], d, repeat=2)
+                    t, err = run([ref, mode] + common + ["-vcf", "calls.vcf", "-threads", th, "-memory", "64", "-output", "ref"], d, repeat=args.repeat)
                     res["ref_%s_s" % mode[1:]] = round(t, 2)
                     a, b = open(os.path.join(d, produced % "ours"), "rb").read(), open(os.path.join(d, produced % "ref"), "rb").read()
                     # the reference writes clusters in the order its worker threads finish them: compare as sets of lines too
