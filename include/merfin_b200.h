@@ -367,6 +367,10 @@ double mfn_getKmetric(double readK, double asmK);                  /* merfin-glo
  * (0 = all cores).  counts receives the record's kasm / kmissing (merfin-dump.C:58-66). */
 int  mfn_dump_write(int fd, const char *ident, uint64_t n, const uint32_t *v_read, const uint32_t *v_asm,
                     const uint8_t *valid, const mfn_kmodel *km, int threads, mfn_seq_counts *counts);
+/* The -completeness join over two RESIDENT tables (both loaded with min_value 0: raw values, Q4): every k-mer
+ * the read table holds against the assembly table, into the same accumulator layout as mfn_completeness_shard.
+ * Runs the join without a database on disk (the benchmark's tables are synthesised on the device). */
+int  mfn_completeness_resident(mfn_ctx *ctx, const mfn_table *reads_raw, const mfn_table *asm_raw, mfn_accum *acc);
 /* -completeness sums from the joint histogram of raw values. */
 int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const mfn_kmodel *km,
                              double *total, double *undr);

@@ -579,6 +579,18 @@ def completeness(ctx: Context, reads_dir: str, asm_dir: str, kmodel: KModel):
     return t.value, u.value, pairs
 
 
+def completeness_resident(ctx: Context, reads: MerylExactLookup, asm: MerylExactLookup, kmodel: KModel):
+    """computeCompleteness over two resident tables (raw values): (total readK, total undercopy, pairs)."""
+    lib = L.load()
+    acc = Accum(ctx, 0)
+    L.check(lib.mfn_completeness_resident(ctx.h, reads.h, asm.h, acc.h))
+    _, pairs = acc.fetch()
+    acc.close()
+    tot, undr = C.c_double(), C.c_double()
+    L.check(lib.mfn_completeness_report(_ptr(pairs), len(pairs), C.byref(kmodel.c), C.byref(tot), C.byref(undr)))
+    return tot.value, undr.value, pairs
+
+
 def completeness_text(total: float, undr: float) -> str:
     return ("TOTAL readK:   %15.2f\nTOTAL undrcpy:    %15.5f\nCOMPLETENESS:             %0.5f\n"
             % (total, undr, 1.0 - undr / total))

@@ -158,6 +158,7 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64)]),
     "mfn_text_free": (None, [_P]),
     "mfn_completeness": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_completeness_resident": (C.c_int, [_P, _P, _P, _P]),
     "mfn_completeness_shard": (C.c_int, [_P, C.c_char_p, _P, C.c_uint32, C.c_uint32, _P]),
     "mfn_hist_report": (C.c_int, [_P, C.c_uint64, C.POINTER(KModel), C.c_uint32, _P, _P, C.c_uint32,
                                   C.POINTER(HistSummary)]),

@@ -547,6 +547,22 @@ def test_midsize_hist_against_reference_binary(ctx, tmp_path, monkeypatch, k, mn
     R.close(); A.close()
 
 
+@pytest.mark.parametrize("name,peak", [("g1_k21", 8), ("g2_k6", 3), ("g3_k31", 6)])
+def test_completeness_over_resident_tables(ctx, golden_dir, name, peak):
+    """The join over two resident tables (mfn_completeness_resident) gives the pairs of the join over the databases
+    on disk, hence the reference's TOTAL / COMPLETENESS lines."""
+    from merfin_b200 import api
+    d = os.path.join(golden_dir, name)
+    km = api.KModel(peak)
+    t0, u0, pairs0 = api.completeness(ctx, os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"), km)
+    R = api.MerylExactLookup.load(ctx, os.path.join(d, "reads.meryl"))
+    A = api.MerylExactLookup.load(ctx, os.path.join(d, "asm.meryl"))
+    t1, u1, pairs1 = api.completeness_resident(ctx, R, A, km)
+    assert len(pairs0) == len(pairs1) and (pairs0 == pairs1).all() and (t0, u0) == (t1, u1)
+    assert open(os.path.join(d, "ref.completeness")).read().endswith(api.completeness_text(t1, u1))
+    R.close(); A.close()
+
+
 def test_completeness_shards_sum_to_the_whole(ctx, golden_dir):
     """-completeness cut into shards of read-database files (what N ranks do before the all-reduce)
     accumulates exactly the joint histogram of the single-call version."""

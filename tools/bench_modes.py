@@ -133,6 +133,23 @@ def main():
             windows = npaths * (plen - k + 1)
             emit({"mode": "-polish path scoring (mfn_score_paths, host buffers, wall clock)", **tinfo, "paths": npaths, "path_len": plen,
                   "windows": windows, "s": dt, "windows_per_s": windows / dt, "paths_per_s": npaths / dt, "valid_windows": int(pk.sum())})
+        if "join" in modes and k == 21:
+            # -completeness over the resident tables: every read k-mer against the assembly table (no database on disk)
+            acc = api.Accum(ctx, 0)
+            f = lambda: (acc.reset(), api.L.check(lib.mfn_completeness_resident(ctx.h, R.h, A.h, acc.h)))
+            ms = ev_ms(f, args.steps)
+            _, pairs = acc.fetch()
+            tot, undr = C.c_double(), C.c_double()
+            km_ = api.KModel(B.PEAK)
+            api.L.check(lib.mfn_completeness_report(pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(km_.c), C.byref(tot), C.byref(undr)))
+            nk = int(R.nKmers())
+            ri = R.info
+            # bytes the join has to move: the read table's slots streamed once + one 32-byte sector of the assembly table per k-mer
+            alg = ri.device_bytes + nk * 32
+            emit({"mode": "-completeness join over resident tables (k_join_tables)", **tinfo, "read_kmers": nk, "asm_kmers": int(A.nKmers()),
+                  "ms": ms, "kmers_per_s": nk / ms * 1e3, "algorithmic_GB": round(alg / 1e9, 2), "achieved_GBs": alg / ms / 1e6,
+                  "roofline_frac": alg / ms / 1e6 / peak_gbs, "completeness": 1.0 - undr.value / tot.value if tot.value else None})
+            acc.close()
         if "completeness" in modes and k == 21 and total <= 300_000_000:
             d = tempfile.mkdtemp(prefix="mfn_modes_")
             try:
