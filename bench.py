@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--sample-mbp", type=float, default=24.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="hist", choices=["hist", "polish"],
-                    help="hist: the headline (BASELINE configs[2]); polish: variants/s of -polish over a synthetic VCF (configs[3], bench_modes.py)")
+                    help="hist: the headline (BASELINE configs[2]); polish: variants/s of -polish over a synthetic VCF (configs[3], tools/bench_polish.py)")
     ap.add_argument("--variants", type=int, default=0, help="--mode polish: VCF records (default 5 000 000 per 3 Gbp)")
     ap.add_argument("--emulate-shards", type=int, default=0,
                     help="development aid, 1 GPU: time shard 0 of N exactly as rank 0 of an N-GPU run would (no collective); "
@@ -346,7 +346,8 @@ def main():
         config["emulated"] = f"shard 0 of {sworld} on one GPU, no collective: development figure, not a bench value"
 
     if args.impl == "reference" and args.mode == "polish":
-        import bench_modes
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_polish as bench_modes
         names = [f"rec{i + 1}" for i in range(len(lens))]
         nvar = int(args.variants if args.variants else round(5_000_000 * total / 3.0e9))
         cb = bench_modes.polish_cpu_baseline(args, sys.modules[__name__], ctx, api, asm_np, lens, names, nvar, total,
@@ -422,7 +423,8 @@ def main():
                         "slot_bits": int(ri.slot_bits), "setup_s": round(setup_s, 1)}
 
     if args.mode == "polish":
-        import bench_modes
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_polish as bench_modes
         rc = bench_modes.polish(args, sys.modules[__name__], ctx, api, lib, torch, dist, rank, world, local, dev, asm_np, lens, off,
                                 R, A, config, setup_s)
         if world > 1:

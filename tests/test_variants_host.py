@@ -136,8 +136,8 @@ def test_bench_vcf_generator_against_reference(harness, tmp_path):
     .polish.vcf / .filter.vcf, in one piece and as 3 cluster ranges per record."""
     import sys
     import numpy as np
-    sys.path.insert(0, ROOT)
-    import bench_modes
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_polish as bench_modes
     from merfin_b200 import synth
     d = str(tmp_path)
     k = 21

@@ -1,4 +1,4 @@
-"""Secondary modes of bench.py (`--mode polish`, `--mode completeness`): BASELINE.json configs[3] / configs[2].
+"""`bench.py --mode polish`: BASELINE.json configs[3].
 
 polish   variants/s of `-polish` over a synthetic VCF on the bench.py assembly and tables (SURVEY 8(d) C4:
          5 000 000 records at 3 Gbp, 80 % SNV / 10 % insertions / 10 % deletions of 1-4 bp, mixed genotypes,
@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 GT_CHOICES = [b"1/1", b"0/1", b"1|0", b"1/2", b"0/0", b"./."]
 GT_P = [0.55, 0.20, 0.10, 0.13, 0.01, 0.01]          # 0/0 + ./. <= 2 % (each silences its whole cluster, Q10)
