@@ -593,7 +593,8 @@ def main():
             if tj.get("dram_bytes_per_base") and bool(tj.get("restricted_table")) == bool(restricted):
                 traffic = tj["dram_bytes_per_base"] * bases_rank
                 traffic_src = tj.get("source")
-        kernel_name = ("k_sweep_scatter<21,false> + k_sweep_probe<false> (range-partitioned scan of the joint table)" if swept
+        kernel_name = ("k_sweep_scatter3<21,GEO,TILES> + k_sweep_probe<false> (range-partitioned scan of the fused table restricted to the rank's shard)" if swept and restricted
+                       else "k_sweep_scatter3 / k_sweep_scatter<21,false> + k_sweep_probe<false> (range-partitioned scan of the full fused table)" if swept
                        else "k_scan<2> (joint table)" if ji.fused else "k_scan<0> (two tables)")
         out = {"metric": "bases/sec (-hist k=21)", "value": value, "unit": "bases/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
