@@ -59,6 +59,8 @@ extern "C" int mfn_ctx_create(mfn_ctx **out, int device) {
   MFN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   MFN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   MFN_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+  MFN_CUDA(cudaStreamCreateWithFlags(&c->probe_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev_probe) MFN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->ev) MFN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   c->stream = c->own_stream;
   // keep stream-ordered workspace (cudaMallocAsync) cached between calls
@@ -85,6 +87,8 @@ extern "C" void mfn_ctx_destroy(mfn_ctx *c) {
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->pack_stream);
+  cudaStreamDestroy(c->probe_stream);
+  for (auto &ev : c->ev_probe) if (ev) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -226,6 +230,9 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
     };
     // Only the LAST sub-sweep's probe pass is exposed (nothing is left to ingest under it), so with two
     // sub-sweeps the first one takes the bigger share of the pieces (MFN_SUBSWEEP_FIRST, default 0.5 = even)
+    const char *ea = getenv("MFN_ASYNC_PROBE");
+    const bool async_probe = ea && atoi(ea) != 0;
+    if (async_probe) ctx->side_probe_ctas = std::max(1, std::min(3, atoi(ea)));
     double first_share = 0.5;
     if (const char *ef = getenv("MFN_SUBSWEEP_FIRST")) { first_share = atof(ef); if (!(first_share > 0.05 && first_share < 0.95)) first_share = 0.5; }
     auto bound = [&](uint64_t sw) -> uint32_t {
@@ -246,8 +253,10 @@ extern "C" int mfn_hist_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_tab
         const uint64_t a = tb + (uint64_t)p * piece_tiles, b = std::min(te, a + piece_tiles);
         if (st == MFN_OK) st = mfn_sweep_scatter(ctx, w, a, b);
       }
-      if (w) { int st2 = mfn_sweep_finish(ctx, w); if (st == MFN_OK) st = st2; }
+      // every probe pass but the last runs on the second compute stream, next to the following sub-sweep's scatters
+      if (w) { int st2 = mfn_sweep_finish(ctx, w, async_probe && sw + 1 < nsw); if (st == MFN_OK) st = st2; }
     }
+    if (async_probe) mfn_sweep_join(ctx);
     mfn_ingest_end(ctx);
     if (zmap) cudaFreeAsync(zmap, ctx->stream);
     return st;

@@ -84,6 +84,9 @@ struct mfn_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;    // H2D of the ASCII staging buffers
   cudaStream_t pack_stream = nullptr;    // k_pack: the only writer of a sequence set's packed arrays
+  cudaStream_t probe_stream = nullptr;   // probe pass of a finished sub-sweep next to the scatter passes of the following one
+  cudaEvent_t  ev_probe[2] = {};
+  int          side_probe_ctas = 1;      // CTAs per SM of a probe pass on the second stream
   cudaEvent_t  ev[MFN_STAGE_BUFS + 3] = {};   // [b]: pack kernel that last read staging buffer b; then copy / pack / order
   int          sm_count = 0;
   std::atomic<uint64_t> launches{0};

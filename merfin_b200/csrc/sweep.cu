@@ -192,15 +192,33 @@ int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t 
   return MFN_OK;
 }
 
-int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w) {
+// side_stream: the probe pass (and the release of the workspace) goes to the ctx's second compute stream, ordered
+// after everything queued on ctx->stream so far, and ctx->stream does NOT wait for it: the scatter passes of the
+// next sub-sweep run next to it (mfn_hist_host; the caller joins the streams at the end with mfn_sweep_join)
+int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w, bool side_stream) {
   SweepParams P = w->P;
+  cudaStream_t st = ctx->stream;
+  if (side_stream) {
+    st = ctx->probe_stream;
+    cudaEventRecord(ctx->ev_probe[0], ctx->stream);
+    cudaStreamWaitEvent(st, ctx->ev_probe[0], 0);
+  }
   P.counter = w->counters;
-  if (P.J.w64) mfn_sweep_launch_probe64(P, ctx->sm_count, ctx->stream);
-  else mfn_sweep_launch_probe32(P, ctx->sm_count, ctx->stream);
+  if (P.J.w64) mfn_sweep_launch_probe64(P, ctx->sm_count, st);
+  else mfn_sweep_launch_probe32(P, ctx->sm_count, st, side_stream ? ctx->side_probe_ctas : 0);
   P.counter = w->counters + 1;
-  mfn_sweep_launch_over(P, ctx->sm_count, ctx->stream);
+  mfn_sweep_launch_over(P, ctx->sm_count, st);
   ctx->launches += 2;
   cudaError_t e = cudaGetLastError();
+  if (side_stream) {
+    cudaFreeAsync(P.entries, st);
+    cudaFreeAsync(w->ctl, st);
+    cudaFreeAsync(P.over_lt, st);
+    cudaFreeAsync(P.over_rec, st);
+    delete w;
+    if (e != cudaSuccess) { mfn_set_error("sweep: %s", cudaGetErrorString(e)); return MFN_ERR_CUDA; }
+    return MFN_OK;
+  }
 #ifdef SW_PROFILE
   {
     unsigned long long h[8];
@@ -232,7 +250,7 @@ int mfn_sweep_hist(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const m
   if (ctx->time_passes) mfn_ctx_mark(ctx);
   int st = mfn_sweep_scatter(ctx, w, tile_begin, tile_end);
   if (ctx->time_passes) mfn_ctx_mark(ctx);
-  int st2 = mfn_sweep_finish(ctx, w);
+  int st2 = mfn_sweep_finish(ctx, w, false);
   if (ctx->time_passes) mfn_ctx_mark(ctx);
   return st != MFN_OK ? st : st2;
 }
@@ -353,4 +371,10 @@ int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, c
   cudaFreeAsync(ctl, ctx->stream);
   if (e2 != cudaSuccess) { mfn_set_error("dump sweep: %s", cudaGetErrorString(e2)); return MFN_ERR_CUDA; }
   return MFN_OK;
+}
+
+// ctx->stream waits for whatever mfn_sweep_finish(..., true) put on the second compute stream
+void mfn_sweep_join(mfn_ctx *ctx) {
+  cudaEventRecord(ctx->ev_probe[1], ctx->probe_stream);
+  cudaStreamWaitEvent(ctx->stream, ctx->ev_probe[1], 0);
 }

@@ -715,6 +715,6 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_over(const __grid_constant
 
 // One translation unit per probe entry (sweep_probe32.cu, sweep_probe64.cu, sweep_over.cu): ptxas
 // 12.9 crashes when two entries that share an out-of-line device function are compiled in one module.
-void mfn_sweep_launch_probe32(const SweepParams &P, int sm_count, cudaStream_t stream);
+void mfn_sweep_launch_probe32(const SweepParams &P, int sm_count, cudaStream_t stream, int cap = 0);
 void mfn_sweep_launch_probe64(const SweepParams &P, int sm_count, cudaStream_t stream);
 void mfn_sweep_launch_over(const SweepParams &P, int grid, cudaStream_t stream);

@@ -90,7 +90,8 @@ struct mfn_sweep;
 int mfn_sweep_begin(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t windows, mfn_accum *acc,
                     const unsigned long long *zmap, uint32_t zlen, uint32_t zhi, mfn_sweep **out);
 int mfn_sweep_scatter(mfn_ctx *ctx, mfn_sweep *w, uint64_t tile_begin, uint64_t tile_end);
-int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w);
+int mfn_sweep_finish(mfn_ctx *ctx, mfn_sweep *w, bool side_stream = false);
+void mfn_sweep_join(mfn_ctx *ctx);
 // -dump through the range-partitioned scan (sweep_dump.cu / sweep.cu)
 bool mfn_sweep_dump_applicable(const mfn_table *R, const mfn_table *A, uint64_t ntiles, bool force);
 int mfn_sweep_dump_piece(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, const mfn_seq *seq, uint64_t tile_begin, uint64_t tile_end,
