@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 10 (2 GPUs): CLI -devices 0,1, bench.py at N = 2 (hist and polish) through torchrun
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call10
 mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 11: fixed/new GPU tests, CLI time-line at 100 Mbp, polish with pieces, ncu launch list + full capture at 3 Gbp
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call11
 mkdir -p $O
 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -x -q -m gpu -k "streamed or variant or devices or overflow" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt

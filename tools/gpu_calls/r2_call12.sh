@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 12: all GPU tests, 8192-window scatter3 with 512 bins of 32 MB, sub-sweep count of the host-buffer path, CLI time-line
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call12
 mkdir -p $O
 timeout 2400 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" | tee -a $O/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 13: -dump through the range-partitioned scan (parity + rate), headline with the 32 MB default, shards of 4 / 8 emulated
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call13
 mkdir -p $O
 timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -x -q -m gpu -k "dump or compressed or golden" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 20: -dump through the range-partitioned scan, second try (queued slow path): parity + per-pass times
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call20
 mkdir -p $O
 timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "dump_through or dump or golden" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt

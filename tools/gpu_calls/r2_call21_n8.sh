@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 21 (8 GPUs): bench.py at N = 8 and N = 4 through torchrun
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call21
 mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 22: everything once more on the final code -- all GPU tests, smoke, headline + reference arm, ncu launch list and full capture, CLI
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call22
 mkdir -p $O
 timeout 2400 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" | tee -a $O/summary.txt

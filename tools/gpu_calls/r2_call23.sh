@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 23: share of the first of two sub-sweeps in the host-buffer path; polish with the leaner replay
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call23
 mkdir -p $O
 show() { python - "$1" "$2" <<'PY' | tee -a gpurun_out/r2_call23/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 24 (8 GPUs): bench.py --mode polish at N = 8 and N = 4
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call24
 mkdir -p $O
 P=29717

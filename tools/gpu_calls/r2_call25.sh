@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 25: scatter3 -hist parity at 110 Mbp; compute-sanitizer memcheck / racecheck over the new kernels
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call25
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "scatter3_hist or dump_through or streamed" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt

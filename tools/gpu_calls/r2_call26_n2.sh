@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 26 (2 GPUs): bench.py at N = 2 with the final code (32 MB slices), CLI -devices tests on two real GPUs
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call26
 mkdir -p $O
 P=29817

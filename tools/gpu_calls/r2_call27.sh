@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 27: -completeness join over resident tables: parity on the goldens, rate at 3 Gbp (3.5 G read k-mers)
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call27
 mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "completeness" > $O/pytest_sel.log 2>&1; echo "pytest selected rc=$?" | tee -a $O/summary.txt

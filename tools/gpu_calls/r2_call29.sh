@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 29: probe pass of the first sub-sweep on a second stream next to the second sub-sweep's scatters (host-buffer path)
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call29
 mkdir -p $O
 show() { python - "$1" "$2" <<'PY' | tee -a gpurun_out/r2_call29/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 3 (re-entry): GPU tests + smoke + headline of HEAD, restricted vs full table, scatter CTA shapes, phase profile, ncu.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call3
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/gpu.txt 2>&1

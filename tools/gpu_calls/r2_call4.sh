@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 4: scatter3 + in-line spill lookup of the probe pass: parity, A/B against the previous scatter, table load, shard emulation, ncu.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call4
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > $O/pytest_parity.log 2>&1; echo "pytest parity rc=$?" | tee -a $O/summary.txt

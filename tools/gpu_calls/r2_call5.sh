@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 5: scatter3 v2 (one 16-window group per thread, single staging buffer, 33-bit bit-field geometry), table load <= 0.62
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call5
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > $O/pytest_parity.log 2>&1; echo "pytest parity rc=$?" | tee -a $O/summary.txt

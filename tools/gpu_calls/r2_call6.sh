@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 6: all GPU tests (variant ABI + CLI shards), spread reservation counters (MFN_BIN_STRIDE) A/B, geometry choices
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call6
 mkdir -p $O
 timeout 1200 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" | tee -a $O/summary.txt

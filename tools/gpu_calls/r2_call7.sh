@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 7: probe pass work-item size / L2 policy A/B at the new default geometry (64 MB slices); first run of bench.py --mode polish
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call7
 mkdir -p $O
 show() { python - "$1" "$2" <<'PY' | tee -a gpurun_out/r2_call7/summary.txt

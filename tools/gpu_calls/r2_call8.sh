@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 8: all GPU tests (CLI -devices, overflow recipe, new k_join), probe work items of 2048/4096 entries, other modes + k sweep
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call8
 mkdir -p $O
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" | tee -a $O/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 9: all GPU tests (streamed read database, 100 Mbp CLI against the reference), -completeness time-line, read-database size sweep
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_call9
 mkdir -p $O
 MFN_TEST_OUT=$PWD/$O/cli_100mbp.json timeout 2400 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" | tee -a $O/summary.txt

@@ -3,7 +3,7 @@
 # out, measured in one go.  Run as
 #   gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_call.sh'
 # Results land in gpurun_out/r2_first/.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/r2_first
 mkdir -p $O
 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
