@@ -519,6 +519,11 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
       work.emplace_back();
       Work &w = work.back();
       w.vm.posGt = pg; w.rStart = rStart; w.rEnd = rEnd; w.first_path = off.size() - 1; w.keep = keep;
+      {
+        // room for the usual two paths (REF and one ALT) up front: the vectors would otherwise grow 1 -> 2 and move
+        VarMer &v = w.vm;
+        v.seqs.reserve(2); v.gtPaths.reserve(2); v.idxPaths.reserve(2); v.lenPaths.reserve(2); v.numMs.reserve(2); v.totdKs.reserve(2);
+      }
       std::vector<int> path;
       traverse(0, idxList, lenList, haps, std::string(seq + rStart, rEnd - rStart), path, w.vm);
       for (const std::string &s : w.vm.seqs) { paths += s; off.push_back(paths.size()); }
