@@ -8,11 +8,12 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <list>
+#include <stdexcept>
 
 namespace mfnv {
 
@@ -29,11 +30,20 @@ static void split_spans(const char *s, size_t n, const char *seps, std::vector<S
     i = j;
   }
 }
+template <class I> static inline void put_int(std::string &out, I v) {
+  char num[24];
+  out.append(num, std::to_chars(num, num + sizeof num, v).ptr);
+}
+
 std::string VcfRecord::save() const {
   char num[64];
-  snprintf(num, sizeof num, "%.1f", qual);
-  return chr + "\t" + std::to_string((int)pos) + "\t" + id + "\t" + ref + "\t" + alts + "\t" + num + "\t" + filter +
-         "\t" + info + "\t" + formats + "\t" + samples + "\n";
+  const int nn = std::min<int>(snprintf(num, sizeof num, "%.1f", qual), (int)sizeof num - 1);
+  std::string out;
+  out.reserve(chr.size() + id.size() + ref.size() + alts.size() + filter.size() + info.size() + formats.size() + samples.size() + 32 + (size_t)nn);
+  out += chr; out += '\t'; put_int(out, (int)pos); out += '\t'; out += id; out += '\t'; out += ref; out += '\t'; out += alts; out += '\t';
+  out.append(num, (size_t)nn); out += '\t'; out += filter; out += '\t'; out += info; out += '\t'; out += formats; out += '\t'; out += samples;
+  out += '\n';
+  return out;
 }
 
 VcfFile::~VcfFile() {
@@ -194,274 +204,394 @@ void VcfFile::mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One cluster: its candidate paths and their scores (the reference's varMer object)
+// One batch of clusters.  What the reference keeps in one varMer object per cluster (the candidate
+// paths, their genotype / index / length lists and their scores) lies side by side in flat arrays for
+// the whole batch: `paths` + `off` are exactly what the scorer takes, nothing is allocated per
+// cluster or per path, and the batch's storage is reused by the next one.
 // ---------------------------------------------------------------------------------------------
-struct VarMer {
+struct Cluster {
   PosGT *posGt = nullptr;
-  std::vector<std::string> seqs;
-  std::vector<std::vector<int>> gtPaths;
-  std::vector<std::vector<uint32_t>> idxPaths, lenPaths;
-  std::vector<uint32_t> numMs;
-  std::vector<std::vector<double>> kstrs, dkstrs;   // per window; kept only for the -debug statistics
-  std::vector<double> totdKs;                        // sum of a path's dkstrs, added up in window order
+  uint32_t rStart = 0, rEnd = 0;
+  uint32_t first_path = 0, npaths = 0;   // paths [first_path, first_path + npaths) of the batch
+  uint32_t nvar = 0;                     // variants of the cluster = entries per path in gt / idx / len
+  size_t first_var = 0;                  // the entries of the cluster's path i start at first_var + i * nvar
+  bool keep = false;
+};
 
-  void addSeqPath(const std::string &seq, const std::vector<int> &path, const std::vector<uint32_t> &idx,
-                  const std::vector<uint32_t> &len) {                                // varMer.C:37-45
-    if (std::find(seqs.begin(), seqs.end(), seq) != seqs.end()) return;
-    seqs.push_back(seq); gtPaths.push_back(path); idxPaths.push_back(idx); lenPaths.push_back(len);
+struct Batch {
+  std::string paths;                     // all candidate sequences of the batch, concatenated
+  std::vector<uint64_t> off;             // path p is paths[off[p], off[p + 1])
+  std::vector<int> gt;                   // varMer::gtPaths
+  std::vector<uint32_t> idx, len;        // varMer::idxPaths / lenPaths
+  std::vector<uint32_t> numM;            // per path
+  std::vector<double> totdK;             // per path: sum of the path's dkstrs, added up in window order
+  std::vector<std::vector<double>> kstrs, dkstrs;   // per path and window; kept only for the -debug statistics
+  std::vector<Cluster> clusters;
+  void clear() {
+    paths.clear(); off.assign(1, 0); gt.clear(); idx.clear(); len.clear(); numM.clear(); totdK.clear();
+    kstrs.clear(); dkstrs.clear(); clusters.clear();
   }
-  double totdK(int i) const { return totdKs[i]; }                                                    // :646-659 (same additions, same order)
-  double minAbsK(int i) const {                                                                      // :553-569
+};
+
+// One cluster of a batch as the selectors and the output records read it (the reference's varMer)
+struct VarMer {
+  const Batch &b;
+  const Cluster &c;
+  size_t npaths() const { return c.npaths; }
+  size_t seqLen(size_t i) const { return (size_t)(b.off[c.first_path + i + 1] - b.off[c.first_path + i]); }
+  const char *seq(size_t i) const { return b.paths.data() + b.off[c.first_path + i]; }
+  const int *gtPath(size_t i) const { return b.gt.data() + c.first_var + i * c.nvar; }
+  uint32_t numM(size_t i) const { return b.numM[c.first_path + i]; }
+  double totdK(size_t i) const { return b.totdK[c.first_path + i]; }                                  // varMer.C:646-659 (same additions, same order)
+  const std::vector<double> &kstr(size_t i) const { return b.kstrs[c.first_path + i]; }
+  double minAbsK(size_t i) const {                                                                    // :553-569
     double m = DBL_MAX;
-    for (double a : kstrs[i]) { if (a < 0) continue; if (a < m) m = a; }
+    for (double a : kstr(i)) { if (a < 0) continue; if (a < m) m = a; }
     return m == DBL_MAX ? -1 : m;
   }
-  double maxAbsK(int i) const { double m = -2; for (double a : kstrs[i]) if (a > m) m = a; return m; }  // :572-584
-  double avgAbsK(int i) const {                                                                      // :586-604
+  double maxAbsK(size_t i) const { double m = -2; for (double a : kstr(i)) if (a > m) m = a; return m; }  // :572-584
+  double avgAbsK(size_t i) const {                                                                    // :586-604
     double s = 0;
-    for (double a : kstrs[i]) if (a >= 0) s += a;
-    if (kstrs[i].size() == numMs[i]) return -1;
-    return s / (kstrs[i].size() - numMs[i]);
+    for (double a : kstr(i)) if (a >= 0) s += a;
+    if (kstr(i).size() == numM(i)) return -1;
+    return s / (kstr(i).size() - numM(i));
   }
-  double medAbsK(int i) const {                                                                      // :606-622
-    std::vector<double> k = kstrs[i];
+  double medAbsK(size_t i) const {                                                                    // :606-622
+    std::vector<double> k = kstr(i);
     std::sort(k.begin(), k.end());
     size_t j = 0;
     for (; j < k.size(); j++) if (k[j] >= 0) break;
     if (j == k.size()) return -1;
     return k[j + (k.size() - j) / 2];
   }
-  std::string homRecord(int idx) const;
-  std::string hetRecord(int idx1, int idx2) const;
+  void homRecord(size_t idx, std::string &out) const;
+  void hetRecord(size_t idx1, size_t idx2, std::string &out) const;
 };
 
-static std::string qual_str(double q) { return std::to_string((int)q); }                // varMer.C:487,534
+// chr <tab> pos <tab> . <tab> REF <tab> ALT[,ALT2] <tab> (int)QUAL <tab> PASS <tab> . <tab> GT <tab> gt   (varMer.C:487,534)
+static inline void put_record(std::string &out, const PosGT *pg, const GtAllele *g, const std::string &alt, const std::string *alt2,
+                              const char *gt) {
+  out += pg->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; out += alt;
+  if (alt2) { out += ','; out += *alt2; }
+  out += '\t'; put_int(out, (int)g->qual); out += "\tPASS\t.\tGT\t"; out += gt; out += '\n';
+}
 
-std::string VarMer::homRecord(int idx) const {                                          // varMer.C:531-550
-  std::string out;
-  for (size_t i = 0; i < gtPaths[idx].size(); i++) {
-    int alt = gtPaths[idx][i];
+void VarMer::homRecord(size_t idx, std::string &out) const {                            // varMer.C:531-550
+  const int *gp = gtPath(idx);
+  for (size_t i = 0; i < c.nvar; i++) {
+    const int alt = gp[i];
     if (alt <= 0) continue;
-    const GtAllele *g = posGt->gts[i];
-    out += posGt->chr + "\t" + std::to_string(g->pos + 1) + "\t.\t" + g->alleles[0] + "\t" + g->alleles[alt] + "\t" +
-           qual_str(g->qual) + "\tPASS\t.\tGT\t1/1\n";
+    const GtAllele *g = c.posGt->gts[i];
+    put_record(out, c.posGt, g, g->alleles[alt], nullptr, "1/1");
   }
-  return out;
 }
 
-std::string VarMer::hetRecord(int idx1, int idx2) const {                               // varMer.C:472-529
-  std::string out;
-  for (size_t i = 0; i < gtPaths[idx1].size(); i++) {
-    int a1 = gtPaths[idx1][i], a2 = gtPaths[idx2][i];
+void VarMer::hetRecord(size_t idx1, size_t idx2, std::string &out) const {              // varMer.C:472-529
+  const int *g1 = gtPath(idx1), *g2 = gtPath(idx2);
+  for (size_t i = 0; i < c.nvar; i++) {
+    const int a1 = g1[i], a2 = g2[i];
     if (a1 + a2 <= 0) continue;
-    const GtAllele *g = posGt->gts[i];
-    out += posGt->chr + "\t" + std::to_string(g->pos + 1) + "\t.\t" + g->alleles[0] + "\t";
-    if (a1 == a2)               out += g->alleles[a1] + "\t" + qual_str(g->qual) + "\tPASS\t.\tGT\t1/1\n";
-    else if (a1 == 0 && a2 > 0) out += g->alleles[a2] + "\t" + qual_str(g->qual) + "\tPASS\t.\tGT\t0/1\n";
-    else if (a1 > 0 && a2 > 0)  out += g->alleles[a1] + "," + g->alleles[a2] + "\t" + qual_str(g->qual) + "\tPASS\t.\tGT\t1/2\n";
-    else if (a1 > 0 && a2 == 0) out += g->alleles[a1] + "\t" + qual_str(g->qual) + "\tPASS\t.\tGT\t1/0\n";
+    const GtAllele *g = c.posGt->gts[i];
+    if (a1 == a2)               put_record(out, c.posGt, g, g->alleles[a1], nullptr, "1/1");
+    else if (a1 == 0 && a2 > 0) put_record(out, c.posGt, g, g->alleles[a2], nullptr, "0/1");
+    else if (a1 > 0 && a2 > 0)  put_record(out, c.posGt, g, g->alleles[a1], &g->alleles[a2], "1/2");
+    else if (a1 > 0 && a2 == 0) put_record(out, c.posGt, g, g->alleles[a1], nullptr, "1/0");
+    else { out += c.posGt->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; }   // (negative index: the reference leaves the line unfinished)
   }
-  return out;
 }
 
-// merfin-variants.C:22-126.  idxList is shared down the recursion (shifted by the length change of
-// every ALT taken so far and restored afterwards); lenList is private to each level.
-static void traverse(uint32_t idx, std::vector<uint32_t> &idxList, std::vector<uint32_t> lenList,
-                     const std::vector<const std::vector<std::string> *> &haps, const std::string &candidate,
-                     std::vector<int> &path, VarMer &vm) {
-  const std::vector<std::string> &alts = *haps[idx];
-  const uint32_t refLen = lenList[idx];
-  const uint32_t last = (uint32_t)idxList.size() - 1;
-  for (size_t j = 0; j < alts.size(); j++) {
-    path.push_back((int)j);
-    std::string changed;                                          // the candidate with this ALT put in (the REF allele keeps `candidate`)
-    const std::string &replaced = j > 0 ? changed : candidate;
-    int skipped = 0, delta = 0;
-    bool overlaps = false, done = false;
-    if (j > 0) {
-      lenList[idx] = refLen;
-      const std::string &hap = alts[j];
-      changed = candidate;
-      changed.replace(idxList[idx], lenList[idx], hap);           // throws like std::string::replace if out of range
-      delta = (int)hap.size() - (int)lenList[idx];
-      const uint32_t affected = idxList[idx] + lenList[idx];
-      lenList[idx] = (uint32_t)hap.size();
-      for (uint32_t i = idx + 1; i < idxList.size(); i++) {       // later variants inside the replaced span keep REF
-        if (idxList[i] >= affected) break;
-        overlaps = true; idx++; path.push_back(0); skipped++;
-      }
-      if (overlaps && idx == last) {
-        vm.addSeqPath(replaced, path, idxList, lenList);
-        done = true;
-      } else {
-        for (uint32_t i = idx + 1; i < idxList.size(); i++) idxList[i] += delta;
-      }
-    }
-    if (!done) {
-      if (idx + 1 < idxList.size()) traverse(idx + 1, idxList, lenList, haps, replaced, path, vm);
-      if (idx == last) vm.addSeqPath(replaced, path, idxList, lenList);
-      for (uint32_t i = idx + 1; i < idxList.size(); i++) idxList[i] -= delta;
-    }
-    for (int s = 0; s < skipped; s++) { path.pop_back(); idx--; }
-    path.pop_back();
+// ---------------------------------------------------------------------------------------------
+// merfin-variants.C:22-126: every combination of the alleles of a cluster's variants.  idxList is
+// shared down the recursion (shifted by the length change of every ALT taken so far and restored
+// afterwards); lenList is private to each level (a row of lenStack); the candidate of a level that
+// goes deeper is built in that level's scratch string, the candidate of a leaf straight at the end
+// of the batch's path buffer.
+// ---------------------------------------------------------------------------------------------
+struct Enumerator {
+  Batch &b;
+  Cluster *cur = nullptr;
+  uint32_t n = 0;                                              // variants of the current cluster
+  std::vector<uint32_t> idxList, lenStack;
+  std::vector<const std::vector<std::string> *> haps;
+  std::vector<int> path;
+  std::vector<std::string> scratch;                            // one per recursion depth, capacity kept
+
+  explicit Enumerator(Batch &batch) : b(batch) {}
+
+  // varMer::addSeqPath (varMer.C:37-45): a sequence already among the cluster's paths is dropped
+  void add(const char *s0, size_t n0, const char *s1, size_t n1, const char *s2, size_t n2, const uint32_t *lenList) {
+    const size_t start = b.paths.size(), L = n0 + n1 + n2;
+    if (n0) b.paths.append(s0, n0);
+    if (n1) b.paths.append(s1, n1);
+    if (n2) b.paths.append(s2, n2);
+    const char *base = b.paths.data();
+    for (uint32_t p = cur->first_path; p < cur->first_path + cur->npaths; p++)
+      if (b.off[p + 1] - b.off[p] == L && memcmp(base + b.off[p], base + start, L) == 0) { b.paths.resize(start); return; }
+    b.off.push_back(b.paths.size());
+    b.gt.insert(b.gt.end(), path.begin(), path.end());
+    b.idx.insert(b.idx.end(), idxList.begin(), idxList.end());
+    b.len.insert(b.len.end(), lenList, lenList + n);
+    cur->npaths++;
   }
-}
+
+  void go(uint32_t idx, uint32_t depth, const char *cand, size_t candLen) {
+    uint32_t *lenList = lenStack.data() + (size_t)depth * n;
+    const std::vector<std::string> &alts = *haps[idx];
+    const uint32_t refLen = lenList[idx];
+    const uint32_t last = n - 1;
+    for (size_t j = 0; j < alts.size(); j++) {
+      path.push_back((int)j);
+      int skipped = 0, delta = 0;
+      if (j == 0) {                                              // the REF allele keeps the candidate
+        if (idx == last) add(cand, candLen, nullptr, 0, nullptr, 0, lenList);
+        else { memcpy(lenList + n, lenList, n * sizeof(uint32_t)); go(idx + 1, depth + 1, cand, candLen); }
+      } else {
+        lenList[idx] = refLen;
+        const std::string &hap = alts[j];
+        const size_t at = idxList[idx];
+        if (at > candLen) throw std::out_of_range("basic_string::replace");      // as the reference's std::string::replace
+        const size_t cut = std::min<size_t>(lenList[idx], candLen - at);
+        delta = (int)hap.size() - (int)lenList[idx];
+        const uint32_t affected = idxList[idx] + lenList[idx];
+        lenList[idx] = (uint32_t)hap.size();
+        for (uint32_t i = idx + 1; i < n; i++) {                  // later variants inside the replaced span keep REF
+          if (idxList[i] >= affected) break;
+          idx++; path.push_back(0); skipped++;
+        }
+        if (idx == last) {
+          add(cand, at, hap.data(), hap.size(), cand + at + cut, candLen - at - cut, lenList);
+        } else {
+          for (uint32_t i = idx + 1; i < n; i++) idxList[i] += delta;
+          std::string &changed = scratch[depth];
+          changed.assign(cand, at); changed.append(hap); changed.append(cand + at + cut, candLen - at - cut);
+          memcpy(lenList + n, lenList, n * sizeof(uint32_t));
+          go(idx + 1, depth + 1, changed.data(), changed.size());
+          for (uint32_t i = idx + 1; i < n; i++) idxList[i] -= delta;
+        }
+      }
+      for (int s = 0; s < skipped; s++) { path.pop_back(); idx--; }
+      path.pop_back();
+    }
+  }
+
+  // the paths of cluster c (its variants' alleles over the region [c.rStart, c.rEnd) of the record)
+  void run(Cluster &c, const char *seq) {
+    cur = &c;
+    const std::vector<GtAllele *> &gts = c.posGt->gts;
+    n = (uint32_t)gts.size();
+    c.nvar = n; c.first_path = (uint32_t)(b.off.size() - 1); c.npaths = 0; c.first_var = b.gt.size();
+    if (n == 0) return;
+    idxList.resize(n); haps.resize(n);
+    lenStack.resize((size_t)(n + 1) * n);
+    if (scratch.size() < n + 1) scratch.resize(n + 1);
+    for (uint32_t i = 0; i < n; i++) { idxList[i] = gts[i]->pos - c.rStart; lenStack[i] = gts[i]->refLen; haps[i] = &gts[i]->alleles; }
+    path.clear();
+    go(0, 0, seq + c.rStart, c.rEnd - c.rStart);
+  }
+};
 
 // merfinGlobal::getK (merfin-globals.C:66-98) per read multiplicity, tabulated once per call of
 // process_sequence: the replay below asks for it once per window of every path
 struct KTable {
   static constexpr uint32_t N = 4096;
-  std::vector<double> rk, pr;
+  struct Entry { double readK, prob; };
+  std::vector<Entry> e;
   const mfn_kmodel *km;
-  explicit KTable(const mfn_kmodel *m) : rk(N), pr(N), km(m) {
-    for (uint32_t v = 0; v < N; v++) { double a; mfn_getK(m, v, 0, &rk[v], &a, &pr[v]); }
+  bool tame = true;                                  // every tabulated value is finite and far from overflow
+  explicit KTable(const mfn_kmodel *m) : e(N), km(m) {
+    for (uint32_t v = 0; v < N; v++) {
+      double a;
+      mfn_getK(m, v, 0, &e[v].readK, &a, &e[v].prob);
+      if (!(fabs(e[v].readK) < 1e100 && fabs(e[v].prob) < 1e100)) tame = false;
+    }
   }
   inline void get(uint32_t vr, double &readK, double &prob) const {
-    if (vr < N) { readK = rk[vr]; prob = pr[vr]; }
+    if (vr < N) { readK = e[vr].readK; prob = e[vr].prob; }
     else { double a; mfn_getK(km, vr, 0, &readK, &a, &prob); }
   }
 };
 
-// varMer.C:48-145 from the integer pairs of every window of every path
-static void score(VarMer &vm, const Options &opt, const KTable &kt, const uint32_t *vr, const uint32_t *va, const uint8_t *ok,
-                  const std::vector<uint64_t> &off, size_t first_path, double &prob) {
+// varMer.C:48-145 from the integer pairs of every window of every path of one cluster.
+//
+// Per window the reference computes oD = |readK - asmK| * prob, adds one to asmK if the window touches
+// an ALT allele of the path, computes nD the same way and adds oD - nD to the path's delta sum.  A path
+// without ALT alleles (the REF path) adds oD - oD, which is +0.0 whenever oD is finite, so for those
+// paths -- and for -filter, which only counts the missing windows -- only the count is done; a window
+// whose K values are not comfortably finite (a zero -peak, odd -prob tables) sends the path through
+// the general loop instead.
+static void score(Batch &b, const Cluster &c, const Options &opt, const KTable &kt, const uint32_t *vr, const uint32_t *va,
+                  const uint8_t *ok, double &prob_io, std::vector<uint32_t> &alt_lo, std::vector<uint32_t> &alt_hi) {
   const uint32_t k = opt.k;
-  for (size_t ii = 0; ii < vm.seqs.size(); ii++) {
-    const size_t L = vm.seqs[ii].size();
-    const uint64_t base = off[first_path + ii];
-    uint32_t numM = 0, idx = 0;
+  double prob = prob_io;
+  const bool keep = opt.debug;                         // the per-window values are only read by the -debug statistics
+  const size_t nvar = c.nvar;
+  const KTable::Entry *tab = kt.e.data();
+  for (size_t ii = 0; ii < c.npaths; ii++) {
+    const size_t p = c.first_path + ii;
+    const uint64_t base = b.off[p];
+    const size_t L = (size_t)(b.off[p + 1] - base);
+    const size_t nwin = L >= k ? L - k + 1 : 0;
+    const uint32_t *ipath = b.idx.data() + c.first_var + ii * nvar, *lpath = b.len.data() + c.first_var + ii * nvar;
+    const int *gpath = b.gt.data() + c.first_var + ii * nvar;
+    const uint32_t *pvr = vr + base, *pva = va + base;
+    const uint8_t *pok = ok + base;
+    // the windows an ALT allele of this path reaches: lo <= window < hi in unsigned arithmetic, as the
+    // reference writes it: ip + 1 - k wraps when ip < k - 1 and the test is then never true (Q5)
+    alt_lo.clear(); alt_hi.clear();
+    for (size_t jj = 0; jj < nvar; jj++)
+      if (gpath[jj] > 0) { alt_lo.push_back((uint32_t)(ipath[jj] + 1 - k)); alt_hi.push_back((uint32_t)(ipath[jj] + lpath[jj] + k)); }
+    const size_t nalt = alt_lo.size();
+
+    if (opt.mode == FILTER || (nalt == 0 && !keep)) {
+      const double prob_in = prob;
+      uint32_t numM = 0;
+      bool exact = true;
+      for (size_t w = 0; w < nwin; w++) {
+        double readK = 0;
+        if (pok[w]) {
+          const uint32_t v = pvr[w];
+          if (v < KTable::N) { readK = tab[v].readK; prob = tab[v].prob; }
+          else { kt.get(v, readK, prob); if (!(fabs(readK) < 1e100 && fabs(prob) < 1e100)) exact = false; }
+        }
+        if (readK == 0) numM++;
+      }
+      if (opt.mode == FILTER || (exact && kt.tame)) { b.numM[p] = numM; b.totdK[p] = 0.0; continue; }
+      prob = prob_in;
+    }
+
+    uint32_t numM = 0;
     std::vector<double> ks, dks;
     double totd = 0;
-    const size_t nwin = L >= k ? L - k + 1 : 0;
-    const bool keep = opt.debug;                     // the per-window values are only read by the -debug statistics
-    if (opt.mode != FILTER && keep) { ks.reserve(nwin); dks.reserve(nwin); }
-    const size_t nvar = vm.idxPaths[ii].size();
-    const uint32_t *ipath = vm.idxPaths[ii].data(), *lpath = vm.lenPaths[ii].data();
-    const int *gpath = vm.gtPaths[ii].data();
+    if (keep) { ks.reserve(nwin); dks.reserve(nwin); }
+    const uint32_t lo0 = nalt ? alt_lo[0] : 1, hi0 = nalt ? alt_hi[0] : 0;
     for (size_t w = 0; w < nwin; w++) {
+      const uint32_t idx = (uint32_t)w;
       double readK = 0, asmK = 0;
-      if (ok[base + w]) { kt.get(vr[base + w], readK, prob); asmK = (double)va[base + w]; }
+      if (pok[w]) { kt.get(pvr[w], readK, prob); asmK = (double)pva[w]; }
       if (readK == 0) numM++;
-      if (opt.mode == FILTER) { idx++; continue; }
       const double oD = fabs(readK - asmK) * prob;
-      for (size_t jj = 0; jj < nvar; jj++) {
-        const uint32_t ip = ipath[jj], lp = lpath[jj];
-        // unsigned arithmetic as in the reference: ip + 1 - k wraps when ip < k - 1 (Q5)
-        if (gpath[jj] > 0 && (uint32_t)(ip + 1 - k) <= idx && idx < (uint32_t)(ip + lp + k)) { asmK++; break; }
-      }
-      double kMetric;
-      if (readK == 0) kMetric = -1;
-      else if (readK > asmK) kMetric = readK / asmK - 1;
-      else kMetric = asmK / readK - 1;
+      bool hit = lo0 <= idx && idx < hi0;
+      for (size_t jj = 1; jj < nalt && !hit; jj++) hit = alt_lo[jj] <= idx && idx < alt_hi[jj];
+      if (hit) asmK++;
       const double nD = fabs(readK - asmK) * prob;
       totd += oD - nD;
-      if (keep) { ks.push_back(kMetric); dks.push_back(oD - nD); }
-      idx++;
+      if (keep) {
+        double kMetric;
+        if (readK == 0) kMetric = -1;
+        else if (readK > asmK) kMetric = readK / asmK - 1;
+        else kMetric = asmK / readK - 1;
+        ks.push_back(kMetric); dks.push_back(oD - nD);
+      }
     }
-    vm.numMs.push_back(numM); vm.totdKs.push_back(totd);
-    if (keep) { vm.kstrs.push_back(std::move(ks)); vm.dkstrs.push_back(std::move(dks)); }
+    b.numM[p] = numM; b.totdK[p] = totd;
+    if (keep) { b.kstrs[p] = std::move(ks); b.dkstrs[p] = std::move(dks); }
   }
+  prob_io = prob;
 }
 
 // ---- selectors (varMer.C:150-467) -------------------------------------------------------------
 static void pick_min_missing(const VarMer &vm, bool le_ref, std::vector<int> &idxs) {   // shared by better/strict/loose
-  const uint32_t refMissing = vm.numMs[0];
+  const uint32_t refMissing = vm.numM(0);
   uint32_t numMissing = refMissing;
-  for (size_t ii = 0; ii < vm.numMs.size(); ii++) {
-    const uint32_t m = vm.numMs[ii];
+  for (size_t ii = 0; ii < vm.npaths(); ii++) {
+    const uint32_t m = vm.numM(ii);
     if (m < numMissing) { numMissing = m; idxs.clear(); idxs.push_back((int)ii); }
     else if (m == numMissing && (le_ref ? m <= refMissing : m < refMissing)) idxs.push_back((int)ii);
   }
 }
 
-static std::string longest_of(const VarMer &vm, const std::vector<int> &idxs) {         // varMer.C:229-246,288-308
+static void longest_of(const VarMer &vm, const std::vector<int> &idxs, std::string &out) {   // varMer.C:229-246,288-308
   int idx = idxs[0];
   if (idxs.size() > 1) {
-    uint32_t best = (uint32_t)vm.seqs[idx].size();
+    uint32_t best = (uint32_t)vm.seqLen(idx);
     for (size_t ii = 1; ii < idxs.size(); ii++) {
-      uint32_t len = (uint32_t)vm.seqs[idxs[ii]].size();
+      uint32_t len = (uint32_t)vm.seqLen(idxs[ii]);
       if (len > best) { best = len; idx = idxs[ii]; }
     }
   }
-  return vm.homRecord(idx);
+  vm.homRecord(idx, out);
 }
 
-static std::string better_or_strict(const VarMer &vm) {                                 // varMer.C:199-309
-  if (vm.numMs.empty()) return "";
-  std::vector<int> idxs;
+static void better_or_strict(const VarMer &vm, std::vector<int> &idxs, std::string &out) {   // varMer.C:199-309
+  if (vm.npaths() == 0) return;
+  idxs.clear();
   pick_min_missing(vm, false, idxs);
-  if (idxs.empty()) return "";
-  return longest_of(vm, idxs);
+  if (idxs.empty()) return;
+  longest_of(vm, idxs, out);
 }
 
-static std::string loose(const VarMer &vm) {                                            // varMer.C:311-391
-  if (vm.numMs.empty()) return "";
-  std::vector<int> idxs;
+static void loose(const VarMer &vm, std::vector<int> &idxs, std::string &out) {              // varMer.C:311-391
+  if (vm.npaths() == 0) return;
+  idxs.clear();
   pick_min_missing(vm, true, idxs);
-  if (idxs.empty()) return "";
-  if (idxs.size() == 1) return vm.homRecord(idxs[0]);
-  if (idxs[0] == 0 && idxs.size() == 2) return vm.homRecord(idxs[1]);
+  if (idxs.empty()) return;
+  if (idxs.size() == 1) { vm.homRecord(idxs[0], out); return; }
+  if (idxs[0] == 0 && idxs.size() == 2) { vm.homRecord(idxs[1], out); return; }
   int maxVars = 0, maxIdx = idxs[0];
   for (size_t ii = 1; ii < idxs.size(); ii++) {
     int count = 0;
-    for (int a : vm.gtPaths[idxs[ii]]) if (a > 0) count++;
+    const int *gp = vm.gtPath(idxs[ii]);
+    for (size_t i = 0; i < vm.c.nvar; i++) if (gp[i] > 0) count++;
     if (count > maxVars) { maxVars = count; maxIdx = idxs[ii]; }
   }
   fprintf(stderr, "[ WARNING ] :: Multiple (%lu) alternate pathes detected in a path beginning with variant : %s",
-          (unsigned long)idxs.size(), vm.posGt->gts[0]->record->save().c_str());
+          (unsigned long)idxs.size(), vm.c.posGt->gts[0]->record->save().c_str());
   fprintf(stderr, "[ WARNING ] :: Max. %d ALT variants selected\n", maxVars);
-  return vm.homRecord(maxIdx);
+  vm.homRecord(maxIdx, out);
 }
 
-// the tie-break container is declared multimap<double,int,greater<int>> (varMer.H:72): keys are
-// compared after conversion to int, descending (Q6)
-struct AsIntDescending { bool operator()(double a, double b) const { return (int)a > (int)b; } };
-
-static std::string best_variant(const VarMer &vm, uint32_t k) {                         // varMer.C:396-467
+// The reference's tie-break container is declared multimap<double,int,greater<int>> (varMer.H:72): keys are
+// compared after conversion to int, descending, and equal keys keep their insertion order (Q6).  Only its
+// first two elements are read: they are picked here with the same comparisons.
+static void best_variant(const VarMer &vm, uint32_t k, std::vector<int> &idxs, std::string &out) {   // varMer.C:396-467
   uint32_t numMissing = UINT32_MAX;
-  std::vector<int> idxs;
-  for (size_t ii = 0; ii < vm.numMs.size(); ii++) {
-    if (vm.numMs[ii] == vm.seqs[ii].size() - k + 1) continue;
-    if (vm.numMs[ii] < numMissing) { numMissing = vm.numMs[ii]; idxs.clear(); idxs.push_back((int)ii); }
-    else if (vm.numMs[ii] == numMissing) idxs.push_back((int)ii);
+  idxs.clear();
+  for (size_t ii = 0; ii < vm.npaths(); ii++) {
+    const uint32_t m = vm.numM(ii);
+    if (m == vm.seqLen(ii) - k + 1) continue;
+    if (m < numMissing) { numMissing = m; idxs.clear(); idxs.push_back((int)ii); }
+    else if (m == numMissing) idxs.push_back((int)ii);
   }
-  if (numMissing == UINT32_MAX) return "";
-  if (idxs.size() == 1) return vm.homRecord(idxs[0]);
+  if (numMissing == UINT32_MAX) return;
+  if (idxs.size() == 1) { vm.homRecord(idxs[0], out); return; }
   if (idxs.size() > 1) {
-    std::multimap<double, int, AsIntDescending> byK;
-    for (int idx : idxs) byK.insert(std::make_pair(vm.totdK(idx), idx));
-    auto it = byK.begin();
-    const double k1 = it->first; const int i1 = it->second;
-    ++it;
-    const double k2 = it->first; const int i2 = it->second;
-    if (k1 == k2) {
-      if (vm.seqs[i1].size() >= vm.seqs[i2].size()) return vm.hetRecord(i1, i2);
-      return vm.hetRecord(i2, i1);
+    double k1 = vm.totdK(idxs[0]), k2 = vm.totdK(idxs[1]);
+    int i1 = idxs[0], i2 = idxs[1];
+    if ((int)k2 > (int)k1) { std::swap(k1, k2); std::swap(i1, i2); }
+    for (size_t ii = 2; ii < idxs.size(); ii++) {
+      const double kk = vm.totdK(idxs[ii]);
+      if ((int)kk > (int)k1) { k2 = k1; i2 = i1; k1 = kk; i1 = idxs[ii]; }
+      else if ((int)kk > (int)k2) { k2 = kk; i2 = idxs[ii]; }
     }
-    return vm.homRecord(i1);
+    if (k1 == k2) {
+      if (vm.seqLen(i1) >= vm.seqLen(i2)) vm.hetRecord(i1, i2, out);
+      else vm.hetRecord(i2, i1, out);
+      return;
+    }
+    vm.homRecord(i1, out);
   }
-  return "";
 }
 
-static std::string best_filter(const VarMer &vm, uint32_t k) {                          // varMer.C:150-194
+static void best_filter(const VarMer &vm, uint32_t k, std::vector<int> &idxs, std::vector<int> &gtIdxs, std::string &out) {   // varMer.C:150-194
   uint32_t numMissing = UINT32_MAX;
-  std::vector<int> idxs;
-  for (size_t ii = 0; ii < vm.numMs.size(); ii++) {
-    if (vm.numMs[ii] == vm.seqs[ii].size() - k + 1) continue;
-    if (vm.numMs[ii] == 0) { idxs.push_back((int)ii); numMissing = 0; }
-    if (vm.numMs[ii] < numMissing) { numMissing = vm.numMs[ii]; idxs.clear(); idxs.push_back((int)ii); }
-    else if (vm.numMs[ii] == numMissing) idxs.push_back((int)ii);
+  idxs.clear();
+  for (size_t ii = 0; ii < vm.npaths(); ii++) {
+    const uint32_t m = vm.numM(ii);
+    if (m == vm.seqLen(ii) - k + 1) continue;
+    if (m == 0) { idxs.push_back((int)ii); numMissing = 0; }
+    if (m < numMissing) { numMissing = m; idxs.clear(); idxs.push_back((int)ii); }
+    else if (m == numMissing) idxs.push_back((int)ii);
   }
-  std::string out;
-  if (idxs.empty()) return out;
-  std::list<int> gtIdxs;
-  for (int idx : idxs)
-    for (size_t i = 0; i < vm.gtPaths[idx].size(); i++)
-      if (vm.gtPaths[idx][i] > 0) gtIdxs.push_back((int)i);
-  gtIdxs.sort();
-  gtIdxs.unique();
-  for (int i : gtIdxs) out += vm.posGt->gts[i]->record->save();
-  return out;
+  if (idxs.empty()) return;
+  gtIdxs.clear();
+  for (int idx : idxs) {
+    const int *gp = vm.gtPath(idx);
+    for (size_t i = 0; i < vm.c.nvar; i++)
+      if (gp[i] > 0) gtIdxs.push_back((int)i);
+  }
+  std::sort(gtIdxs.begin(), gtIdxs.end());
+  gtIdxs.erase(std::unique(gtIdxs.begin(), gtIdxs.end()), gtIdxs.end());
+  for (int i : gtIdxs) out += vm.c.posGt->gts[i]->record->save();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -482,74 +612,66 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
   const size_t PREROLL = 4;
   const size_t first = cluster_begin > PREROLL ? cluster_begin - PREROLL : 0;
 
-  struct Work { VarMer vm; uint32_t rStart, rEnd; size_t first_path; bool keep; };
-  std::vector<Work> work;
-  std::string paths;
-  std::vector<uint64_t> off;
+  Batch B;
+  Enumerator E(B);
   ScoreOut sc;
   Options sopt = opt;
   sopt.debug = debug != nullptr;                     // the per-window values are kept exactly when the debug records are written
   const KTable kt(&opt.km);
+  std::vector<int> idxs, gtIdxs;                     // the selectors' lists, reused
+  std::vector<uint32_t> alt_lo, alt_hi;
+  const uint32_t K_PADD = opt.k - 1;
   for (size_t b0 = first; b0 < cluster_end;) {
     // the pre-roll clusters ride along with the first batch
     const size_t b1 = std::min(cluster_end, (b0 < cluster_begin ? cluster_begin : b0) + batch_clusters);
-    work.clear();
-    work.reserve(b1 - b0);
-    paths.clear();
-    off.assign(1, 0);
+    B.clear();
+    B.clusters.reserve(b1 - b0);
     for (size_t ci = b0; ci < b1; ci++) {
       PosGT *pg = clusters[ci];
       uint32_t rStart = pg->rStart, rEnd = pg->rEnd;
-      const uint32_t K_PADD = opt.k - 1;
       if (rStart > K_PADD) rStart -= K_PADD; else rStart = 0;
       if (rEnd < seqLen - K_PADD) rEnd += K_PADD; else rEnd = (uint32_t)seqLen;        // (unsigned, as the reference)
-      std::vector<uint32_t> idxList, lenList;
-      std::vector<const std::vector<std::string> *> haps;
-      for (GtAllele *g : pg->gts) { idxList.push_back(g->pos - rStart); lenList.push_back(g->refLen); haps.push_back(&g->alleles); }
       const bool keep = ci >= cluster_begin;
       if (rEnd < rStart || seqLen < rEnd) {                                            // dnaSeq::copy fails (sequence.C:521)
         if (keep) fprintf(stderr, "PANIC : Invalid region specified: %s : %u - %u\n", ident.c_str(), rStart, rEnd);
         continue;
       }
-      if (idxList.size() > opt.comb) {
+      if (pg->gts.size() > opt.comb) {
         if (keep) fprintf(stderr, "PANIC : Combination %s:%u-%u has too many variants ( found %lu > %u ) to evaluate. Consider filtering the vcf upfront. Skipping...\n",
                           ident.c_str(), rStart, rEnd, (unsigned long)pg->gts.size(), opt.comb);
         continue;
       }
-      work.emplace_back();
-      Work &w = work.back();
-      w.vm.posGt = pg; w.rStart = rStart; w.rEnd = rEnd; w.first_path = off.size() - 1; w.keep = keep;
-      {
-        // room for the usual two paths (REF and one ALT) up front: the vectors would otherwise grow 1 -> 2 and move
-        VarMer &v = w.vm;
-        v.seqs.reserve(2); v.gtPaths.reserve(2); v.idxPaths.reserve(2); v.lenPaths.reserve(2); v.numMs.reserve(2); v.totdKs.reserve(2);
-      }
-      std::vector<int> path;
-      traverse(0, idxList, lenList, haps, std::string(seq + rStart, rEnd - rStart), path, w.vm);
-      for (const std::string &s : w.vm.seqs) { paths += s; off.push_back(paths.size()); }
+      B.clusters.emplace_back();
+      Cluster &c = B.clusters.back();
+      c.posGt = pg; c.rStart = rStart; c.rEnd = rEnd; c.keep = keep;
+      E.run(c, seq);
     }
 
-    if (!paths.empty() || off.size() > 1) {
-      int st = scorer(paths, off, sc);
+    const size_t npaths = B.off.size() - 1;
+    if (npaths > 0) {
+      int st = scorer(B.paths, B.off, sc);
       if (st != 0) return st;
     }
+    B.numM.assign(npaths, 0); B.totdK.assign(npaths, 0.0);
+    if (sopt.debug) { B.kstrs.assign(npaths, std::vector<double>()); B.dkstrs.assign(npaths, std::vector<double>()); }
 
-    for (Work &w : work) {
-      VarMer &vm = w.vm;
-      score(vm, sopt, kt, sc.v_read, sc.v_asm, sc.valid, off, w.first_path, prob);
-      if (!w.keep) continue;
+    for (const Cluster &c : B.clusters) {
+      score(B, c, sopt, kt, sc.v_read, sc.v_asm, sc.valid, prob, alt_lo, alt_hi);
+      if (!c.keep) continue;
+      const VarMer vm{B, c};
       if (debug) {
         char buf[512];
-        for (size_t idx = 0; idx < vm.seqs.size(); idx++) {
-          snprintf(buf, sizeof buf, "%lu\t%s:%u-%u\t", (unsigned long)varMerId++, ident.c_str(), w.rStart, w.rEnd);
-          *debug += buf; *debug += vm.seqs[idx];
-          snprintf(buf, sizeof buf, "\t%u\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\t", vm.numMs[idx], vm.minAbsK((int)idx), vm.maxAbsK((int)idx),
-                   vm.medAbsK((int)idx), vm.avgAbsK((int)idx), vm.totdK((int)idx));
+        for (size_t idx = 0; idx < vm.npaths(); idx++) {
+          snprintf(buf, sizeof buf, "%lu\t%s:%u-%u\t", (unsigned long)varMerId++, ident.c_str(), c.rStart, c.rEnd);
+          *debug += buf; debug->append(vm.seq(idx), vm.seqLen(idx));
+          snprintf(buf, sizeof buf, "\t%u\t%.5f\t%.5f\t%.5f\t%.5f\t%.5f\t", vm.numM(idx), vm.minAbsK(idx), vm.maxAbsK(idx),
+                   vm.medAbsK(idx), vm.avgAbsK(idx), vm.totdK(idx));
           *debug += buf;
-          for (size_t i = 0; i < vm.gtPaths[idx].size(); i++) {
-            int alt = vm.gtPaths[idx][i];
+          const int *gp = vm.gtPath(idx);
+          for (size_t i = 0; i < c.nvar; i++) {
+            const int alt = gp[i];
             if (alt > 0) {
-              const GtAllele *g = vm.posGt->gts[i];
+              const GtAllele *g = c.posGt->gts[i];
               *debug += ident + " " + std::to_string(g->pos + 1) + " . " + g->alleles[0] + " " + g->alleles[alt] + " . PASS . GT 1/1  ";
             }
           }
@@ -557,11 +679,11 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
         }
       }
       switch (opt.mode) {
-        case POLISH: result += best_variant(vm, opt.k); break;
-        case BETTER: result += better_or_strict(vm); break;
-        case STRICT: result += better_or_strict(vm); break;
-        case LOOSE:  result += loose(vm); break;
-        default:     result += best_filter(vm, opt.k); break;
+        case POLISH: best_variant(vm, opt.k, idxs, result); break;
+        case BETTER: better_or_strict(vm, idxs, result); break;
+        case STRICT: better_or_strict(vm, idxs, result); break;
+        case LOOSE:  loose(vm, idxs, result); break;
+        default:     best_filter(vm, opt.k, idxs, gtIdxs, result); break;
       }
     }
     b0 = b1;
