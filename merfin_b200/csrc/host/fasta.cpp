@@ -38,8 +38,16 @@ bool slurp_file(const std::string &path, std::vector<char> &data, std::string &e
   }
   if (!F) { err = "cannot open '" + path + "'"; return false; }
   data.clear();
-  std::vector<char> buf(1 << 24);
   size_t n;
+  if (!piped) {                                       // a plain file: one read of its size (more follows if it grew)
+    struct stat st;
+    if (fstat(fileno(F), &st) == 0 && st.st_size > 0) {
+      data.resize((size_t)st.st_size);
+      n = fread(data.data(), 1, data.size(), F);
+      data.resize(n);
+    }
+  }
+  std::vector<char> buf(1 << 22);
   while ((n = fread(buf.data(), 1, buf.size(), F)) > 0) data.insert(data.end(), buf.begin(), buf.begin() + n);
   if (piped) pclose(F); else fclose(F);
   return true;

@@ -2,6 +2,7 @@
 // cited against the reference line it reproduces.
 #include "variants.h"
 
+#include <atomic>
 #include <thread>
 
 #include "fasta.h"
@@ -19,15 +20,16 @@ namespace mfnv {
 
 // strings.C:188-249: runs of separators collapse, empty words do not exist
 typedef std::pair<const char *, size_t> Span;
-static void split_spans(const char *s, size_t n, const char *seps, std::vector<Span> &out) {
+static void split_spans(const char *s, size_t n, char sep, std::vector<Span> &out) {
   out.clear();
-  size_t i = 0;
-  while (i < n) {
-    while (i < n && strchr(seps, s[i])) i++;
-    size_t j = i;
-    while (j < n && !strchr(seps, s[j])) j++;
-    if (j > i) out.emplace_back(s + i, j - i);
-    i = j;
+  const char *p = s, *const e = s + n;
+  while (p < e) {
+    while (p < e && *p == sep) p++;
+    if (p == e) break;
+    const char *q = (const char *)memchr(p, sep, (size_t)(e - p));
+    if (!q) q = e;
+    out.emplace_back(p, (size_t)(q - p));
+    p = q;
   }
 }
 template <class I> static inline void put_int(std::string &out, I v) {
@@ -39,30 +41,26 @@ std::string VcfRecord::save() const {
   char num[64];
   const int nn = std::min<int>(snprintf(num, sizeof num, "%.1f", qual), (int)sizeof num - 1);
   std::string out;
-  out.reserve(chr.size() + id.size() + ref.size() + alts.size() + filter.size() + info.size() + formats.size() + samples.size() + 32 + (size_t)nn);
-  out += chr; out += '\t'; put_int(out, (int)pos); out += '\t'; out += id; out += '\t'; out += ref; out += '\t'; out += alts; out += '\t';
-  out.append(num, (size_t)nn); out += '\t'; out += filter; out += '\t'; out += info; out += '\t'; out += formats; out += '\t'; out += samples;
+  size_t need = 32 + (size_t)nn;
+  for (int i = 0; i < NCOL; i++) need += col_len[i];
+  out.reserve(need);
+  out += col(CHROM); out += '\t'; put_int(out, (int)pos); out += '\t'; out += col(ID); out += '\t'; out += col(REF); out += '\t';
+  out += col(ALT); out += '\t'; out.append(num, (size_t)nn);
+  for (int i = FILTER; i < NCOL; i++) { out += '\t'; out += col(i); }
   out += '\n';
   return out;
 }
 
-VcfFile::~VcfFile() {
-  for (auto *r : records) delete r;
-  for (auto *a : alleles) delete a;
-  for (auto &kv : byChr) for (auto *p : kv.second) delete p;
-}
-
-// vcf.C:23-87
-static GtAllele *make_allele(const VcfRecord *r) {
-  GtAllele *g = new GtAllele();
+// vcf.C:23-87: the alleles the sample's genotype names.  alts: the ALT column split at ','; gt: the first
+// ':'-separated field of the sample column.
+static void make_allele(GtAllele *g, const VcfRecord *r, const std::vector<Span> &alts, std::string_view gt) {
+  const std::string_view ref = r->col(VcfRecord::REF);
   g->record = r;
   g->pos = r->pos - 1;
-  g->refLen = (uint32_t)r->ref.size();
+  g->refLen = (uint32_t)ref.size();
   g->qual = r->qual;
-  const std::string &gt = r->sample_fields.empty() ? std::string() : r->sample_fields[0];
-  if (gt.compare(0, 3, "./.") == 0 || gt.compare(0, 3, "0/0") == 0) return g;      // no alleles at all (Q10)
-  g->alleles.reserve(3);
-  g->alleles.push_back(r->ref);
+  if (gt.compare(0, 3, "./.") == 0 || gt.compare(0, 3, "0/0") == 0) return;            // no alleles at all (Q10)
+  g->alleles.push_back(ref);
   int used[8];                                        // ALT column entries taken so far (a sample names a handful at most)
   size_t nused = 0;
   std::vector<int> used_more;
@@ -79,72 +77,83 @@ static GtAllele *make_allele(const VcfRecord *r) {
     p = q;
     long idx = strtol(tok, nullptr, 10);
     if (idx <= 0) continue;
-    if ((size_t)idx > r->alt_list.size()) continue;
+    if ((size_t)idx > alts.size()) continue;
     bool seen = std::find(used, used + nused, (int)idx) != used + nused ||
                 std::find(used_more.begin(), used_more.end(), (int)idx) != used_more.end();
     if (seen) continue;                                                             // same ALT column entry again
     if (nused < 8) used[nused++] = (int)idx; else used_more.push_back((int)idx);
-    const std::string &hap = r->alt_list[idx - 1];
-    if (hap == r->ref) continue;
+    const std::string_view hap(alts[idx - 1].first, alts[idx - 1].second);
+    if (hap == ref) continue;
     g->alleles.push_back(hap);
   }
-  return g;
 }
 
 // vcf.C:93-151.  Lines are independent, so they are parsed on host threads (contiguous ranges of
 // lines per thread) and appended in file order afterwards: the order inside byChr is what the
-// reference's (unstable) sort starts from, so it must be the file order.
+// reference's (unstable) sort starts from, so it must be the file order.  Nothing is allocated per
+// line: a thread's records, alleles and clusters-to-be are three arrays sized for its share of the
+// lines (they never move, so the pointers between them hold), and all text is spans of text_.
 bool VcfFile::load(const std::string &path, std::string &err) {
-  std::vector<char> data;
-  if (!slurp_file(path, data, err)) return false;
+  if (!slurp_file(path, text_, err)) return false;
+  const std::vector<char> &data = text_;
   const size_t N = data.size();
-  std::vector<size_t> starts;                       // first byte of every line
-  for (size_t p = 0; p < N;) {
-    starts.push_back(p);
-    const char *nl = (const char *)memchr(data.data() + p, '\n', N - p);
-    p = nl ? (size_t)(nl - data.data()) + 1 : N;
-  }
-  starts.push_back(N);
-  const size_t nlines = starts.size() - 1;
-  struct Item { std::string header; VcfRecord *r = nullptr; GtAllele *g = nullptr; PosGT *pg = nullptr; bool excluded = false; };
   unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  if (nlines < 20000) T = 1;
+  if (N < (1u << 20)) T = 1;
   if (const char *env = getenv("MFN_VCF_THREADS")) T = (unsigned)std::max(1, atoi(env));     // (tests force the threaded path on small files)
-  T = (unsigned)std::max<size_t>(1, std::min<size_t>(T, nlines));
-  std::vector<std::vector<Item>> parts(T);
+  T = (unsigned)std::max<size_t>(1, std::min<size_t>(T, N / 64 + 1));
+  struct Part { std::vector<std::string> headers; uint64_t excluded = 0; };
+  std::vector<Part> parts(T);
+  records_.assign(T, {}); alleles_.assign(T, {}); posgts_.assign(T, {});
+  // thread t takes the lines that START in bytes [N t / T, N (t + 1) / T)
+  auto line_start_at_or_after = [&](size_t p) -> size_t {
+    if (p == 0 || p >= N) return std::min(p, N);
+    if (data[p - 1] == '\n') return p;
+    const char *nl = (const char *)memchr(data.data() + p, '\n', N - p);
+    return nl ? (size_t)(nl - data.data()) + 1 : N;
+  };
   auto parse = [&](unsigned t) {
-    const size_t l0 = nlines * t / T, l1 = nlines * (t + 1) / T;
-    std::vector<Item> &out = parts[t];
-    out.reserve(l1 - l0);
-    std::vector<Span> w, sub;                        // reused for every line of this thread
-    w.reserve(16); sub.reserve(8);
-    for (size_t l = l0; l < l1; l++) {
-      size_t p = starts[l], e = starts[l + 1];
+    const size_t b0 = line_start_at_or_after(N * t / T), b1 = line_start_at_or_after(N * (t + 1) / T);
+    size_t nl_count = 0;
+    for (size_t p = b0; p < b1;) {
+      const char *nl = (const char *)memchr(data.data() + p, '\n', b1 - p);
+      nl_count++;
+      p = nl ? (size_t)(nl - data.data()) + 1 : b1;
+    }
+    std::vector<VcfRecord> &recs = records_[t];
+    std::vector<GtAllele> &als = alleles_[t];
+    std::vector<PosGT> &pgs = posgts_[t];
+    recs.reserve(nl_count); als.reserve(nl_count); pgs.reserve(nl_count);     // (never grown: the elements must not move)
+    std::vector<Span> w, alts, fields;               // reused for every line of this thread
+    w.reserve(16); alts.reserve(8); fields.reserve(8);
+    for (size_t next = b0; next < b1;) {
+      size_t p = next, e;
+      {
+        const char *nl = (const char *)memchr(data.data() + p, '\n', b1 - p);
+        e = next = nl ? (size_t)(nl - data.data()) + 1 : b1;
+      }
       while (e > p && (data[e - 1] == '\r' || data[e - 1] == '\n')) e--;
       if (e == p) continue;
       const char *line = data.data() + p;
       const size_t len = e - p;
-      Item it;
-      if (line[0] == '#') { it.header.assign(line, len); out.push_back(std::move(it)); continue; }
-      split_spans(line, len, "\t", w);
-      if (w.size() < 10) { it.excluded = true; out.push_back(std::move(it)); continue; }   // vcfRecord.H:53-56
-      auto str = [&](int i) { return std::string(w[i].first, w[i].second); };
-      VcfRecord *r = new VcfRecord();
+      if (line[0] == '#') { parts[t].headers.emplace_back(line, len); continue; }
+      split_spans(line, len, '\t', w);
+      if (w.size() < 10) { parts[t].excluded++; continue; }                            // vcfRecord.H:53-56
+      recs.emplace_back();
+      VcfRecord *r = &recs.back();
+      r->line = line;
+      for (int i = 0; i < VcfRecord::NCOL; i++) { r->col_off[i] = (uint32_t)(w[i].first - line); r->col_len[i] = (uint32_t)w[i].second; }
       char num[64];
       auto cstr = [&](int i) { const size_t n = std::min<size_t>(w[i].second, sizeof num - 1); memcpy(num, w[i].first, n); num[n] = 0; return num; };
-      r->chr = str(0); r->pos = (uint32_t)strtoul(cstr(1), nullptr, 10); r->id = str(2); r->ref = str(3); r->alts = str(4);
-      r->qual = strtod(cstr(5), nullptr); r->filter = str(6); r->info = str(7); r->formats = str(8); r->samples = str(9);
-      split_spans(r->alts.data(), r->alts.size(), ",", sub);
-      r->alt_list.reserve(sub.size());
-      for (const Span &x : sub) r->alt_list.emplace_back(x.first, x.second);
-      split_spans(r->samples.data(), r->samples.size(), ":", sub);
-      r->sample_fields.reserve(sub.size());
-      for (const Span &x : sub) r->sample_fields.emplace_back(x.first, x.second);
-      GtAllele *g = make_allele(r);
-      PosGT *pg = new PosGT();
-      pg->chr = r->chr; pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
-      it.r = r; it.g = g; it.pg = pg;
-      out.push_back(std::move(it));
+      r->pos = (uint32_t)strtoul(cstr(VcfRecord::POS), nullptr, 10);
+      r->qual = strtod(cstr(VcfRecord::QUAL), nullptr);
+      split_spans(w[VcfRecord::ALT].first, w[VcfRecord::ALT].second, ',', alts);
+      split_spans(w[VcfRecord::SAMPLE].first, w[VcfRecord::SAMPLE].second, ':', fields);
+      als.emplace_back();
+      GtAllele *g = &als.back();
+      make_allele(g, r, alts, fields.empty() ? std::string_view() : std::string_view(fields[0].first, fields[0].second));
+      pgs.emplace_back();
+      PosGT *pg = &pgs.back();
+      pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
     }
   };
   {
@@ -153,33 +162,42 @@ bool VcfFile::load(const std::string &path, std::string &err) {
     parse(0);
     for (auto &x : th) x.join();
   }
-  for (auto &part : parts)
-    for (Item &it : part) {
-      if (it.excluded) { excluded++; continue; }
-      if (!it.r) {
-        if (it.header.compare(0, 12, "##contig=<ID") == 0) numChr++;
-        headers.push_back(std::move(it.header));
-        continue;
-      }
-      records.push_back(it.r);
-      alleles.push_back(it.g);
-      byChr[it.r->chr].push_back(it.pg);
+  std::string_view last_chr;
+  std::pair<const std::string, std::vector<PosGT *>> *cur = nullptr;
+  for (unsigned t = 0; t < T; t++) {
+    excluded += parts[t].excluded;
+    for (std::string &h : parts[t].headers) {
+      if (h.compare(0, 12, "##contig=<ID") == 0) numChr++;
+      headers.push_back(std::move(h));
     }
+    num_records += records_[t].size();
+    for (size_t i = 0; i < records_[t].size(); i++) {
+      const std::string_view chr = records_[t][i].col(VcfRecord::CHROM);
+      if (!cur || chr != last_chr) { cur = &*byChr.try_emplace(std::string(chr)).first; last_chr = chr; }
+      posgts_[t][i].chr = &cur->first;
+      cur->second.push_back(&posgts_[t][i]);
+    }
+  }
   return true;
 }
 
 // vcf.C:156-246.  std::sort with the reference's comparator on the reference's initial (file) order.
 void VcfFile::mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit) {
   const uint32_t K_OFFSET = 2 * ksize;
-  for (auto &kv : byChr) {
-    std::vector<PosGT *> &in = kv.second;
+  const bool quiet = getenv("MFN_QUIET") != nullptr;
+  // the sequences are independent of each other: one at a time per host thread, messages printed in map order afterwards
+  std::vector<std::pair<const std::string, std::vector<PosGT *>> *> chrs;
+  for (auto &kv : byChr) chrs.push_back(&kv);
+  std::vector<std::string> msgs(chrs.size());
+  auto one = [&](size_t ci) {
+    const std::string &name = chrs[ci]->first;
+    std::vector<PosGT *> &in = chrs[ci]->second;
     std::vector<PosGT *> out;
     uint32_t removed = 0, nsplit = 0, merged = 0;
     std::sort(in.begin(), in.end(), [](PosGT *const &A, PosGT *const &B) { return A->rStart < B->rStart; });
     out.push_back(in[0]);
-    std::vector<PosGT *> dead;
     for (size_t ii = 1; ii < in.size(); ii++) {
-      if (in[ii]->gts.empty()) { removed++; dead.push_back(in[ii]); continue; }
+      if (in[ii]->gts.empty()) { removed++; continue; }
       const bool overlapping = in[ii]->rStart < out.back()->rEnd + K_OFFSET;
       const bool toomany = out.back()->gts.size() >= comb;
       if (!overlapping) { out.push_back(in[ii]); continue; }
@@ -189,18 +207,28 @@ void VcfFile::mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit) {
       out.back()->rStart = std::min(out.back()->rStart, g->pos);
       out.back()->rEnd = std::max(out.back()->rEnd, g->pos + g->refLen);
       merged++;
-      dead.push_back(in[ii]);
     }
-    if (!getenv("MFN_QUIET")) {
-      fprintf(stderr, "%s : Reduced %lu variants down to %lu combinations for evaluation:\n", kv.first.c_str(),
-              (unsigned long)in.size(), (unsigned long)out.size());
-      if (removed > 0) fprintf(stderr, "%s :   Removed %u empty alleles.\n", kv.first.c_str(), removed);
-      if (nsplit > 0) fprintf(stderr, "%s :   Split   %u complicated combinations.\n", kv.first.c_str(), nsplit);
-      if (merged > 0) fprintf(stderr, "%s :   Merged  %u variants into combinations.\n", kv.first.c_str(), merged);
+    if (!quiet) {
+      char buf[256];
+      std::string &m = msgs[ci];
+      snprintf(buf, sizeof buf, " : Reduced %lu variants down to %lu combinations for evaluation:\n", (unsigned long)in.size(), (unsigned long)out.size());
+      m += name; m += buf;
+      if (removed > 0) { snprintf(buf, sizeof buf, " :   Removed %u empty alleles.\n", removed); m += name; m += buf; }
+      if (nsplit > 0) { snprintf(buf, sizeof buf, " :   Split   %u complicated combinations.\n", nsplit); m += name; m += buf; }
+      if (merged > 0) { snprintf(buf, sizeof buf, " :   Merged  %u variants into combinations.\n", merged); m += name; m += buf; }
     }
-    for (auto *d : dead) delete d;
     in.swap(out);
-  }
+  };
+  unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (num_records < 200000) T = 1;
+  T = (unsigned)std::max<size_t>(1, std::min<size_t>(T, chrs.size()));
+  std::atomic<size_t> next{0};
+  auto worker = [&]() { for (size_t ci; (ci = next.fetch_add(1)) < chrs.size();) one(ci); };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < T; t++) th.emplace_back(worker);
+  worker();
+  for (auto &x : th) x.join();
+  for (const std::string &m : msgs) fputs(m.c_str(), stderr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,9 +297,9 @@ struct VarMer {
 };
 
 // chr <tab> pos <tab> . <tab> REF <tab> ALT[,ALT2] <tab> (int)QUAL <tab> PASS <tab> . <tab> GT <tab> gt   (varMer.C:487,534)
-static inline void put_record(std::string &out, const PosGT *pg, const GtAllele *g, const std::string &alt, const std::string *alt2,
+static inline void put_record(std::string &out, const PosGT *pg, const GtAllele *g, std::string_view alt, const std::string_view *alt2,
                               const char *gt) {
-  out += pg->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; out += alt;
+  out += *pg->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; out += alt;
   if (alt2) { out += ','; out += *alt2; }
   out += '\t'; put_int(out, (int)g->qual); out += "\tPASS\t.\tGT\t"; out += gt; out += '\n';
 }
@@ -294,9 +322,9 @@ void VarMer::hetRecord(size_t idx1, size_t idx2, std::string &out) const {      
     const GtAllele *g = c.posGt->gts[i];
     if (a1 == a2)               put_record(out, c.posGt, g, g->alleles[a1], nullptr, "1/1");
     else if (a1 == 0 && a2 > 0) put_record(out, c.posGt, g, g->alleles[a2], nullptr, "0/1");
-    else if (a1 > 0 && a2 > 0)  put_record(out, c.posGt, g, g->alleles[a1], &g->alleles[a2], "1/2");
+    else if (a1 > 0 && a2 > 0)  { const std::string_view second = g->alleles[a2]; put_record(out, c.posGt, g, g->alleles[a1], &second, "1/2"); }
     else if (a1 > 0 && a2 == 0) put_record(out, c.posGt, g, g->alleles[a1], nullptr, "1/0");
-    else { out += c.posGt->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; }   // (negative index: the reference leaves the line unfinished)
+    else { out += *c.posGt->chr; out += '\t'; put_int(out, (uint32_t)(g->pos + 1)); out += "\t.\t"; out += g->alleles[0]; out += '\t'; }   // (negative index: the reference leaves the line unfinished)
   }
 }
 
@@ -312,7 +340,7 @@ struct Enumerator {
   Cluster *cur = nullptr;
   uint32_t n = 0;                                              // variants of the current cluster
   std::vector<uint32_t> idxList, lenStack;
-  std::vector<const std::vector<std::string> *> haps;
+  std::vector<const SmallVec<std::string_view, 3> *> haps;
   std::vector<int> path;
   std::vector<std::string> scratch;                            // one per recursion depth, capacity kept
 
@@ -336,7 +364,7 @@ struct Enumerator {
 
   void go(uint32_t idx, uint32_t depth, const char *cand, size_t candLen) {
     uint32_t *lenList = lenStack.data() + (size_t)depth * n;
-    const std::vector<std::string> &alts = *haps[idx];
+    const SmallVec<std::string_view, 3> &alts = *haps[idx];
     const uint32_t refLen = lenList[idx];
     const uint32_t last = n - 1;
     for (size_t j = 0; j < alts.size(); j++) {
@@ -347,7 +375,7 @@ struct Enumerator {
         else { memcpy(lenList + n, lenList, n * sizeof(uint32_t)); go(idx + 1, depth + 1, cand, candLen); }
       } else {
         lenList[idx] = refLen;
-        const std::string &hap = alts[j];
+        const std::string_view hap = alts[j];
         const size_t at = idxList[idx];
         if (at > candLen) throw std::out_of_range("basic_string::replace");      // as the reference's std::string::replace
         const size_t cut = std::min<size_t>(lenList[idx], candLen - at);
@@ -363,7 +391,7 @@ struct Enumerator {
         } else {
           for (uint32_t i = idx + 1; i < n; i++) idxList[i] += delta;
           std::string &changed = scratch[depth];
-          changed.assign(cand, at); changed.append(hap); changed.append(cand + at + cut, candLen - at - cut);
+          changed.assign(cand, at); changed.append(hap.data(), hap.size()); changed.append(cand + at + cut, candLen - at - cut);
           memcpy(lenList + n, lenList, n * sizeof(uint32_t));
           go(idx + 1, depth + 1, changed.data(), changed.size());
           for (uint32_t i = idx + 1; i < n; i++) idxList[i] -= delta;
@@ -377,7 +405,7 @@ struct Enumerator {
   // the paths of cluster c (its variants' alleles over the region [c.rStart, c.rEnd) of the record)
   void run(Cluster &c, const char *seq) {
     cur = &c;
-    const std::vector<GtAllele *> &gts = c.posGt->gts;
+    const SmallVec<GtAllele *, 2> &gts = c.posGt->gts;
     n = (uint32_t)gts.size();
     c.nvar = n; c.first_path = (uint32_t)(b.off.size() - 1); c.npaths = 0; c.first_var = b.gt.size();
     if (n == 0) return;
@@ -672,7 +700,7 @@ int process_sequence(const std::string &ident, const char *seq, uint64_t seqLen,
             const int alt = gp[i];
             if (alt > 0) {
               const GtAllele *g = c.posGt->gts[i];
-              *debug += ident + " " + std::to_string(g->pos + 1) + " . " + g->alleles[0] + " " + g->alleles[alt] + " . PASS . GT 1/1  ";
+              *debug += ident + " " + std::to_string(g->pos + 1) + " . "; *debug += g->alleles[0]; *debug += " "; *debug += g->alleles[alt]; *debug += " . PASS . GT 1/1  ";
             }
           }
           *debug += "\n";

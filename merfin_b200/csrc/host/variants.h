@@ -14,6 +14,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <string_view>
 #include <vector>
 
 #include "../../../include/merfin_b200.h"
@@ -22,11 +23,28 @@ namespace mfnv {
 
 enum Mode { FILTER = 4, POLISH = 5, BETTER = 6, STRICT = 7, LOOSE = 8 };   // merfin-globals.H:32-40
 
+// Inline storage for the first N elements (a cluster nearly always holds one or two variants, a genotype
+// two or three alleles): no allocation per VCF record.  T is trivially copyable.
+template <class T, unsigned N> class SmallVec {
+  T inl_[N];
+  std::vector<T> rest_;
+  uint32_t n_ = 0;
+ public:
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  void push_back(const T &v) { if (n_ < N) inl_[n_] = v; else rest_.push_back(v); n_++; }
+  const T &operator[](size_t i) const { return i < N ? inl_[i] : rest_[i - N]; }
+  T &operator[](size_t i) { return i < N ? inl_[i] : rest_[i - N]; }
+};
+
+// One data line.  The text itself stays in the VcfFile's copy of the file; the ten columns are spans of it.
 struct VcfRecord {
-  std::string chr, id, ref, alts, filter, info, formats, samples;
+  enum { CHROM, POS, ID, REF, ALT, QUAL, FILTER, INFO, FORMAT, SAMPLE, NCOL };
+  const char *line = nullptr;
+  uint32_t col_off[NCOL] = {}, col_len[NCOL] = {};
   uint32_t pos = 0;
   double qual = 0.0;
-  std::vector<std::string> alt_list, sample_fields;
+  std::string_view col(int i) const { return std::string_view(line + col_off[i], col_len[i]); }
   std::string save() const;                 // vcfRecord.H:78-99: the first ten columns, QUAL as %.1f
 };
 
@@ -34,25 +52,29 @@ struct GtAllele {                           // vcf.H:37-50
   const VcfRecord *record = nullptr;
   uint32_t pos = 0, refLen = 0;
   double qual = 0.0;
-  std::vector<std::string> alleles;         // [0] is the reference allele; may be EMPTY (Q10)
+  SmallVec<std::string_view, 3> alleles;    // [0] is the reference allele; may be EMPTY (Q10)
 };
 
 struct PosGT {                              // vcf.H:59-90: a cluster of nearby variants
-  std::string chr;
+  const std::string *chr = nullptr;         // (the key of VcfFile::byChr)
   uint32_t rStart = 0, rEnd = 0;
-  std::vector<GtAllele *> gts;
+  SmallVec<GtAllele *, 2> gts;
 };
 
 struct VcfFile {
   std::vector<std::string> headers;
-  std::vector<VcfRecord *> records;
-  std::vector<GtAllele *> alleles;          // owned
+  uint64_t num_records = 0;
   std::map<std::string, std::vector<PosGT *>> byChr;
   uint64_t excluded = 0;
   int numChr = 0;
-  ~VcfFile();
   bool load(const std::string &path, std::string &err);              // vcf.C:93-151
   void mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit);   // vcf.C:156-246
+ private:
+  // the file's text and the objects of every data line, in the pieces the parsing threads made them in
+  std::vector<char> text_;
+  std::vector<std::vector<VcfRecord>> records_;
+  std::vector<std::vector<GtAllele>> alleles_;
+  std::vector<std::vector<PosGT>> posgts_;
 };
 
 // paths: concatenated path strings + offsets (as mfn_score_paths takes them); the scorer leaves one

@@ -75,7 +75,7 @@ extern "C" int mfn_vcf_cluster(mfn_vcf *v, uint32_t k, uint32_t comb, int nospli
 extern "C" int mfn_vcf_info(const mfn_vcf *v, mfn_vcf_info_t *info) {
   if (!v || !info) return MFN_ERR_INVALID;
   info->headers = v->file.headers.size();
-  info->records = v->file.records.size();
+  info->records = v->file.num_records;
   info->contigs = v->file.byChr.size();
   info->contig_ids = (uint64_t)v->file.numChr;
   info->excluded = v->file.excluded;

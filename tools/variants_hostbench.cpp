@@ -112,7 +112,7 @@ int main(int argc, char **argv) {
     out_bytes += t.out.size();
     for (char c : t.out) { digest = mix(digest ^ (unsigned char)c); out_lines += c == '\n'; }
   }
-  const double nrec = (double)vcf.records.size();
+  const double nrec = (double)vcf.num_records;
   printf("{\"records\": %.0f, \"mode\": \"%s\", \"threads\": %u, \"load_s\": %.3f, \"cluster_s\": %.3f, \"step_s\": %.4f, \"scorer_s\": %.4f, "
          "\"host_us_per_record_per_thread\": %.3f, \"out_lines\": %llu, \"out_bytes\": %llu, \"digest\": \"%016llx\"}\n",
          nrec, mode.c_str(), T, t_load1 - t_load0, t_cluster - t_load1, best, scorer_best, (best - scorer_best) * 1e6 * T / nrec,
