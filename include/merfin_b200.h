@@ -187,6 +187,11 @@ int  mfn_meryl_info(const char *meryl_dir, mfn_meryl_info_t *info);
 /* The stored value histogram (value, number of distinct k-mers with it), ascending value;
  * MFN_ERR_CAPACITY with *n = entries needed when cap is too small. */
 int  mfn_meryl_histogram(const char *meryl_dir, uint64_t *values, uint64_t *counts, uint64_t cap, uint64_t *n);
+/* Every (k-mer, value) of a database in stored (ascending k-mer) order, decoded on the host
+ * (merylFileBlockReader::decodeBlock, kmers-files.C:82-128): k <= 64, a k-mer is kmers_hi << 64 | kmers_lo
+ * (kmers_hi may be NULL for k <= 32).  All arrays NULL: *n = the number of k-mers.  MFN_ERR_CAPACITY
+ * with *n = entries needed when cap is too small. */
+int  mfn_meryl_read(const char *meryl_dir, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *values, uint64_t cap, uint64_t *n);
 
 /* ---- sequences: replaces dnaSeq + kmerIterator::nextBase ------------------
  * kmers-iterator.H:93-160.  bases = concatenated ASCII records, record i is

@@ -616,6 +616,19 @@ def meryl_histogram(path: str):
     return v, c
 
 
+def meryl_read(path: str):
+    """(kmers_lo, kmers_hi, values) of every k-mer of a database in stored order, decoded on the host
+    (mfn_meryl_read); a k-mer is kmers_hi << 64 | kmers_lo (k <= 64)."""
+    lib = L.load()
+    n = C.c_uint64(0)
+    L.check(lib.mfn_meryl_read(path.encode(), None, None, None, 0, C.byref(n)))
+    lo = np.zeros(n.value, dtype=np.uint64)
+    hi = np.zeros(n.value, dtype=np.uint64)
+    v = np.zeros(n.value, dtype=np.uint32)
+    L.check(lib.mfn_meryl_read(path.encode(), _ptr(lo), _ptr(hi), _ptr(v), n.value, C.byref(n)))
+    return lo, hi, v
+
+
 def meryl_write(path: str, k: int, kmers, values):
     km = np.ascontiguousarray(kmers, dtype=np.uint64)
     vv = np.ascontiguousarray(values, dtype=np.uint32)

@@ -200,6 +200,81 @@ int meryl_decode_file(const MerylIndex &idx, uint32_t file,
   return MFN_OK;
 }
 
+// The same for any k <= 64: k-mers as (hi, lo) halves of the 128-bit kmdata (kmers-tiny.H:29).  The binary
+// part of a suffix wider than 64 bits is stored as two values, its top binaryBits - 64 bits and then its low
+// 64 bits (kmers-files.C:88-107); each is framed on its own (a value never straddles sub-blocks).
+int meryl_decode_file_wide(const MerylIndex &idx, uint32_t file,
+                           const std::function<void(const uint64_t *, const uint64_t *, const uint32_t *, uint64_t)> &sink) {
+  typedef unsigned __int128 u128;
+  std::vector<uint8_t> buf;
+  std::string path = meryl_file_name(idx, file, false);
+  if (!read_file(path, buf)) { mfn_set_error("cannot read '%s'", path.c_str()); return MFN_ERR_IO; }
+  size_t size = buf.size() - 16, off = 0;
+  std::vector<uint64_t> hi, lo;
+  std::vector<uint32_t> values;
+  if (idx.suffixSize >= 128 || idx.prefixSize + idx.suffixSize > 128) { mfn_set_error("'%s': k-mers wider than 128 bits", path.c_str()); return MFN_ERR_UNSUPPORTED; }
+  while (off < size) {
+    BitBlocks bb;
+    if (!bb.parse(buf.data() + off, size - off)) { mfn_set_error("'%s': truncated block", path.c_str()); return MFN_ERR_FORMAT; }
+    off += bb.bytes;
+    if (bb.total_bits() == 0) break;
+    BitCursor c(bb);
+    if (c.binary(64) != MAGIC_DATA_1 || c.binary(64) != MAGIC_DATA_2) {
+      mfn_set_error("'%s': block magic number mismatch", path.c_str());
+      return MFN_ERR_FORMAT;
+    }
+    const uint64_t blockPrefix = (uint32_t)c.binary(64);
+    const uint64_t n = c.binary(64);
+    const uint32_t kCode = (uint32_t)c.binary(8);
+    (void)c.binary(32);                                   // unaryBits (informational)
+    const uint32_t binaryBits = (uint32_t)c.binary(32);
+    (void)c.binary(64);
+    const uint32_t cCode = (uint32_t)c.binary(8);
+    (void)c.binary(64); (void)c.binary(64);
+    if (kCode != 1 || (cCode != 1 && cCode != 2)) { mfn_set_error("'%s': unknown block coding %u/%u", path.c_str(), kCode, cCode); return MFN_ERR_FORMAT; }
+    if (binaryBits > 128) { mfn_set_error("'%s': k-mer suffix wider than 128 bits", path.c_str()); return MFN_ERR_FORMAT; }
+    hi.resize(n); lo.resize(n); values.resize(n);
+    const uint32_t ls = binaryBits <= 64 ? 0 : binaryBits - 64, rs = binaryBits <= 64 ? binaryBits : 64;
+    const u128 base = (u128)blockPrefix << idx.suffixSize;
+    u128 high = 0;
+    for (uint64_t i = 0; i < n; i++) {
+      high += c.unary();
+      u128 suf = high;
+      if (ls) suf = (suf << ls) | c.binary(ls);
+      if (rs == 64) suf = ((suf << 32) << 32) | c.binary(64);
+      else if (rs) suf = (suf << rs) | c.binary(rs);
+      const u128 km = base | suf;
+      lo[i] = (uint64_t)km; hi[i] = (uint64_t)(km >> 64);
+    }
+    const uint32_t vw = cCode == 1 ? 32 : 64;
+    for (uint64_t i = 0; i < n; i++) values[i] = (uint32_t)c.binary(vw);
+    sink(hi.data(), lo.data(), values.data(), n);
+  }
+  return MFN_OK;
+}
+
+// Every (k-mer, value) of a database in stored order (ascending k-mer), decoded on the host.
+extern "C" int mfn_meryl_read(const char *dir, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *values, uint64_t cap, uint64_t *n) {
+  if (!dir || !n) return MFN_ERR_INVALID;
+  MerylIndex idx;
+  MFN_TRY(meryl_open(dir, idx));
+  if (idx.k > 64) { mfn_set_error("'%s': k=%u; k-mers hold at most 64 bases", dir, idx.k); return MFN_ERR_UNSUPPORTED; }
+  if (idx.k > 32 && kmers_lo && !kmers_hi) { mfn_set_error("'%s': k=%u needs kmers_hi", dir, idx.k); return MFN_ERR_INVALID; }
+  uint64_t fill = 0;
+  const uint32_t nfiles = 1u << idx.numFilesBits;
+  for (uint32_t f = 0; f < nfiles; f++)
+    MFN_TRY(meryl_decode_file_wide(idx, f, [&](const uint64_t *h, const uint64_t *l, const uint32_t *v, uint64_t m) {
+      for (uint64_t i = 0; i < m; i++, fill++) {
+        if (fill >= cap) continue;
+        if (kmers_lo) kmers_lo[fill] = l[i];
+        if (kmers_hi) kmers_hi[fill] = h[i];
+        if (values) values[fill] = v[i];
+      }
+    }));
+  *n = fill;
+  return fill > cap && (kmers_lo || kmers_hi || values) ? MFN_ERR_CAPACITY : MFN_OK;
+}
+
 int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,
                            const std::function<int(const unsigned long long *, const uint32_t *, uint64_t)> &fn,
                            uint32_t file_begin, uint32_t file_end) {

@@ -27,6 +27,9 @@ std::string meryl_file_name(const MerylIndex &idx, uint32_t file, bool index);
 // k-mers are 64-bit (k <= 32).
 int meryl_decode_file(const MerylIndex &idx, uint32_t file,
                       const std::function<void(const uint64_t *, const uint32_t *, uint64_t)> &sink);
+// Any k <= 64: sink(hi, lo, values, n) with the two halves of every 128-bit k-mer.
+int meryl_decode_file_wide(const MerylIndex &idx, uint32_t file,
+                           const std::function<void(const uint64_t *, const uint64_t *, const uint32_t *, uint64_t)> &sink);
 // Stream a whole database to the device in chunks; fn(d_kmers, d_values, n) is called per chunk
 // on ctx->stream with device arrays that stay valid until the next call.
 int meryl_stream_to_device(mfn_ctx *ctx, const MerylIndex &idx,

@@ -123,6 +123,7 @@ SIGNATURES = {
     "mfn_meryl_write": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, C.c_uint64]),
     "mfn_meryl_info": (C.c_int, [C.c_char_p, C.POINTER(MerylInfo)]),
     "mfn_meryl_histogram": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "mfn_meryl_read": (C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_seq_create": (C.c_int, [_P, _P, _P, C.c_uint32, _PP]),
     "mfn_seq_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "mfn_seq_free": (None, [_P]),

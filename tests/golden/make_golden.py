@@ -136,4 +136,8 @@ if __name__ == "__main__":
     make_set("g2_k6", 6, 1500, 2, 12, 6, 3, 40)
     # G3: k=31 (62-bit k-mers, 64-bit table slots)
     make_set("g3_k31", 31, 6000, 3, 13, 8, 6, 200)
+    # G4: k=40 (80-bit k-mers: the 128-bit path), with a -prob table and the variant modes
+    make_set("g4_k40", 40, 6000, 3, 14, 8, 6, 200, extra=("prob", "variants"))
+    # G5: k=64, the widest k-mer the reference's 128-bit kmdata holds (even k: palindromes)
+    make_set("g5_k64", 64, 4000, 2, 15, 8, 6, 150)
     print("golden sets written under", HERE)

@@ -141,6 +141,23 @@ def test_meryl_info_matches_the_reference_listing(golden_dir, name, k):
         assert (hv == uv).all() and (hc == uc.astype(np.uint64)).all()
 
 
+@pytest.mark.parametrize("name,k", [("g1_k21", 21), ("g2_k6", 6), ("g3_k31", 31), ("g4_k40", 40), ("g5_k64", 64)])
+def test_meryl_read_matches_meryl_print(golden_dir, name, k):
+    """mfn_meryl_read (host decoder, any k <= 64: 128-bit k-mers as two halves) against the reference's
+    `meryl print` of the same databases, k-mer by k-mer in stored order."""
+    import gzip
+    from merfin_b200 import api
+    for db in ("reads", "asm"):
+        lines = [l.split() for l in gzip.open(os.path.join(golden_dir, name, db + ".print.gz"), "rt")]
+        lo, hi, v = api.meryl_read(os.path.join(golden_dir, name, db + ".meryl"))
+        assert api.meryl_info(os.path.join(golden_dir, name, db + ".meryl"))["k"] == k
+        assert len(lines) == len(lo)
+        assert [O.kmer_from_string(a) for a, _ in lines] == [(int(h) << 64) | int(l) for h, l in zip(hi, lo)]
+        assert [int(b) for _, b in lines] == [int(x) for x in v]
+        if k <= 32:
+            assert not hi.any()
+
+
 def test_meryl_info_errors(tmp_path):
     info = L.MerylInfo()
     assert L.load().mfn_meryl_info(str(tmp_path).encode(), C.byref(info)) == L.MFN_ERR_IO

@@ -8,7 +8,7 @@ import pytest
 
 import oracle_lib as O
 
-SETS = [("g1_k21", 21, 8.0), ("g2_k6", 6, 3.0), ("g3_k31", 31, 6.0)]
+SETS = [("g1_k21", 21, 8.0), ("g2_k6", 6, 3.0), ("g3_k31", 31, 6.0), ("g4_k40", 40, 6.0), ("g5_k64", 64, 6.0)]
 
 
 def _load(golden_dir, name):
