@@ -34,7 +34,7 @@ typedef enum {
   MFN_ERR_CUDA           = -2,   /* a CUDA call failed; see mfn_last_error()            */
   MFN_ERR_IO             = -3,   /* file missing / unreadable                           */
   MFN_ERR_FORMAT         = -4,   /* not a meryl database / corrupt block                */
-  MFN_ERR_UNSUPPORTED    = -5,   /* k > 32, multiset database, ...                      */
+  MFN_ERR_UNSUPPORTED    = -5,   /* k > 64, multiset database, a 64-bit-only call on a k > 32 table */
   MFN_ERR_INVALID        = -6,   /* bad argument                                        */
   MFN_ERR_CAPACITY       = -7,   /* caller buffer or internal side table too small      */
   MFN_ERR_K_MISMATCH     = -8,   /* tables built for different k (kmers-reader.C:171)   */
@@ -65,7 +65,17 @@ int  mfn_host_alloc(void **p, size_t bytes);
 void mfn_host_free(void *p);
 
 /* ---- tables: replaces merylExactLookup::load / ::value -------------------
- * kmers-lookup.H:118-137, kmers-exact.C:34-73 (filter, offset), 648-671.      */
+ * kmers-lookup.H:118-137, kmers-exact.C:34-73 (filter, offset), 648-671.
+ *
+ * Mer sizes: 1 <= k <= 64, like the reference's 128-bit kmdata (kmers-tiny.H:29).  Up to k = 32 a
+ * k-mer is one 64-bit word and the tables are the bucketed ones all the fast paths are built on.
+ * For k = 33..64 mfn_table_load / mfn_table_count_seq build a table of sorted 128-bit k-mers
+ * (csrc/wide.cu); mfn_hist*, mfn_dump*, mfn_score_paths, mfn_variants_process and mfn_completeness*
+ * take such tables and give the reference's numbers through a plain scan that looks every window up
+ * in both orientations; the entry points that exist only for 64-bit k-mers (mfn_table_from_kmers,
+ * mfn_table_lookup, mfn_table_export, mfn_tables_fuse / _restrict*, mfn_joint_lookup, mfn_meryl_write,
+ * mfn_table_synth_reads) return MFN_ERR_UNSUPPORTED for them, and mfn_table_info reports
+ * canonical = 0 and slot_bits = 128.                                                             */
 
 /* Load an on-disk meryl database (formats v01-v03; kmers-reader.C:127-206,
  * kmers-files.C:24-128).  minV/maxV follow merfin's -min/-max: 0 -> 1,
@@ -106,6 +116,9 @@ void mfn_table_free(mfn_table *t);
  * value of kmers[i] exactly as given (no canonicalisation), 0 if absent. */
 int  mfn_table_lookup(mfn_ctx *ctx, const mfn_table *t, const uint64_t *kmers, uint64_t n,
                       uint32_t *out);
+/* The same for a table of k = 33..64: k-mer i is kmers_hi[i] << 64 | kmers_lo[i]. */
+int  mfn_table_lookup_wide(mfn_ctx *ctx, const mfn_table *t, const uint64_t *kmers_lo, const uint64_t *kmers_hi,
+                           uint64_t n, uint32_t *out);
 /* Export every stored (k-mer, stored value), ascending k-mer order. */
 int  mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmers, uint32_t *values,
                       uint64_t cap, uint64_t *n);

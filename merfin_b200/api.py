@@ -169,6 +169,14 @@ class MerylExactLookup:
     def value(self, kmer: int) -> int:
         return int(self.values([kmer])[0])
 
+    def values_wide(self, kmers_lo, kmers_hi) -> np.ndarray:
+        """merylExactLookup::value for a table of k = 33..64: k-mer i is kmers_hi[i] << 64 | kmers_lo[i]."""
+        lo = np.ascontiguousarray(kmers_lo, dtype=np.uint64)
+        hi = np.ascontiguousarray(kmers_hi, dtype=np.uint64)
+        out = np.zeros(len(lo), dtype=np.uint32)
+        L.check(self._lib.mfn_table_lookup_wide(self.ctx.h, self.h, _ptr(lo), _ptr(hi), len(lo), _ptr(out)))
+        return out
+
     def fuse(self, asm: "MerylExactLookup"):
         """Attach the fused (self, asm) table: scans over this pair then cost one probe per window."""
         L.check(self._lib.mfn_tables_fuse(self.ctx.h, self.h, asm.h))

@@ -410,6 +410,7 @@ extern "C" int mfn_completeness_shard(mfn_ctx *ctx, const char *reads_dir, const
   const uint32_t nfiles = 1u << idx.numFilesBits;
   const uint32_t fb = (uint32_t)((uint64_t)nfiles * shard / nshards), fe = (uint32_t)((uint64_t)nfiles * (shard + 1) / nshards);
   if (fb >= fe) return MFN_OK;
+  if (asm_raw->wide) return mfn_wide_completeness(ctx, idx, asm_raw, fb, fe, acc);                                    // k > 32
   return meryl_stream(ctx, idx, [&](const unsigned long long *dk, const uint32_t *dv, uint64_t n) {
     int grid = (int)std::min<uint64_t>(ceil_div_u64(n, 256), (uint64_t)ctx->sm_count * 8);
     k_join<<<grid, 256, 0, ctx->stream>>>(asm_raw->dev, dk, dv, n, acc->d_buf, acc->sparse);

@@ -26,6 +26,15 @@ void mfn_set_error(const char *fmt, ...);
     }                                                                                        \
   } while (0)
 
+// entry points that only exist for 64-bit k-mers
+#define MFN_REJECT_WIDE(t, what)                                                                        \
+  do {                                                                                                  \
+    if ((t) && (t)->wide) {                                                                             \
+      mfn_set_error("%s: not available for k > 32 (tables of 128-bit k-mers)", what);                    \
+      return MFN_ERR_UNSUPPORTED;                                                                       \
+    }                                                                                                   \
+  } while (0)
+
 #define MFN_TRY(call)                 \
   do {                                \
     int s_ = (call);                  \
@@ -109,12 +118,14 @@ struct mfn_ctx {
 };
 
 struct mfn_joint;
+struct mfn_wide;                       // k > 32: sorted 128-bit k-mers (wide.cu)
 
 struct mfn_table {
   mfn_ctx   *ctx = nullptr;
   int        device = 0;          // (kept apart from ctx: the object may be freed after its ctx)
   mfn_joint *joint = nullptr;     // fused (this, assembly) table built by mfn_tables_fuse
   mfn_joint *hot = nullptr;       // fused table restricted to the k-mers of one sequence shard (mfn_tables_restrict)
+  mfn_wide  *wide = nullptr;      // k > 32: the table lives here and `dev` only carries k
   bool       streamed = false;    // no per-database table behind this handle: the database was streamed into `hot` (joint_stream.cu)
   DevTable   dev{};
   TableStats host_stats{};

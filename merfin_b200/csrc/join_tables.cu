@@ -33,6 +33,7 @@ extern "C" int mfn_completeness_resident(mfn_ctx *ctx, const mfn_table *reads_ra
   if (reads_raw->value_offset != 0 || asm_raw->value_offset != 0) { mfn_set_error("-completeness joins raw values: load both tables with minV = 0"); return MFN_ERR_INVALID; }
   if (reads_raw->dev.k != asm_raw->dev.k) { mfn_set_error("mer size mismatch: reads k=%u, assembly k=%u", reads_raw->dev.k, asm_raw->dev.k); return MFN_ERR_K_MISMATCH; }
   MFN_CUDA(cudaSetDevice(ctx->device));
+  if (reads_raw->wide || asm_raw->wide) return mfn_wide_completeness_resident(ctx, reads_raw, asm_raw, acc);      // k > 32
   k_join_tables<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reads_raw->dev, asm_raw->dev, acc->d_buf, acc->sparse);
   ctx->launches++;
   MFN_CUDA(cudaGetLastError());

@@ -219,6 +219,7 @@ int mfn_joint_build(mfn_ctx *ctx, const mfn_table *R, const mfn_table *A, mfn_jo
 // ---- C ABI ------------------------------------------------------------------------------------
 extern "C" int mfn_tables_fuse(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_) {
   if (!ctx || !reads || !asm_) return MFN_ERR_INVALID;
+  MFN_REJECT_WIDE(reads, "mfn_tables_fuse"); MFN_REJECT_WIDE(asm_, "mfn_tables_fuse");
   if (reads->joint && reads->joint->asm_ == asm_) return MFN_OK;
   mfn_joint_free(reads->joint);
   reads->joint = nullptr;
@@ -235,6 +236,7 @@ extern "C" int mfn_tables_unfuse(mfn_table *reads) {
 extern "C" int mfn_tables_restrict(mfn_ctx *ctx, mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq,
                                    uint32_t shard, uint32_t nshards) {
   if (!ctx || !reads || !asm_ || !seq || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  MFN_REJECT_WIDE(reads, "mfn_tables_restrict"); MFN_REJECT_WIDE(asm_, "mfn_tables_restrict");
   mfn_joint_free(reads->hot);
   reads->hot = nullptr;
   const uint64_t tb = seq->ntiles * shard / nshards, te = seq->ntiles * (shard + 1) / nshards;

@@ -105,7 +105,8 @@ extern "C" int mfn_tables_restrict_stream(mfn_ctx *ctx, const char *reads_dir, u
   if (!ctx || !reads_dir || !asm_ || !seq || !reads_out || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
   MerylIndex idx;
   MFN_TRY(meryl_open(reads_dir, idx));
-  if (idx.k > 32) { mfn_set_error("'%s': k=%u; this build supports k <= 32", reads_dir, idx.k); return MFN_ERR_UNSUPPORTED; }
+  if (idx.k > 32) { mfn_set_error("'%s': k=%u; the streamed (restricted) table holds 64-bit k-mers: load the database with mfn_table_load", reads_dir, idx.k); return MFN_ERR_UNSUPPORTED; }
+  MFN_REJECT_WIDE(asm_, "mfn_tables_restrict_stream");
   if (idx.flags & 1) { mfn_set_error("'%s' is a multiset database; not supported", reads_dir); return MFN_ERR_UNSUPPORTED; }
   if (minV == 0) minV = 1;                                                 // kmers-exact.C:43
   if (maxV == 0xffffffffu && !idx.histValue.empty()) maxV = (uint32_t)idx.histValue.back();
@@ -150,6 +151,7 @@ extern "C" int mfn_tables_restrict_synth(mfn_ctx *ctx, const mfn_table *asm_, co
                                          double cov, uint64_t n_error, uint64_t seed, uint64_t chunk_kmers, mfn_table **reads_out,
                                          mfn_stream_stats *stats) {
   if (!ctx || !asm_ || !seq || !reads_out || nshards == 0 || shard >= nshards) return MFN_ERR_INVALID;
+  MFN_REJECT_WIDE(asm_, "mfn_tables_restrict_synth");
   const auto t0 = std::chrono::steady_clock::now();
   mfn_table *reads = nullptr, *keys = nullptr;
   mfn_joint *j = nullptr;

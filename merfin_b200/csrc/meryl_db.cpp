@@ -341,8 +341,9 @@ extern "C" int mfn_table_load(mfn_ctx *ctx, const char *dir, uint32_t minV, uint
   if (!ctx || !dir || !out) return MFN_ERR_INVALID;
   MerylIndex idx;
   MFN_TRY(meryl_open(dir, idx));
-  if (idx.k > 32) { mfn_set_error("'%s': k=%u; this build supports k <= 32", dir, idx.k); return MFN_ERR_UNSUPPORTED; }
+  if (idx.k > 64) { mfn_set_error("'%s': k=%u; k-mers hold at most 64 bases", dir, idx.k); return MFN_ERR_UNSUPPORTED; }
   if (idx.flags & 1) { mfn_set_error("'%s' is a multiset database; not supported", dir); return MFN_ERR_UNSUPPORTED; }
+  if (idx.k > 32) return mfn_wide_load(ctx, idx, minV, maxV, out);          // 128-bit k-mers: wide.cu
   const uint32_t nfiles = 1u << idx.numFilesBits;
   if (idx.version != 3) {
     // older master indexes carry a different statistics layout: take the value histogram from the data

@@ -90,6 +90,7 @@ int mfn_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, 
   MFN_TRY(check_tables(reads, asm_));
   if (acc->nseq < seq->nseq) { mfn_set_error("accumulator has %u record slots, sequence set has %u", acc->nseq, seq->nseq); return MFN_ERR_INVALID; }
   MFN_CUDA(cudaSetDevice(ctx->device));
+  if (reads->wide || asm_->wide) return mfn_wide_hist_tiles(ctx, reads, asm_, seq, km, tile_begin, tile_end, acc);     // k > 32
   ScanParams P{};
   P.R = reads->dev; P.A = asm_->dev;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;
@@ -128,6 +129,7 @@ extern "C" int mfn_dump_resident(mfn_ctx *ctx, const mfn_table *reads, const mfn
   if (!ctx || !seq || !d_v_read || !d_v_asm || !d_valid) return MFN_ERR_INVALID;
   MFN_TRY(check_tables(reads, asm_, true));
   MFN_CUDA(cudaSetDevice(ctx->device));
+  if (reads->wide || asm_->wide) return mfn_wide_dump(ctx, reads, asm_, seq, d_v_read, d_v_asm, d_valid);              // k > 32
   ScanParams P{};
   P.R = reads->dev; P.A = asm_->dev;
   P.seq2 = seq->d_seq2; P.ok = seq->d_ok; P.rec_start = seq->d_rec_start; P.nseq = seq->nseq;

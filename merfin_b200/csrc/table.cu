@@ -245,7 +245,7 @@ static void level_geometry(uint32_t k, uint64_t buckets, TableLevel &lv, uint32_
 
 int mfn_table_alloc(mfn_ctx *ctx, uint32_t k, uint64_t n_expected, mfn_table **out,
                     const std::function<uint64_t(uint32_t)> &count_big) {
-  if (k < 1 || k > 32) { mfn_set_error("k=%u: this build supports 1 <= k <= 32 (64-bit k-mers)", k); return MFN_ERR_UNSUPPORTED; }
+  if (k < 1 || k > 32) { mfn_set_error("k=%u: the bucketed tables hold 64-bit k-mers (1 <= k <= 32); k-mers of 33..64 bases come from mfn_table_load / mfn_table_count_seq", k); return MFN_ERR_UNSUPPORTED; }
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_table *t = new mfn_table();
   t->ctx = ctx;
@@ -360,12 +360,20 @@ extern "C" void mfn_table_free(mfn_table *t) {
   mfn_joint_free(t->joint);
   mfn_joint_free(t->hot);
   for (void *p : t->allocs) cudaFree(p);
+  mfn_wide_free(t->wide);
   delete t;
 }
 
 extern "C" int mfn_table_info(const mfn_table *t, mfn_table_info_t *info) {
   if (!t || !info) return MFN_ERR_INVALID;
   memset(info, 0, sizeof *info);
+  if (t->wide) {
+    mfn_wide_info(t, info);
+    info->min_value = t->min_value; info->max_value = t->max_value; info->value_offset = t->value_offset;
+    info->n_kmers = t->n_kmers;
+    info->device_bytes = t->device_bytes;
+    return MFN_OK;
+  }
   info->k = t->dev.k;
   info->canonical = t->dev.probe_both ? 0 : 1;
   info->slot_bits = t->dev.w64 ? 64 : 32;
@@ -422,6 +430,7 @@ extern "C" int mfn_table_from_kmers(mfn_ctx *ctx, uint32_t k, const uint64_t *km
 
 extern "C" int mfn_table_lookup(mfn_ctx *ctx, const mfn_table *t, const uint64_t *kmers, uint64_t n, uint32_t *out) {
   if (!ctx || !t || (n && (!kmers || !out))) return MFN_ERR_INVALID;
+  MFN_REJECT_WIDE(t, "mfn_table_lookup (use mfn_table_lookup_wide)");
   MFN_CUDA(cudaSetDevice(ctx->device));
   const uint64_t CH = 1ull << 22;
   unsigned long long *dk; uint32_t *dv;
@@ -445,6 +454,7 @@ extern "C" int mfn_table_lookup(mfn_ctx *ctx, const mfn_table *t, const uint64_t
 extern "C" int mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmers, uint32_t *values,
                                 uint64_t cap, uint64_t *n_out) {
   if (!ctx || !t || !n_out) return MFN_ERR_INVALID;
+  MFN_REJECT_WIDE(t, "mfn_table_export");
   MFN_CUDA(cudaSetDevice(ctx->device));
   unsigned long long *dk = nullptr, *dn = nullptr; uint32_t *dv = nullptr;
   uint64_t c = std::max<uint64_t>(cap, 1);
@@ -480,6 +490,7 @@ extern "C" int mfn_table_export(mfn_ctx *ctx, const mfn_table *t, uint64_t *kmer
 
 extern "C" int mfn_table_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, mfn_table **out) {
   if (!ctx || !seq || !out) return MFN_ERR_INVALID;
+  if (k > 32) return mfn_wide_count_seq(ctx, k, seq, out);                  // 128-bit k-mers: sort-based count (wide.cu)
   return mfn_table_count_seq_range(ctx, k, seq, 0, seq->G, out);
 }
 

@@ -50,6 +50,18 @@ inline int meryl_stream(mfn_ctx *ctx, const MerylIndex &idx,
                             : meryl_stream_to_device_gpu(ctx, idx, fn, file_begin, file_end);
 }
 
+// ---- k > 32 (wide.cu) -----------------------------------------------------------------
+int mfn_wide_load(mfn_ctx *ctx, MerylIndex &idx, uint32_t minV, uint32_t maxV, mfn_table **out);
+void mfn_wide_free(mfn_wide *w);
+void mfn_wide_info(const mfn_table *t, mfn_table_info_t *info);
+int mfn_wide_hist_tiles(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq, const mfn_kmodel *km,
+                        uint64_t tile_begin, uint64_t tile_end, mfn_accum *acc);
+int mfn_wide_dump(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_, const mfn_seq *seq, uint32_t *d_v_read,
+                  uint32_t *d_v_asm, uint8_t *d_valid);
+int mfn_wide_completeness(mfn_ctx *ctx, const MerylIndex &idx, const mfn_table *asm_raw, uint32_t file_begin, uint32_t file_end, mfn_accum *acc);
+int mfn_wide_completeness_resident(mfn_ctx *ctx, const mfn_table *reads_raw, const mfn_table *asm_raw, mfn_accum *acc);
+int mfn_wide_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, mfn_table **out);
+
 // ---- sequences ------------------------------------------------------------------
 int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out);
 // done == nullptr: the compute stream is made to wait for the packed range; otherwise `done` is

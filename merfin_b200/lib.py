@@ -109,6 +109,7 @@ SIGNATURES = {
     "mfn_table_info": (C.c_int, [_P, C.POINTER(TableInfo)]),
     "mfn_table_free": (None, [_P]),
     "mfn_table_lookup": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
+    "mfn_table_lookup_wide": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
     "mfn_table_export": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mfn_tables_fuse": (C.c_int, [_P, _P, _P]),
     "mfn_tables_unfuse": (C.c_int, [_P]),
