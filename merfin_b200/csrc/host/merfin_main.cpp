@@ -333,7 +333,8 @@ int main(int argc, char **argv) {
   // -hist does not need the read database resident: it is streamed through the device into the table
   // restricted to the k-mers of each device's share of the sequences (mfn_tables_restrict_stream);
   // the resident tables are loaded only if that is not possible (non-canonical database, odd batch)
-  bool stream_reads = G.report == OP_HIST && !G.nofuse && !getenv("MFN_NO_STREAM") && S.nseq() > 0;
+  // (k > 32: tables of 128-bit k-mers, loaded whole and scanned directly; nothing to stream into or fuse)
+  bool stream_reads = G.report == OP_HIST && !G.nofuse && !getenv("MFN_NO_STREAM") && S.nseq() > 0 && K <= 32;
   fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.readDBname);
   if (G.seqDBname) fprintf(stderr, "-- Loading kmers from '%s' into lookup table.\n", G.seqDBname);
   else fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", K, G.seqName);
