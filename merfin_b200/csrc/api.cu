@@ -311,7 +311,7 @@ static int dump_host(mfn_ctx *ctx, const mfn_table *reads, const mfn_table *asm_
   std::lock_guard<std::mutex> lk(ctx->dump_mu);
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_seq *seq = nullptr;
-  MFN_TRY(mfn_seq_create(ctx, bases, off, (uint32_t)nrec, &seq));
+  MFN_TRY(mfn_seq_create_in(ctx, bases, off, (uint32_t)nrec, &seq, true));
   uint64_t n = seq->total_bases;
   uint32_t *dr = nullptr, *da = nullptr; uint8_t *dv = nullptr;
   int st = MFN_OK;

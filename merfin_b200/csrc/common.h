@@ -148,6 +148,7 @@ struct mfn_seq {
   unsigned long long *d_rec_start = nullptr;   // [nseq+1] global coordinate of each record start
   std::vector<uint64_t> rec_start;             // host copy
   uint64_t  device_bytes = 0;
+  bool      pooled = false;       // device arrays come from the stream-ordered pool (mfn_seq_create_in)
 };
 
 // Dense tier of the joint histogram: v_read < MFN_DENSE_R and v_asm < MFN_DENSE_A.

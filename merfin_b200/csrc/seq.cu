@@ -52,10 +52,11 @@ __global__ void __launch_bounds__(256) k_pack(const unsigned char *__restrict__ 
   if (m) atomicOr(&ok[wi], m);
 }
 
-int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out) {
+int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out, bool pooled) {
   MFN_CUDA(cudaSetDevice(ctx->device));
   mfn_seq *s = new mfn_seq();
   s->ctx = ctx;
+  s->pooled = pooled;
   s->device = ctx->device;
   s->nseq = nseq;
   s->total_bases = nseq ? seq_off[nseq] - seq_off[0] : 0;
@@ -65,9 +66,11 @@ int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq 
   s->ntiles = std::max<uint64_t>(1, ceil_div_u64(s->G, MFN_TILE));
   uint64_t gpad = (s->ntiles + 1) * MFN_TILE + 256;      // one spare tile + halo, all invalid
   size_t b2 = (gpad / 32 + 8) * 8, bo = (gpad / 64 + 8) * 8, br = ((size_t)nseq + 1) * 8;
-  cudaError_t e = cudaMalloc(&s->d_seq2, b2);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_ok, bo);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_rec_start, br);
+  // pooled: a short-lived set (one mfn_dump / mfn_score_paths call) takes its arrays from the stream-ordered pool,
+  // on the stream that fills them; no cudaMalloc / cudaFree (and the device-wide sync of the latter) per call
+  cudaError_t e = pooled ? cudaMallocAsync(&s->d_seq2, b2, ctx->pack_stream) : cudaMalloc(&s->d_seq2, b2);
+  if (e == cudaSuccess) e = pooled ? cudaMallocAsync(&s->d_ok, bo, ctx->pack_stream) : cudaMalloc(&s->d_ok, bo);
+  if (e == cudaSuccess) e = pooled ? cudaMallocAsync(&s->d_rec_start, br, ctx->pack_stream) : cudaMalloc(&s->d_rec_start, br);
   if (e != cudaSuccess) { mfn_set_error("cudaMalloc(sequence): %s", cudaGetErrorString(e)); mfn_seq_free(s); return MFN_ERR_NOMEM; }
   s->device_bytes = b2 + bo + br;
   // the packed arrays are only ever written on the pack stream (see mfn_seq_pack_range)
@@ -142,11 +145,15 @@ int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t
 }
 
 extern "C" int mfn_seq_create(mfn_ctx *ctx, const char *bases, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out) {
+  return mfn_seq_create_in(ctx, bases, seq_off, nseq, out, false);
+}
+
+int mfn_seq_create_in(mfn_ctx *ctx, const char *bases, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out, bool pooled) {
   if (!ctx || !out || !seq_off || (nseq && !bases)) return MFN_ERR_INVALID;
   for (uint32_t i = 0; i < nseq; i++)
     if (seq_off[i + 1] < seq_off[i]) { mfn_set_error("seq_off must be non-decreasing"); return MFN_ERR_INVALID; }
   mfn_seq *s = nullptr;
-  MFN_TRY(mfn_seq_alloc(ctx, seq_off, nseq, &s));
+  MFN_TRY(mfn_seq_alloc(ctx, seq_off, nseq, &s, pooled));
   int st = mfn_seq_pack_range(s, bases + seq_off[0], 0, s->G);
   if (st == MFN_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { mfn_set_error("pack failed: %s", cudaGetErrorString(cudaGetLastError())); st = MFN_ERR_CUDA; }
   if (st != MFN_OK) { mfn_seq_free(s); return st; }
@@ -165,6 +172,13 @@ extern "C" int mfn_seq_info(const mfn_seq *s, uint64_t *total_bases, uint32_t *n
 extern "C" void mfn_seq_free(mfn_seq *s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->d_seq2); cudaFree(s->d_ok); cudaFree(s->d_rec_start);
+  if (s->pooled) {
+    // (freed in stream order behind the scans the caller queued on the compute stream)
+    if (s->d_seq2) cudaFreeAsync(s->d_seq2, s->ctx->stream);
+    if (s->d_ok) cudaFreeAsync(s->d_ok, s->ctx->stream);
+    if (s->d_rec_start) cudaFreeAsync(s->d_rec_start, s->ctx->stream);
+  } else {
+    cudaFree(s->d_seq2); cudaFree(s->d_ok); cudaFree(s->d_rec_start);
+  }
   delete s;
 }

@@ -63,7 +63,9 @@ int mfn_wide_completeness_resident(mfn_ctx *ctx, const mfn_table *reads_raw, con
 int mfn_wide_count_seq(mfn_ctx *ctx, uint32_t k, const mfn_seq *seq, mfn_table **out);
 
 // ---- sequences ------------------------------------------------------------------
-int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out);
+int mfn_seq_alloc(mfn_ctx *ctx, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out, bool pooled = false);
+// mfn_seq_create; pooled: device arrays from the stream-ordered pool (a set that lives for one call; freed while its ctx is alive)
+int mfn_seq_create_in(mfn_ctx *ctx, const char *bases, const uint64_t *seq_off, uint32_t nseq, mfn_seq **out, bool pooled);
 // done == nullptr: the compute stream is made to wait for the packed range; otherwise `done` is
 // recorded on the pack stream instead and the caller orders its own streams
 int mfn_seq_pack_range(mfn_seq *s, const char *bases, uint64_t g_begin, uint64_t g_end, cudaEvent_t done = nullptr);
