@@ -52,6 +52,11 @@ const char *mfn_version(void);
 
 /* ---- context ------------------------------------------------------------ */
 
+/* A ctx = one device + its own streams, events and staging buffers.  Several contexts may exist on one
+ * device; tables, sequence sets and VCFs are plain device / host objects that any ctx OF THE SAME DEVICE
+ * may read (scans never write them), so a host that wants the device parts of concurrent mfn_dump /
+ * mfn_score_paths / mfn_variants_process calls to overlap gives each group of threads its own ctx over
+ * one set of tables (bench.py --mode polish does: "scorer lanes"). */
 int  mfn_ctx_create(mfn_ctx **ctx, int device);
 void mfn_ctx_destroy(mfn_ctx *ctx);
 int  mfn_ctx_device(const mfn_ctx *ctx);

@@ -184,6 +184,11 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
         os.environ.setdefault("MFN_QUIET", "1")
         os.environ.setdefault("MFN_VCF_THREADS", str(threads))
         base = asm_np.ctypes.data
+        # Scorer lanes: the device part of a scorer call (upload, pack, scan, D2H) holds its ctx's lock; extra contexts
+        # on the same device (own streams and staging, the SAME resident tables: they are read-only) let the calls of
+        # different host threads overlap on the device.
+        nlanes = max(1, int(os.environ.get("MFN_POLISH_LANES", "2")))
+        lanes = [ctx] + [api.Context(local) for _ in range(nlanes - 1)]
 
         def load_vcf():
             v = api.Vcf(vpath)
@@ -216,7 +221,7 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
                         return
                     _, i, s_, S = tasks[j]
                     try:
-                        parts[(i, s_)] = api.variants_process(ctx, R, A, v, names[i], base + int(off[i]), "polish", km,
+                        parts[(i, s_)] = api.variants_process(lanes[j % nlanes], R, A, v, names[i], base + int(off[i]), "polish", km,
                                                               shard=rank * S + s_, nshards=world * S, seq_len=int(lens[i]))
                     except Exception as e:                       # noqa: BLE001
                         err.append(e)
@@ -248,17 +253,22 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
         sampler = B.ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
-        l0, h0 = ctx.launches, ctx.h2d_bytes
-        ctx.time_passes(True)
+        l0, h0 = sum(c.launches for c in lanes), sum(c.h2d_bytes for c in lanes)
+        for c in lanes:
+            c.time_passes(True)
         w0 = time.time()
         for _ in range(steps):
             texts = process(vcf)
         barrier()
         wall = time.time() - w0
-        scan_ms, d2h_ms, ncalls = ctx.pass_times()
-        ctx.time_passes(False)
+        scan_ms = d2h_ms = 0.0
+        ncalls = 0
+        for c in lanes:
+            a_, b_, n_ = c.pass_times()
+            scan_ms += a_; d2h_ms += b_; ncalls += n_
+            c.time_passes(False)
         clocks = sampler.stop() if sampler else None
-        launches, path_bytes = ctx.launches - l0, (ctx.h2d_bytes - h0) // steps
+        launches, path_bytes = sum(c.launches for c in lanes) - l0, (sum(c.h2d_bytes for c in lanes) - h0) // steps
         t = torch.tensor([wall], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,7 +318,7 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
                    "config": dict(config, workload=config["workload"].replace("-hist", "-polish") +
                                   f" + {info.records} VCF records ({info.clusters} clusters; 80% SNV, 10% ins, 10% del of 1-4 bp; 20% with a neighbour within 15 bp)",
                                   parallelism=f"clusters of every record split over {world} GPU(s) (mfn_variants_process shard/nshards), tables replicated, "
-                                              f"{threads} host threads per rank, no collective on the data path",
+                                              f"{threads} host threads per rank, {nlanes} scorer context(s) per GPU, no collective on the data path",
                                   l2_policy="inputs larger than L2 (every step uploads fresh path strings; the fused table is 25 GB)"),
                    "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": int(path_bytes_all),
                            "d2h_bytes_per_step": int(path_bytes_all * 9), "ms_per_step": 1e3 * e_wall / e_steps, "steps": e_steps,
@@ -332,6 +342,8 @@ def polish(args, B, ctx, api, lib, torch, dist, rank, world, local, dev, asm_np,
                                            "sample": "failed: %s" % (str(e)[:200],)}
             print(json.dumps(out))
     finally:
+        for c in locals().get("lanes", [])[1:]:
+            c.close()
         if rank == 0:
             import shutil
             shutil.rmtree(work, ignore_errors=True)
