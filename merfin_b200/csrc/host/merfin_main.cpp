@@ -565,6 +565,21 @@ int main(int argc, char **argv) {
       for (size_t i = 0; i < order.size(); i++) order[i] = i;
       nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, tasks.size()));
       if (nthreads > 1) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tasks[a].weight > tasks[b].weight; });
+      // Scorer lanes: the device part of a scorer call (upload, pack, scan, D2H of the pairs) holds its ctx's lock.  A
+      // second context per device over the SAME resident tables (they are only read) lets the calls of different
+      // host threads overlap on the device (MFN_LANES, default 2; one with -debug or a single thread).
+      size_t nlanes = 2;
+      if (const char *le = getenv("MFN_LANES")) nlanes = (size_t)std::max(1, std::min(8, atoi(le)));
+      if (nthreads == 1) nlanes = 1;
+      std::vector<std::vector<mfn_ctx *>> lanes(devs.size());
+      for (size_t d = 0; d < devs.size(); d++) {
+        lanes[d].push_back(devs[d].ctx);
+        for (size_t l = 1; l < nlanes; l++) {
+          mfn_ctx *c = nullptr;
+          if (mfn_ctx_create(&c, devs[d].id) != MFN_OK) break;          // (fewer lanes: still correct)
+          lanes[d].push_back(c);
+        }
+      }
       std::atomic<size_t> next{0};
       std::vector<int> tstatus(tasks.size(), MFN_OK);
       auto worker = [&]() {
@@ -572,7 +587,8 @@ int main(int argc, char **argv) {
           Task &t = tasks[order[j]];
           uint64_t localId = 0;
           Dev &D = devs[t.dev];
-          tstatus[order[j]] = mfn_variants_process(D.ctx, D.R, D.A, vcf, S.ident[t.rec].c_str(), S.seq(t.rec), S.length(t.rec), mode, G.comb, &km,
+          mfn_ctx *lane = lanes[t.dev][j % lanes[t.dev].size()];
+          tstatus[order[j]] = mfn_variants_process(lane, D.R, D.A, vcf, S.ident[t.rec].c_str(), S.seq(t.rec), S.length(t.rec), mode, G.comb, &km,
                                                    t.shard, t.nshards, &t.text, nullptr, G.debug ? &dbgs[t.rec] : nullptr, nullptr,
                                                    nthreads == 1 ? &varMerId : &localId);
           if (tstatus[order[j]] != MFN_OK) fprintf(stderr, "scoring failed: %s\n", mfn_last_error());
@@ -582,6 +598,7 @@ int main(int argc, char **argv) {
       for (unsigned t = 1; t < nthreads; t++) th.emplace_back(worker);
       worker();
       for (auto &t : th) t.join();
+      for (auto &dl : lanes) for (size_t l = 1; l < dl.size(); l++) mfn_ctx_destroy(dl[l]);
       // the pieces of a record, in order, are its result
       std::vector<std::string> joined(nrec);
       std::vector<char> has(nrec, 0);

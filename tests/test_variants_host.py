@@ -165,3 +165,48 @@ def test_bench_vcf_generator_against_reference(harness, tmp_path):
         assert _run(harness, d, mode, 10, "--shards", "3", "--batch", "50") == want, mode
         total += sum(1 for l in want.splitlines() if not l.startswith("#"))
     assert total > 10                          # (random edits are mostly rejected by the selectors)
+
+
+@pytest.mark.skipif(not os.path.exists(MERFIN), reason="oracle/_ref not built (reference sources absent)")
+def test_many_alleles_and_crowded_clusters_against_reference(harness, golden_dir, tmp_path):
+    """Genotypes that name three and four ALT alleles (a record's allele list longer than the three kept in line by
+    the front-end's small vectors) and runs of five variants inside one cluster (more than the two kept in line),
+    added to the golden VCF: same output as the unmodified reference run now, all five selectors."""
+    import shutil
+    d0 = os.path.join(golden_dir, "g1_k21")
+    d = str(tmp_path)
+    for f in ("asm.fa", "prob.csv"):
+        shutil.copy(os.path.join(d0, f), d)
+    for sub in ("reads.meryl", "asm.meryl"):
+        shutil.copytree(os.path.join(d0, sub), os.path.join(d, sub))
+    recs = dict(O_read_fasta(os.path.join(d0, "asm.fa")))
+    lines = open(os.path.join(d0, "calls.vcf")).read().splitlines()
+    head = [l for l in lines if l.startswith("#")]
+    body = [l for l in lines if not l.startswith("#")]
+    extra = []
+    for name, at, gt in (("seq1", 1200, "1/2/3"), ("seq1", 4100, "1|2|3|4"), ("seq2", 700, "3/1/2"), ("seq2", 3300, "4/4/2/1")):
+        ref = chr(recs[name][at]).upper()
+        alts = [b for b in "ACGT" if b != ref] + [ref + "TT"]
+        extra.append("%s\t%d\t.\t%s\t%s\t33\tPASS\t.\tGT\t%s" % (name, at + 1, ref, ",".join(alts), gt))
+    for name, at in (("seq1", 5000), ("seq2", 5200)):          # five SNVs 6 bp apart: one cluster of five
+        for j in range(5):
+            p = at + 6 * j
+            ref = chr(recs[name][p]).upper()
+            extra.append("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT\t%s" % (name, p + 1, ref, "A" if ref != "A" else "C", ("1/1", "0/1")[j % 2]))
+    allrecs = sorted(body + extra, key=lambda l: (l.split("\t")[0], int(l.split("\t")[1])))
+    open(os.path.join(d, "calls.vcf"), "w").write("\n".join(head + allrecs) + "\n")
+    for mode in ("polish", "filter", "better", "strict", "loose"):
+        p = subprocess.run([MERFIN, "-" + mode, "-sequence", "asm.fa", "-seqmers", "asm.meryl", "-readmers", "reads.meryl",
+                            "-vcf", "calls.vcf", "-peak", "8", "-threads", "1", "-memory", "4", "-output", "ref." + mode],
+                           cwd=d, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        want = open(os.path.join(d, "ref.%s.%s.vcf" % (mode, "polish" if mode == "polish" else "filter"))).read()
+        assert _run(harness, d, mode, 8) == want, mode
+        assert _run(harness, d, mode, 8, "--shards", "2", "--batch", "3") == want, mode
+
+
+def O_read_fasta(path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    return oracle_lib.read_fasta(path)
