@@ -138,7 +138,6 @@ static double histoQV(double kval, double ktot, uint32_t k) {          // merfin
 struct Dev {
   int id = 0;
   mfn_ctx *ctx = nullptr;
-  mfn_ctx *aux = nullptr;          // second context of the same device (concurrent table loads)
   mfn_table *R = nullptr, *A = nullptr;
   mfn_accum *acc = nullptr;
   int status = MFN_OK;
@@ -258,14 +257,6 @@ int main(int argc, char **argv) {
   load_Kmetric(G);
   mfn_kmodel km = {G.peak, (uint32_t)G.probK.size(), G.probK.data(), G.probP.data()};
 
-  // The FASTA file is read on a host thread while the CUDA contexts come up (0.3 s of driver start-up that needs no input).
-  SeqSet S;
-  std::string seq_err;
-  bool seq_ok = true;
-  std::thread seq_loader;
-  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } seq_joiner{seq_loader};
-  if (G.report != OP_COMPL && G.seqName) seq_loader = std::thread([&]() { seq_ok = load_sequences(G.seqName, S, seq_err); });
-
   if (G.devices.empty()) G.devices.push_back(G.device);
   std::vector<Dev> devs(G.devices.size());
   for (size_t d = 0; d < devs.size(); d++) devs[d].id = G.devices[d];
@@ -330,8 +321,9 @@ int main(int argc, char **argv) {
 
   // ---- sequences and tables (merfin-globals.C:114-195) -------------------------------------------
   fprintf(stderr, "-- Opening sequences in '%s'.\n", G.seqName);
-  if (seq_loader.joinable()) seq_loader.join();
-  if (!seq_ok) { fprintf(stderr, "ERROR: %s\n", seq_err.c_str()); return 1; }
+  SeqSet S;
+  std::string e;
+  if (!load_sequences(G.seqName, S, e)) { fprintf(stderr, "ERROR: %s\n", e.c_str()); return 1; }
 
   mark("sequences loaded");
   // every device loads its own replica of the tables (the databases are decoded on the device)
@@ -348,21 +340,7 @@ int main(int argc, char **argv) {
   else fprintf(stderr, "-- No -seqmer given. Counting the %u-mers of '%s' on the GPU.\n", K, G.seqName);
   auto load_reads = [&](Dev &D) -> int { return mfn_table_load(D.ctx, G.readDBname, (uint32_t)G.minV, (uint32_t)G.maxV, &D.R); };
   on_devices(devs, [&](Dev &D, size_t) {
-    // both databases at once when both come from disk: the assembly's through a second context of the device (its own
-    // stream and staging; tables belong to the device, not to the context that loaded them)
-    std::thread asm_loader;
-    int stA = MFN_OK;
-    std::string errA;
-    if (!stream_reads && G.seqDBname && mfn_ctx_create(&D.aux, D.id) == MFN_OK)
-      asm_loader = std::thread([&]() { stA = mfn_table_load(D.aux, G.seqDBname, 0, 0xffffffffu, &D.A); if (stA != MFN_OK) errA = mfn_last_error(); });
     int st = stream_reads ? MFN_OK : load_reads(D);
-    if (st != MFN_OK) D.error = mfn_last_error();
-    if (asm_loader.joinable()) {
-      asm_loader.join();
-      if (st == MFN_OK && stA != MFN_OK) { st = stA; D.error = errA; }
-      D.status = st;
-      return;
-    }
     if (st == MFN_OK) {
       if (G.seqDBname) st = mfn_table_load(D.ctx, G.seqDBname, 0, 0xffffffffu, &D.A);
       else {
@@ -661,7 +639,6 @@ int main(int argc, char **argv) {
   for (Dev &D : devs) {
     mfn_table_free(D.R);
     mfn_table_free(D.A);
-    if (D.aux) mfn_ctx_destroy(D.aux);
     mfn_ctx_destroy(D.ctx);
   }
   mark("device memory released");
