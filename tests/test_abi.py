@@ -180,3 +180,38 @@ def test_header_is_plain_c_and_example_links(tmp_path):
         p = subprocess.run([exe, os.path.join(g, "reads.meryl"), os.path.join(g, "asm.meryl"), "8", "ACGT" * 10],
                            capture_output=True, text=True)
         assert p.returncode == 1 and "no usable CUDA device" in p.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3, 7, 64])
+def test_vcf_loader_edge_cases(tmp_path, monkeypatch, threads):
+    """mfn_vcf_load / _info / _header / _cluster (host only; vcf.C:93-246) on a file with CRLF and blank lines, runs of
+    tabs, header lines in the middle, records with fewer than ten columns, a last line without a newline -- the same
+    counts whatever number of parsing threads the byte ranges are cut for."""
+    from merfin_b200 import api
+    recs = []
+    for i in range(400):
+        chrom = "chrA" if i % 3 else "chrB"
+        recs.append("%s\t%d\t.\tA\tC,G\t%d\tPASS\t.\tGT:DP\t%s:7" % (chrom, 10 + 37 * i, 20 + i % 30, ("1/1", "0/1", "1/2", "0/0", "./.")[i % 5]))
+    lines = ["##fileformat=VCFv4.2", "##contig=<ID=chrA,length=100000>", "##contig=<ID=chrB,length=100000>",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS"]
+    lines += recs[:100] + ["", "##late=header"] + recs[100:200] + ["chrA\t5\t.\tA\tC\t1\tPASS\t.\tGT"]          # 9 columns: excluded
+    lines += [recs[200].replace("\t", "\t\t", 3)] + [l + "\r" for l in recs[201:300]] + ["\r", "chrB\t7"] + recs[300:]
+    p = tmp_path / "odd.vcf"
+    p.write_bytes("\n".join(lines).encode())                      # no newline after the last record
+    monkeypatch.setenv("MFN_VCF_THREADS", str(threads))
+    monkeypatch.setenv("MFN_QUIET", "1")
+    v = api.Vcf(str(p))
+    i = v.info
+    assert (i.headers, i.records, i.excluded, i.contigs, i.contig_ids) == (5, 400, 2, 2, 2)
+    assert v.header() == ("\n".join(lines[:4] + ["##late=header"]) + "\n").encode()
+    assert v.clusters_of("chrA") + v.clusters_of("chrB") == 400 and v.clusters_of("chrC") == 0
+    v.cluster(21)
+    # chrA's records come in pairs 37 bp apart (closer than 2k = 42: merged), chrB's are 111 bp apart (left alone)
+    assert v.clusters_of("chrA") == 133 and v.clusters_of("chrB") == 134
+    counts = (v.clusters_of("chrA"), v.clusters_of("chrB"))
+    v.close()
+    monkeypatch.setenv("MFN_VCF_THREADS", "1")
+    v1 = api.Vcf(str(p))
+    v1.cluster(21)
+    assert (v1.clusters_of("chrA"), v1.clusters_of("chrB")) == counts
+    v1.close()
