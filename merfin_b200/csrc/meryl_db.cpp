@@ -455,7 +455,8 @@ extern "C" int mfn_meryl_histogram(const char *dir, uint64_t *values, uint64_t *
 }
 
 extern "C" int mfn_meryl_write(const char *dir, uint32_t k, const uint64_t *kmers, const uint32_t *values, uint64_t n) {
-  if (!dir || k < 4 || k > 32 || (n && (!kmers || !values))) { mfn_set_error("mfn_meryl_write: need 4 <= k <= 32"); return MFN_ERR_INVALID; }
+  if (k > 32) { mfn_set_error("mfn_meryl_write: k=%u; k-mers are passed in one 64-bit word (k <= 32)", k); return MFN_ERR_UNSUPPORTED; }
+  if (!dir || k < 4 || (n && (!kmers || !values))) { mfn_set_error("mfn_meryl_write: need 4 <= k <= 32"); return MFN_ERR_INVALID; }
   const uint32_t filesBits = 6;
   uint32_t blocksBits = 0;
   while (blocksBits < 16 && (n >> (filesBits + blocksBits)) > 8192) blocksBits++;
