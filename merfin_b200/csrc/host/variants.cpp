@@ -16,6 +16,11 @@
 #include <cstring>
 #include <stdexcept>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace mfnv {
 
 // strings.C:188-249: runs of separators collapse, empty words do not exist
@@ -93,31 +98,49 @@ static void make_allele(GtAllele *g, const VcfRecord *r, const std::vector<Span>
 // reference's (unstable) sort starts from, so it must be the file order.  Nothing is allocated per
 // line: a thread's records, alleles and clusters-to-be are three arrays sized for its share of the
 // lines (they never move, so the pointers between them hold), and all text is spans of text_.
+FileText::~FileText() { if (map_) munmap(map_, map_len_); }
+
+bool FileText::load(const std::string &path, std::string &err) {
+  auto ends = [&](const char *suf) { const size_t m = strlen(suf); return path.size() >= m && path.compare(path.size() - m, m, suf) == 0; };
+  struct stat st;
+  if (!ends(".gz") && !ends(".bz2") && !ends(".xz") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "cannot open '" + path + "'"; return false; }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (m != MAP_FAILED) { map_ = m; map_len_ = (size_t)st.st_size; p = (const char *)m; n = map_len_; return true; }
+  }
+  if (!slurp_file(path, owned_, err)) return false;      // compressed files, pipes, empty files
+  p = owned_.data(); n = owned_.size();
+  return true;
+}
+
 bool VcfFile::load(const std::string &path, std::string &err) {
-  if (!slurp_file(path, text_, err)) return false;
-  const std::vector<char> &data = text_;
-  const size_t N = data.size();
+  if (!text_.load(path, err)) return false;
+  const char *const data = text_.p;
+  const size_t N = text_.n;
   unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   if (N < (1u << 20)) T = 1;
   if (const char *env = getenv("MFN_VCF_THREADS")) T = (unsigned)std::max(1, atoi(env));     // (tests force the threaded path on small files)
   T = (unsigned)std::max<size_t>(1, std::min<size_t>(T, N / 64 + 1));
-  struct Part { std::vector<std::string> headers; uint64_t excluded = 0; };
+  struct Run { std::string_view chr; size_t first, count; };      // consecutive records of one sequence (indices into the thread's arrays)
+  struct Part { std::vector<std::string> headers; uint64_t excluded = 0; std::vector<Run> runs; };
   std::vector<Part> parts(T);
   records_.assign(T, {}); alleles_.assign(T, {}); posgts_.assign(T, {});
   // thread t takes the lines that START in bytes [N t / T, N (t + 1) / T)
   auto line_start_at_or_after = [&](size_t p) -> size_t {
     if (p == 0 || p >= N) return std::min(p, N);
     if (data[p - 1] == '\n') return p;
-    const char *nl = (const char *)memchr(data.data() + p, '\n', N - p);
-    return nl ? (size_t)(nl - data.data()) + 1 : N;
+    const char *nl = (const char *)memchr(data + p, '\n', N - p);
+    return nl ? (size_t)(nl - data) + 1 : N;
   };
   auto parse = [&](unsigned t) {
     const size_t b0 = line_start_at_or_after(N * t / T), b1 = line_start_at_or_after(N * (t + 1) / T);
     size_t nl_count = 0;
     for (size_t p = b0; p < b1;) {
-      const char *nl = (const char *)memchr(data.data() + p, '\n', b1 - p);
+      const char *nl = (const char *)memchr(data + p, '\n', b1 - p);
       nl_count++;
-      p = nl ? (size_t)(nl - data.data()) + 1 : b1;
+      p = nl ? (size_t)(nl - data) + 1 : b1;
     }
     std::vector<VcfRecord> &recs = records_[t];
     std::vector<GtAllele> &als = alleles_[t];
@@ -128,12 +151,12 @@ bool VcfFile::load(const std::string &path, std::string &err) {
     for (size_t next = b0; next < b1;) {
       size_t p = next, e;
       {
-        const char *nl = (const char *)memchr(data.data() + p, '\n', b1 - p);
-        e = next = nl ? (size_t)(nl - data.data()) + 1 : b1;
+        const char *nl = (const char *)memchr(data + p, '\n', b1 - p);
+        e = next = nl ? (size_t)(nl - data) + 1 : b1;
       }
       while (e > p && (data[e - 1] == '\r' || data[e - 1] == '\n')) e--;
       if (e == p) continue;
-      const char *line = data.data() + p;
+      const char *line = data + p;
       const size_t len = e - p;
       if (line[0] == '#') { parts[t].headers.emplace_back(line, len); continue; }
       split_spans(line, len, '\t', w);
@@ -154,6 +177,10 @@ bool VcfFile::load(const std::string &path, std::string &err) {
       pgs.emplace_back();
       PosGT *pg = &pgs.back();
       pg->rStart = g->pos; pg->rEnd = g->pos + g->refLen; pg->gts.push_back(g);
+      const std::string_view chr = r->col(VcfRecord::CHROM);
+      std::vector<Run> &runs = parts[t].runs;
+      if (runs.empty() || runs.back().chr != chr) runs.push_back(Run{chr, recs.size() - 1, 1});
+      else runs.back().count++;
     }
   };
   {
@@ -162,8 +189,12 @@ bool VcfFile::load(const std::string &path, std::string &err) {
     parse(0);
     for (auto &x : th) x.join();
   }
-  std::string_view last_chr;
-  std::pair<const std::string, std::vector<PosGT *>> *cur = nullptr;
+  // Every sequence's list of clusters-to-be, in file order: the runs are placed serially (where each run of a thread
+  // goes in its sequence's list), the lists sized once, and then every thread fills in its own runs.
+  typedef std::pair<const std::string, std::vector<PosGT *>> ChrNode;
+  struct Job { size_t first, count, dst; ChrNode *node; };
+  std::vector<std::vector<Job>> jobs(T);
+  std::map<ChrNode *, size_t> fill;
   for (unsigned t = 0; t < T; t++) {
     excluded += parts[t].excluded;
     for (std::string &h : parts[t].headers) {
@@ -171,12 +202,27 @@ bool VcfFile::load(const std::string &path, std::string &err) {
       headers.push_back(std::move(h));
     }
     num_records += records_[t].size();
-    for (size_t i = 0; i < records_[t].size(); i++) {
-      const std::string_view chr = records_[t][i].col(VcfRecord::CHROM);
-      if (!cur || chr != last_chr) { cur = &*byChr.try_emplace(std::string(chr)).first; last_chr = chr; }
-      posgts_[t][i].chr = &cur->first;
-      cur->second.push_back(&posgts_[t][i]);
+    for (const Run &r : parts[t].runs) {
+      ChrNode *node = &*byChr.try_emplace(std::string(r.chr)).first;
+      size_t &at = fill[node];
+      jobs[t].push_back(Job{r.first, r.count, at, node});
+      at += r.count;
     }
+  }
+  for (auto &kv : fill) kv.first->second.resize(kv.second);
+  auto place = [&](unsigned t) {
+    for (const Job &j : jobs[t])
+      for (size_t i = 0; i < j.count; i++) {
+        PosGT *pg = &posgts_[t][j.first + i];
+        pg->chr = &j.node->first;
+        j.node->second[j.dst + i] = pg;
+      }
+  };
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back(place, t);
+    place(0);
+    for (auto &x : th) x.join();
   }
   return true;
 }

@@ -61,6 +61,22 @@ struct PosGT {                              // vcf.H:59-90: a cluster of nearby 
   SmallVec<GtAllele *, 2> gts;
 };
 
+// The bytes of a file: a read-only mapping of a plain file (no copy, no page touched twice), or what the decompressor
+// of a .gz / .bz2 / .xz file wrote.
+struct FileText {
+  const char *p = nullptr;
+  size_t n = 0;
+  FileText() = default;
+  FileText(const FileText &) = delete;
+  FileText &operator=(const FileText &) = delete;
+  ~FileText();
+  bool load(const std::string &path, std::string &err);
+ private:
+  std::vector<char> owned_;
+  void *map_ = nullptr;
+  size_t map_len_ = 0;
+};
+
 struct VcfFile {
   std::vector<std::string> headers;
   uint64_t num_records = 0;
@@ -71,7 +87,7 @@ struct VcfFile {
   void mergeChrPosGT(uint32_t ksize, uint32_t comb, bool nosplit);   // vcf.C:156-246
  private:
   // the file's text and the objects of every data line, in the pieces the parsing threads made them in
-  std::vector<char> text_;
+  FileText text_;
   std::vector<std::vector<VcfRecord>> records_;
   std::vector<std::vector<GtAllele>> alleles_;
   std::vector<std::vector<PosGT>> posgts_;
