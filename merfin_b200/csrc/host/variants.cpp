@@ -167,8 +167,30 @@ bool VcfFile::load(const std::string &path, std::string &err) {
       for (int i = 0; i < VcfRecord::NCOL; i++) { r->col_off[i] = (uint32_t)(w[i].first - line); r->col_len[i] = (uint32_t)w[i].second; }
       char num[64];
       auto cstr = [&](int i) { const size_t n = std::min<size_t>(w[i].second, sizeof num - 1); memcpy(num, w[i].first, n); num[n] = 0; return num; };
-      r->pos = (uint32_t)strtoul(cstr(VcfRecord::POS), nullptr, 10);
-      r->qual = strtod(cstr(VcfRecord::QUAL), nullptr);
+      // POS and QUAL as strtoul / strtod read them; plain decimal numbers of a few digits take the exact short cut
+      // (an integer below 2^53 divided by a power of ten up to 10^22 is correctly rounded, i.e. what strtod returns)
+      {
+        const char *q = w[VcfRecord::POS].first;
+        const size_t n = w[VcfRecord::POS].second;
+        uint64_t v = 0;
+        size_t i = 0;
+        for (; i < n && i < 18 && q[i] >= '0' && q[i] <= '9'; i++) v = v * 10 + (uint64_t)(q[i] - '0');
+        r->pos = (i == n && n > 0) ? (uint32_t)v : (uint32_t)strtoul(cstr(VcfRecord::POS), nullptr, 10);
+      }
+      {
+        static const double P10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+        const char *q = w[VcfRecord::QUAL].first;
+        const size_t n = w[VcfRecord::QUAL].second;
+        uint64_t v = 0;
+        size_t i = 0, digits = 0, frac = 0;
+        bool dot = false, plain = n > 0 && n <= 16;
+        for (; plain && i < n; i++) {
+          if (q[i] >= '0' && q[i] <= '9') { v = v * 10 + (uint64_t)(q[i] - '0'); digits++; if (dot) frac++; }
+          else if (q[i] == '.' && !dot) dot = true;
+          else plain = false;
+        }
+        r->qual = (plain && digits > 0 && digits <= 15) ? (double)v / P10[frac] : strtod(cstr(VcfRecord::QUAL), nullptr);
+      }
       split_spans(w[VcfRecord::ALT].first, w[VcfRecord::ALT].second, ',', alts);
       split_spans(w[VcfRecord::SAMPLE].first, w[VcfRecord::SAMPLE].second, ':', fields);
       als.emplace_back();

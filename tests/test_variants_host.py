@@ -193,6 +193,10 @@ def test_many_alleles_and_crowded_clusters_against_reference(harness, golden_dir
             p = at + 6 * j
             ref = chr(recs[name][p]).upper()
             extra.append("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT\t%s" % (name, p + 1, ref, "A" if ref != "A" else "C", ("1/1", "0/1")[j % 2]))
+    # POS / QUAL spellings beyond plain integers (the loader's short cut for plain decimals must agree with strtoul / strtod)
+    quals = ["30.", ".5", "1e1", "007.25", "+4", "12345678901234567", "45.123456789012345", "0", ".", "3.0e-1", "99.95", "1234567890.12345"]
+    body = ["\t".join(f[:5] + [quals[i % len(quals)]] + f[6:]) if i % 2 else "\t".join(f) for i, f in enumerate(l.split("\t") for l in body)]
+    body = ["\t".join([f[0], "0" * (i % 3) + f[1]] + f[2:]) for i, f in enumerate(l.split("\t") for l in body)]
     allrecs = sorted(body + extra, key=lambda l: (l.split("\t")[0], int(l.split("\t")[1])))
     open(os.path.join(d, "calls.vcf"), "w").write("\n".join(head + allrecs) + "\n")
     for mode in ("polish", "filter", "better", "strict", "loose"):
