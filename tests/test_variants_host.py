@@ -214,3 +214,27 @@ def O_read_fasta(path):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     return oracle_lib.read_fasta(path)
+
+
+def test_front_end_under_address_and_ub_sanitizers(golden_dir, tmp_path):
+    """variants.cpp + fasta.cpp built with ASan + UBSan: the golden cases (k = 21 with shards / small batches / the
+    threaded parse / -debug, and the k = 40 set) run clean and still give the reference's files.  The records are spans
+    of the mapped file and the paths live in flat arrays: any over-read would show here."""
+    exe = str(tmp_path / "variant_harness_asan")
+    src = os.path.join(ROOT, "merfin_b200", "csrc", "host")
+    so_dir = os.path.join(ROOT, "merfin_b200")
+    obj = str(tmp_path / "mfn_oracle.o")
+    subprocess.check_call(["gcc", "-O1", "-w", "-std=gnu11", "-c", os.path.join(ROOT, "oracle", "mfn_oracle.c"), "-o", obj])
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c++17", "-ffp-contract=off", "-w",
+                           "-o", exe, os.path.join(ROOT, "tests", "variant_harness.cpp"), os.path.join(src, "variants.cpp"),
+                           os.path.join(src, "fasta.cpp"), obj, "-L" + so_dir, "-lmerfin_b200", "-Wl,-rpath," + so_dir, "-lm", "-pthread"])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", MFN_VCF_THREADS="3")       # (the harness never frees its oracle tables)
+    cases = [("g1_k21", "polish", 8, ()), ("g1_k21", "filter", 8, ("--shards", "3", "--batch", "2")), ("g1_k21", "loose", 8, ()),
+             ("g1_k21", "polish", 8, ("--debug",)), ("g4_k40", "polish", 6, ()), ("g4_k40", "better", 6, ("--batch", "1"))]
+    for name, mode, peak, extra in cases:
+        d = os.path.join(golden_dir, name)
+        p = subprocess.run([exe, os.path.join(d, "asm.fa"), os.path.join(d, "reads.meryl"), os.path.join(d, "asm.meryl"),
+                            os.path.join(d, "calls.vcf"), mode, str(peak), *extra], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+        assert p.returncode == 0, p.stderr[-3000:]
+        assert "AddressSanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-3000:]
+        assert p.stdout == open(os.path.join(d, f"ref.{mode}.vcf")).read(), (name, mode)
