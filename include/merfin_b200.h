@@ -406,7 +406,7 @@ int  mfn_completeness_report(const mfn_pair_count *pairs, uint64_t npairs, const
  * resp. / 64 words.  Used by mfn_hist_host's host packing lane; thread-safe on disjoint ranges. */
 void mfn_pack_host_range(const char *bases, const uint64_t *rec_start, uint32_t nseq, uint64_t g_begin,
                          uint64_t g_end, uint64_t *seq2_out, uint64_t *ok_out);
-const char *mfn_pack_host_isa(void);       /* "avx2" or "scalar" */
+const char *mfn_pack_host_isa(void);       /* "avx2" or "scalar" ("avx512" on request: MFN_PACK_ISA) */
 
 /* ---- choice of the -hist scan ------------------------------------------------------------
  * -hist over a big batch runs as the range-partitioned scan whenever a fused or

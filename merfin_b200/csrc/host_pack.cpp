@@ -6,8 +6,8 @@
 // base.  A packed piece is 0.375 bytes per base, so pieces packed by idle host cores cross the
 // link 2.7x cheaper; mfn_hist_host runs both lanes side by side (api.cu).
 //
-// Plain C++ (compiled by g++, not nvcc); the 32-base inner kernel uses AVX2 when the CPU has it
-// (runtime dispatch), a scalar loop otherwise.  Bit-identical to k_pack by construction; the GPU
+// Plain C++ (compiled by g++, not nvcc); the inner kernel is chosen at run time: AVX2 (two 32-base halves per 64-base
+// block) where the CPU has it, a scalar loop otherwise, and a 64-base AVX-512BW kernel on request.  Bit-identical to k_pack by construction; the GPU
 // parity test packs the same records both ways and compares the arrays.
 #include <algorithm>
 #include <cstdint>
@@ -33,11 +33,10 @@ static inline void pack32_scalar(const unsigned char *p, uint64_t *codes, uint32
 __attribute__((target("avx2"))) static inline void pack32_avx2(const unsigned char *p, uint64_t *codes, uint32_t *okmask) {
   const __m256i v = _mm256_loadu_si256((const __m256i *)p);
   const __m256i u = _mm256_or_si256(v, _mm256_set1_epi8(0x20));
-  // expected byte for each low nibble: 1 -> 'a', 3 -> 'c', 7 -> 'g', 4 -> 't', anything else never matches
-  const __m256i lut = _mm256_setr_epi8((char)0xff, 'a', (char)0xff, 'c', 't', (char)0xff, (char)0xff, 'g', (char)0xff, (char)0xff,
-                                       (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff, 'a',
-                                       (char)0xff, 'c', 't', (char)0xff, (char)0xff, 'g', (char)0xff, (char)0xff, (char)0xff,
-                                       (char)0xff, (char)0xff, (char)0xff, (char)0xff, (char)0xff);
+  // expected byte for each low nibble: 1 -> 'a', 3 -> 'c', 7 -> 'g', 4 -> 't'; 0 for every other nibble, which no byte
+  // with bit 0x20 set can equal (0xff as the "never" value made the bytes 0xdf and 0xff valid bases)
+  const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
+                                       0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
   const __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(u, _mm256_set1_epi8(0x0f)));
   const __m256i ok = _mm256_cmpeq_epi8(want, u);
   *okmask = (uint32_t)_mm256_movemask_epi8(ok);
@@ -52,6 +51,23 @@ __attribute__((target("avx2"))) static inline void pack32_avx2(const unsigned ch
                                                             0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
   const uint32_t lo = (uint32_t)_mm256_extract_epi32(z, 0), hi = (uint32_t)_mm256_extract_epi32(z, 4);
   *codes = ((uint64_t)hi << 32) | lo;
+}
+
+// 64 bases at p with AVX-512BW: the validity comparison yields the 64-bit mask directly, and the down-conversion of the
+// sixteen 32-bit lanes (each holding four bases' codes in its low byte) yields the two code words
+__attribute__((target("avx512f,avx512bw"))) static inline void pack64_avx512(const unsigned char *p, uint64_t *c0, uint64_t *c1, uint64_t *okmask) {
+  const __m512i v = _mm512_loadu_si512((const void *)p);
+  const __m512i u = _mm512_or_si512(v, _mm512_set1_epi8(0x20));
+  const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
+  const __m512i want = _mm512_shuffle_epi8(lut, _mm512_and_si512(u, _mm512_set1_epi8(0x0f)));
+  const __mmask64 ok = _mm512_cmpeq_epi8_mask(want, u);
+  const __m512i c = _mm512_maskz_mov_epi8(ok, _mm512_and_si512(_mm512_srli_epi16(v, 1), _mm512_set1_epi8(3)));
+  const __m512i x = _mm512_maddubs_epi16(c, _mm512_set1_epi16(0x0401));
+  const __m512i y = _mm512_madd_epi16(x, _mm512_set1_epi32(0x00100001));
+  const __m128i z = _mm512_cvtepi32_epi8(y);                    // byte j = bases 4j .. 4j + 3
+  *c0 = (uint64_t)_mm_cvtsi128_si64(z);
+  *c1 = (uint64_t)_mm_extract_epi64(z, 1);
+  *okmask = (uint64_t)ok;
 }
 
 // OR `n` (<= 32) bases starting at global position g into the word arrays (which hold zeros there)
@@ -77,8 +93,8 @@ static inline void zero_words(uint64_t *s2, uint64_t *so, uint64_t z0, uint64_t 
 // are NOT zeroed beforehand: whole 64-position blocks inside the segment are stored outright, and
 // `z` (a multiple of 64) says up to where everything else has been zeroed so far; blocks that only
 // get part of their bits from this segment are zeroed here before the bits are OR-ed in.
-template <class PACK32>
-static inline __attribute__((always_inline)) void pack_segment(PACK32 pack32, const unsigned char *p, uint64_t a, uint64_t b,
+template <class PACK32, class PACK64>
+static inline __attribute__((always_inline)) void pack_segment(PACK32 pack32, PACK64 pack64, const unsigned char *p, uint64_t a, uint64_t b,
                                                                uint64_t *s2, uint64_t *so, uint64_t &z) {
   uint64_t g = a;
   auto dep = [&](uint64_t n) {                       // n <= 32 bases at g, OR-ed into zeroed words
@@ -102,13 +118,11 @@ static inline __attribute__((always_inline)) void pack_segment(PACK32 pack32, co
       const uint64_t nblk = (fb - fa) >> 6;
       for (uint64_t i = 0; i < nblk; i++, q += 64) {
         _mm_prefetch((const char *)q + MFN_PACK_PREFETCH, _MM_HINT_T0);
-        uint64_t c0, c1;
-        uint32_t m0, m1;
-        pack32(q, &c0, &m0);
-        pack32(q + 32, &c1, &m1);
+        uint64_t c0, c1, m;
+        pack64(q, &c0, &c1, &m);
         o2[2 * i] = c0;
         o2[2 * i + 1] = c1;
-        oo[i] = ((uint64_t)m1 << 32) | m0;
+        oo[i] = m;
       }
       p = q; g = fb;
     }
@@ -125,19 +139,49 @@ static inline __attribute__((always_inline)) void pack_segment(PACK32 pack32, co
     while (g < b) dep(std::min<uint64_t>(32, b - g));
   }
 }
+static inline void pack64_scalar(const unsigned char *q, uint64_t *c0, uint64_t *c1, uint64_t *m) {
+  uint32_t m0, m1;
+  pack32_scalar(q, c0, &m0);
+  pack32_scalar(q + 32, c1, &m1);
+  *m = ((uint64_t)m1 << 32) | m0;
+}
+__attribute__((target("avx2"))) static inline void pack64_avx2(const unsigned char *q, uint64_t *c0, uint64_t *c1, uint64_t *m) {
+  uint32_t m0, m1;
+  pack32_avx2(q, c0, &m0);
+  pack32_avx2(q + 32, c1, &m1);
+  *m = ((uint64_t)m1 << 32) | m0;
+}
 static void pack_segment_scalar(const unsigned char *p, uint64_t a, uint64_t b, uint64_t *s2, uint64_t *so, uint64_t &z) {
-  pack_segment(pack32_scalar, p, a, b, s2, so, z);
+  pack_segment(pack32_scalar, pack64_scalar, p, a, b, s2, so, z);
 }
 __attribute__((target("avx2"))) static void pack_segment_avx2(const unsigned char *p, uint64_t a, uint64_t b, uint64_t *s2, uint64_t *so, uint64_t &z) {
-  pack_segment(pack32_avx2, p, a, b, s2, so, z);
+  pack_segment(pack32_avx2, pack64_avx2, p, a, b, s2, so, z);
+}
+__attribute__((target("avx512f,avx512bw,avx2"))) static void pack_segment_avx512(const unsigned char *p, uint64_t a, uint64_t b, uint64_t *s2, uint64_t *so, uint64_t &z) {
+  pack_segment(pack32_avx2, pack64_avx512, p, a, b, s2, so, z);
 }
 typedef void (*segment_fn)(const unsigned char *, uint64_t, uint64_t, uint64_t *, uint64_t *, uint64_t &);
-static bool use_avx2() {
+// The kernel: AVX2 where the CPU has it, else scalar.  MFN_PACK_ISA = scalar | avx2 | avx512 picks another one the CPU
+// supports (tests compare all three; MFN_PACK_SCALAR=1 is the older spelling of "scalar").  The AVX-512 kernel is not the
+// default: one core packs 5-10 % faster with it, but from a handful of threads on both are bound by memory bandwidth
+// (8 threads: 41-49 GB/s of ASCII either way on the development host).
+static int pack_level() {
   __builtin_cpu_init();
-  const char *env = getenv("MFN_PACK_SCALAR");           // tests compare the two kernels
-  return __builtin_cpu_supports("avx2") && !(env && atoi(env));
+  const bool avx2 = __builtin_cpu_supports("avx2");
+  const bool avx512 = avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+  int level = avx2 ? 1 : 0;
+  const char *env = getenv("MFN_PACK_SCALAR");
+  if (env && atoi(env)) level = 0;
+  if (const char *isa = getenv("MFN_PACK_ISA")) {
+    if (!strcmp(isa, "scalar")) level = 0;
+    else if (!strcmp(isa, "avx512") && avx512) level = 2;
+  }
+  return level;
 }
-static segment_fn pick_segment() { return use_avx2() ? pack_segment_avx2 : pack_segment_scalar; }
+static segment_fn pick_segment() {
+  const int level = pack_level();
+  return level == 2 ? pack_segment_avx512 : level == 1 ? pack_segment_avx2 : pack_segment_scalar;
+}
 
 // Pack global positions [g_begin, g_end) (both multiples of 64) of a sequence set into
 // seq2_out / ok_out, whose word 0 is global word g_begin/32 resp. g_begin/64.  rec_start[r] is the
@@ -164,4 +208,4 @@ extern "C" void mfn_pack_host_range(const char *bases, const uint64_t *rec_start
 }
 
 // Which inner kernel this CPU gets (for logs and tests).
-extern "C" const char *mfn_pack_host_isa(void) { return use_avx2() ? "avx2" : "scalar"; }
+extern "C" const char *mfn_pack_host_isa(void) { const int level = pack_level(); return level == 2 ? "avx512" : level == 1 ? "avx2" : "scalar"; }

@@ -47,9 +47,10 @@ def test_pack_host_range_matches_definition(seed, lens):
     assert (gotok == wantok).all()
 
 
-def test_scalar_and_avx2_kernels_agree(tmp_path):
-    """The packer picks its 32-base kernel once per process; run the same input through a child
-    process with the scalar kernel forced and compare the packed words."""
+def test_scalar_avx2_and_avx512_kernels_agree(tmp_path):
+    """The packer picks its inner kernel once per process; run the same input through child processes with each
+    kernel forced (MFN_PACK_ISA) and compare the packed words.  The input holds EVERY byte value (the AVX2 kernel once
+    took 0xdf and 0xff for bases: its "matches nothing" table entry was 0xff) next to the usual alphabet."""
     import os
     import subprocess
     import sys
@@ -61,22 +62,32 @@ from merfin_b200 import lib as L
 lib = L.load()
 rng = np.random.default_rng(21)
 b = rng.choice(np.frombuffer(b"ACGTacgtNn-*", dtype=np.uint8), size=200_003)
+b[1000:1256] = np.arange(256, dtype=np.uint8)
+b[150_000:150_000 + 4096] = rng.integers(0, 256, size=4096, dtype=np.uint8)
 rs = np.array([0, 70_001, 70_001 + 130_002 + 1], dtype=np.uint64)
 G = (int(rs[-1]) + 2047) // 2048 * 2048
 s2 = np.zeros(G // 32, dtype=np.uint64); ok = np.zeros(G // 64, dtype=np.uint64)
 lib.mfn_pack_host_range(C.c_void_p(b.ctypes.data), C.c_void_p(rs.ctypes.data), 2, C.c_uint64(0), C.c_uint64(G),
                         C.c_void_p(s2.ctypes.data), C.c_void_p(ok.ctypes.data))
-sys.stdout.write(lib.mfn_pack_host_isa().decode() + " " + str(int(s2.sum() & np.uint64(0xffffffffffff))) + " " + str(int(np.bitwise_xor.reduce(s2))) + " " + str(int(np.bitwise_xor.reduce(ok))))
+valid = [int(b[i]) for i in range(1000, 1256) if (int(ok[i // 64]) >> (i %% 64)) & 1]
+sys.stdout.write(lib.mfn_pack_host_isa().decode() + " " + str(int(s2.sum() & np.uint64(0xffffffffffff))) + " " + str(int(np.bitwise_xor.reduce(s2))) + " " + str(int(np.bitwise_xor.reduce(ok))) + " " + ",".join(map(str, valid)))
 """ % root
     outs = {}
-    for scalar in ("0", "1"):
-        env = dict(os.environ, MFN_PACK_SCALAR=scalar)
+    for isa in ("scalar", "avx2", "avx512"):
+        env = dict(os.environ, MFN_PACK_ISA=isa)
         p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
         assert p.returncode == 0, p.stderr
-        isa, *digest = p.stdout.split()
-        outs[scalar] = (isa, digest)
-    assert outs["1"][0] == "scalar"
-    assert outs["0"][1] == outs["1"][1]
+        got, *digest = p.stdout.split()
+        outs[isa] = (got, digest)
+    assert outs["scalar"][0] == "scalar"
+    assert outs["scalar"][1][3] == ",".join(str(c) for c in sorted(b"ACGTacgt"))          # exactly the eight letters are bases
+    assert outs["avx2"][1] == outs["scalar"][1] and outs["avx512"][1] == outs["scalar"][1]
+    import subprocess as sp
+    flags = open("/proc/cpuinfo").read()
+    if " avx2" in flags:
+        assert outs["avx2"][0] == "avx2"
+    if " avx512bw" in flags:
+        assert outs["avx512"][0] == "avx512"                      # (else the request falls back to what the CPU has)
 
 
 @pytest.mark.parametrize("seed", range(12))
