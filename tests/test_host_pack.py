@@ -126,7 +126,7 @@ def test_pack_host_range_block_boundaries(seed):
 def test_packer_under_address_sanitizer(tmp_path):
     """host_pack.cpp built with ASan+UBSan and driven by tests/pack_sanitize_harness.cpp: every piece is
     packed into its own exact-size allocation from an exact-size source (no access outside either), and
-    compared with a per-base loop; both the AVX2 and the scalar kernel."""
+    compared with a per-base loop; the scalar, the AVX2 and (where the CPU has it) the AVX-512 kernel."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -137,6 +137,6 @@ def test_packer_under_address_sanitizer(tmp_path):
     if b.returncode != 0 and ("cannot find -l" in b.stderr or "libasan" in b.stderr):
         pytest.skip("sanitizer runtime not installed")
     assert b.returncode == 0, b.stderr[-2000:]
-    for scalar in ("0", "1"):
-        p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, MFN_PACK_SCALAR=scalar))
-        assert p.returncode == 0 and p.stdout.strip() == "ok", (scalar, p.stdout[-500:], p.stderr[-3000:])
+    for isa in ("avx2", "scalar", "avx512"):
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, MFN_PACK_ISA=isa))
+        assert p.returncode == 0 and p.stdout.strip() == "ok", (isa, p.stdout[-500:], p.stderr[-3000:])
